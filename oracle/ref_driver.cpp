@@ -1,0 +1,226 @@
+/*
+ * ref_driver.cpp -- TEST INFRASTRUCTURE ONLY (never linked into the product).
+ *
+ * A plain C ABI around the UNMODIFIED reference library (oracle/_ref/libgrok_ref.so,
+ * built by oracle/Makefile.ref from /root/reference).  It lets the Python tests call the
+ * reference's own stage functions on raw buffers so that the C restatement (gb_oracle.c)
+ * and the CUDA kernels can be pinned against the real thing:
+ *
+ *   ref_mct_*          -> grk::mct::{encode,decode}_{rev,irrev}     mct/mct.cpp:85,143,195,352
+ *   ref_dwt_encode     -> grk::Wavelet::encode                      transform/Wavelet.cpp:35
+ *   ref_dwt_decode     -> grk::Wavelet::decode                      transform/Wavelet.cpp, dwt.cpp:1208,2154
+ *   ref_t1_encode_cblk -> grk::t1_encode_cblk                       t1/t1_part1/t1.cpp:1182
+ *   ref_t1_decode_cblk -> grk::t1_decode_cblk                       t1/t1_part1/t1.cpp:1038
+ *   ref_dwt_norm       -> grk::dwt_utils::getnorm_{53,97}           transform/dwt_utils.cpp:143
+ *   ref_band_stepsize  -> grk::Quantizer::setBandStepSizeAndBps     codestream/Quantizer.cpp:65
+ *   ref_qcd_generate   -> grk::param_qcd::generate                  codestream/HTParams.cpp:164
+ *
+ * Only the reference's headers are included (a build-time include dependency); no reference
+ * source is copied here.
+ */
+#include "grok_includes.h"
+#include "t1_common.h"
+#include "Tier1.h"
+#include "dwt53.h"
+#include "dwt97.h"
+#include "HTParams.h"
+#include <cstring>
+#include <cstdlib>
+#include <new>
+
+using namespace grk;
+
+static inline uint32_t cdp2(uint32_t a, uint32_t b) { return (uint32_t) (((uint64_t) a + ((uint64_t) 1 << b) - 1) >> b); }
+
+extern "C" {
+
+int ref_init(uint32_t nthreads) {
+	return grk_initialize(nullptr, nthreads) ? 0 : 1;
+}
+
+void ref_mct_encode_rev(int32_t *c0, int32_t *c1, int32_t *c2, uint64_t n) { mct::encode_rev(c0, c1, c2, n); }
+void ref_mct_decode_rev(int32_t *c0, int32_t *c1, int32_t *c2, uint64_t n) { mct::decode_rev(c0, c1, c2, n); }
+void ref_mct_encode_irrev(int32_t *c0, int32_t *c1, int32_t *c2, uint64_t n) { mct::encode_irrev(c0, c1, c2, n); }
+void ref_mct_decode_irrev(float *c0, float *c1, float *c2, uint64_t n) { mct::decode_irrev(c0, c1, c2, n); }
+
+double ref_dwt_norm(uint32_t level, uint32_t orient, int reversible) {
+	return reversible ? dwt_utils::getnorm_53(level, (uint8_t) orient) : dwt_utils::getnorm_97(level, (uint8_t) orient);
+}
+double ref_mct_norm(uint32_t compno, int reversible) {
+	return reversible ? mct::get_norms_rev()[compno] : mct::get_norms_irrev()[compno];
+}
+
+/* A TileComponent carrying just what Wavelet::{encode,decode} read: the resolution rectangles,
+ * the tile-component rectangle and a TileBuffer that aliases the caller's plane. */
+struct FakeTilec {
+	TileComponent *tc;
+	FakeTilec(int32_t *data, uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1, uint32_t numres,
+			uint32_t numres_decode, bool encoder) {
+		tc = new TileComponent();
+		tc->numresolutions = numres;
+		tc->numAllocatedResolutions = numres;
+		tc->minimum_num_resolutions = numres_decode;
+		tc->m_is_encoder = encoder;
+		tc->resolutions = new grk_tcd_resolution[numres];
+		for (uint32_t r = 0; r < numres; ++r) {
+			uint32_t lvl = numres - 1 - r;
+			auto res = tc->resolutions + r;
+			res->x0 = cdp2(x0, lvl);
+			res->y0 = cdp2(y0, lvl);
+			res->x1 = cdp2(x1, lvl);
+			res->y1 = cdp2(y1, lvl);
+			for (int b = 0; b < 3; ++b)
+				res->bands[b].precincts = nullptr;
+		}
+		auto top = tc->resolutions + (encoder ? numres : numres_decode) - 1;
+		tc->x0 = top->x0; tc->y0 = top->y0; tc->x1 = top->x1; tc->y1 = top->y1;
+		tc->buf = new TileBuffer();
+		tc->buf->data = data;
+		tc->buf->owns_data = false;
+		tc->buf->data_size = 0;
+		tc->buf->data_size_needed = 0;
+		tc->buf->reduced_image_dim = grk_rect(top->x0, top->y0, top->x1, top->y1);
+		tc->buf->reduced_tile_dim = tc->buf->reduced_image_dim;
+	}
+	~FakeTilec() {
+		tc->buf->data = nullptr;
+		delete tc;
+	}
+};
+
+/* in place on `data` (row stride = x1-x0), tile-component canvas rectangle [x0,x1)x[y0,y1) */
+int ref_dwt_encode(int32_t *data, uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1, uint32_t numres,
+		int qmfbid) {
+	FakeTilec f(data, x0, y0, x1, y1, numres, numres, true);
+	Wavelet w;
+	return w.encode(f.tc, (uint8_t) qmfbid) ? 0 : 1;
+}
+
+/* in place; row stride = width of resolution numres_decode-1 (how -r works, dwt.cpp:735) */
+int ref_dwt_decode(int32_t *data, uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1, uint32_t numres,
+		uint32_t numres_decode, int qmfbid) {
+	FakeTilec f(data, x0, y0, x1, y1, numres, numres_decode, false);
+	/* Wavelet::decode only reads p_tcd->whole_tile_decoding */
+	void *mem = grk_calloc(1, sizeof(TileProcessor));
+	auto tp = reinterpret_cast<TileProcessor*>(mem);
+	tp->whole_tile_decoding = true;
+	Wavelet w;
+	bool ok = w.decode(tp, f.tc, numres_decode, (uint8_t) qmfbid);
+	grok_free(mem);
+	return ok ? 0 : 1;
+}
+
+/* Tier-1 encode of one code block.  `data` holds w*h quantised coefficients WITH the 6 fractional
+ * bits (what T1Part1::preEncode produces).  Returns total passes; fills numbps, per-pass rate/len/
+ * distortion, and the byte stream (out must hold >= w*h*4+16 bytes). */
+int ref_t1_encode_cblk(const int32_t *data, uint32_t w, uint32_t h, uint32_t orient, uint32_t compno,
+		uint32_t level, uint32_t qmfbid, double stepsize, uint32_t cblksty, const double *mct_norms,
+		uint32_t mct_numcomps, int do_rate_control, uint8_t *out, uint32_t *numbps, uint32_t *rates,
+		uint32_t *lens, double *dists, double *total_dist) {
+	t1_info *t1 = t1_create(true);
+	if (!t1 || !t1_allocate_buffers(t1, w, h))
+		return -1;
+	t1->data_stride = w;
+	uint32_t mx = 0;
+	for (uint32_t i = 0; i < w * h; ++i) {
+		t1->data[i] = data[i];
+		uint32_t a = (uint32_t) abs(data[i]);
+		if (a > mx) mx = a;
+	}
+	/* reference allocates 2 zeroed pad bytes in front (TileProcessor.cpp:1997-2018) */
+	size_t cap = (size_t) w * h * 4 + 64;
+	uint8_t *buf = (uint8_t*) grk_calloc(1, cap);
+	tcd_cblk_enc_t cblk;
+	memset(&cblk, 0, sizeof(cblk));
+	cblk.x0 = 0; cblk.y0 = 0; cblk.x1 = w; cblk.y1 = h;
+	cblk.data = buf + 2;
+	cblk.data_size = (uint32_t) (cap - 2);
+	double d = t1_encode_cblk(t1, &cblk, mx, (uint8_t) orient, compno, level, qmfbid, stepsize, cblksty,
+			mct_norms, mct_numcomps, do_rate_control != 0);
+	*numbps = cblk.numbps;
+	int np = (int) cblk.totalpasses;
+	for (int i = 0; i < np; ++i) {
+		rates[i] = cblk.passes[i].rate;
+		lens[i] = cblk.passes[i].len;
+		dists[i] = cblk.passes[i].distortiondec;
+	}
+	if (np > 0)
+		memcpy(out, cblk.data, rates[np - 1]);
+	if (total_dist) *total_dist = d;
+	t1_code_block_enc_deallocate(&cblk);
+	grok_free(buf);
+	t1_destroy(t1);
+	return np;
+}
+
+/* Tier-1 decode of one single-segment code block; out gets t1->data (values still carry the
+ * extra low bit; T1Part1::post_decode halves them). */
+int ref_t1_decode_cblk(const uint8_t *bytes, uint32_t len, uint32_t numpasses, uint32_t numbps,
+		uint32_t orient, uint32_t roishift, uint32_t cblksty, uint32_t w, uint32_t h, int32_t *out) {
+	t1_info *t1 = t1_create(false);
+	if (!t1)
+		return -1;
+	uint8_t *buf = (uint8_t*) grk_calloc(1, (size_t) len + 16);
+	memcpy(buf, bytes, len);
+	tcd_seg_data_chunk_t chunk;
+	chunk.data = buf;
+	chunk.len = len + GRK_FAKE_MARKER_BYTES;
+	tcd_seg_t seg;
+	memset(&seg, 0, sizeof(seg));
+	seg.len = len;
+	seg.real_num_passes = numpasses;
+	tcd_cblk_dec_t cblk;
+	memset(&cblk, 0, sizeof(cblk));
+	cblk.numchunks = 1;
+	cblk.chunks = &chunk;
+	cblk.x0 = 0; cblk.y0 = 0; cblk.x1 = w; cblk.y1 = h;
+	cblk.real_num_segs = 1;
+	cblk.segs = &seg;
+	cblk.numbps = numbps;
+	bool ok = t1_decode_cblk(t1, &cblk, orient, roishift, cblksty, false);
+	if (ok)
+		memcpy(out, t1->data, (size_t) w * h * sizeof(int32_t));
+	grok_free(buf);
+	t1_destroy(t1);
+	return ok ? 0 : 1;
+}
+
+/* default quantisation: exponent/mantissa per band as grk_compress derives them
+ * (j2k.cpp:1839-1841 -> HTParams.cpp:164).  expn/mant have 3*decomps+1 entries. */
+void ref_qcd_generate(uint32_t guard_bits, uint32_t decomps, int reversible, uint32_t prec,
+		int color_transform, int is_signed, uint32_t *expn, uint32_t *mant) {
+	param_qcd q;
+	q.generate((uint8_t) guard_bits, decomps, reversible != 0, prec, color_transform != 0, is_signed != 0);
+	grk_stepsize steps[GRK_J2K_MAXBANDS];
+	memset(steps, 0, sizeof(steps));
+	q.pull(steps, reversible != 0);
+	for (uint32_t i = 0; i < 3 * decomps + 1; ++i) {
+		expn[i] = steps[i].expn;
+		mant[i] = steps[i].mant;
+	}
+}
+
+/* band stepsize / numbps / inv_step exactly as Quantizer::setBandStepSizeAndBps computes them */
+void ref_band_stepsize(uint32_t expn, uint32_t mant, uint32_t resno, uint32_t bandno_in_res, uint32_t orient,
+		int qmfbid, uint32_t numgbits, uint32_t prec, float fraction, float *stepsize, uint32_t *numbps,
+		uint32_t *inv_step) {
+	grk_tcp tcp;
+	tcp.isHT = false;
+	grk_tccp tccp;
+	memset(&tccp, 0, sizeof(tccp));
+	tccp.qmfbid = (uint8_t) qmfbid;
+	tccp.numgbits = (uint8_t) numgbits;
+	tccp.roishift = 0;
+	uint32_t offset = (resno == 0) ? 0 : 3 * resno - 2;
+	tccp.stepsizes[offset + bandno_in_res].expn = (uint8_t) expn;
+	tccp.stepsizes[offset + bandno_in_res].mant = (uint16_t) mant;
+	grk_tcd_band band;
+	band.bandno = (uint8_t) orient;
+	Quantizer q;
+	q.setBandStepSizeAndBps(&tcp, &band, resno, (uint8_t) bandno_in_res, &tccp, prec, fraction);
+	*stepsize = band.stepsize;
+	*numbps = band.numbps;
+	*inv_step = band.inv_step;
+}
+
+} /* extern "C" */

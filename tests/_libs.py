@@ -1,0 +1,156 @@
+"""ctypes loaders for the three native libraries the tests talk to.
+
+oracle()  -> oracle/libgb_oracle.so       the CPU restatement (checker)
+ref()     -> oracle/_ref/libgrkref_driver.so   the compiled, unmodified reference (checker of the checker)
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+
+i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
+f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+i16p = np.ctypeslib.ndpointer(np.int16, flags="C_CONTIGUOUS")
+
+_oracle = None
+_ref = None
+
+
+def aligned(a, align=64):
+    """Copy of `a` whose data pointer is `align`-byte aligned (the reference's AVX2 loops use
+    aligned loads on tile buffers)."""
+    a = np.ascontiguousarray(a)
+    raw = np.empty(a.nbytes + align, np.uint8)
+    off = (-raw.ctypes.data) % align
+    out = raw[off:off + a.nbytes].view(a.dtype).reshape(a.shape)
+    out[...] = a
+    return out
+
+
+class GboBlock(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in
+                ("resno", "orient", "precno", "cblkno", "x0", "y0", "x1", "y1", "off_x", "off_y")]
+
+
+def oracle():
+    global _oracle
+    if _oracle is not None:
+        return _oracle
+    so = os.path.join(ORACLE_DIR, "libgb_oracle.so")
+    src = os.path.join(ORACLE_DIR, "gb_oracle.c")
+    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "libgb_oracle.so"])
+    L = C.CDLL(so)
+    L.gbo_dc_shift_fwd.argtypes = [i32p, C.c_uint64, C.c_int32, C.c_int]
+    L.gbo_dc_shift_inv.argtypes = [i32p, C.c_uint64, C.c_int32, C.c_int, C.c_int32, C.c_int32]
+    for n in ("gbo_rct_fwd", "gbo_rct_inv", "gbo_ict_fwd"):
+        getattr(L, n).argtypes = [i32p, i32p, i32p, C.c_uint64]
+    L.gbo_ict_inv.argtypes = [f32p, f32p, f32p, C.c_uint64]
+    L.gbo_dwt_fwd.argtypes = [i32p] + [C.c_uint32] * 5 + [C.c_int]
+    L.gbo_dwt_inv.argtypes = [i32p] + [C.c_uint32] * 6 + [C.c_int]
+    L.gbo_quantise_block.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int32, i32p]
+    L.gbo_quantise_block.restype = C.c_uint32
+    L.gbo_dequantise_block.argtypes = [i32p, C.c_uint32, C.c_uint32, C.c_int, C.c_float, C.c_void_p, C.c_uint32]
+    L.gbo_t1_encode_block.argtypes = [i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p,
+                                      C.POINTER(C.c_uint32), u32p, f64p, C.POINTER(C.c_uint64)]
+    L.gbo_t1_decode_block.argtypes = [u8p, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i32p]
+    L.gbo_nmsedec_tables.argtypes = [i16p] * 4
+    L.gbo_context_tables.argtypes = [u8p, u8p, u8p]
+    L.gbo_enumerate_blocks.argtypes = [C.c_uint32] * 7 + [u32p, C.c_void_p]
+    _oracle = L
+    return L
+
+
+def have_ref():
+    return os.path.exists(os.path.join(ORACLE_DIR, "_ref", "libgrkref_driver.so"))
+
+
+def ref():
+    global _ref
+    if _ref is not None:
+        return _ref
+    L = C.CDLL(os.path.join(ORACLE_DIR, "_ref", "libgrkref_driver.so"))
+    L.ref_init.argtypes = [C.c_uint32]
+    for n in ("ref_mct_encode_rev", "ref_mct_decode_rev", "ref_mct_encode_irrev"):
+        getattr(L, n).argtypes = [i32p, i32p, i32p, C.c_uint64]
+    L.ref_mct_decode_irrev.argtypes = [f32p, f32p, f32p, C.c_uint64]
+    L.ref_dwt_norm.argtypes = [C.c_uint32, C.c_uint32, C.c_int]
+    L.ref_dwt_norm.restype = C.c_double
+    L.ref_mct_norm.argtypes = [C.c_uint32, C.c_int]
+    L.ref_mct_norm.restype = C.c_double
+    L.ref_dwt_encode.argtypes = [i32p] + [C.c_uint32] * 5 + [C.c_int]
+    L.ref_dwt_decode.argtypes = [i32p] + [C.c_uint32] * 6 + [C.c_int]
+    L.ref_t1_encode_cblk.argtypes = [i32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                     C.c_double, C.c_uint32, C.c_void_p, C.c_uint32, C.c_int, u8p,
+                                     C.POINTER(C.c_uint32), u32p, u32p, f64p, C.POINTER(C.c_double)]
+    L.ref_t1_decode_cblk.argtypes = [u8p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                     C.c_uint32, C.c_uint32, i32p]
+    L.ref_qcd_generate.argtypes = [C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_int, C.c_int, u32p, u32p]
+    L.ref_band_stepsize.argtypes = [C.c_uint32] * 5 + [C.c_int, C.c_uint32, C.c_uint32, C.c_float,
+                                                       C.POINTER(C.c_float), C.POINTER(C.c_uint32),
+                                                       C.POINTER(C.c_uint32)]
+    L.ref_init(int(os.environ.get("GRK_REF_THREADS", "4")))
+    _ref = L
+    return L
+
+
+# ---- convenience wrappers ------------------------------------------------------------------
+
+def oracle_t1_encode(blk, orient, do_rd=False, wbase=0.0):
+    """blk: int32 [h,w] with 6 fractional bits. -> (bytes, numbps, rates, dists, nsym)"""
+    L = oracle()
+    h, w = blk.shape
+    buf = np.zeros(w * h * 4 + 16, np.uint8)
+    rates = np.zeros(128, np.uint32)
+    dists = np.zeros(128, np.float64)
+    nb = C.c_uint32()
+    ns = C.c_uint64()
+    n = L.gbo_t1_encode_block(np.ascontiguousarray(blk, np.int32).ravel(), w, h, orient, int(do_rd), wbase,
+                              buf.ctypes.data + 1, C.byref(nb), rates, dists, C.byref(ns))
+    assert n >= 0
+    total = int(rates[n - 1]) if n else 0
+    return bytes(buf[1:1 + total]), nb.value, rates[:n].copy(), dists[:n].copy(), ns.value
+
+
+def ref_t1_encode(blk, orient, compno=0, level=0, qmfbid=1, stepsize=1.0, mct_norms=None, do_rd=False):
+    L = ref()
+    h, w = blk.shape
+    buf = np.zeros(w * h * 4 + 64, np.uint8)
+    rates = np.zeros(128, np.uint32)
+    lens = np.zeros(128, np.uint32)
+    dists = np.zeros(128, np.float64)
+    nb = C.c_uint32()
+    td = C.c_double()
+    if mct_norms is not None:
+        mn = np.ascontiguousarray(mct_norms, np.float64)
+        mp, nm = mn.ctypes.data, len(mn)
+    else:
+        mp, nm = None, 0
+    n = L.ref_t1_encode_cblk(np.ascontiguousarray(blk, np.int32).ravel(), w, h, orient, compno, level, qmfbid,
+                             stepsize, 0, mp, nm, int(do_rd), buf, C.byref(nb), rates, lens, dists, C.byref(td))
+    assert n >= 0
+    total = int(rates[n - 1]) if n else 0
+    return bytes(buf[:total]), nb.value, rates[:n].copy(), dists[:n].copy()
+
+
+def oracle_t1_decode(data, numpasses, numbps, orient, w, h):
+    out = np.zeros((h, w), np.int32)
+    b = np.frombuffer(bytes(data) + b"\0\0", np.uint8).copy()
+    rc = oracle().gbo_t1_decode_block(b, len(data), numpasses, numbps, orient, w, h, out.ravel())
+    assert rc == 0
+    return out
+
+
+def ref_t1_decode(data, numpasses, numbps, orient, w, h):
+    out = np.zeros((h, w), np.int32)
+    b = np.frombuffer(bytes(data) + b"\0\0", np.uint8).copy()
+    rc = ref().ref_t1_decode_cblk(b, len(data), numpasses, numbps, orient, 0, 0, w, h, out.ravel())
+    assert rc == 0
+    return out
