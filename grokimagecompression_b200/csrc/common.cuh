@@ -1,0 +1,81 @@
+// Internal declarations shared by the kernels and the C-ABI layer of libgrok_b200.so.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace gb {
+
+// One tile-component plane of one decomposition level, as the DWT kernels see it.
+// (a-4..a-7 of SURVEY.md section 8: WaveletForward.h:40-161, dwt.cpp:724-858, 1544-1738)
+struct DwtPlane {
+	const int32_t *src;   // forward: samples of the level-l LL region; inverse: LL_{l+1} (low-low quadrant)
+	const int32_t *band;  // inverse only: buffer holding HL/LH/HH of this level in Mallat position
+	int32_t *dst;         // forward: Mallat layout of this level; inverse: reconstructed LL_l
+	uint32_t src_stride, band_stride, dst_stride;
+	uint32_t rw, rh;      // size of the level-l region
+	uint32_t sw, sh;      // low-pass counts (size of LL_{l+1})
+	uint32_t cas_x, cas_y; // parity of the region origin on the canvas (1: first sample is high-pass)
+	uint32_t tiles_x, tiles_y; // CTA tiling of this plane
+	uint32_t first_cta;   // prefix sum of CTAs over the planes of the launch
+	uint32_t pad;
+};
+
+// Encoder-side code block (a-8, a-9 of SURVEY.md section 8: T1Part1.cpp:58-133, t1.cpp:1182-1326)
+struct EncBlock {
+	const int32_t *src;  // top-left coefficient of the block inside its sub-band (DWT output)
+	uint32_t stride;
+	uint16_t w, h;
+	uint8_t orient, reversible, pad0, pad1;
+	int32_t inv_step;
+	uint32_t pass_offset; // first slot in rates/dists
+	uint32_t max_passes;
+	uint32_t scratch_cap; // byte capacity reserved for this block
+	uint64_t scratch_off; // byte offset of the block's scratch area (one pad byte precedes the stream)
+	double rd_weight;
+};
+
+struct EncResult { // == gb200_cblk_enc
+	uint32_t numbps, numpasses, data_len, decisions;
+	uint64_t data_offset;
+};
+
+// Decoder-side code block (a-13: t1.cpp:1038-1130, T1Part1.cpp:135-329)
+struct DecBlock {
+	int32_t *dst;        // top-left of the block inside the coefficient plane
+	uint32_t stride;
+	uint16_t w, h;
+	uint8_t orient, reversible, pad0, pad1;
+	float stepsize;
+	uint32_t pad2;
+};
+
+struct DecInput { // == gb200_cblk_dec
+	uint32_t numbps, numpasses, data_len, reserved;
+	uint64_t data_offset;
+};
+
+// tables.cu
+void upload_tables();
+
+// mct.cu : DC level shift fused with RCT/ICT.  n samples per plane.
+void launch_dcshift_fwd(int32_t *x, uint64_t n, int32_t shift, int reversible, cudaStream_t s);
+void launch_mct_fwd(int32_t *c0, int32_t *c1, int32_t *c2, uint64_t n, int32_t s0, int32_t s1, int32_t s2,
+		int reversible, int do_shift, cudaStream_t s);
+void launch_dcshift_inv(int32_t *x, uint64_t n, int32_t shift, int reversible, int32_t lo, int32_t hi, cudaStream_t s);
+void launch_mct_inv(int32_t *c0, int32_t *c1, int32_t *c2, uint64_t n, const int32_t shift[3], const int32_t lo[3],
+		const int32_t hi[3], int reversible, int do_shift_clamp, cudaStream_t s);
+
+// dwt.cu : one launch = one decomposition level of every plane in `planes` (device array).
+void launch_dwt_fwd(const DwtPlane *planes_dev, uint32_t total_ctas, int reversible, cudaStream_t s);
+void launch_dwt_inv(const DwtPlane *planes_dev, uint32_t total_ctas, int reversible, cudaStream_t s);
+void dwt_tile_shape(uint32_t *tw, uint32_t *th);
+
+// t1_enc.cu / t1_dec.cu : one warp per code block.
+void launch_t1_encode(const EncBlock *blocks, uint32_t nblocks, int rate_control, uint8_t *scratch, EncResult *results,
+		uint32_t *rates, double *dists, cudaStream_t s);
+void launch_t1_gather(const EncBlock *blocks, EncResult *results, uint32_t nblocks, const uint8_t *scratch,
+		uint8_t *data, cudaStream_t s);
+void launch_t1_decode(const DecBlock *blocks, const DecInput *inputs, uint32_t nblocks, const uint8_t *data,
+		uint32_t max_planes, cudaStream_t s);
+
+} // namespace gb

@@ -1,0 +1,415 @@
+// K4 (+K6): EBCOT Tier-1 encoder, one warp per code block, quantisation fused into the load.
+//
+//   T1Part1::preEncode   T1Part1.cpp:58-95    quantise (x64 or fixed-point multiply), block max
+//   t1_encode_cblk       t1.cpp:1182-1326     plane loop, pass order, rates, distortion
+//   sig / ref / cln pass t1.cpp:287-338, 498-555, 739-782 (steps 197-231, 443-463, 639-699)
+//   MQ encoder           mqc_enc.cpp:168-287
+//
+// Design (not the reference's column-serial flag-word walk):
+//  * Block state is five 64-bit row masks per row in shared memory (significant, negative,
+//    visited, refined, current bit-plane), built with warp ballots; a 64-bit word is one row.
+//  * Which samples a pass codes is computed BIT-PARALLEL for a whole stripe (4 rows x 64 columns)
+//    with shifts and ORs.  The significance-propagation pass needs the samples that became
+//    significant earlier in the same pass; because the encoder knows every bit in advance this is
+//    a monotone fixed point over the stripe's masks, reached in a few iterations.
+//  * The 32 lanes then form contexts for 32 columns at once (8-neighbour windows cut from the
+//    masks, the scan-order visibility of newly significant neighbours applied with masks), and
+//    write (context, decision) symbols in scan order into a shared-memory queue (warp prefix sum).
+//  * The MQ coder consumes the queue; A/C/CT live in registers, identical in all lanes, so the
+//    serial part is divergence free.  Bytes leave through lane 0 with a one-byte carry delay.
+#include "common.cuh"
+#include "t1_tables.cuh"
+
+namespace gb {
+
+constexpr int ENC_WARPS = 4;
+constexpr int QCAP = 32 * 11 + 32;
+
+struct EncWarp {
+	uint64_t sig[66], neg[66], vis[66], refd[66], bit[66]; // index = row + 1 (rows -1 and 64 stay zero)
+	uint8_t queue[QCAP];
+};
+
+struct EncLuts {
+	uint8_t zc[4][256];
+	uint8_t sc[256];
+	int16_t nmsedec[4][128];
+};
+
+__device__ __forceinline__ uint64_t hor(uint64_t m) { return (m << 1) | (m >> 1); }
+__device__ __forceinline__ uint64_t full(uint64_t m) { return m | (m << 1) | (m >> 1); }
+// bits (x-1, x, x+1) of a row mask as bits 0..2
+__device__ __forceinline__ uint32_t win3(uint64_t m, int x) {
+	return (uint32_t) (x == 0 ? (m << 1) : (m >> (x - 1))) & 7u;
+}
+
+struct Mq {
+	uint32_t a, c;
+	int ct;
+	int pos;        // index of the byte held in `last`; -1 = the pad byte in front of the stream
+	uint32_t last;
+	uint8_t *out;   // stream start (out[-1] is the pad)
+	uint32_t cap;
+	uint32_t overflow;
+	uint32_t nsym;
+	uint32_t cst;   // MQ context `lane`: state index << 1 | mps (lanes 0..18), read with a shuffle
+};
+
+__device__ __forceinline__ void mq_byteout(Mq &q, int lane) {
+	if (q.last != 0xFF && (q.c & 0x8000000u)) { // carry into the delayed byte
+		q.last++;
+		q.c &= 0x7FFFFFFu;
+	}
+	if (q.pos >= 0) {
+		if ((uint32_t) q.pos < q.cap) { if (lane == 0) q.out[q.pos] = (uint8_t) q.last; }
+		else q.overflow = 1;
+	}
+	q.pos++;
+	if (q.last == 0xFF) { q.last = (q.c >> 20) & 0xFF; q.c &= 0xFFFFFu; q.ct = 7; }
+	else { q.last = (q.c >> 19) & 0xFF; q.c &= 0x7FFFFu; q.ct = 8; }
+}
+
+__device__ __forceinline__ void mq_encode(Mq &q, uint32_t sym, int lane) {
+	uint32_t cx = sym >> 1, d = sym & 1;
+	uint32_t st = __shfl_sync(0xffffffffu, q.cst, cx);
+	uint32_t row = c_mq[st >> 1];
+	uint32_t qe = row & 0xFFFFu;
+	q.nsym++;
+	q.a -= qe;
+	if (d == (st & 1)) {
+		if (q.a & 0x8000u) { q.c += qe; return; }
+		if (q.a < qe) q.a = qe; else q.c += qe;
+		st = (((row >> 16) & 63u) << 1) | (st & 1);
+	} else {
+		if (q.a < qe) q.c += qe; else q.a = qe;
+		st = (((row >> 22) & 63u) << 1) | ((st & 1) ^ (row >> 28));
+	}
+	if (lane == (int) cx) q.cst = st;
+	int sh = __clz(q.a) - 16; // bits to bring A back to >= 0x8000
+	while (sh > 0) {
+		int n = sh < q.ct ? sh : q.ct;
+		q.a <<= n; q.c <<= n; q.ct -= n; sh -= n;
+		if (q.ct == 0) mq_byteout(q, lane);
+	}
+}
+
+__device__ __forceinline__ void mq_flush(Mq &q, int lane) {
+	uint32_t t = q.c + q.a;
+	q.c |= 0xFFFFu;
+	if (q.c >= t) q.c -= 0x8000u;
+	q.c <<= q.ct; mq_byteout(q, lane);
+	q.c <<= q.ct; mq_byteout(q, lane);
+	if (q.last != 0xFF) {
+		if ((uint32_t) q.pos < q.cap) { if (lane == 0) q.out[q.pos] = (uint8_t) q.last; }
+		else q.overflow = 1;
+		q.pos++;
+	}
+}
+
+// quantised magnitude with 6 fractional bits and sign (T1Part1.cpp:45-56, 75, 85)
+__device__ __forceinline__ int32_t quantise(int32_t x, bool rev, int32_t inv_step) {
+	return rev ? x * 64 : (int32_t) (((int64_t) x * inv_step + (1 << 17)) >> 18);
+}
+
+// warp-wide: lanes hand in `cnt` symbols each (packed 8 bits per symbol, first symbol lowest);
+// they are appended to the queue in lane order and then MQ-coded by the whole warp.
+__device__ __forceinline__ void emit_and_code(EncWarp &W, Mq &q, uint64_t lo, uint32_t hi, int cnt, int lane) {
+	int incl = cnt;
+	#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		int t = __shfl_up_sync(0xffffffffu, incl, o);
+		if (lane >= o) incl += t;
+	}
+	int total = __shfl_sync(0xffffffffu, incl, 31);
+	if (total == 0) return;
+	int off = incl - cnt;
+	for (int j = 0; j < cnt; ++j) {
+		uint32_t s = j < 8 ? (uint32_t) (lo >> (8 * j)) & 0xFF : (hi >> (8 * (j - 8))) & 0xFF;
+		W.queue[off + j] = (uint8_t) s;
+	}
+	__syncwarp();
+	for (int i = 0; i < total; ++i)
+		mq_encode(q, W.queue[i], lane);
+	__syncwarp();
+}
+
+#define PUSH(sym) do { uint32_t s_ = (sym); if (cnt < 8) lo |= (uint64_t) s_ << (8 * cnt); else hi |= s_ << (8 * (cnt - 8)); cnt++; } while (0)
+
+__global__ void __launch_bounds__(ENC_WARPS * 32) t1_encode_kernel(const EncBlock *__restrict__ blocks, uint32_t nblocks,
+		int rate_control, uint8_t *__restrict__ scratch, EncResult *__restrict__ results, uint32_t *__restrict__ rates,
+		double *__restrict__ dists) {
+	__shared__ EncWarp warps[ENC_WARPS];
+	__shared__ EncLuts L;
+	for (int i = threadIdx.x; i < 1024; i += blockDim.x) L.zc[i >> 8][i & 255] = c_zc[i >> 8][i & 255];
+	for (int i = threadIdx.x; i < 256; i += blockDim.x) L.sc[i] = c_sc[i];
+	for (int i = threadIdx.x; i < 512; i += blockDim.x) L.nmsedec[i >> 7][i & 127] = c_nmsedec[i >> 7][i & 127];
+	__syncthreads();
+
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	const uint32_t bid = blockIdx.x * ENC_WARPS + wid;
+	if (bid >= nblocks) return;
+	EncWarp &W = warps[wid];
+	const EncBlock B = blocks[bid];
+	const int w = B.w, h = B.h;
+	const bool rev = B.reversible != 0;
+	const uint64_t wmask = w >= 64 ? ~0ull : ((1ull << w) - 1);
+	const uint8_t *zc = L.zc[B.orient];
+
+	// ---- quantise, block maximum, sign masks ------------------------------------------------
+	for (int i = lane; i < 66; i += 32) { W.sig[i] = 0; W.neg[i] = 0; W.vis[i] = 0; W.refd[i] = 0; W.bit[i] = 0; }
+	__syncwarp();
+	uint32_t mx = 0;
+	for (int y = 0; y < h; ++y) {
+		const int32_t *row = B.src + (size_t) y * B.stride;
+		int32_t v0 = lane < w ? quantise(row[lane], rev, B.inv_step) : 0;
+		int32_t v1 = lane + 32 < w ? quantise(row[lane + 32], rev, B.inv_step) : 0;
+		mx = max(mx, (uint32_t) abs(v0));
+		mx = max(mx, (uint32_t) abs(v1));
+		uint32_t n0 = __ballot_sync(0xffffffffu, v0 < 0), n1 = __ballot_sync(0xffffffffu, v1 < 0);
+		if (lane == 0) W.neg[y + 1] = (uint64_t) n0 | ((uint64_t) n1 << 32);
+	}
+	#pragma unroll
+	for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+	const int nbits = 32 - __clz(mx);
+	const int numbps = nbits > 6 ? nbits - 6 : 0; // t1.cpp:1202-1208
+	if (numbps == 0) {
+		if (lane == 0) { EncResult r = {0, 0, 0, 0, 0}; results[bid] = r; }
+		return;
+	}
+
+	Mq q;
+	q.a = 0x8000; q.c = 0; q.ct = 12; q.pos = -1; q.last = 0; q.overflow = 0; q.nsym = 0;
+	q.out = scratch + B.scratch_off + 1;
+	q.cap = B.scratch_cap - 1;
+	q.cst = lane == CTX_ZC0 ? (4 << 1) : lane == CTX_AGG ? (3 << 1) : lane == CTX_UNI ? (46 << 1) : 0; // mqc_dec.cpp:207-214
+
+	uint32_t *my_rates = rates + B.pass_offset;
+	double *my_dists = dists + B.pass_offset;
+	int npass = 0;
+	double cum = 0.0;
+
+	for (int bp = numbps - 1; bp >= 0; --bp) {
+		// ---- bit-plane masks for this plane -------------------------------------------------
+		for (int y = 0; y < h; ++y) {
+			const int32_t *row = B.src + (size_t) y * B.stride;
+			uint32_t m0 = lane < w ? (uint32_t) abs(quantise(row[lane], rev, B.inv_step)) : 0;
+			uint32_t m1 = lane + 32 < w ? (uint32_t) abs(quantise(row[lane + 32], rev, B.inv_step)) : 0;
+			uint32_t b0 = __ballot_sync(0xffffffffu, (m0 >> (bp + 6)) & 1), b1 = __ballot_sync(0xffffffffu, (m1 >> (bp + 6)) & 1);
+			if (lane == 0) W.bit[y + 1] = (uint64_t) b0 | ((uint64_t) b1 << 32);
+		}
+		__syncwarp();
+
+		for (int type = (bp == numbps - 1 ? 2 : 0); type < 3; ++type) {
+			int nmsedec = 0;
+			for (int y0 = 0; y0 < h; y0 += 4) {
+				const int nk = min(4, h - y0);
+				uint64_t S[6], Bm[4], M[4], N[4], H0[4];
+				#pragma unroll
+				for (int j = 0; j < 6; ++j) S[j] = W.sig[y0 + j];
+				#pragma unroll
+				for (int k = 0; k < 4; ++k) {
+					Bm[k] = W.bit[y0 + 1 + k];
+					H0[k] = hor(S[k + 1]) | full(S[k]) | full(S[k + 2]);
+					N[k] = 0;
+				}
+				uint64_t rl = 0;
+				if (type == 0) {
+					// membership of the significance-propagation pass: least fixed point
+					bool changed = true;
+					while (changed) {
+						changed = false;
+						#pragma unroll
+						for (int k = 0; k < 4; ++k) {
+							uint64_t up = k > 0 ? N[k - 1] : 0;
+							uint64_t west = (up | N[k] | (k < 3 ? N[k + 1] : 0)) << 1;
+							M[k] = k < nk ? (~S[k + 1] & (H0[k] | west | up) & wmask) : 0;
+							uint64_t n = M[k] & Bm[k];
+							if (n != N[k]) { changed = true; N[k] = n; }
+						}
+					}
+				} else if (type == 1) {
+					#pragma unroll
+					for (int k = 0; k < 4; ++k) M[k] = k < nk ? (S[k + 1] & ~W.vis[y0 + 1 + k] & wmask) : 0;
+				} else {
+					#pragma unroll
+					for (int k = 0; k < 4; ++k) {
+						M[k] = k < nk ? (~S[k + 1] & ~W.vis[y0 + 1 + k] & wmask) : 0;
+						N[k] = M[k] & Bm[k];
+					}
+					if (nk == 4)
+						rl = M[0] & M[1] & M[2] & M[3] & ~full(S[0] | S[1] | S[2] | S[3] | S[4] | S[5])
+								& ~((N[0] | N[1] | N[2] | N[3]) << 1);
+				}
+				const uint64_t any = M[0] | M[1] | M[2] | M[3];
+				if (any) {
+					for (int ch = 0; ch * 32 < w; ++ch) {
+						if (((any >> (32 * ch)) & 0xffffffffull) == 0) continue;
+						const int gx = ch * 32 + lane;
+						uint64_t lo = 0; uint32_t hi = 0; int cnt = 0;
+						uint32_t mem4 = 0;
+						#pragma unroll
+						for (int k = 0; k < 4; ++k) mem4 |= (uint32_t) ((M[k] >> gx) & 1) << k;
+						if (mem4) {
+							if (type == 1) {
+								#pragma unroll
+								for (int k = 0; k < 4; ++k) if (mem4 >> k & 1) {
+									uint32_t ctx = (W.refd[y0 + 1 + k] >> gx & 1) ? CTX_MR0 + 2 : (H0[k] >> gx & 1) ? CTX_MR0 + 1 : CTX_MR0;
+									PUSH(ctx << 1 | (uint32_t) (Bm[k] >> gx & 1));
+									if (rate_control) {
+										uint32_t mag = (uint32_t) abs(quantise(B.src[(size_t) (y0 + k) * B.stride + gx], rev, B.inv_step));
+										nmsedec += L.nmsedec[bp > 0 ? 2 : 3][(mag >> bp) & 127];
+									}
+								}
+							} else {
+								uint32_t sw[6], nw[4], gw[6];
+								#pragma unroll
+								for (int j = 0; j < 6; ++j) { sw[j] = win3(S[j], gx); gw[j] = win3(W.neg[y0 + j], gx); }
+								#pragma unroll
+								for (int k = 0; k < 4; ++k) nw[k] = win3(N[k], gx);
+								int k0 = 0;
+								bool implied = false; // first sample after a run: its 1 is implied, go straight to the sign
+								if (type == 2 && (rl >> gx & 1)) {
+									uint32_t b4 = (uint32_t) (Bm[0] >> gx & 1) | (uint32_t) (Bm[1] >> gx & 1) << 1
+											| (uint32_t) (Bm[2] >> gx & 1) << 2 | (uint32_t) (Bm[3] >> gx & 1) << 3;
+									int r = b4 ? __ffs(b4) - 1 : 4;
+									PUSH(CTX_AGG << 1 | (r != 4));
+									if (r == 4) k0 = 4;
+									else {
+										PUSH(CTX_UNI << 1 | (r >> 1));
+										PUSH(CTX_UNI << 1 | (r & 1));
+										k0 = r;
+										implied = true;
+									}
+								}
+								#pragma unroll
+								for (int k = 0; k < 4; ++k) {
+									if (k < k0 || !(mem4 >> k & 1)) continue;
+									// 8-neighbourhood as visible when the scan reaches (gx, y0+k): newly
+									// significant samples count only in the west column and above in this column
+									uint32_t top = k == 0 ? sw[0] : (sw[k] | (nw[k - 1] & 3));
+									uint32_t mid = sw[k + 1] | (nw[k] & 1);
+									uint32_t bot = k == 3 ? sw[5] : (sw[k + 2] | (nw[k + 1] & 1));
+									uint32_t d = (uint32_t) (Bm[k] >> gx & 1);
+									if (!(implied && k == k0)) {
+										uint32_t idx = top | (mid & 1) << 3 | (mid >> 2) << 4 | bot << 5;
+										PUSH((uint32_t) zc[idx] << 1 | d);
+									}
+									if (d) {
+										uint32_t sN = top >> 1 & 1, sW = mid & 1, sE = mid >> 2 & 1, sS = bot >> 1 & 1;
+										uint32_t gN = gw[k] >> 1 & 1, gW = gw[k + 1] & 1, gE = gw[k + 1] >> 2 & 1, gS = gw[k + 2] >> 1 & 1;
+										uint32_t idx = sN | sW << 1 | sE << 2 | sS << 3 | (gN & sN) << 4 | (gW & sW) << 5 | (gE & sE) << 6 | (gS & sS) << 7;
+										uint32_t v = L.sc[idx];
+										uint32_t sgn = gw[k + 1] >> 1 & 1;
+										PUSH((v & 31) << 1 | (sgn ^ (v >> 5)));
+										if (rate_control) {
+											uint32_t mag = (uint32_t) abs(quantise(B.src[(size_t) (y0 + k) * B.stride + gx], rev, B.inv_step));
+											nmsedec += L.nmsedec[bp > 0 ? 0 : 1][(mag >> bp) & 127];
+										}
+									}
+								}
+							}
+						}
+						emit_and_code(W, q, lo, hi, cnt, lane);
+					}
+				}
+				// commit the stripe
+				if (lane == 0) {
+					#pragma unroll
+					for (int k = 0; k < 4; ++k) if (k < nk) {
+						if (type != 1) W.sig[y0 + 1 + k] |= N[k];
+						if (type == 0) W.vis[y0 + 1 + k] |= M[k];
+						if (type == 1) W.refd[y0 + 1 + k] |= M[k];
+					}
+				}
+				__syncwarp();
+			}
+			if (type == 2) {
+				for (int i = lane; i < 66; i += 32) W.vis[i] = 0;
+				__syncwarp();
+			}
+			// ---- pass bookkeeping (t1.cpp:1255-1290) ----------------------------------------
+			if (rate_control) {
+				#pragma unroll
+				for (int o = 16; o; o >>= 1) nmsedec += __shfl_xor_sync(0xffffffffu, nmsedec, o);
+				double x = __dmul_rn(B.rd_weight, (double) (1 << bp));
+				x = __dmul_rn(x, __ddiv_rn(__dmul_rn(x, (double) nmsedec), 8192.0));
+				cum = __dadd_rn(cum, x);
+			}
+			uint32_t rate;
+			if (type == 2 && bp == 0) { mq_flush(q, lane); rate = (uint32_t) q.pos; }
+			else rate = (uint32_t) q.pos + (q.ct < 5 ? 6 : 5);
+			if (lane == 0 && (uint32_t) npass < B.max_passes) { my_rates[npass] = rate; my_dists[npass] = rate_control ? cum : 0.0; }
+			npass++;
+		}
+	}
+	__syncwarp();
+	// ---- rate fix-ups (t1.cpp:1300-1324): non-increasing from the end, no trailing 0xFF ------
+	if (lane == 0) {
+		int np = min(npass, (int) B.max_passes);
+		uint32_t lastr = (uint32_t) q.pos;
+		for (int i = np - 1; i >= 0; --i) {
+			uint32_t r = my_rates[i];
+			if (r > lastr) { r = lastr; my_rates[i] = r; } else lastr = r;
+		}
+		for (int i = 0; i < np; ++i) {
+			uint32_t r = my_rates[i];
+			uint8_t prev = r >= 1 && r - 1 < q.cap ? q.out[r - 1] : 0;
+			if (prev == 0xFF) my_rates[i] = r - 1;
+		}
+		EncResult res;
+		res.numbps = (uint32_t) numbps;
+		res.numpasses = (q.overflow || npass > (int) B.max_passes) ? 0xFFFFFFFFu : (uint32_t) npass;
+		res.data_len = np ? my_rates[np - 1] : 0;
+		res.decisions = q.nsym;
+		res.data_offset = 0;
+		results[bid] = res;
+	}
+}
+
+// ---- compaction: exclusive prefix sum of the block lengths, then one warp copies each block ----
+__global__ void __launch_bounds__(1024) t1_offsets_kernel(EncResult *results, uint32_t nblocks) {
+	__shared__ uint64_t part[1024];
+	const uint32_t per = (nblocks + 1023) / 1024;
+	const uint32_t b0 = threadIdx.x * per, b1 = min(nblocks, b0 + per);
+	uint64_t s = 0;
+	for (uint32_t i = b0; i < b1; ++i) s += results[i].data_len;
+	part[threadIdx.x] = s;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		uint64_t run = 0;
+		for (int i = 0; i < 1024; ++i) { uint64_t t = part[i]; part[i] = run; run += t; }
+	}
+	__syncthreads();
+	uint64_t off = part[threadIdx.x];
+	for (uint32_t i = b0; i < b1; ++i) { results[i].data_offset = off; off += results[i].data_len; }
+}
+
+__global__ void __launch_bounds__(256) t1_gather_kernel(const EncBlock *__restrict__ blocks, const EncResult *__restrict__ results,
+		uint32_t nblocks, const uint8_t *__restrict__ scratch, uint8_t *__restrict__ data) {
+	const uint32_t bid = blockIdx.x * 8 + (threadIdx.x >> 5);
+	if (bid >= nblocks) return;
+	const int lane = threadIdx.x & 31;
+	const uint8_t *src = scratch + blocks[bid].scratch_off + 1;
+	uint8_t *dst = data + results[bid].data_offset;
+	const uint32_t n = results[bid].data_len;
+	for (uint32_t i = lane; i < n; i += 32) dst[i] = src[i];
+}
+
+static bool g_tables_ready = false;
+
+void launch_t1_encode(const EncBlock *blocks, uint32_t nblocks, int rate_control, uint8_t *scratch, EncResult *results,
+		uint32_t *rates, double *dists, cudaStream_t s) {
+	if (!nblocks) return;
+	if (!g_tables_ready) { build_and_upload_t1_tables(); g_tables_ready = true; }
+	t1_encode_kernel<<<(nblocks + ENC_WARPS - 1) / ENC_WARPS, ENC_WARPS * 32, 0, s>>>(blocks, nblocks, rate_control, scratch,
+			results, rates, dists);
+}
+
+void launch_t1_gather(const EncBlock *blocks, EncResult *results, uint32_t nblocks, const uint8_t *scratch, uint8_t *data,
+		cudaStream_t s) {
+	if (!nblocks) return;
+	t1_offsets_kernel<<<1, 1024, 0, s>>>(results, nblocks);
+	t1_gather_kernel<<<(nblocks + 7) / 8, 256, 0, s>>>(blocks, results, nblocks, scratch, data);
+}
+
+} // namespace gb
