@@ -59,6 +59,7 @@ SYMBOLS = [
     "gb200_plan_num_samples", "gb200_plan_blocks", "gb200_plan_data_capacity",
     "gb200_encode_tiles", "gb200_decode_tiles", "gb200_encode_upload", "gb200_encode_run", "gb200_encode_download",
     "gb200_decode_upload", "gb200_decode_run", "gb200_decode_download", "gb200_sync",
+    "gb200_encode_stash", "gb200_encode_restore",
     "gb200_encode_run_stage", "gb200_decode_run_stage", "gb200_encode_get_coefficients",
     "gb200_decode_set_coefficients",
     "gb200_mct_encode_rev", "gb200_mct_decode_rev", "gb200_mct_encode_irrev", "gb200_mct_decode_irrev",
@@ -105,6 +106,8 @@ def lib():
     L.gb200_decode_upload.argtypes = [vp, vp, vp, u64]
     L.gb200_decode_run.argtypes = [vp]
     L.gb200_decode_download.argtypes = [vp, C.POINTER(vp)]
+    L.gb200_encode_stash.argtypes = [vp]
+    L.gb200_encode_restore.argtypes = [vp]
     L.gb200_encode_run_stage.argtypes = [vp, C.c_int]
     L.gb200_decode_run_stage.argtypes = [vp, C.c_int]
     L.gb200_encode_get_coefficients.argtypes = [vp, u32, u32, vp]
@@ -285,6 +288,12 @@ class Plan:
 
     def encode_upload(self, planes):
         check(lib().gb200_encode_upload(self._h, self._ptr_array(planes)))
+
+    def encode_stash(self):
+        check(lib().gb200_encode_stash(self._h))
+
+    def encode_restore(self):
+        check(lib().gb200_encode_restore(self._h))
 
     def encode_run(self):
         check(lib().gb200_encode_run(self._h))

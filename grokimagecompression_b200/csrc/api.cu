@@ -88,6 +88,7 @@ struct gb200_plan {
 	std::vector<EncResult> h_results;
 	// where each tile-component's final decoded plane lives (0 A, 1 B, 2 C)
 	std::vector<int> final_role;
+	std::vector<DevBuf> stash;
 };
 
 extern "C" {
@@ -213,6 +214,7 @@ void gb200_plan_destroy(gb200_plan *pl) {
 	for (auto &b : pl->bufA) b.release();
 	for (auto &b : pl->bufB) b.release();
 	for (auto &b : pl->bufC) b.release();
+	for (auto &b : pl->stash) b.release();
 	for (int r = 0; r < 2; ++r) for (auto &l : pl->lvl[r]) l.dev.release();
 	pl->d_blocks.release(); pl->d_results.release(); pl->d_rates.release(); pl->d_dists.release();
 	pl->d_scratch.release(); pl->d_data.release(); pl->d_inputs.release();
@@ -447,6 +449,25 @@ int gb200_encode_upload(gb200_plan *pl, const int32_t *const *planes) {
 			size_t bytes = (size_t) cg.w * cg.h * sizeof(int32_t);
 			if (bytes) CK(cudaMemcpyAsync(plane_ptr(pl, 0, c, cg.plane_off), planes[i], bytes, cudaMemcpyHostToDevice, pl->ctx->stream));
 		}
+	return GB200_OK;
+}
+
+int gb200_encode_stash(gb200_plan *pl) {
+	if (!pl || !pl->encoder) FAIL(GB200_ERR_PARAM, "not an encoder plan");
+	CK(cudaSetDevice(pl->ctx->device));
+	pl->stash.resize(pl->maxcomps);
+	for (uint32_t c = 0; c < pl->maxcomps; ++c) {
+		if (pl->stash[c].bytes != pl->bufA[c].bytes && pl->stash[c].alloc(pl->bufA[c].bytes)) FAIL(GB200_ERR_NOMEM, "cudaMalloc failed");
+		CK(cudaMemcpyAsync(pl->stash[c].p, pl->bufA[c].p, pl->bufA[c].bytes, cudaMemcpyDeviceToDevice, pl->ctx->stream));
+	}
+	return GB200_OK;
+}
+
+int gb200_encode_restore(gb200_plan *pl) {
+	if (!pl || !pl->encoder || pl->stash.size() != pl->maxcomps) FAIL(GB200_ERR_PARAM, "nothing stashed");
+	CK(cudaSetDevice(pl->ctx->device));
+	for (uint32_t c = 0; c < pl->maxcomps; ++c)
+		CK(cudaMemcpyAsync(pl->bufA[c].p, pl->stash[c].p, pl->bufA[c].bytes, cudaMemcpyDeviceToDevice, pl->ctx->stream));
 	return GB200_OK;
 }
 

@@ -147,6 +147,10 @@ GB200_API int gb200_decode_upload(gb200_plan *plan, const gb200_cblk_dec *blocks
 GB200_API int gb200_decode_run(gb200_plan *plan);      /* asynchronous on gb200_stream() */
 GB200_API int gb200_decode_download(gb200_plan *plan, int32_t *const *planes_out);
 GB200_API int gb200_sync(gb200_ctx *ctx);
+/* keep / bring back a device-side copy of the uploaded input planes, so that gb200_encode_run can be
+ * repeated on HBM-resident input (the run transforms the planes in place) */
+GB200_API int gb200_encode_stash(gb200_plan *plan);
+GB200_API int gb200_encode_restore(gb200_plan *plan); /* asynchronous device-to-device copy */
 /* run only one stage of an uploaded plan (for per-kernel timing): 0 dc+mct, 1 dwt, 2 t1 */
 GB200_API int gb200_encode_run_stage(gb200_plan *plan, int stage);
 GB200_API int gb200_decode_run_stage(gb200_plan *plan, int stage);

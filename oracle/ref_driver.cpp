@@ -27,6 +27,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <new>
+#include <vector>
 
 using namespace grk;
 
@@ -221,6 +222,104 @@ void ref_band_stepsize(uint32_t expn, uint32_t mant, uint32_t resno, uint32_t ba
 	*stepsize = band.stepsize;
 	*numbps = band.numbps;
 	*inv_step = band.inv_step;
+}
+
+/* ---- whole codec through the reference's public API (grok.h), memory streams only ------------ */
+
+static void quiet_cb(const char *, void *) {}
+
+/* grk_compress-equivalent: planar int32 image -> raw J2K codestream.
+ *   tile_w/tile_h 0 = single tile;  rates[numlayers] = compression ratios (-r); numlayers 0 = lossless
+ *   cinema2k_fps 24/48 = -w profile.  Returns the codestream length, or -1. */
+int64_t ref_encode_image(uint32_t numcomps, uint32_t w, uint32_t h, uint32_t prec, uint32_t sgnd,
+		const int32_t *const *planes, uint32_t tile_w, uint32_t tile_h, uint32_t numres, uint32_t cblkw, uint32_t cblkh,
+		int irreversible, uint32_t numlayers, const double *rates, int cinema2k_fps, uint32_t rc_algorithm,
+		uint8_t *out, uint64_t cap) {
+	grk_set_info_handler(quiet_cb, nullptr);
+	grk_set_warning_handler(quiet_cb, nullptr);
+	grk_set_error_handler(quiet_cb, nullptr);
+	grk_cparameters param;
+	grk_set_default_encoder_parameters(&param);
+	param.numresolution = numres;
+	param.cblockw_init = cblkw;
+	param.cblockh_init = cblkh;
+	param.irreversible = irreversible != 0;
+	param.rateControlAlgorithm = rc_algorithm;
+	if (tile_w && tile_h) {
+		param.tile_size_on = true;
+		param.cp_tdx = tile_w;
+		param.cp_tdy = tile_h;
+	}
+	if (numlayers) {
+		param.tcp_numlayers = numlayers;
+		for (uint32_t i = 0; i < numlayers; ++i) param.tcp_rates[i] = rates[i];
+		param.cp_disto_alloc = 1;
+	} else {
+		/* grk_compress.cpp: no -r/-q given => one lossless layer */
+		param.tcp_numlayers = 1;
+		param.tcp_rates[0] = 0;
+		param.cp_disto_alloc = 1;
+	}
+	if (cinema2k_fps) {
+		param.rsiz = GRK_PROFILE_CINEMA_2K;
+		param.framerate = cinema2k_fps;
+		if (cinema2k_fps == 24) { param.max_cs_size = GRK_CINEMA_24_CS; param.max_comp_size = GRK_CINEMA_24_COMP; }
+		else { param.max_cs_size = GRK_CINEMA_48_CS; param.max_comp_size = GRK_CINEMA_48_COMP; }
+	}
+	param.tcp_mct = (numcomps >= 3) ? 1 : 0; /* grk_compress.cpp:1997-1998 */
+	std::vector<grk_image_cmptparm> cp(numcomps);
+	for (uint32_t i = 0; i < numcomps; ++i) {
+		memset(&cp[i], 0, sizeof(grk_image_cmptparm));
+		cp[i].dx = cp[i].dy = 1;
+		cp[i].w = w; cp[i].h = h;
+		cp[i].prec = prec; cp[i].sgnd = sgnd;
+	}
+	grk_image *image = grk_image_create(numcomps, cp.data(), numcomps >= 3 ? GRK_CLRSPC_SRGB : GRK_CLRSPC_GRAY);
+	if (!image) return -1;
+	image->x0 = 0; image->y0 = 0; image->x1 = w; image->y1 = h;
+	for (uint32_t i = 0; i < numcomps; ++i)
+		memcpy(image->comps[i].data, planes[i], (size_t) w * h * sizeof(int32_t));
+	int64_t len = -1;
+	grk_stream *stream = grk_stream_create_mem_stream(out, cap, false, false);
+	grk_codec *codec = stream ? grk_create_compress(GRK_CODEC_J2K, stream) : nullptr;
+	if (codec && grk_setup_encoder(codec, &param, image) && grk_start_compress(codec, image)
+			&& grk_encode(codec) && grk_end_compress(codec))
+		len = (int64_t) grk_stream_get_write_mem_stream_length(stream);
+	if (stream) grk_stream_destroy(stream);
+	if (codec) grk_destroy_codec(codec);
+	grk_image_destroy(image);
+	return len;
+}
+
+/* grk_decompress-equivalent. planes_out[c] must hold the (reduced) component; returns 0 on success and
+ * fills dims[0..1] = decoded width/height, dims[2] = numcomps. */
+int ref_decode_image(const uint8_t *buf, uint64_t len, uint32_t reduce, uint32_t layers, int32_t *const *planes_out,
+		uint64_t plane_capacity, uint32_t *dims) {
+	grk_set_info_handler(quiet_cb, nullptr);
+	grk_set_warning_handler(quiet_cb, nullptr);
+	grk_set_error_handler(quiet_cb, nullptr);
+	grk_dparameters dp;
+	grk_set_default_decoder_parameters(&dp);
+	dp.cp_reduce = reduce;
+	dp.cp_layer = layers;
+	grk_stream *stream = grk_stream_create_mem_stream(const_cast<uint8_t*>(buf), len, false, true);
+	grk_codec *codec = stream ? grk_create_decompress(GRK_CODEC_J2K, stream) : nullptr;
+	grk_image *image = nullptr;
+	int rc = 1;
+	if (codec && grk_setup_decoder(codec, &dp) && grk_read_header(codec, nullptr, &image)
+			&& grk_decode(codec, nullptr, image) && grk_end_decompress(codec)) {
+		rc = 0;
+		dims[0] = image->comps[0].w; dims[1] = image->comps[0].h; dims[2] = image->numcomps;
+		for (uint32_t c = 0; c < image->numcomps; ++c) {
+			uint64_t n = (uint64_t) image->comps[c].w * image->comps[c].h;
+			if (n > plane_capacity || !image->comps[c].data) { rc = 2; break; }
+			memcpy(planes_out[c], image->comps[c].data, n * sizeof(int32_t));
+		}
+	}
+	if (stream) grk_stream_destroy(stream);
+	if (codec) grk_destroy_codec(codec);
+	if (image) grk_image_destroy(image);
+	return rc;
 }
 
 } /* extern "C" */

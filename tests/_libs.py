@@ -96,9 +96,42 @@ def ref():
     L.ref_band_stepsize.argtypes = [C.c_uint32] * 5 + [C.c_int, C.c_uint32, C.c_uint32, C.c_float,
                                                        C.POINTER(C.c_float), C.POINTER(C.c_uint32),
                                                        C.POINTER(C.c_uint32)]
-    L.ref_init(int(os.environ.get("GRK_REF_THREADS", "4")))
+    L.ref_encode_image.argtypes = [C.c_uint32] * 5 + [C.POINTER(C.c_void_p)] + [C.c_uint32] * 5 + [C.c_int, C.c_uint32,
+                                   C.c_void_p, C.c_int, C.c_uint32, u8p, C.c_uint64]
+    L.ref_encode_image.restype = C.c_int64
+    L.ref_decode_image.argtypes = [u8p, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p), C.c_uint64, u32p]
+    L.ref_init(int(os.environ.get("GRK_REF_THREADS", "0")) or (os.cpu_count() or 1))
     _ref = L
     return L
+
+
+def ref_encode_image(planes, prec, sgnd=0, tile=(0, 0), numres=6, cblk=(64, 64), irreversible=False, rates=(),
+                     cinema2k_fps=0, rc_algorithm=0):
+    """planes: list of int32 [h,w] -> J2K codestream bytes produced by the unmodified reference"""
+    L = ref()
+    h, w = planes[0].shape
+    keep = [aligned(np.ascontiguousarray(p, np.int32)) for p in planes]
+    pa = (C.c_void_p * len(keep))(*[k.ctypes.data for k in keep])
+    cap = w * h * len(planes) * 4 + (1 << 20)
+    out = np.zeros(cap, np.uint8)
+    r = np.ascontiguousarray(rates, np.float64)
+    n = L.ref_encode_image(len(planes), w, h, prec, sgnd, pa, tile[0] or 0, tile[1] or 0, numres, cblk[0], cblk[1],
+                           int(irreversible), len(r), r.ctypes.data if len(r) else None, cinema2k_fps, rc_algorithm, out, cap)
+    assert n > 0, "reference encode failed"
+    return bytes(out[:n])
+
+
+def ref_decode_image(cs, numcomps, width, height, reduce=0, layers=0):
+    L = ref()
+    buf = np.frombuffer(cs, np.uint8).copy()
+    cd = lambda v: (v + (1 << reduce) - 1) >> reduce
+    planes = [np.zeros((cd(height), cd(width)), np.int32) for _ in range(numcomps)]
+    pa = (C.c_void_p * numcomps)(*[p.ctypes.data for p in planes])
+    dims = np.zeros(4, np.uint32)
+    rc = L.ref_decode_image(buf, len(buf), reduce, layers, pa, planes[0].size, dims)
+    assert rc == 0, f"reference decode failed rc={rc}"
+    assert (dims[0], dims[1], dims[2]) == (planes[0].shape[1], planes[0].shape[0], numcomps), dims
+    return planes
 
 
 # ---- convenience wrappers ------------------------------------------------------------------

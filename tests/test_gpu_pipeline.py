@@ -1,0 +1,172 @@
+"""GPU parity of the whole path (plan API: upload -> DC/MCT -> DWT -> T1 -> download) against the oracle
+pipeline on small tiled images, and size-independent properties at the BASELINE.json sizes."""
+import numpy as np
+import pytest
+
+import grokimagecompression_b200 as gb
+from grokimagecompression_b200 import params as P
+from grokimagecompression_b200.synth import synthetic_planes
+import oracle_pipeline as OP
+
+pytestmark = pytest.mark.gpu
+
+
+def _enc_to_dec_inputs(res, rates=None, blocks=None, truncate=None):
+    inp = np.zeros(len(res), gb.CBLK_DEC_DTYPE)
+    inp["numbps"], inp["numpasses"], inp["data_len"], inp["data_offset"] = res["numbps"], res["numpasses"], res["data_len"], res["data_offset"]
+    return inp
+
+
+def _check_encode(ctx, tiles, planes, check_coeffs=True):
+    plan = gb.Plan(ctx, tiles, encoder=True)
+    res, rates, dists, data = plan.encode(planes)
+    oracle_blocks, coeffs = OP.encode_tiles(tiles, planes)
+    assert plan.num_blocks == len(oracle_blocks)
+    if check_coeffs:
+        i = 0
+        for t, tile in enumerate(tiles):
+            for c in range(len(tile["comps"])):
+                assert (plan.coefficients(t, c) == coeffs[i]).all(), (t, c)
+                i += 1
+    for i, ob in enumerate(oracle_blocks):
+        info = plan.blocks[i]
+        assert (info["tileno"], info["compno"], info["resno"], info["bandno"]) == (ob["tileno"], ob["compno"], ob["resno"], ob["orient"])
+        assert (info["x0"], info["y0"], info["x1"], info["y1"]) == (ob["x0"], ob["y0"], ob["x1"], ob["y1"])
+        r = res[i]
+        n = len(ob["rates"])
+        assert r["numbps"] == ob["numbps"] and r["numpasses"] == n, i
+        po = int(info["pass_offset"])
+        assert (rates[po:po + n] == ob["rates"]).all(), i
+        assert (dists[po:po + n] == ob["dists"]).all(), i
+        assert bytes(data[int(r["data_offset"]):int(r["data_offset"]) + int(r["data_len"])]) == ob["data"], i
+    return plan, res, rates, dists, data, oracle_blocks
+
+
+def _check_decode(ctx, tiles_dec, res, data, numres_decode=0):
+    for t in tiles_dec:
+        t["numres_decode"] = numres_decode
+    plan = gb.Plan(ctx, tiles_dec, encoder=False)
+    return plan
+
+
+CASES = [
+    # width, height, comps, prec, reversible, tile, numres, cblk
+    (200, 150, 1, 8, True, (None, None), 6, (6, 6)),
+    (300, 217, 3, 8, True, (128, 128), 4, (5, 5)),
+    (256, 200, 3, 8, False, (128, 112), 6, (6, 6)),
+    (130, 70, 3, 12, False, (None, None), 6, (5, 5)),
+    (190, 133, 3, 16, True, (96, 64), 3, (6, 4)),
+    (65, 33, 1, 8, True, (None, None), 1, (6, 6)),
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_encode_decode_vs_oracle(ctx, case):
+    width, height, nc, prec, rev, tile, numres, cblk = case
+    img = synthetic_planes(width, height, nc, prec, seed=width + height, kind="smooth")
+    rc = not rev
+    tiles = P.image_tiles(width, height, nc, prec, rev, tile, numres, rate_control=rc, cblk_expn=cblk)
+    planes = P.split_planes(img, width, height, tile)
+    plan, res, rates, dists, data, ob = _check_encode(ctx, tiles, planes)
+    # decode what was encoded (all passes), full resolution and reduced
+    for nd in (0, max(1, numres - 2)):
+        tiles_d = P.image_tiles(width, height, nc, prec, rev, tile, numres, cblk_expn=cblk, encoder=False, numres_decode=nd)
+        dplan = gb.Plan(ctx, tiles_d, encoder=False)
+        keep = np.array([(nd == 0) or (plan.blocks[i]["resno"] < nd) for i in range(plan.num_blocks)], bool)
+        assert dplan.num_blocks == int(keep.sum())
+        inp = _enc_to_dec_inputs(res[keep])
+        got = dplan.decode(inp, data)
+        binputs = [dict(data=ob[i]["data"], numbps=ob[i]["numbps"], numpasses=len(ob[i]["rates"])) for i in range(len(ob)) if keep[i]]
+        exp = OP.decode_tiles(tiles_d, binputs)
+        for g, e in zip(got, exp):
+            assert (g == e).all()
+        if rev and nd == 0:
+            full = P.join_planes(got, width, height, nc, tile)
+            for a, b in zip(full, img):
+                assert (a == b).all()
+
+
+def test_truncated_layers_decode(ctx):
+    """decode a prefix of the passes of every block, as a lower quality layer would deliver them"""
+    width, height = 192, 160
+    img = synthetic_planes(width, height, 3, 8, seed=9)
+    tiles = P.image_tiles(width, height, 3, 8, False, (None, None), 5, rate_control=True)
+    planes = P.split_planes(img, width, height, (None, None))
+    plan = gb.Plan(ctx, tiles, encoder=True)
+    res, rates, dists, data = plan.encode(planes)
+    rng = np.random.default_rng(3)
+    inp = _enc_to_dec_inputs(res)
+    binputs = []
+    for i in range(plan.num_blocks):
+        n = int(res[i]["numpasses"])
+        k = int(rng.integers(0, n + 1)) if n else 0
+        ln = int(rates[int(plan.blocks[i]["pass_offset"]) + k - 1]) if k else 0
+        inp[i]["numpasses"], inp[i]["data_len"] = k, ln
+        off = int(res[i]["data_offset"])
+        binputs.append(dict(data=bytes(data[off:off + ln]), numbps=int(res[i]["numbps"]), numpasses=k))
+    tiles_d = P.image_tiles(width, height, 3, 8, False, (None, None), 5, encoder=False)
+    got = gb.Plan(ctx, tiles_d, encoder=False).decode(inp, data)
+    exp = OP.decode_tiles(tiles_d, binputs)
+    for g, e in zip(got, exp):
+        assert (g == e).all()
+
+
+def _psnr(a, b, prec):
+    mse = np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2)
+    return 10 * np.log10(((1 << prec) - 1) ** 2 / max(mse, 1e-12))
+
+
+def _roundtrip(ctx, width, height, nc, prec, rev, tile, numres, cblk=(6, 6), kind="smooth", seed=1):
+    img = synthetic_planes(width, height, nc, prec, seed=seed, kind=kind)
+    tiles = P.image_tiles(width, height, nc, prec, rev, tile, numres, rate_control=not rev, cblk_expn=cblk)
+    planes = P.split_planes(img, width, height, tile)
+    plan = gb.Plan(ctx, tiles, encoder=True)
+    res, rates, dists, data = plan.encode(planes)
+    tiles_d = P.image_tiles(width, height, nc, prec, rev, tile, numres, cblk_expn=cblk, encoder=False)
+    dplan = gb.Plan(ctx, tiles_d, encoder=False)
+    got = dplan.decode(_enc_to_dec_inputs(res), data)
+    full = P.join_planes(got, width, height, nc, tile)
+    plan.close()
+    dplan.close()
+    return img, full, res, data
+
+
+def test_c1_lossless_roundtrip_full_size(ctx):
+    # config 1: 2048x2048 8-bit gray, 5/3, 1 tile, 64x64 blocks, 5 levels
+    for kind in ("smooth", "random", "constant"):
+        img, full, res, data = _roundtrip(ctx, 2048, 2048, 1, 8, True, (None, None), 6, kind=kind, seed=1234)
+        assert (full[0] == img[0]).all(), kind
+        assert len(res) == 1024
+        if kind == "constant":
+            assert int(res["numpasses"].sum()) == 0  # every block quantises below one bit plane
+
+
+def test_c2_lossy_psnr_full_size(ctx):
+    # config 2: 4096x2160 RGB 8-bit, 9/7 + ICT, 1024x1024 tiles; all passes kept -> near-lossless
+    img, full, res, data = _roundtrip(ctx, 4096, 2160, 3, 8, False, (1024, 1024), 6, seed=42)
+    for c in range(3):
+        assert _psnr(full[c], img[c], 8) > 45.0
+
+
+def test_c3_lossless_16bit_tiled(ctx):
+    # config 3 geometry (16-bit, RCT, 1024x1024 tiles) on a 4096x2048 crop of the 8192x8192 canvas
+    img, full, res, data = _roundtrip(ctx, 4096, 2048, 3, 16, True, (1024, 1024), 6, seed=3)
+    for c in range(3):
+        assert (full[c] == img[c]).all()
+
+
+def test_c4_cinema_frame(ctx):
+    # config 4: 2048x1080 12-bit, 3 components, 9/7 + ICT, 32x32 blocks, 5 levels
+    img, full, res, data = _roundtrip(ctx, 2048, 1080, 3, 12, False, (None, None), 6, cblk=(5, 5), seed=1000)
+    for c in range(3):
+        assert _psnr(full[c], img[c], 12) > 50.0
+
+
+def test_idempotent_and_deterministic(ctx):
+    img = synthetic_planes(512, 512, 3, 8, seed=5)
+    tiles = P.image_tiles(512, 512, 3, 8, True, (256, 256), 5)
+    planes = P.split_planes(img, 512, 512, (256, 256))
+    plan = gb.Plan(ctx, tiles, encoder=True)
+    a = plan.encode(planes)
+    b = plan.encode(planes)
+    assert (a[0] == b[0]).all() and (a[1] == b[1]).all() and bytes(a[3]) == bytes(b[3])
