@@ -1,0 +1,62 @@
+"""CPU: the C-ABI library loads, exports every symbol include/grok_b200.h declares, the ctypes mirror of the
+structs has the C layout, and the product fails loudly (no CPU fallback) without a CUDA device."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import grokimagecompression_b200 as gb
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "grok_b200.h")).read()
+    return sorted(set(re.findall(r"GB200_API[^;(]*?\b(gb200_\w+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported():
+    L = gb.lib()
+    names = _declared()
+    assert len(names) >= 36
+    for n in names:
+        assert hasattr(L, n), n
+    assert sorted(gb.SYMBOLS) == names
+    out = subprocess.check_output(["nm", "-D", "--defined-only", gb.LIB_PATH], text=True)
+    exported = set(re.findall(r" T (gb200_\w+)", out))
+    assert exported == set(names)
+    assert L.gb200_abi_version() == 1
+
+
+def test_struct_layouts_match_c(tmp_path):
+    prog = tmp_path / "sz.c"
+    prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "grok_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n",'
+                    'sizeof(gb200_comp_params),offsetof(gb200_comp_params,stepsize),offsetof(gb200_comp_params,rd_weight),'
+                    'sizeof(gb200_tile_params),sizeof(gb200_cblk_info),sizeof(gb200_cblk_enc),sizeof(gb200_cblk_dec),sizeof(gb200_t1_block));return 0;}')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)])
+    got = [int(v) for v in subprocess.check_output([str(exe)], text=True).split()]
+    want = [C.sizeof(gb.CompParams), gb.CompParams.stepsize.offset, gb.CompParams.rd_weight.offset, C.sizeof(gb.TileParams),
+            gb.CBLK_INFO_DTYPE.itemsize, gb.CBLK_ENC_DTYPE.itemsize, gb.CBLK_DEC_DTYPE.itemsize, gb.T1_BLOCK_DTYPE.itemsize]
+    assert got == want
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(gb.GrokB200Error) as e:
+        gb.Context(0)
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_product_does_not_reference_the_oracle():
+    pkg = os.path.join(ROOT, "grokimagecompression_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "gb_oracle" not in txt and "libgrkref" not in txt and "oracle/" not in txt, f
