@@ -12,7 +12,7 @@ MAX_RES = 33
 MAX_BANDS = 3 * MAX_RES - 2
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgrok_b200.so")
+LIB_PATH = os.environ.get("GB200_LIB") or os.path.join(_HERE, "libgrok_b200.so")  # GB200_LIB: A/B builds of the same ABI
 
 
 class GrokB200Error(RuntimeError):

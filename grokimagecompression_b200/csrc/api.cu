@@ -81,7 +81,7 @@ struct gb200_plan {
 	// Tier-1
 	std::vector<EncBlock> encblocks;
 	std::vector<DecBlock> decblocks;
-	DevBuf d_blocks, d_results, d_rates, d_dists, d_scratch, d_data, d_inputs;
+	DevBuf d_blocks, d_results, d_rates, d_dists, d_scratch, d_data, d_inputs, d_planes;
 	uint64_t d_data_len = 0;
 	uint32_t max_planes = 1;
 	bool uniform = true; // every tile shares mct / qmfbid / shift / range parameters
@@ -217,7 +217,7 @@ void gb200_plan_destroy(gb200_plan *pl) {
 	for (auto &b : pl->stash) b.release();
 	for (int r = 0; r < 2; ++r) for (auto &l : pl->lvl[r]) l.dev.release();
 	pl->d_blocks.release(); pl->d_results.release(); pl->d_rates.release(); pl->d_dists.release();
-	pl->d_scratch.release(); pl->d_data.release(); pl->d_inputs.release();
+	pl->d_scratch.release(); pl->d_data.release(); pl->d_inputs.release(); pl->d_planes.release();
 	delete pl;
 }
 
@@ -420,7 +420,8 @@ int gb200_plan_create(gb200_ctx *ctx, uint32_t ntiles, const gb200_tile_params *
 		cudaMemsetAsync(pl->d_scratch.p, 0, pl->d_scratch.bytes, ctx->stream);
 		pl->h_results.resize(nb);
 	} else {
-		if (pl->d_blocks.alloc(std::max<size_t>(nb, 1) * sizeof(DecBlock)) || pl->d_inputs.alloc(std::max<size_t>(nb, 1) * sizeof(DecInput)))
+		if (pl->d_blocks.alloc(std::max<size_t>(nb, 1) * sizeof(DecBlock)) || pl->d_inputs.alloc(std::max<size_t>(nb, 1) * sizeof(DecInput))
+				|| pl->d_planes.alloc(std::max<size_t>(t1_decode_scratch_bytes((uint32_t) nb, pl->max_planes), 16)))
 			return bail(GB200_ERR_NOMEM, "cudaMalloc failed for the Tier-1 buffers");
 		if (nb && cudaMemcpyAsync(pl->d_blocks.p, pl->decblocks.data(), nb * sizeof(DecBlock), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
 			return bail(GB200_ERR_CUDA, "upload of the block table failed");
@@ -635,7 +636,7 @@ static int run_t1_dec(gb200_plan *pl) {
 	const uint32_t nb = (uint32_t) pl->blocks.size();
 	if (!nb) return GB200_OK;
 	launch_t1_decode((const DecBlock*) pl->d_blocks.p, (const DecInput*) pl->d_inputs.p, nb, (const uint8_t*) pl->d_data.p,
-			pl->max_planes, pl->ctx->stream);
+			pl->max_planes, (uint64_t*) pl->d_planes.p, pl->ctx->stream);
 	return launch_check(pl->ctx, 1);
 }
 
@@ -920,8 +921,8 @@ int gb200_t1_decode_blocks(gb200_ctx *ctx, int32_t *plane, uint32_t width, uint3
 	CK(cudaSetDevice(ctx->device));
 	cudaStream_t s = ctx->stream;
 	std::vector<DecBlock> db(nblocks);
-	DevBuf d_plane, d_blocks, d_inputs, d_data;
-	auto freeall = [&]() { d_plane.release(); d_blocks.release(); d_inputs.release(); d_data.release(); };
+	DevBuf d_plane, d_blocks, d_inputs, d_data, d_planes;
+	auto freeall = [&]() { d_plane.release(); d_blocks.release(); d_inputs.release(); d_data.release(); d_planes.release(); };
 	if (d_plane.alloc(std::max<size_t>((size_t) width * height * 4, 16))) FAIL(GB200_ERR_NOMEM, "cudaMalloc failed");
 	uint32_t maxp = 1;
 	for (uint32_t i = 0; i < nblocks; ++i) {
@@ -937,12 +938,12 @@ int gb200_t1_decode_blocks(gb200_ctx *ctx, int32_t *plane, uint32_t width, uint3
 		maxp = std::max(maxp, inputs[i].numbps);
 	}
 	if (d_blocks.alloc(std::max<size_t>(nblocks, 1) * sizeof(DecBlock)) || d_inputs.alloc(std::max<size_t>(nblocks, 1) * sizeof(DecInput))
-			|| d_data.alloc(align_up(data_len + 16, 256))) { freeall(); FAIL(GB200_ERR_NOMEM, "cudaMalloc failed"); }
+			|| d_data.alloc(align_up(data_len + 16, 256)) || d_planes.alloc(std::max<size_t>(t1_decode_scratch_bytes(nblocks, maxp), 16))) { freeall(); FAIL(GB200_ERR_NOMEM, "cudaMalloc failed"); }
 	cudaMemcpyAsync(d_plane.p, plane, (size_t) width * height * 4, cudaMemcpyHostToDevice, s);
 	cudaMemcpyAsync(d_blocks.p, db.data(), nblocks * sizeof(DecBlock), cudaMemcpyHostToDevice, s);
 	cudaMemcpyAsync(d_inputs.p, inputs, nblocks * sizeof(DecInput), cudaMemcpyHostToDevice, s);
 	if (data_len) cudaMemcpyAsync(d_data.p, data, data_len, cudaMemcpyHostToDevice, s);
-	launch_t1_decode((const DecBlock*) d_blocks.p, (const DecInput*) d_inputs.p, nblocks, (const uint8_t*) d_data.p, maxp, s);
+	launch_t1_decode((const DecBlock*) d_blocks.p, (const DecInput*) d_inputs.p, nblocks, (const uint8_t*) d_data.p, maxp, (uint64_t*) d_planes.p, s);
 	int rc = launch_check(ctx, 1);
 	cudaMemcpyAsync(plane, d_plane.p, (size_t) width * height * 4, cudaMemcpyDeviceToHost, s);
 	cudaError_t e = cudaStreamSynchronize(s);

@@ -75,7 +75,9 @@ void launch_t1_encode(const EncBlock *blocks, uint32_t nblocks, int rate_control
 		uint32_t *rates, double *dists, cudaStream_t s);
 void launch_t1_gather(const EncBlock *blocks, EncResult *results, uint32_t nblocks, const uint8_t *scratch,
 		uint8_t *data, cudaStream_t s);
+// plane_scratch: t1_decode_scratch_bytes() of device memory (512 B per bit-plane per block)
+size_t t1_decode_scratch_bytes(uint32_t nblocks, uint32_t max_planes);
 void launch_t1_decode(const DecBlock *blocks, const DecInput *inputs, uint32_t nblocks, const uint8_t *data,
-		uint32_t max_planes, cudaStream_t s);
+		uint32_t max_planes, uint64_t *plane_scratch, cudaStream_t s);
 
 } // namespace gb

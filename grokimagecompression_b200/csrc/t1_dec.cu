@@ -5,15 +5,22 @@
 //   sig / ref / cln pass            t1.cpp:381-441, 588-637, 784-870
 //   MQ decoder                      mqc_dec.cpp:161-214, mqc_dec_inl.h:60-189
 //
-// Decoding is serial by nature (each decision selects the next context).  The warp therefore runs
-// the scan as one uniform instruction stream; what the 32 lanes add is
-//  * the block state as 64-bit row masks, so "which columns of this stripe can be coded at all"
-//    is a handful of shifts/ORs and the scan jumps from candidate column to candidate column
-//    (find-first-set) instead of visiting 64 x 4 positions,
-//  * the MQ context table spread over the lanes (one shuffle per decision), the compressed bytes
-//    held as a 128-byte register window across the lanes (no memory access on the decision path),
-//  * magnitudes kept as one row mask per bit-plane in shared memory and turned into samples,
-//    de-quantised and written coalesced by all lanes at the end (no read-modify-write of HBM).
+// Decoding is serial by nature (each decision selects the next context), so the warp runs the scan
+// as ONE uniform instruction stream and the design goal is the shortest possible dependent chain
+// per decision with few live registers (occupancy hides the rest):
+//  * State of a stripe column is one 32-bit word: significance of the 3x6 neighbourhood, signs of
+//    the own column, visited and refined bits.  The 64 words of the current stripe live in the
+//    lanes' registers (lane l owns columns l and l+32); the scan fetches a column's word with one
+//    shuffle, works on it with 32-bit logic, and the lanes owning the west/east columns update
+//    their own copies when a sample turns significant.  Other stripes wait in shared memory.
+//  * Warp ballots turn the per-lane words into the list of columns that can be coded in this pass
+//    at all; the scan jumps between them with find-first-set instead of visiting 64 x 4 positions.
+//  * The MQ probability state of context i lives in lane i as the packed table row, so a decision
+//    costs one shuffle and no table access on its critical path; compressed bytes are held as a
+//    128-byte register window across the lanes.
+//  * Decoded magnitude bits are collected as per-lane nibbles, turned into row masks with ballots
+//    at the end of a stripe, kept per bit-plane, and only at the very end expanded to samples,
+//    de-quantised and written coalesced (no read-modify-write of the coefficient plane).
 // The reference's artificial FF FF end marker (mqc_dec.cpp:161-177) is emulated by reading 0xFF
 // past the end of the segment.
 #include "common.cuh"
@@ -22,17 +29,21 @@
 namespace gb {
 
 constexpr int DEC_WARPS = 4;
+#ifndef DEC_MIN_CTAS
+#define DEC_MIN_CTAS 8
+#endif
+
+// stripe-column word: bit 3r+j = significance of row r-1 (r = 0..5), column j-1 (j = 0 west, 1 own, 2 east);
+// bit 18+r = sign of own column row r-1; bit 24+k = visited (k = 0..3); bit 28+k = refined before
+__device__ __forceinline__ constexpr uint32_t fsig(int r, int j) { return 1u << (3 * r + j); }
+constexpr uint32_t F_PI_ALL = 0xFu << 24;
+constexpr uint32_t F_SIG_OWN4 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 13);
 
 struct DecWarp {
-	uint64_t sig[66], neg[66], vis[66], refd[66]; // index = row + 1
-	uint64_t lastcoded[64];                       // samples coded in the plane of the last pass
+	uint32_t F[18][64];   // [stripe + 1][column]; stripes -1 and 16 are never read as a current stripe
+	uint64_t pcur[64];    // magnitude bits of the current bit-plane, one row mask per row
+	uint64_t lastc[64];   // samples coded in the final (possibly partial) plane
 };
-
-__device__ __forceinline__ uint64_t dhor(uint64_t m) { return (m << 1) | (m >> 1); }
-__device__ __forceinline__ uint64_t dfull(uint64_t m) { return m | (m << 1) | (m >> 1); }
-__device__ __forceinline__ uint32_t dwin3(uint64_t m, int x) {
-	return (uint32_t) (x == 0 ? (m << 1) : (m >> (x - 1))) & 7u;
-}
 
 struct MqD {
 	uint32_t a, c;
@@ -41,7 +52,7 @@ struct MqD {
 	const uint8_t *buf;
 	uint32_t wbase;  // first byte index of the register window
 	uint32_t word;   // this lane's 4 bytes of the window
-	uint32_t cst;    // context `lane`
+	uint32_t crow;   // context `lane`: Table C.2 row (qe | nmps<<16 | nlps<<22 | switch<<28) | mps << 29
 };
 
 __device__ __forceinline__ void mqd_fill(MqD &q, uint32_t base, int lane) {
@@ -64,7 +75,7 @@ __device__ __forceinline__ uint32_t mqd_byte(MqD &q, uint32_t i, int lane) {
 	return (w >> (8 * (o & 3))) & 0xFFu;
 }
 
-__device__ __forceinline__ void mqd_bytein(MqD &q, int lane) {
+__device__ __noinline__ void mqd_bytein(MqD &q, int lane) {
 	uint32_t cur = mqd_byte(q, q.pos, lane);
 	uint32_t next = mqd_byte(q, q.pos + 1, lane);
 	if (cur == 0xFF) {
@@ -74,9 +85,8 @@ __device__ __forceinline__ void mqd_bytein(MqD &q, int lane) {
 }
 
 __device__ __forceinline__ uint32_t mqd_decode(MqD &q, uint32_t cx, int lane) {
-	uint32_t st = __shfl_sync(0xffffffffu, q.cst, cx);
-	uint32_t row = c_mq[st >> 1];
-	uint32_t qe = row & 0xFFFFu, mps = st & 1, d;
+	const uint32_t row = __shfl_sync(0xffffffffu, q.crow, cx);
+	const uint32_t qe = row & 0xFFFFu, mps = (row >> 29) & 1u;
 	q.a -= qe;
 	bool lps;
 	if ((q.c >> 16) < qe) {
@@ -87,26 +97,30 @@ __device__ __forceinline__ uint32_t mqd_decode(MqD &q, uint32_t cx, int lane) {
 		if (q.a & 0x8000u) return mps;
 		lps = q.a < qe;
 	}
-	if (lps) { d = mps ^ 1; st = (((row >> 22) & 63u) << 1) | (mps ^ (row >> 28)); }
-	else { d = mps; st = (((row >> 16) & 63u) << 1) | mps; }
-	if (lane == (int) cx) q.cst = st;
+	const uint32_t next = lps ? (row >> 22) & 63u : (row >> 16) & 63u;
+	const uint32_t nmps = lps ? mps ^ ((row >> 28) & 1u) : mps;
+	const uint32_t nrow = c_mq[next] | (nmps << 29);
+	if (lane == (int) cx) q.crow = nrow;
 	int sh = __clz(q.a) - 16;
 	while (sh > 0) {
 		if (q.ct == 0) mqd_bytein(q, lane);
 		int n = sh < q.ct ? sh : q.ct;
 		q.a <<= n; q.c <<= n; q.ct -= n; sh -= n;
 	}
-	return d;
+	return lps ? mps ^ 1u : mps;
 }
 
-extern __shared__ uint64_t dec_dyn_smem[];
-
-__global__ void __launch_bounds__(DEC_WARPS * 32) t1_decode_kernel(const DecBlock *__restrict__ blocks,
-		const DecInput *__restrict__ inputs, uint32_t nblocks, const uint8_t *__restrict__ data, uint32_t max_planes) {
+__global__ void __launch_bounds__(DEC_WARPS * 32, DEC_MIN_CTAS) t1_decode_kernel(const DecBlock *__restrict__ blocks,
+		const DecInput *__restrict__ inputs, uint32_t nblocks, const uint8_t *__restrict__ data, uint32_t max_planes,
+		uint64_t *__restrict__ plane_scratch) {
 	__shared__ DecWarp warps[DEC_WARPS];
-	__shared__ uint8_t Lzc[4][256];
+	__shared__ uint8_t Lzc[4][512]; // zero-coding context by the 9 neighbourhood bits of a stripe-column word
 	__shared__ uint8_t Lsc[256];
-	for (int i = threadIdx.x; i < 1024; i += blockDim.x) Lzc[i >> 8][i & 255] = c_zc[i >> 8][i & 255];
+	for (int i = threadIdx.x; i < 2048; i += blockDim.x) {
+		int o = i >> 9, n9 = i & 511;
+		int idx8 = (n9 & 7) | ((n9 >> 3) & 1) << 3 | ((n9 >> 5) & 1) << 4 | ((n9 >> 6) & 7) << 5;
+		Lzc[o][n9] = c_zc[o][idx8];
+	}
 	for (int i = threadIdx.x; i < 256; i += blockDim.x) Lsc[i] = c_sc[i];
 	__syncthreads();
 
@@ -114,168 +128,212 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) t1_decode_kernel(const DecBloc
 	const uint32_t bid = blockIdx.x * DEC_WARPS + wid;
 	if (bid >= nblocks) return;
 	DecWarp &W = warps[wid];
-	uint64_t *planes = dec_dyn_smem + (size_t) wid * max_planes * 64; // [plane-1][row]
+	uint64_t *planes = plane_scratch + (size_t) bid * max_planes * 64; // [plane-1][row], global scratch
 	const DecBlock B = blocks[bid];
 	const DecInput I = inputs[bid];
 	const int w = B.w, h = B.h;
-	const uint64_t wmask = w >= 64 ? ~0ull : ((1ull << w) - 1);
 	const uint8_t *zc = Lzc[B.orient];
-	int numbps = (int) I.numbps;
+	const int numbps = (int) I.numbps;
+	const bool two = w > 32;
+	const bool valid0 = lane < w, valid1 = lane + 32 < w;
 
-	bool empty = I.numpasses == 0 || I.data_len == 0 || numbps == 0 || numbps > (int) max_planes; // T1Part1.cpp:139
-	if (!empty) {
-		for (int i = lane; i < 66; i += 32) { W.sig[i] = 0; W.neg[i] = 0; W.vis[i] = 0; W.refd[i] = 0; }
-		for (int i = lane; i < 64; i += 32) W.lastcoded[i] = 0;
-		for (int i = lane; i < numbps * 64; i += 32) planes[i] = 0;
-		__syncwarp();
-
-		MqD q;
-		q.buf = data + I.data_offset;
-		q.len = I.data_len;
-		q.pos = 0;
-		q.cst = lane == CTX_ZC0 ? (4 << 1) : lane == CTX_AGG ? (3 << 1) : lane == CTX_UNI ? (46 << 1) : 0;
-		mqd_fill(q, 0, lane);
-		q.c = mqd_byte(q, 0, lane) << 16; // INITDEC, mqc_dec.cpp:179-201
-		mqd_bytein(q, lane);
-		q.c <<= 7;
-		q.ct -= 7;
-		q.a = 0x8000;
-
-		int bp1 = numbps, type = 2, lastplane = numbps;
-		for (uint32_t pass = 0; pass < I.numpasses && bp1 >= 1; ++pass) {
-			uint64_t *P = planes + (size_t) (bp1 - 1) * 64;
-			lastplane = bp1;
-			if (type == 0) { for (int i = lane; i < 64; i += 32) W.lastcoded[i] = 0; __syncwarp(); }
-			for (int y0 = 0; y0 < h; y0 += 4) {
-				const int nk = min(4, h - y0);
-				uint64_t S[6], G[6], M[4], N[4], H0[4];
-				#pragma unroll
-				for (int j = 0; j < 6; ++j) { S[j] = W.sig[y0 + j]; G[j] = W.neg[y0 + j]; }
-				uint64_t cols = 0;
-				#pragma unroll
-				for (int k = 0; k < 4; ++k) {
-					H0[k] = dhor(S[k + 1]) | dfull(S[k]) | dfull(S[k + 2]);
-					N[k] = 0;
-					uint64_t valid = k < nk ? wmask : 0;
-					if (type == 0) M[k] = ~S[k + 1] & H0[k] & valid;          // initial candidates
-					else if (type == 1) M[k] = S[k + 1] & ~W.vis[y0 + 1 + k] & valid;
-					else M[k] = ~S[k + 1] & ~W.vis[y0 + 1 + k] & valid;
-					cols |= M[k];
-				}
-				uint64_t V[4] = {0, 0, 0, 0}; // visited in this pass (sig pass)
-				uint64_t R[4] = {0, 0, 0, 0}; // magnitude bits decoded in this pass
-				const uint64_t nbr_all = dfull(S[0] | S[1] | S[2] | S[3] | S[4] | S[5]);
-				while (cols) {
-					const int x = __ffsll((long long) cols) - 1;
-					const uint64_t xb = 1ull << x;
-					cols &= ~xb;
-					if (type == 1) {
-						#pragma unroll
-						for (int k = 0; k < 4; ++k) if (M[k] & xb) {
-							uint32_t ctx = (W.refd[y0 + 1 + k] & xb) ? CTX_MR0 + 2 : (H0[k] & xb) ? CTX_MR0 + 1 : CTX_MR0;
-							if (mqd_decode(q, ctx, lane)) R[k] |= xb;
-						}
-						continue;
-					}
-					int k0 = 0;
-					bool implied = false;
-					if (type == 2 && nk == 4 && (M[0] & M[1] & M[2] & M[3] & xb) && !(nbr_all & xb)
-							&& !(((N[0] | N[1] | N[2] | N[3]) << 1) & xb)) {
-						if (!mqd_decode(q, CTX_AGG, lane)) continue;
-						uint32_t r = mqd_decode(q, CTX_UNI, lane);
-						r = (r << 1) | mqd_decode(q, CTX_UNI, lane);
-						k0 = (int) r;
-						implied = true;
-					}
-					#pragma unroll
-					for (int k = 0; k < 4; ++k) {
-						if (k < k0 || k >= nk) continue;
-						const uint64_t up = k > 0 ? N[k - 1] : 0;
-						if (type == 0) {
-							if (S[k + 1] & xb) continue;
-							uint64_t west = (up | N[k] | (k < 3 ? N[k + 1] : 0)) << 1;
-							if (!((H0[k] | west | up) & xb)) continue;
-						} else if (!(M[k] & xb)) continue;
-						uint32_t top = k == 0 ? dwin3(S[0], x) : (dwin3(S[k], x) | (dwin3(N[k - 1], x) & 3));
-						uint32_t mid = dwin3(S[k + 1], x) | (dwin3(N[k], x) & 1);
-						uint32_t bot = k == 3 ? dwin3(S[5], x) : (dwin3(S[k + 2], x) | (dwin3(N[k + 1], x) & 1));
-						uint32_t d = 1;
-						if (!(implied && k == k0)) {
-							uint32_t idx = top | (mid & 1) << 3 | (mid >> 2) << 4 | bot << 5;
-							d = mqd_decode(q, zc[idx], lane);
-						}
-						if (type == 0) V[k] |= xb;
-						if (d) {
-							uint32_t gt = dwin3(G[k], x), gm = dwin3(G[k + 1], x), gb = dwin3(G[k + 2], x);
-							uint32_t sN = top >> 1 & 1, sW = mid & 1, sE = mid >> 2 & 1, sS = bot >> 1 & 1;
-							uint32_t idx = sN | sW << 1 | sE << 2 | sS << 3 | ((gt >> 1) & sN) << 4 | (gm & sW) << 5
-									| ((gm >> 2) & sE) << 6 | ((gb >> 1) & sS) << 7;
-							uint32_t v = Lsc[idx];
-							uint32_t neg = mqd_decode(q, v & 31, lane) ^ (v >> 5);
-							N[k] |= xb;
-							if (neg) G[k + 1] |= xb;
-							if (type == 0 && x + 1 < w) cols |= xb << 1; // east column may have become a candidate
-						}
-					}
-				}
-				// commit the stripe
-				if (lane == 0) {
-					#pragma unroll
-					for (int k = 0; k < 4; ++k) if (k < nk) {
-						const int y = y0 + k;
-						if (type == 1) {
-							W.refd[y + 1] |= M[k];
-							P[y] |= R[k];
-							W.lastcoded[y] |= M[k];
-						} else {
-							W.sig[y + 1] = S[k + 1] | N[k];
-							W.neg[y + 1] = G[k + 1];
-							P[y] |= N[k];
-							W.lastcoded[y] |= N[k];
-							if (type == 0) W.vis[y + 1] |= V[k];
-						}
-					}
-				}
-				__syncwarp();
-			}
-			if (type == 2) { for (int i = lane; i < 66; i += 32) W.vis[i] = 0; __syncwarp(); }
-			if (++type == 3) { type = 0; bp1--; }
-		}
-		__syncwarp();
-		// ---- reconstruct, de-quantise, scatter (T1Part1.cpp:216-329) -----------------------------
-		for (int y = 0; y < h; ++y) {
-			const uint64_t srow = W.sig[y + 1], nrow = W.neg[y + 1], lrow = W.lastcoded[y];
-			for (int x = lane; x < w; x += 32) {
-				int32_t v = 0;
-				if (srow >> x & 1) {
-					uint32_t mag = 0;
-					for (int p = lastplane; p <= numbps; ++p) mag |= (uint32_t) (planes[(size_t) (p - 1) * 64 + y] >> x & 1) << p;
-					mag |= (lrow >> x & 1) ? (1u << lastplane) >> 1 : 1u << lastplane;
-					v = (nrow >> x & 1) ? -(int32_t) mag : (int32_t) mag;
-				}
-				int32_t o;
-				if (B.reversible) o = v / 2;
-				else o = __float_as_int(__fmul_rn((float) v, B.stepsize));
-				B.dst[(size_t) y * B.stride + x] = o;
-			}
-		}
-	} else {
+	const bool empty = I.numpasses == 0 || I.data_len == 0 || numbps == 0 || numbps > (int) max_planes; // T1Part1.cpp:139
+	if (empty) {
 		// nothing decoded: the reference leaves the zero-initialised tile buffer untouched
 		for (int y = 0; y < h; ++y)
 			for (int x = lane; x < w; x += 32) B.dst[(size_t) y * B.stride + x] = 0;
+		return;
+	}
+	for (int i = lane; i < 18 * 64; i += 32) (&W.F[0][0])[i] = 0;
+	for (int i = lane; i < 64; i += 32) { W.pcur[i] = 0; W.lastc[i] = 0; }
+	__syncwarp();
+
+	MqD q;
+	q.buf = data + I.data_offset;
+	q.len = I.data_len;
+	q.pos = 0;
+	q.crow = c_mq[lane == CTX_ZC0 ? 4 : lane == CTX_AGG ? 3 : lane == CTX_UNI ? 46 : 0]; // mqc_dec.cpp:207-214, mps = 0
+	mqd_fill(q, 0, lane);
+	q.c = mqd_byte(q, 0, lane) << 16; // INITDEC, mqc_dec.cpp:179-201
+	mqd_bytein(q, lane);
+	q.c <<= 7;
+	q.ct -= 7;
+	q.a = 0x8000;
+
+	// plane of the last pass that will run: passes go cln(numbps), then sig/ref/cln per lower plane
+	const int npass_eff = min((int) I.numpasses, 3 * numbps - 2);
+	const int finalplane = numbps - (npass_eff + 1) / 3;
+	const int nstripes = (h + 3) >> 2;
+
+	int bp1 = numbps, type = 2;
+	for (int pass = 0; pass < npass_eff; ++pass) {
+		const bool track_last = bp1 == finalplane;
+		for (int s = 0; s < nstripes; ++s) {
+			const int nk = min(4, h - 4 * s);
+			uint32_t f0 = W.F[s + 1][lane], f1 = two ? W.F[s + 1][lane + 32] : 0u;
+			// which columns hold a sample this pass can code (ballot of a per-lane test)
+			auto wants = [&](uint32_t f) -> bool {
+				bool any = false;
+				#pragma unroll
+				for (int k = 0; k < 4; ++k) {
+					if (k >= nk) break;
+					const bool sig = f & fsig(k + 1, 1), vis = f & (1u << (24 + k));
+					const bool nbr = (f >> (3 * k)) & 0x1EFu;
+					if (type == 0) any |= !sig && !vis && nbr;
+					else if (type == 1) any |= sig && !vis;
+					else any |= !sig && !vis;
+				}
+				return any;
+			};
+			uint64_t cols = (uint64_t) __ballot_sync(0xffffffffu, valid0 && wants(f0));
+			if (two) cols |= (uint64_t) __ballot_sync(0xffffffffu, valid1 && wants(f1)) << 32;
+			uint32_t mb0 = 0, mb1 = 0, lc0 = 0, lc1 = 0; // per-lane nibbles: magnitude bit decoded / sample coded
+			while (cols) {
+				const int x = __ffsll((long long) cols) - 1;
+				cols &= cols - 1;
+				const int src = x & 31;
+				const bool hi = x >= 32;
+				uint32_t f = __shfl_sync(0xffffffffu, hi ? f1 : f0, src);
+				uint32_t mb = 0, lc = 0;
+				if (type == 1) {
+					#pragma unroll 1
+					for (int k = 0; k < nk; ++k) {
+						if (!(f & fsig(k + 1, 1)) || (f & (1u << (24 + k)))) continue;
+						const uint32_t ctx = (f & (1u << (28 + k))) ? CTX_MR0 + 2 : ((f >> (3 * k)) & 0x1EFu) ? CTX_MR0 + 1 : CTX_MR0;
+						if (mqd_decode(q, ctx, lane)) mb |= 1u << k;
+						f |= 1u << (28 + k);
+						lc |= 1u << k;
+					}
+				} else {
+					int k0 = 0;
+					bool implied = false;
+					if (type == 2 && nk == 4 && (f & 0x0F03FFFFu) == 0) { // run-length mode: nothing significant or visited around
+						if (!mqd_decode(q, CTX_AGG, lane)) continue;
+						k0 = (int) mqd_decode(q, CTX_UNI, lane) << 1;
+						k0 |= (int) mqd_decode(q, CTX_UNI, lane);
+						implied = true;
+					}
+					uint32_t fW = 0, fE = 0;
+					bool have_nb = false;
+					#pragma unroll 1
+					for (int k = k0; k < nk; ++k) {
+						if (f & (fsig(k + 1, 1) | (1u << (24 + k)))) continue;
+						const uint32_t n9 = (f >> (3 * k)) & 0x1FFu;
+						if (type == 0 && !(n9 & 0x1EFu)) continue;
+						uint32_t d = 1;
+						if (!(implied && k == k0)) d = mqd_decode(q, zc[n9], lane);
+						if (type == 0) f |= 1u << (24 + k);
+						if (!d) continue;
+						if (!have_nb) { // signs of the west / east columns live in their owners' words
+							const int xm = x - 1, xp = x + 1;
+							const uint32_t a0 = __shfl_sync(0xffffffffu, xm >= 32 ? f1 : f0, xm & 31);
+							const uint32_t a1 = __shfl_sync(0xffffffffu, xp >= 32 ? f1 : f0, xp & 31);
+							fW = xm >= 0 ? a0 : 0u;
+							fE = xp < w ? a1 : 0u;
+							have_nb = true;
+						}
+						const uint32_t sN = n9 >> 1 & 1, sW = n9 >> 3 & 1, sE = n9 >> 5 & 1, sS = n9 >> 7 & 1;
+						const uint32_t gN = f >> (18 + k) & 1, gS = f >> (20 + k) & 1, gW = fW >> (19 + k) & 1, gE = fE >> (19 + k) & 1;
+						const uint32_t idx = sN | sW << 1 | sE << 2 | sS << 3 | (gN & sN) << 4 | (gW & sW) << 5 | (gE & sE) << 6 | (gS & sS) << 7;
+						const uint32_t v = Lsc[idx];
+						const uint32_t neg = mqd_decode(q, v & 31u, lane) ^ (v >> 5);
+						f |= fsig(k + 1, 1) | (neg << (19 + k));
+						mb |= 1u << k;
+						lc |= 1u << k;
+						// the sample is the east neighbour of column x-1 and the west neighbour of column x+1
+						if (x > 0 && lane == ((x - 1) & 31)) { if (x - 1 >= 32) f1 |= fsig(k + 1, 2); else f0 |= fsig(k + 1, 2); }
+						if (x + 1 < w) {
+							if (lane == ((x + 1) & 31)) { if (x + 1 >= 32) f1 |= fsig(k + 1, 0); else f0 |= fsig(k + 1, 0); }
+							if (type == 0) cols |= 1ull << (x + 1); // may have become codable in this pass
+						}
+						// rows -1 / 4 of the stripes below / above
+						if ((k == 0 && s > 0) || (k == 3 && s + 1 < nstripes)) {
+							const int ts = k == 0 ? s : s + 2; // index into F (stripe + 1)
+							const int r = k == 0 ? 5 : 0;
+							if (lane < 3) {
+								const int cc = x + lane - 1;
+								if (cc >= 0 && cc < w)
+									atomicOr(&W.F[ts][cc], fsig(r, 2 - lane) | (lane == 1 ? neg << (18 + r) : 0u));
+							}
+						}
+					}
+				}
+				if (lane == src) {
+					if (hi) { f1 = f; mb1 |= mb; lc1 |= lc; } else { f0 = f; mb0 |= mb; lc0 |= lc; }
+				}
+			}
+			if (type == 2) { f0 &= ~F_PI_ALL; f1 &= ~F_PI_ALL; }
+			W.F[s + 1][lane] = f0;
+			if (two) W.F[s + 1][lane + 32] = f1;
+			// per-lane nibbles -> row masks of the current plane
+			if (__any_sync(0xffffffffu, (mb0 | mb1 | lc0 | lc1) != 0)) {
+				#pragma unroll
+				for (int k = 0; k < 4; ++k) {
+					const uint64_t m = (uint64_t) __ballot_sync(0xffffffffu, mb0 >> k & 1) | (uint64_t) __ballot_sync(0xffffffffu, mb1 >> k & 1) << 32;
+					const uint64_t l = (uint64_t) __ballot_sync(0xffffffffu, lc0 >> k & 1) | (uint64_t) __ballot_sync(0xffffffffu, lc1 >> k & 1) << 32;
+					if (lane == k && k < nk) {
+						W.pcur[4 * s + k] |= m;
+						if (track_last) W.lastc[4 * s + k] |= l;
+					}
+				}
+			}
+			__syncwarp();
+		}
+		if (++type == 3) {
+			// plane finished: park its magnitude bits in the scratch area
+			for (int i = lane; i < 64; i += 32) { planes[(size_t) (bp1 - 1) * 64 + i] = W.pcur[i]; W.pcur[i] = 0; }
+			__syncwarp();
+			type = 0;
+			bp1--;
+		}
+	}
+	const int lastplane = finalplane;
+	if (type != 0) { // the last plane was left unfinished (no cleanup pass): park what there is
+		for (int i = lane; i < 64; i += 32) planes[(size_t) (lastplane - 1) * 64 + i] = W.pcur[i];
+	}
+	__syncwarp();
+	// ---- reconstruct, de-quantise, scatter (T1Part1.cpp:216-329) -----------------------------
+	for (int y = 0; y < h; ++y) {
+		const int s = y >> 2, k = y & 3;
+		const uint64_t lrow = W.lastc[y];
+		uint32_t mag0 = 0, mag1 = 0;
+		for (int p = lastplane; p <= numbps; ++p) {
+			const uint64_t m = planes[(size_t) (p - 1) * 64 + y];
+			mag0 |= (uint32_t) (m >> lane & 1) << p;
+			mag1 |= (uint32_t) (m >> (lane + 32) & 1) << p;
+		}
+		#pragma unroll
+		for (int half = 0; half < 2; ++half) {
+			const int x = lane + 32 * half;
+			if (x >= w) continue;
+			const uint32_t f = W.F[s + 1][x];
+			int32_t v = 0;
+			if (f & fsig(k + 1, 1)) {
+				uint32_t mag = half ? mag1 : mag0;
+				mag |= (lrow >> x & 1) ? (1u << lastplane) >> 1 : 1u << lastplane;
+				v = (f >> (19 + k) & 1) ? -(int32_t) mag : (int32_t) mag;
+			}
+			int32_t o;
+			if (B.reversible) o = v / 2;
+			else o = __float_as_int(__fmul_rn((float) v, B.stepsize));
+			B.dst[(size_t) y * B.stride + x] = o;
+		}
 	}
 }
 
 static bool g_dec_tables_ready = false;
 
+size_t t1_decode_scratch_bytes(uint32_t nblocks, uint32_t max_planes) {
+	return (size_t) nblocks * (max_planes < 1 ? 1 : max_planes) * 64 * sizeof(uint64_t);
+}
+
 void launch_t1_decode(const DecBlock *blocks, const DecInput *inputs, uint32_t nblocks, const uint8_t *data,
-		uint32_t max_planes, cudaStream_t s) {
+		uint32_t max_planes, uint64_t *plane_scratch, cudaStream_t s) {
 	if (!nblocks) return;
 	if (!g_dec_tables_ready) { build_and_upload_t1_tables(); g_dec_tables_ready = true; }
 	if (max_planes < 1) max_planes = 1;
-	size_t dyn = (size_t) DEC_WARPS * max_planes * 64 * sizeof(uint64_t);
-	cudaFuncSetAttribute(t1_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dyn);
-	t1_decode_kernel<<<(nblocks + DEC_WARPS - 1) / DEC_WARPS, DEC_WARPS * 32, dyn, s>>>(blocks, inputs, nblocks, data, max_planes);
+	t1_decode_kernel<<<(nblocks + DEC_WARPS - 1) / DEC_WARPS, DEC_WARPS * 32, 0, s>>>(blocks, inputs, nblocks, data, max_planes,
+			plane_scratch);
 }
 
 } // namespace gb

@@ -23,6 +23,9 @@
 namespace gb {
 
 constexpr int ENC_WARPS = 4;
+#ifndef ENC_MIN_CTAS
+#define ENC_MIN_CTAS 6
+#endif
 constexpr int QCAP = 32 * 11 + 32;
 
 struct EncWarp {
@@ -135,7 +138,7 @@ __device__ __forceinline__ void emit_and_code(EncWarp &W, Mq &q, uint64_t lo, ui
 
 #define PUSH(sym) do { uint32_t s_ = (sym); if (cnt < 8) lo |= (uint64_t) s_ << (8 * cnt); else hi |= s_ << (8 * (cnt - 8)); cnt++; } while (0)
 
-__global__ void __launch_bounds__(ENC_WARPS * 32) t1_encode_kernel(const EncBlock *__restrict__ blocks, uint32_t nblocks,
+__global__ void __launch_bounds__(ENC_WARPS * 32, ENC_MIN_CTAS) t1_encode_kernel(const EncBlock *__restrict__ blocks, uint32_t nblocks,
 		int rate_control, uint8_t *__restrict__ scratch, EncResult *__restrict__ results, uint32_t *__restrict__ rates,
 		double *__restrict__ dists) {
 	__shared__ EncWarp warps[ENC_WARPS];
