@@ -75,7 +75,7 @@ __device__ __forceinline__ uint32_t mqd_byte(MqD &q, uint32_t i, int lane) {
 	return (w >> (8 * (o & 3))) & 0xFFu;
 }
 
-__device__ __noinline__ void mqd_bytein(MqD &q, int lane) {
+__device__ __forceinline__ void mqd_bytein(MqD &q, int lane) {
 	uint32_t cur = mqd_byte(q, q.pos, lane);
 	uint32_t next = mqd_byte(q, q.pos + 1, lane);
 	if (cur == 0xFF) {

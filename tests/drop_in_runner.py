@@ -1,0 +1,56 @@
+"""Runs the UNMODIFIED reference codec (oracle/_ref/libgrok_ref.so via ref_driver) on seeded synthetic images,
+either pure (CPU) or with integration/grok_tcd_shim.cpp loaded in front of it, in which case Grok's TCD stage
+calls land in libgrok_b200.so.  Writes codestreams and decoded pixels to an .npz for the caller to compare.
+
+    python tests/drop_in_runner.py {pure|shim} out.npz [case ...]
+"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, HERE)
+sys.path.insert(0, ROOT)
+
+CASES = {
+    # name: (width, height, comps, prec, reversible, tile, numres, cblk, rates, reduce)
+    "gray53": (160, 112, 1, 8, True, (0, 0), 4, (32, 32), (), 0),
+    "rgb53_tiled": (200, 150, 3, 8, True, (64, 64), 4, (32, 32), (), 1),
+    "rgb97_layers": (256, 200, 3, 8, False, (128, 112), 6, (64, 64), (20, 8, 3), 2),
+    "rgb16_53": (130, 90, 3, 16, True, (0, 0), 3, (64, 64), (), 0),
+    "c1_full": (2048, 2048, 1, 8, True, (0, 0), 6, (64, 64), (), 0),
+    "c2_crop": (2048, 1080, 3, 8, False, (1024, 1024), 6, (64, 64), (40, 20, 10, 5), 0),
+    "c4_frame": (2048, 1080, 3, 12, False, (0, 0), 6, (32, 32), (10,), 0),
+}
+
+
+def main():
+    mode, out = sys.argv[1], sys.argv[2]
+    names = sys.argv[3:] or ["gray53", "rgb53_tiled", "rgb97_layers", "rgb16_53"]
+    shim = None
+    if mode == "shim":
+        shim = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libgrok_b200_tcd.so"), mode=C.RTLD_GLOBAL)
+    import _libs
+    from grokimagecompression_b200.synth import synthetic_planes
+    res = {}
+    for name in names:
+        w, h, nc, prec, rev, tile, numres, cblk, rates, reduce = CASES[name]
+        img = synthetic_planes(w, h, nc, prec, seed=len(name) + w)
+        # rate-control algorithm 1 so that a single lossless layer is formed from the synced pass data
+        cs = _libs.ref_encode_image(img, prec, tile=tile, numres=numres, cblk=cblk, irreversible=not rev, rates=rates, rc_algorithm=1)
+        res[name + "_cs"] = np.frombuffer(cs, np.uint8)
+        res[name + "_dec"] = np.stack(_libs.ref_decode_image(cs, nc, w, h))
+        if reduce:
+            res[name + "_dec_r"] = np.stack(_libs.ref_decode_image(cs, nc, w, h, reduce=reduce))
+        res[name + "_img"] = np.stack(img)
+    if shim is not None:
+        shim.grok_b200_shim_calls.restype = C.c_uint64
+        res["calls"] = np.array([shim.grok_b200_shim_calls(i) for i in range(8)], np.uint64)
+    np.savez_compressed(out, **res)
+
+
+if __name__ == "__main__":
+    main()
