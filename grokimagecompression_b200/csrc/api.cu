@@ -296,8 +296,6 @@ int gb200_plan_create(gb200_ctx *ctx, uint32_t ntiles, const gb200_tile_params *
 		if (!pl->encoder) cudaMemsetAsync(pl->bufC[c].p, 0, bytes, ctx->stream);
 	}
 	// ---- DWT launch tables ------------------------------------------------------------------------
-	uint32_t TWt, THt;
-	dwt_tile_shape(&TWt, &THt);
 	for (int r = 0; r < 2; ++r) pl->lvl[r].resize(pl->maxlevels);
 	pl->final_role.clear();
 	for (auto &tg : pl->tiles)
@@ -305,6 +303,8 @@ int gb200_plan_create(gb200_ctx *ctx, uint32_t ntiles, const gb200_tile_params *
 			CompGeom &cg = tg.comps[c];
 			const gb200_comp_params &p = cg.p;
 			const int rev = p.qmfbid == 1;
+			uint32_t TWt, THt;
+			dwt_tile_shape(rev, &TWt, &THt);
 			int role_final = 0;
 			for (uint32_t i = 0; i < cg.levels; ++i) {
 				// encoder: i-th launch transforms decomposition level cg.top + i (finest first)

@@ -6,24 +6,42 @@
 // inverse 5/3  dwt.cpp:724-858, 256-363, 661-718             (int32, exact)
 // inverse 9/7  dwt.cpp:1544-1738, 1413-1537, constants 172-178 (fp32, multiply-then-add, no FMA)
 //
-// A CTA owns a TW x TH tile of the interleaved (spatial) domain of one plane, stages it in shared
-// memory with a halo of 2 (5/3) or 4 (9/7) samples, extended by whole-sample symmetric reflection
-// at the region border, runs the vertical and the horizontal lifting there and writes the four
-// sub-bands (forward) or the reconstructed tile (inverse) once: HBM sees one read and one write of
-// the level's region (8 B/sample algorithmic).  Launches are out of place (ping-pong planes), so
-// no CTA ever reads what another CTA of the same launch writes.
+// HBM-bound by design: one read and one write of the level's region (8 B/sample algorithmic), and
+// few enough instructions per sample that issue does not get in the way.  A CTA of 128 threads owns
+// a tile of the interleaved (spatial) domain, 128 columns wide INCLUDING the halo of 2 (5/3) or
+// 4 (9/7) samples each side, 64 rows high plus halo.  Lifting runs in REGISTERS, fully unrolled:
+//   forward: thread = column; it loads its 64+2H samples straight from global memory (every load of
+//            the warp is one coalesced row segment, all loads in flight at once), lifts vertically,
+//            parks the 64 valid rows in shared memory; then thread = half a row lifts horizontally
+//            from shared memory; the four sub-bands leave through shared memory as coalesced rows.
+//   inverse: the four sub-bands are interleaved into shared memory (coalesced per sub-band row),
+//            thread = half a row lifts horizontally, thread = column lifts vertically and stores its
+//            64 rows coalesced.
+// Launches are out of place (ping-pong planes): no CTA reads what another CTA of the launch writes.
 //
-// Lifting on a symmetrically extended signal keeps the signal symmetric, so it produces exactly
-// the reference's clamped-neighbour results at the borders (the (c+c)*x special case of
-// dwt.cpp:1463-1469 is the same rounding as (x+x)*c).  Lines of length 1 are the exception and are
-// handled explicitly (dwt53.cpp:160, dwt.cpp:344-349, 1482-1490).
+// Borders use whole-sample symmetric reflection of the source index.  Lifting on a symmetrically
+// extended signal keeps it symmetric, so this produces exactly the reference's clamped-neighbour
+// results (the (c+c)*x special case of dwt.cpp:1463-1469 rounds like (x+x)*c).  Lines of length 1
+// are the exception and are handled explicitly (dwt53.cpp:160, dwt.cpp:344-349, 1482-1490).
 #include "common.cuh"
 
 namespace gb {
 
-constexpr int TW = 64, TH = 64;
+constexpr int NCOL = 128; // columns staged per CTA, halo included
+constexpr int TH = 64;    // valid rows per CTA
 
-void dwt_tile_shape(uint32_t *tw, uint32_t *th) { *tw = TW; *th = TH; }
+template<bool REV> struct Geo {
+	static constexpr int H = REV ? 2 : 4;
+	static constexpr int TW = NCOL - 2 * H;   // valid columns per CTA
+	static constexpr int NR = TH + 2 * H;     // rows held per column
+	static constexpr int HALF = TW / 2;       // valid columns per horizontal work item
+	static constexpr int NU = HALF + 2 * H;   // samples held per horizontal work item
+};
+
+void dwt_tile_shape(int reversible, uint32_t *tw, uint32_t *th) {
+	*tw = reversible ? Geo<true>::TW : Geo<false>::TW;
+	*th = TH;
+}
 
 __device__ __forceinline__ int reflect(int i, int len) {
 	// whole-sample symmetric extension, any distance
@@ -39,230 +57,221 @@ __device__ __forceinline__ int32_t fix13(int32_t a, int32_t b) {
 }
 
 __device__ __forceinline__ const DwtPlane &find_plane(const DwtPlane *planes, uint32_t &cta) {
-	// planes are sorted by first_cta; linear walk is fine for the few hundred planes of a launch
 	uint32_t lo = 0;
 	while (planes[lo].first_cta + planes[lo].tiles_x * planes[lo].tiles_y <= cta) ++lo;
 	cta -= planes[lo].first_cta;
 	return planes[lo];
 }
 
-// One lifting step over the shared tile.  Updates samples whose LOCAL index along the lifted axis
-// has parity `par`, using both neighbours; the outermost line of the tile has no neighbour and is
-// left alone (it is halo).  VERT: axis = rows.  Threads walk the non-lifted axis fastest for the
-// vertical pass (conflict-free rows) and the lifted axis slowest for the horizontal pass with an
-// odd pitch (conflict-free columns).
-template<int OP, bool VERT, int PITCH, typename T>
-__device__ __forceinline__ void lift(T *sm, int nrows, int ncols, int par, int k) {
-	int nlift = VERT ? nrows : ncols;
-	int first = par ? 1 : 2;              // skip local index 0
-	int cnt = (nlift - first) / 2;         // indices first, first+2, ... <= nlift-2
-	if (cnt < 0) cnt = 0;
-	int other = VERT ? ncols : nrows;
-	for (int idx = threadIdx.x; idx < cnt * other; idx += blockDim.x) {
-		int o = idx % other, l = first + 2 * (idx / other);
-		T *p = VERT ? &sm[l * PITCH + o] : &sm[o * PITCH + l];
-		const int step = VERT ? PITCH : 1;
-		if (OP == 0) *p -= (p[-step] + p[step]) >> 1;                 // 5/3 predict
-		else if (OP == 1) *p += (p[-step] + p[step] + 2) >> 2;        // 5/3 update
-		else if (OP == 2) *p -= (p[-step] + p[step] + 2) >> 2;        // 5/3 inverse update
-		else if (OP == 3) *p += (p[-step] + p[step]) >> 1;            // 5/3 inverse predict
-		else if (OP == 4) *p -= fix13(p[-step] + p[step], k);         // 9/7 analysis
-		else if (OP == 5) *p += fix13(p[-step] + p[step], k);
-	}
-	__syncthreads();
+// ---- lifting on a register array; HP = parity (index & 1) of the high-pass positions --------------
+// After the call positions [H, N-H) are final; the outer H positions are scratch.
+
+template<int N, int HP>
+__device__ __forceinline__ void fwd53(int32_t (&x)[N]) {
+	#pragma unroll
+	for (int i = 1; i <= N - 2; ++i) if ((i & 1) == HP) x[i] -= (x[i - 1] + x[i + 1]) >> 1;
+	#pragma unroll
+	for (int i = 2; i <= N - 3; ++i) if ((i & 1) != HP) x[i] += (x[i - 1] + x[i + 1] + 2) >> 2;
 }
 
-template<bool VERT, int PITCH>
-__device__ __forceinline__ void scale97_fwd(int32_t *sm, int nrows, int ncols, int low_par) {
-	for (int idx = threadIdx.x; idx < nrows * ncols; idx += blockDim.x) {
-		int r = idx / ncols, c = idx % ncols;
-		int l = VERT ? r : c;
-		int32_t *p = &sm[r * PITCH + c];
-		*p = fix13(*p, (l & 1) == low_par ? 6659 : 5039);
-	}
-	__syncthreads();
+template<int N, int HP>
+__device__ __forceinline__ void inv53(int32_t (&x)[N]) {
+	#pragma unroll
+	for (int i = 1; i <= N - 2; ++i) if ((i & 1) != HP) x[i] -= (x[i - 1] + x[i + 1] + 2) >> 2;
+	#pragma unroll
+	for (int i = 2; i <= N - 3; ++i) if ((i & 1) == HP) x[i] += (x[i - 1] + x[i + 1]) >> 1;
 }
 
-template<bool VERT, int PITCH>
-__device__ __forceinline__ void lift97f(float *sm, int nrows, int ncols, int par, float c) {
-	int nlift = VERT ? nrows : ncols;
-	int first = par ? 1 : 2;
-	int cnt = (nlift - first) / 2;
-	if (cnt < 0) cnt = 0;
-	int other = VERT ? ncols : nrows;
-	for (int idx = threadIdx.x; idx < cnt * other; idx += blockDim.x) {
-		int o = idx % other, l = first + 2 * (idx / other);
-		float *p = VERT ? &sm[l * PITCH + o] : &sm[o * PITCH + l];
-		const int step = VERT ? PITCH : 1;
-		*p = __fadd_rn(*p, __fmul_rn(__fadd_rn(p[-step], p[step]), c));
-	}
-	__syncthreads();
+template<int N, int HP>
+__device__ __forceinline__ void fwd97(int32_t (&x)[N]) {
+	#pragma unroll
+	for (int i = 1; i <= N - 2; ++i) if ((i & 1) == HP) x[i] -= fix13(x[i - 1] + x[i + 1], 12994);
+	#pragma unroll
+	for (int i = 2; i <= N - 3; ++i) if ((i & 1) != HP) x[i] -= fix13(x[i - 1] + x[i + 1], 434);
+	#pragma unroll
+	for (int i = 3; i <= N - 4; ++i) if ((i & 1) == HP) x[i] += fix13(x[i - 1] + x[i + 1], 7233);
+	#pragma unroll
+	for (int i = 4; i <= N - 5; ++i) if ((i & 1) != HP) x[i] += fix13(x[i - 1] + x[i + 1], 3633);
+	#pragma unroll
+	for (int i = 4; i <= N - 5; ++i) x[i] = fix13(x[i], (i & 1) == HP ? 5039 : 6659);
 }
 
-template<bool VERT, int PITCH>
-__device__ __forceinline__ void scale97_inv(float *sm, int nrows, int ncols, int low_par) {
-	for (int idx = threadIdx.x; idx < nrows * ncols; idx += blockDim.x) {
-		int r = idx / ncols, c = idx % ncols;
-		int l = VERT ? r : c;
-		float *p = &sm[r * PITCH + c];
-		*p = __fmul_rn(*p, (l & 1) == low_par ? 1.230174105f : 1.625732422f);
+template<int N, int HP>
+__device__ __forceinline__ void inv97(int32_t (&xi)[N]) {
+	float x[N];
+	#pragma unroll
+	for (int i = 0; i < N; ++i) x[i] = __fmul_rn(__int_as_float(xi[i]), (i & 1) == HP ? 1.625732422f : 1.230174105f);
+	#pragma unroll
+	for (int i = 1; i <= N - 2; ++i) if ((i & 1) != HP) x[i] = __fadd_rn(x[i], __fmul_rn(__fadd_rn(x[i - 1], x[i + 1]), -0.443506852f));
+	#pragma unroll
+	for (int i = 2; i <= N - 3; ++i) if ((i & 1) == HP) x[i] = __fadd_rn(x[i], __fmul_rn(__fadd_rn(x[i - 1], x[i + 1]), -0.882911075f));
+	#pragma unroll
+	for (int i = 3; i <= N - 4; ++i) if ((i & 1) != HP) x[i] = __fadd_rn(x[i], __fmul_rn(__fadd_rn(x[i - 1], x[i + 1]), 0.052980118f));
+	#pragma unroll
+	for (int i = 4; i <= N - 5; ++i) if ((i & 1) == HP) x[i] = __fadd_rn(x[i], __fmul_rn(__fadd_rn(x[i - 1], x[i + 1]), 1.586134342f));
+	#pragma unroll
+	for (int i = 0; i < N; ++i) xi[i] = __float_as_int(x[i]);
+}
+
+// len  : length of the lifted line in the region (1 = degenerate: no lifting)
+// hp   : parity of the high-pass positions in the register array
+// cas  : parity of the line's first sample on the canvas (1: a lone sample is high-pass)
+template<bool FWD, bool REV, int N>
+__device__ __forceinline__ void lift_line(int32_t (&x)[N], int len, int hp, int cas) {
+	if (len > 1) {
+		if (FWD) {
+			if (REV) { if (hp) fwd53<N, 1>(x); else fwd53<N, 0>(x); }
+			else { if (hp) fwd97<N, 1>(x); else fwd97<N, 0>(x); }
+		} else {
+			if (REV) { if (hp) inv53<N, 1>(x); else inv53<N, 0>(x); }
+			else { if (hp) inv97<N, 1>(x); else inv97<N, 0>(x); }
+		}
+	} else if (REV && cas) {
+		#pragma unroll
+		for (int i = 0; i < N; ++i) x[i] = FWD ? x[i] * 2 : x[i] / 2; // dwt53.cpp:160 / dwt.cpp:349 (C division)
 	}
-	__syncthreads();
 }
 
 template<bool REV>
-__global__ void __launch_bounds__(256) dwt_fwd_kernel(const DwtPlane *__restrict__ planes) {
-	constexpr int H = REV ? 2 : 4;
-	constexpr int NR = TH + 2 * H, NC = TW + 2 * H, PITCH = NC | 1;
-	__shared__ int32_t sm[NR * PITCH];
+__global__ void __launch_bounds__(NCOL) dwt_fwd_kernel(const DwtPlane *__restrict__ planes) {
+	using G = Geo<REV>;
+	constexpr int H = G::H, TW = G::TW, NR = G::NR, HALF = G::HALF, NU = G::NU, PITCH = NCOL + 1;
+	__shared__ int32_t sm[TH * PITCH];
 
 	uint32_t cta = blockIdx.x;
 	const DwtPlane &P = find_plane(planes, cta);
 	const int X0 = (cta % P.tiles_x) * TW, Y0 = (cta / P.tiles_x) * TH;
 	const int rw = P.rw, rh = P.rh;
-
-	// stage tile + halo, reflected at the region border
-	for (int idx = threadIdx.x; idx < NR * NC; idx += blockDim.x) {
-		int r = idx / NC, c = idx % NC;
-		int gy = reflect(Y0 + r - H, rh), gx = reflect(X0 + c - H, rw);
-		sm[r * PITCH + c] = P.src[(size_t) gy * P.src_stride + gx];
-	}
-	__syncthreads();
-
-	// local index l <-> region index X0 + l - H ; H and X0 are even, so parity(l) == parity(region index).
-	// A sample is high-pass when (region index + cas) is odd.
-	const int hpx = 1 - (int) P.cas_x, hpy = 1 - (int) P.cas_y; // local parity of high-pass samples
-	// vertical first (WaveletForward.h:91-121), then horizontal (:124-152)
-	if (rh > 1) {
-		if (REV) {
-			lift<0, true, PITCH>(sm, NR, NC, hpy, 0);
-			lift<1, true, PITCH>(sm, NR, NC, 1 - hpy, 0);
-		} else {
-			lift<4, true, PITCH>(sm, NR, NC, hpy, 12994);
-			lift<4, true, PITCH>(sm, NR, NC, 1 - hpy, 434);
-			lift<5, true, PITCH>(sm, NR, NC, hpy, 7233);
-			lift<5, true, PITCH>(sm, NR, NC, 1 - hpy, 3633);
-			scale97_fwd<true, PITCH>(sm, NR, NC, 1 - hpy);
-		}
-	} else if (REV && P.cas_y) { // single high-pass row: doubled (dwt53.cpp:160)
-		for (int idx = threadIdx.x; idx < NR * NC; idx += blockDim.x)
-			sm[(idx / NC) * PITCH + idx % NC] *= 2;
-		__syncthreads();
-	}
-	if (rw > 1) {
-		if (REV) {
-			lift<0, false, PITCH>(sm, NR, NC, hpx, 0);
-			lift<1, false, PITCH>(sm, NR, NC, 1 - hpx, 0);
-		} else {
-			lift<4, false, PITCH>(sm, NR, NC, hpx, 12994);
-			lift<4, false, PITCH>(sm, NR, NC, 1 - hpx, 434);
-			lift<5, false, PITCH>(sm, NR, NC, hpx, 7233);
-			lift<5, false, PITCH>(sm, NR, NC, 1 - hpx, 3633);
-			scale97_fwd<false, PITCH>(sm, NR, NC, 1 - hpx);
-		}
-	} else if (REV && P.cas_x) {
-		for (int idx = threadIdx.x; idx < NR * NC; idx += blockDim.x)
-			sm[(idx / NC) * PITCH + idx % NC] *= 2;
-		__syncthreads();
-	}
-
-	// de-interleave to Mallat layout (dwt_utils.cpp:84-127): low halves first.
-	// Thread order: sub-band quadrant, row, column -> 128-byte row segments per quadrant.
-	constexpr int QW = TW / 2, QH = TH / 2;
-	for (int idx = threadIdx.x; idx < TW * TH; idx += blockDim.x) {
-		int q = idx / (QW * QH), rem = idx % (QW * QH);
-		int qr = rem / QW, qc = rem % QW;
-		int hx = q & 1, hy = q >> 1; // 1: high-pass in that direction
-		// local (unhaloed) coordinate with the wanted parity
-		int lx = 2 * qc + (hx ? hpx : 1 - hpx), ly = 2 * qr + (hy ? hpy : 1 - hpy);
-		int gx = X0 + lx, gy = Y0 + ly;
-		if (gx >= rw || gy >= rh) continue;
-		int ox = (gx >> 1) + (hx ? (int) P.sw : 0), oy = (gy >> 1) + (hy ? (int) P.sh : 0);
-		P.dst[(size_t) oy * P.dst_stride + ox] = sm[(ly + H) * PITCH + lx + H];
-	}
-}
-
-template<bool REV>
-__global__ void __launch_bounds__(256) dwt_inv_kernel(const DwtPlane *__restrict__ planes) {
-	constexpr int H = REV ? 2 : 4;
-	constexpr int NR = TH + 2 * H, NC = TW + 2 * H, PITCH = NC | 1;
-	__shared__ int32_t sm[NR * PITCH];
-
-	uint32_t cta = blockIdx.x;
-	const DwtPlane &P = find_plane(planes, cta);
-	const int X0 = (cta % P.tiles_x) * TW, Y0 = (cta / P.tiles_x) * TH;
-	const int rw = P.rw, rh = P.rh;
+	const int t = threadIdx.x;
+	// local index l of a line <-> region index origin + l - H; origin and H are even, so the local
+	// parity of the high-pass samples is 1 - cas
 	const int hpx = 1 - (int) P.cas_x, hpy = 1 - (int) P.cas_y;
 
-	// interleave the four sub-bands into the tile (dwt.cpp:1219-1316 for 9/7; implicit in the
-	// single-sweep 5/3 routines).  LL comes from the previous level's output, the rest from the
-	// coefficient plane.
-	for (int idx = threadIdx.x; idx < NR * NC; idx += blockDim.x) {
-		int r = idx / NC, c = idx % NC;
-		int gy = reflect(Y0 + r - H, rh), gx = reflect(X0 + c - H, rw);
-		int hx = (gx & 1) == hpx, hy = (gy & 1) == hpy;
-		int sx = (gx >> 1) + (hx ? (int) P.sw : 0), sy = (gy >> 1) + (hy ? (int) P.sh : 0);
-		int32_t v;
-		if (!hx && !hy) v = P.src[(size_t) sy * P.src_stride + sx];
-		else v = P.band[(size_t) sy * P.band_stride + sx];
-		sm[r * PITCH + c] = v;
+	{ // vertical (WaveletForward.h:91-121): thread = column
+		const int gx = reflect(X0 - H + t, rw);
+		const int32_t *col = P.src + gx;
+		int32_t v[NR];
+		if (Y0 - H >= 0 && Y0 - H + NR <= rh) { // interior rows: no reflection
+			const int32_t *p = col + (size_t) (Y0 - H) * P.src_stride;
+			#pragma unroll
+			for (int r = 0; r < NR; ++r) v[r] = p[(size_t) r * P.src_stride];
+		} else {
+			#pragma unroll
+			for (int r = 0; r < NR; ++r) v[r] = col[(size_t) reflect(Y0 - H + r, rh) * P.src_stride];
+		}
+		lift_line<true, REV, NR>(v, rh, hpy, (int) P.cas_y);
+		#pragma unroll
+		for (int r = 0; r < TH; ++r) sm[r * PITCH + t] = v[r + H];
 	}
 	__syncthreads();
-
-	// horizontal first, then vertical (dwt.cpp:775-853, 1586-1733)
-	if (REV) {
-		if (rw > 1) {
-			lift<2, false, PITCH>(sm, NR, NC, 1 - hpx, 0);
-			lift<3, false, PITCH>(sm, NR, NC, hpx, 0);
-		} else if (P.cas_x) {
-			for (int idx = threadIdx.x; idx < NR * NC; idx += blockDim.x)
-				sm[(idx / NC) * PITCH + idx % NC] /= 2; // C division (dwt.cpp:349)
-			__syncthreads();
-		}
-		if (rh > 1) {
-			lift<2, true, PITCH>(sm, NR, NC, 1 - hpy, 0);
-			lift<3, true, PITCH>(sm, NR, NC, hpy, 0);
-		} else if (P.cas_y) {
-			for (int idx = threadIdx.x; idx < NR * NC; idx += blockDim.x)
-				sm[(idx / NC) * PITCH + idx % NC] /= 2;
-			__syncthreads();
-		}
-	} else {
-		float *fs = reinterpret_cast<float*>(sm);
-		if (rw > 1) {
-			scale97_inv<false, PITCH>(fs, NR, NC, 1 - hpx);
-			lift97f<false, PITCH>(fs, NR, NC, 1 - hpx, -0.443506852f);
-			lift97f<false, PITCH>(fs, NR, NC, hpx, -0.882911075f);
-			lift97f<false, PITCH>(fs, NR, NC, 1 - hpx, 0.052980118f);
-			lift97f<false, PITCH>(fs, NR, NC, hpx, 1.586134342f);
-		}
-		if (rh > 1) {
-			scale97_inv<true, PITCH>(fs, NR, NC, 1 - hpy);
-			lift97f<true, PITCH>(fs, NR, NC, 1 - hpy, -0.443506852f);
-			lift97f<true, PITCH>(fs, NR, NC, hpy, -0.882911075f);
-			lift97f<true, PITCH>(fs, NR, NC, 1 - hpy, 0.052980118f);
-			lift97f<true, PITCH>(fs, NR, NC, hpy, 1.586134342f);
+	{ // horizontal (WaveletForward.h:124-152): thread = half a row; results go back de-interleaved
+		const int row = t >> 1, c0 = (t & 1) * HALF;
+		int32_t u[NU];
+		#pragma unroll
+		for (int i = 0; i < NU; ++i) u[i] = sm[row * PITCH + c0 + i];
+		lift_line<true, REV, NU>(u, rw, hpx, (int) P.cas_x);
+		__syncthreads();
+		// valid samples i in [H, H+HALF): tile column c0 + i - H; low-pass first, then high-pass
+		#pragma unroll
+		for (int i = H; i < H + HALF; ++i) {
+			const int lc = c0 + i - H;
+			const int dst = (lc >> 1) + (((i & 1) == hpx) ? TW / 2 : 0);
+			sm[row * PITCH + dst] = u[i];
 		}
 	}
+	__syncthreads();
+	// de-interleave rows and store (dwt_utils.cpp:84-127): shared row r, column c holds the sample of
+	// tile row r and, horizontally, low-pass index c (c < TW/2) or high-pass index c - TW/2
+	const int lowx = (X0 >> 1), lowy = (Y0 >> 1);
+	// number of valid low/high columns of this tile
+	const int vw = min(TW, rw - X0), vh = min(TH, rh - Y0);
+	const int nlow_x = (vw + (hpx ? 1 : 0)) >> 1, nhigh_x = vw - nlow_x;
+	for (int idx = t; idx < TH * TW; idx += NCOL) {
+		const int r = idx / TW, c = idx - r * TW;
+		if (r >= vh) break;
+		const bool hx = c >= TW / 2;
+		const int k = hx ? c - TW / 2 : c;
+		if (k >= (hx ? nhigh_x : nlow_x)) continue;
+		const bool hy = (r & 1) == hpy;
+		const int ox = lowx + k + (hx ? (int) P.sw : 0);
+		const int oy = lowy + (r >> 1) + (hy ? (int) P.sh : 0);
+		P.dst[(size_t) oy * P.dst_stride + ox] = sm[r * PITCH + c];
+	}
+}
 
-	for (int idx = threadIdx.x; idx < TW * TH; idx += blockDim.x) {
-		int ly = idx / TW, lx = idx % TW;
-		int gx = X0 + lx, gy = Y0 + ly;
-		if (gx >= rw || gy >= rh) continue;
-		P.dst[(size_t) gy * P.dst_stride + gx] = sm[(ly + H) * PITCH + lx + H];
+template<bool REV>
+__global__ void __launch_bounds__(NCOL) dwt_inv_kernel(const DwtPlane *__restrict__ planes) {
+	using G = Geo<REV>;
+	constexpr int H = G::H, TW = G::TW, NR = G::NR, HALF = G::HALF, NU = G::NU, PITCH = NCOL + 1;
+	__shared__ int32_t sm[NR * PITCH];
+
+	uint32_t cta = blockIdx.x;
+	const DwtPlane &P = find_plane(planes, cta);
+	const int X0 = (cta % P.tiles_x) * TW, Y0 = (cta / P.tiles_x) * TH;
+	const int rw = P.rw, rh = P.rh;
+	const int t = threadIdx.x;
+	const int hpx = 1 - (int) P.cas_x, hpy = 1 - (int) P.cas_y;
+
+	{ // interleave the four sub-bands into the tile (dwt.cpp:1219-1316 for 9/7; implicit in the 5/3 sweeps):
+	  // thread = column; LL comes from the previous level's output, the rest from the coefficient plane
+		const int gx = reflect(X0 - H + t, rw);
+		const bool hx = (gx & 1) == hpx;
+		const int sx = (gx >> 1) + (hx ? (int) P.sw : 0);
+		#pragma unroll 8
+		for (int r = 0; r < NR; ++r) {
+			const int gy = reflect(Y0 - H + r, rh);
+			const bool hy = (gy & 1) == hpy;
+			const int sy = (gy >> 1) + (hy ? (int) P.sh : 0);
+			const int32_t *p = (!hx && !hy) ? P.src + (size_t) sy * P.src_stride : P.band + (size_t) sy * P.band_stride;
+			sm[r * PITCH + t] = p[sx];
+		}
+	}
+	__syncthreads();
+	// horizontal first (dwt.cpp:775-803, 1586-1650): work item = half a row, NR rows -> 2*NR items.
+	// The two items of a row sit in adjacent lanes; each rewrites only its own valid span, which
+	// overlaps the halo the other one reads, hence the warp barrier between the reads and the writes.
+	for (int base = 0; base < 2 * NR; base += NCOL) {
+		const int item = base + t;
+		const bool active = item < 2 * NR;
+		const int row = active ? item >> 1 : 0, c0 = (item & 1) * HALF;
+		int32_t u[NU];
+		#pragma unroll
+		for (int i = 0; i < NU; ++i) u[i] = sm[row * PITCH + c0 + i];
+		lift_line<false, REV, NU>(u, rw, hpx, (int) P.cas_x);
+		__syncwarp();
+		if (active) {
+			#pragma unroll
+			for (int i = H; i < H + HALF; ++i) sm[row * PITCH + c0 + i] = u[i];
+		}
+	}
+	__syncthreads();
+	{ // vertical (dwt.cpp:822-853, 1653-1733): thread = column, only the TW valid columns
+		int32_t v[NR];
+		#pragma unroll
+		for (int r = 0; r < NR; ++r) v[r] = sm[r * PITCH + t];
+		lift_line<false, REV, NR>(v, rh, hpy, (int) P.cas_y);
+		const int gx = X0 + t - H;
+		if (t >= H && t < H + TW && gx < rw) {
+			int32_t *col = P.dst + gx;
+			#pragma unroll
+			for (int r = 0; r < TH; ++r) {
+				const int gy = Y0 + r;
+				if (gy < rh) col[(size_t) gy * P.dst_stride] = v[r + H];
+			}
+		}
 	}
 }
 
 void launch_dwt_fwd(const DwtPlane *planes_dev, uint32_t total_ctas, int reversible, cudaStream_t s) {
 	if (!total_ctas) return;
-	if (reversible) dwt_fwd_kernel<true><<<total_ctas, 256, 0, s>>>(planes_dev);
-	else dwt_fwd_kernel<false><<<total_ctas, 256, 0, s>>>(planes_dev);
+	if (reversible) dwt_fwd_kernel<true><<<total_ctas, NCOL, 0, s>>>(planes_dev);
+	else dwt_fwd_kernel<false><<<total_ctas, NCOL, 0, s>>>(planes_dev);
 }
 
 void launch_dwt_inv(const DwtPlane *planes_dev, uint32_t total_ctas, int reversible, cudaStream_t s) {
 	if (!total_ctas) return;
-	if (reversible) dwt_inv_kernel<true><<<total_ctas, 256, 0, s>>>(planes_dev);
-	else dwt_inv_kernel<false><<<total_ctas, 256, 0, s>>>(planes_dev);
+	if (reversible) dwt_inv_kernel<true><<<total_ctas, NCOL, 0, s>>>(planes_dev);
+	else dwt_inv_kernel<false><<<total_ctas, NCOL, 0, s>>>(planes_dev);
 }
 
 } // namespace gb
