@@ -59,7 +59,8 @@ struct DevBuf {
 
 struct LevelLaunch {
 	std::vector<DwtPlane> host;
-	DevBuf dev;
+	std::vector<uint32_t> cta_plane; // CTA -> index into host
+	DevBuf dev, map;
 	uint32_t ctas = 0;
 };
 
@@ -215,7 +216,7 @@ void gb200_plan_destroy(gb200_plan *pl) {
 	for (auto &b : pl->bufB) b.release();
 	for (auto &b : pl->bufC) b.release();
 	for (auto &b : pl->stash) b.release();
-	for (int r = 0; r < 2; ++r) for (auto &l : pl->lvl[r]) l.dev.release();
+	for (int r = 0; r < 2; ++r) for (auto &l : pl->lvl[r]) { l.dev.release(); l.map.release(); }
 	pl->d_blocks.release(); pl->d_results.release(); pl->d_rates.release(); pl->d_dists.release();
 	pl->d_scratch.release(); pl->d_data.release(); pl->d_inputs.release(); pl->d_planes.release();
 	delete pl;
@@ -338,14 +339,19 @@ int gb200_plan_create(gb200_ctx *ctx, uint32_t ntiles, const gb200_tile_params *
 				LevelLaunch &L = pl->lvl[rev][i];
 				d.first_cta = L.ctas;
 				L.ctas += d.tiles_x * d.tiles_y;
-				if (d.tiles_x * d.tiles_y) L.host.push_back(d);
+				if (d.tiles_x * d.tiles_y) {
+					L.cta_plane.insert(L.cta_plane.end(), (size_t) d.tiles_x * d.tiles_y, (uint32_t) L.host.size());
+					L.host.push_back(d);
+				}
 			}
 			pl->final_role.push_back(role_final);
 		}
 	for (int r = 0; r < 2; ++r)
 		for (auto &L : pl->lvl[r]) {
 			if (L.host.empty()) continue;
-			if (L.dev.alloc(L.host.size() * sizeof(DwtPlane))) return bail(GB200_ERR_NOMEM, "cudaMalloc failed");
+			if (L.dev.alloc(L.host.size() * sizeof(DwtPlane)) || L.map.alloc(L.cta_plane.size() * sizeof(uint32_t))) return bail(GB200_ERR_NOMEM, "cudaMalloc failed");
+			if (cudaMemcpyAsync(L.map.p, L.cta_plane.data(), L.cta_plane.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
+				return bail(GB200_ERR_CUDA, "upload of DWT tables failed");
 			if (cudaMemcpyAsync(L.dev.p, L.host.data(), L.host.size() * sizeof(DwtPlane), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
 				return bail(GB200_ERR_CUDA, "upload of DWT tables failed");
 		}
@@ -520,8 +526,8 @@ static int run_dwt(gb200_plan *pl, bool fwd) {
 		for (int r = 0; r < 2; ++r) {
 			LevelLaunch &L = pl->lvl[r][i];
 			if (!L.ctas) continue;
-			if (fwd) launch_dwt_fwd((const DwtPlane*) L.dev.p, L.ctas, r, ctx->stream);
-			else launch_dwt_inv((const DwtPlane*) L.dev.p, L.ctas, r, ctx->stream);
+			if (fwd) launch_dwt_fwd((const DwtPlane*) L.dev.p, (const uint32_t*) L.map.p, L.ctas, r, ctx->stream);
+			else launch_dwt_inv((const DwtPlane*) L.dev.p, (const uint32_t*) L.map.p, L.ctas, r, ctx->stream);
 			n++;
 		}
 	return launch_check(ctx, n);

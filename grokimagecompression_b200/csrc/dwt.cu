@@ -56,11 +56,11 @@ __device__ __forceinline__ int32_t fix13(int32_t a, int32_t b) {
 	return (int32_t) (((int64_t) a * (int64_t) b + 4096) >> 13);
 }
 
-__device__ __forceinline__ const DwtPlane &find_plane(const DwtPlane *planes, uint32_t &cta) {
-	uint32_t lo = 0;
-	while (planes[lo].first_cta + planes[lo].tiles_x * planes[lo].tiles_y <= cta) ++lo;
-	cta -= planes[lo].first_cta;
-	return planes[lo];
+// cta_plane[blockIdx.x] = index of the plane this CTA works on (built by the host with the launch table)
+__device__ __forceinline__ DwtPlane find_plane(const DwtPlane *planes, const uint32_t *cta_plane, uint32_t &cta) {
+	const DwtPlane P = planes[cta_plane[cta]];
+	cta -= P.first_cta;
+	return P;
 }
 
 // ---- lifting on a register array; HP = parity (index & 1) of the high-pass positions --------------
@@ -133,13 +133,13 @@ __device__ __forceinline__ void lift_line(int32_t (&x)[N], int len, int hp, int 
 }
 
 template<bool REV>
-__global__ void __launch_bounds__(NCOL) dwt_fwd_kernel(const DwtPlane *__restrict__ planes) {
+__global__ void __launch_bounds__(NCOL) dwt_fwd_kernel(const DwtPlane *__restrict__ planes, const uint32_t *__restrict__ cta_plane) {
 	using G = Geo<REV>;
 	constexpr int H = G::H, TW = G::TW, NR = G::NR, HALF = G::HALF, NU = G::NU, PITCH = NCOL + 1;
 	__shared__ int32_t sm[TH * PITCH];
 
 	uint32_t cta = blockIdx.x;
-	const DwtPlane &P = find_plane(planes, cta);
+	const DwtPlane P = find_plane(planes, cta_plane, cta);
 	const int X0 = (cta % P.tiles_x) * TW, Y0 = (cta / P.tiles_x) * TH;
 	const int rw = P.rw, rh = P.rh;
 	const int t = threadIdx.x;
@@ -186,27 +186,25 @@ __global__ void __launch_bounds__(NCOL) dwt_fwd_kernel(const DwtPlane *__restric
 	// number of valid low/high columns of this tile
 	const int vw = min(TW, rw - X0), vh = min(TH, rh - Y0);
 	const int nlow_x = (vw + (hpx ? 1 : 0)) >> 1, nhigh_x = vw - nlow_x;
-	for (int idx = t; idx < TH * TW; idx += NCOL) {
-		const int r = idx / TW, c = idx - r * TW;
-		if (r >= vh) break;
-		const bool hx = c >= TW / 2;
-		const int k = hx ? c - TW / 2 : c;
-		if (k >= (hx ? nhigh_x : nlow_x)) continue;
+	// warp w stores tile rows w, w+4, ...; lanes walk the row: low-pass part, then high-pass part
+	const int lane = t & 31, warp = t >> 5;
+	for (int r = warp; r < vh; r += NCOL / 32) {
 		const bool hy = (r & 1) == hpy;
-		const int ox = lowx + k + (hx ? (int) P.sw : 0);
-		const int oy = lowy + (r >> 1) + (hy ? (int) P.sh : 0);
-		P.dst[(size_t) oy * P.dst_stride + ox] = sm[r * PITCH + c];
+		int32_t *orow = P.dst + (size_t) (lowy + (r >> 1) + (hy ? (int) P.sh : 0)) * P.dst_stride + lowx;
+		const int32_t *srow = sm + r * PITCH;
+		for (int k = lane; k < nlow_x; k += 32) orow[k] = srow[k];
+		for (int k = lane; k < nhigh_x; k += 32) orow[P.sw + k] = srow[TW / 2 + k];
 	}
 }
 
 template<bool REV>
-__global__ void __launch_bounds__(NCOL) dwt_inv_kernel(const DwtPlane *__restrict__ planes) {
+__global__ void __launch_bounds__(NCOL) dwt_inv_kernel(const DwtPlane *__restrict__ planes, const uint32_t *__restrict__ cta_plane) {
 	using G = Geo<REV>;
 	constexpr int H = G::H, TW = G::TW, NR = G::NR, HALF = G::HALF, NU = G::NU, PITCH = NCOL + 1;
 	__shared__ int32_t sm[NR * PITCH];
 
 	uint32_t cta = blockIdx.x;
-	const DwtPlane &P = find_plane(planes, cta);
+	const DwtPlane P = find_plane(planes, cta_plane, cta);
 	const int X0 = (cta % P.tiles_x) * TW, Y0 = (cta / P.tiles_x) * TH;
 	const int rw = P.rw, rh = P.rh;
 	const int t = threadIdx.x;
@@ -262,16 +260,16 @@ __global__ void __launch_bounds__(NCOL) dwt_inv_kernel(const DwtPlane *__restric
 	}
 }
 
-void launch_dwt_fwd(const DwtPlane *planes_dev, uint32_t total_ctas, int reversible, cudaStream_t s) {
+void launch_dwt_fwd(const DwtPlane *planes_dev, const uint32_t *cta_plane_dev, uint32_t total_ctas, int reversible, cudaStream_t s) {
 	if (!total_ctas) return;
-	if (reversible) dwt_fwd_kernel<true><<<total_ctas, NCOL, 0, s>>>(planes_dev);
-	else dwt_fwd_kernel<false><<<total_ctas, NCOL, 0, s>>>(planes_dev);
+	if (reversible) dwt_fwd_kernel<true><<<total_ctas, NCOL, 0, s>>>(planes_dev, cta_plane_dev);
+	else dwt_fwd_kernel<false><<<total_ctas, NCOL, 0, s>>>(planes_dev, cta_plane_dev);
 }
 
-void launch_dwt_inv(const DwtPlane *planes_dev, uint32_t total_ctas, int reversible, cudaStream_t s) {
+void launch_dwt_inv(const DwtPlane *planes_dev, const uint32_t *cta_plane_dev, uint32_t total_ctas, int reversible, cudaStream_t s) {
 	if (!total_ctas) return;
-	if (reversible) dwt_inv_kernel<true><<<total_ctas, NCOL, 0, s>>>(planes_dev);
-	else dwt_inv_kernel<false><<<total_ctas, NCOL, 0, s>>>(planes_dev);
+	if (reversible) dwt_inv_kernel<true><<<total_ctas, NCOL, 0, s>>>(planes_dev, cta_plane_dev);
+	else dwt_inv_kernel<false><<<total_ctas, NCOL, 0, s>>>(planes_dev, cta_plane_dev);
 }
 
 } // namespace gb

@@ -6,6 +6,10 @@ import csv, re, subprocess, sys, collections
 src, cubin, kname = sys.argv[1], sys.argv[2], sys.argv[3]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 rows = list(csv.reader(open(src)))
+for _i in range(2, len(rows)):
+    if rows[_i] and rows[_i][0] == "Kernel Name":
+        rows = rows[:_i]
+        break
 hdr = rows[1]
 ia, ii, isamp = hdr.index("Address"), hdr.index("Instructions Executed"), hdr.index("# Samples")
 sass = [(r[ia], int(r[ii] or 0), int(r[isamp] or 0), r[hdr.index("Source")]) for r in rows[2:] if len(r) > ii]
