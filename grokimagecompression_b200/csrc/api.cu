@@ -62,6 +62,8 @@ struct LevelLaunch {
 	std::vector<uint32_t> cta_plane; // CTA -> index into host
 	DevBuf dev, map;
 	uint32_t ctas = 0;
+	uint32_t ctas64 = 0;  // CTA count with 64-row tiles (decides tile_rows)
+	int tile_rows = 64;
 };
 
 } // namespace
@@ -298,19 +300,41 @@ int gb200_plan_create(gb200_ctx *ctx, uint32_t ntiles, const gb200_tile_params *
 	}
 	// ---- DWT launch tables ------------------------------------------------------------------------
 	for (int r = 0; r < 2; ++r) pl->lvl[r].resize(pl->maxlevels);
+	// rows per CTA of each level launch: big levels use 64-row tiles; a level that would not even fill the
+	// machine once is cut finer, because then the latency of one CTA is what the launch costs
+	auto level_of = [&](const CompGeom &cg, uint32_t i) { return pl->encoder ? cg.top + i : cg.p.numres - 2 - i; };
+	for (auto &tg : pl->tiles)
+		for (uint32_t c = 0; c < tg.numcomps; ++c) {
+			const CompGeom &cg = tg.comps[c];
+			uint32_t tw;
+			dwt_tile_shape(cg.p.qmfbid == 1, &tw);
+			for (uint32_t i = 0; i < cg.levels; ++i) {
+				const uint32_t lvl = level_of(cg, i);
+				const uint32_t rw = cdiv2n(cg.p.x1, lvl) - cdiv2n(cg.p.x0, lvl), rh = cdiv2n(cg.p.y1, lvl) - cdiv2n(cg.p.y0, lvl);
+				if (rw && rh) pl->lvl[cg.p.qmfbid == 1][i].ctas64 += ((rw + tw - 1) / tw) * ((rh + 63) / 64);
+			}
+		}
+	{
+		int sms = 148;
+		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+		for (int r = 0; r < 2; ++r)
+			for (auto &L : pl->lvl[r])
+				L.tile_rows = L.ctas64 >= (uint32_t) sms * 6 ? 64 : (L.ctas64 >= (uint32_t) sms * 2 ? 32 : 16);
+	}
 	pl->final_role.clear();
 	for (auto &tg : pl->tiles)
 		for (uint32_t c = 0; c < tg.numcomps; ++c) {
 			CompGeom &cg = tg.comps[c];
 			const gb200_comp_params &p = cg.p;
 			const int rev = p.qmfbid == 1;
-			uint32_t TWt, THt;
-			dwt_tile_shape(rev, &TWt, &THt);
+			uint32_t TWt;
+			dwt_tile_shape(rev, &TWt);
 			int role_final = 0;
 			for (uint32_t i = 0; i < cg.levels; ++i) {
 				// encoder: i-th launch transforms decomposition level cg.top + i (finest first)
 				// decoder: i-th launch reconstructs level (numres-2-i) (coarsest first)
-				const uint32_t lvl = pl->encoder ? cg.top + i : p.numres - 2 - i;
+				const uint32_t lvl = level_of(cg, i);
+				const uint32_t THt = (uint32_t) pl->lvl[rev][i].tile_rows;
 				DwtPlane d;
 				memset(&d, 0, sizeof(d));
 				d.rw = cdiv2n(p.x1, lvl) - cdiv2n(p.x0, lvl);
@@ -526,8 +550,8 @@ static int run_dwt(gb200_plan *pl, bool fwd) {
 		for (int r = 0; r < 2; ++r) {
 			LevelLaunch &L = pl->lvl[r][i];
 			if (!L.ctas) continue;
-			if (fwd) launch_dwt_fwd((const DwtPlane*) L.dev.p, (const uint32_t*) L.map.p, L.ctas, r, ctx->stream);
-			else launch_dwt_inv((const DwtPlane*) L.dev.p, (const uint32_t*) L.map.p, L.ctas, r, ctx->stream);
+			if (fwd) launch_dwt_fwd((const DwtPlane*) L.dev.p, (const uint32_t*) L.map.p, L.ctas, r, L.tile_rows, ctx->stream);
+			else launch_dwt_inv((const DwtPlane*) L.dev.p, (const uint32_t*) L.map.p, L.ctas, r, L.tile_rows, ctx->stream);
 			n++;
 		}
 	return launch_check(ctx, n);

@@ -66,9 +66,12 @@ void launch_mct_inv(int32_t *c0, int32_t *c1, int32_t *c2, uint64_t n, const int
 		const int32_t hi[3], int reversible, int do_shift_clamp, cudaStream_t s);
 
 // dwt.cu : one launch = one decomposition level of every plane in `planes` (device array).
-void launch_dwt_fwd(const DwtPlane *planes_dev, const uint32_t *cta_plane_dev, uint32_t total_ctas, int reversible, cudaStream_t s);
-void launch_dwt_inv(const DwtPlane *planes_dev, const uint32_t *cta_plane_dev, uint32_t total_ctas, int reversible, cudaStream_t s);
-void dwt_tile_shape(int reversible, uint32_t *tw, uint32_t *th);
+// tile_rows: 64, 32 or 16 valid rows per CTA (DwtPlane::tiles_y must have been computed with the same value)
+void launch_dwt_fwd(const DwtPlane *planes_dev, const uint32_t *cta_plane_dev, uint32_t total_ctas, int reversible, int tile_rows,
+		cudaStream_t s);
+void launch_dwt_inv(const DwtPlane *planes_dev, const uint32_t *cta_plane_dev, uint32_t total_ctas, int reversible, int tile_rows,
+		cudaStream_t s);
+void dwt_tile_shape(int reversible, uint32_t *tw); // valid columns per CTA
 
 // t1_enc.cu / t1_dec.cu : one warp per code block.
 void launch_t1_encode(const EncBlock *blocks, uint32_t nblocks, int rate_control, uint8_t *scratch, EncResult *results,

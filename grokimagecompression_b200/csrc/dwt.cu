@@ -28,9 +28,10 @@
 namespace gb {
 
 constexpr int NCOL = 128; // columns staged per CTA, halo included
-constexpr int TH = 64;    // valid rows per CTA
 
-template<bool REV> struct Geo {
+// TH = valid rows per CTA: 64 for the big levels (least halo work), 32 / 16 for the small ones, where a
+// launch is a single partial wave and the latency of one CTA is what the level costs
+template<bool REV, int TH> struct Geo {
 	static constexpr int H = REV ? 2 : 4;
 	static constexpr int TW = NCOL - 2 * H;   // valid columns per CTA
 	static constexpr int NR = TH + 2 * H;     // rows held per column
@@ -38,9 +39,8 @@ template<bool REV> struct Geo {
 	static constexpr int NU = HALF + 2 * H;   // samples held per horizontal work item
 };
 
-void dwt_tile_shape(int reversible, uint32_t *tw, uint32_t *th) {
-	*tw = reversible ? Geo<true>::TW : Geo<false>::TW;
-	*th = TH;
+void dwt_tile_shape(int reversible, uint32_t *tw) {
+	*tw = reversible ? Geo<true, 64>::TW : Geo<false, 64>::TW;
 }
 
 __device__ __forceinline__ int reflect(int i, int len) {
@@ -132,9 +132,9 @@ __device__ __forceinline__ void lift_line(int32_t (&x)[N], int len, int hp, int 
 	}
 }
 
-template<bool REV>
+template<bool REV, int TH>
 __global__ void __launch_bounds__(NCOL) dwt_fwd_kernel(const DwtPlane *__restrict__ planes, const uint32_t *__restrict__ cta_plane) {
-	using G = Geo<REV>;
+	using G = Geo<REV, TH>;
 	constexpr int H = G::H, TW = G::TW, NR = G::NR, HALF = G::HALF, NU = G::NU, PITCH = NCOL + 1;
 	__shared__ int32_t sm[TH * PITCH];
 
@@ -164,19 +164,22 @@ __global__ void __launch_bounds__(NCOL) dwt_fwd_kernel(const DwtPlane *__restric
 		for (int r = 0; r < TH; ++r) sm[r * PITCH + t] = v[r + H];
 	}
 	__syncthreads();
-	{ // horizontal (WaveletForward.h:124-152): thread = half a row; results go back de-interleaved
-		const int row = t >> 1, c0 = (t & 1) * HALF;
+	{ // horizontal (WaveletForward.h:124-152): work item = half a row; results go back de-interleaved
+		const bool active = t < 2 * TH;
+		const int row = active ? t >> 1 : 0, c0 = (t & 1) * HALF;
 		int32_t u[NU];
 		#pragma unroll
 		for (int i = 0; i < NU; ++i) u[i] = sm[row * PITCH + c0 + i];
 		lift_line<true, REV, NU>(u, rw, hpx, (int) P.cas_x);
 		__syncthreads();
 		// valid samples i in [H, H+HALF): tile column c0 + i - H; low-pass first, then high-pass
-		#pragma unroll
-		for (int i = H; i < H + HALF; ++i) {
-			const int lc = c0 + i - H;
-			const int dst = (lc >> 1) + (((i & 1) == hpx) ? TW / 2 : 0);
-			sm[row * PITCH + dst] = u[i];
+		if (active) {
+			#pragma unroll
+			for (int i = H; i < H + HALF; ++i) {
+				const int lc = c0 + i - H;
+				const int dst = (lc >> 1) + (((i & 1) == hpx) ? TW / 2 : 0);
+				sm[row * PITCH + dst] = u[i];
+			}
 		}
 	}
 	__syncthreads();
@@ -197,9 +200,9 @@ __global__ void __launch_bounds__(NCOL) dwt_fwd_kernel(const DwtPlane *__restric
 	}
 }
 
-template<bool REV>
+template<bool REV, int TH>
 __global__ void __launch_bounds__(NCOL) dwt_inv_kernel(const DwtPlane *__restrict__ planes, const uint32_t *__restrict__ cta_plane) {
-	using G = Geo<REV>;
+	using G = Geo<REV, TH>;
 	constexpr int H = G::H, TW = G::TW, NR = G::NR, HALF = G::HALF, NU = G::NU, PITCH = NCOL + 1;
 	__shared__ int32_t sm[NR * PITCH];
 
@@ -260,16 +263,31 @@ __global__ void __launch_bounds__(NCOL) dwt_inv_kernel(const DwtPlane *__restric
 	}
 }
 
-void launch_dwt_fwd(const DwtPlane *planes_dev, const uint32_t *cta_plane_dev, uint32_t total_ctas, int reversible, cudaStream_t s) {
-	if (!total_ctas) return;
-	if (reversible) dwt_fwd_kernel<true><<<total_ctas, NCOL, 0, s>>>(planes_dev, cta_plane_dev);
-	else dwt_fwd_kernel<false><<<total_ctas, NCOL, 0, s>>>(planes_dev, cta_plane_dev);
+template<bool REV>
+static void launch_fwd_t(const DwtPlane *p, const uint32_t *m, uint32_t n, int th, cudaStream_t s) {
+	if (th == 64) dwt_fwd_kernel<REV, 64><<<n, NCOL, 0, s>>>(p, m);
+	else if (th == 32) dwt_fwd_kernel<REV, 32><<<n, NCOL, 0, s>>>(p, m);
+	else dwt_fwd_kernel<REV, 16><<<n, NCOL, 0, s>>>(p, m);
+}
+template<bool REV>
+static void launch_inv_t(const DwtPlane *p, const uint32_t *m, uint32_t n, int th, cudaStream_t s) {
+	if (th == 64) dwt_inv_kernel<REV, 64><<<n, NCOL, 0, s>>>(p, m);
+	else if (th == 32) dwt_inv_kernel<REV, 32><<<n, NCOL, 0, s>>>(p, m);
+	else dwt_inv_kernel<REV, 16><<<n, NCOL, 0, s>>>(p, m);
 }
 
-void launch_dwt_inv(const DwtPlane *planes_dev, const uint32_t *cta_plane_dev, uint32_t total_ctas, int reversible, cudaStream_t s) {
+void launch_dwt_fwd(const DwtPlane *planes_dev, const uint32_t *cta_plane_dev, uint32_t total_ctas, int reversible, int tile_rows,
+		cudaStream_t s) {
 	if (!total_ctas) return;
-	if (reversible) dwt_inv_kernel<true><<<total_ctas, NCOL, 0, s>>>(planes_dev, cta_plane_dev);
-	else dwt_inv_kernel<false><<<total_ctas, NCOL, 0, s>>>(planes_dev, cta_plane_dev);
+	if (reversible) launch_fwd_t<true>(planes_dev, cta_plane_dev, total_ctas, tile_rows, s);
+	else launch_fwd_t<false>(planes_dev, cta_plane_dev, total_ctas, tile_rows, s);
+}
+
+void launch_dwt_inv(const DwtPlane *planes_dev, const uint32_t *cta_plane_dev, uint32_t total_ctas, int reversible, int tile_rows,
+		cudaStream_t s) {
+	if (!total_ctas) return;
+	if (reversible) launch_inv_t<true>(planes_dev, cta_plane_dev, total_ctas, tile_rows, s);
+	else launch_inv_t<false>(planes_dev, cta_plane_dev, total_ctas, tile_rows, s);
 }
 
 } // namespace gb
