@@ -84,7 +84,7 @@ struct gb200_plan {
 	// Tier-1
 	std::vector<EncBlock> encblocks;
 	std::vector<DecBlock> decblocks;
-	DevBuf d_blocks, d_results, d_rates, d_dists, d_scratch, d_data, d_inputs, d_planes;
+	DevBuf d_blocks, d_results, d_rates, d_dists, d_scratch, d_data, d_inputs, d_planes, d_symbols;
 	uint64_t d_data_len = 0;
 	uint32_t max_planes = 1;
 	bool uniform = true; // every tile shares mct / qmfbid / shift / range parameters
@@ -220,7 +220,7 @@ void gb200_plan_destroy(gb200_plan *pl) {
 	for (auto &b : pl->stash) b.release();
 	for (int r = 0; r < 2; ++r) for (auto &l : pl->lvl[r]) { l.dev.release(); l.map.release(); }
 	pl->d_blocks.release(); pl->d_results.release(); pl->d_rates.release(); pl->d_dists.release();
-	pl->d_scratch.release(); pl->d_data.release(); pl->d_inputs.release(); pl->d_planes.release();
+	pl->d_scratch.release(); pl->d_data.release(); pl->d_inputs.release(); pl->d_planes.release(); pl->d_symbols.release();
 	delete pl;
 }
 
@@ -381,7 +381,7 @@ int gb200_plan_create(gb200_ctx *ctx, uint32_t ntiles, const gb200_tile_params *
 		}
 	// ---- block table ------------------------------------------------------------------------------
 	std::vector<BlockGeom> geo;
-	uint64_t scratch_off = 0;
+	uint64_t scratch_off = 0, sym_off = 0;
 	size_t tc = 0;
 	for (uint32_t t = 0; t < pl->tiles.size(); ++t) {
 		TileGeom &tg = pl->tiles[t];
@@ -421,6 +421,9 @@ int gb200_plan_create(gb200_ctx *ctx, uint32_t ntiles, const gb200_tile_params *
 					eb.scratch_cap = (uint32_t) align_up((uint64_t) bw * bh * 4 + 2, 16);
 					eb.scratch_off = scratch_off;
 					eb.rd_weight = p.rd_weight[g.band_index];
+					eb.sym_off = sym_off;
+					eb.sym_cap = t1_symbol_capacity(bw, bh, std::max<uint32_t>(p.band_numbps[g.band_index], 1));
+					sym_off += eb.sym_cap;
 					scratch_off += eb.scratch_cap;
 					pl->encblocks.push_back(eb);
 				} else {
@@ -443,7 +446,8 @@ int gb200_plan_create(gb200_ctx *ctx, uint32_t ntiles, const gb200_tile_params *
 		if (pl->d_blocks.alloc(std::max<size_t>(nb, 1) * sizeof(EncBlock)) || pl->d_results.alloc(std::max<size_t>(nb, 1) * sizeof(EncResult))
 				|| pl->d_rates.alloc(std::max<uint64_t>(pl->pass_slots, 1) * sizeof(uint32_t))
 				|| pl->d_dists.alloc(std::max<uint64_t>(pl->pass_slots, 1) * sizeof(double))
-				|| pl->d_scratch.alloc(std::max<uint64_t>(scratch_off, 16)) || pl->d_data.alloc(std::max<uint64_t>(scratch_off, 16)))
+				|| pl->d_scratch.alloc(std::max<uint64_t>(scratch_off, 16)) || pl->d_data.alloc(std::max<uint64_t>(scratch_off, 16))
+				|| pl->d_symbols.alloc(std::max<uint64_t>(sym_off, 16) + 64))
 			return bail(GB200_ERR_NOMEM, "cudaMalloc failed for the Tier-1 buffers");
 		if (nb && cudaMemcpyAsync(pl->d_blocks.p, pl->encblocks.data(), nb * sizeof(EncBlock), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
 			return bail(GB200_ERR_CUDA, "upload of the block table failed");
@@ -563,11 +567,11 @@ static int run_t1_enc(gb200_plan *pl) {
 	if (!nb) return GB200_OK;
 	int rc = 0;
 	for (auto &tg : pl->tiles) rc |= (int) tg.rate_control;
-	launch_t1_encode((const EncBlock*) pl->d_blocks.p, nb, rc, (uint8_t*) pl->d_scratch.p, (EncResult*) pl->d_results.p,
-			(uint32_t*) pl->d_rates.p, (double*) pl->d_dists.p, ctx->stream);
+	launch_t1_encode((const EncBlock*) pl->d_blocks.p, nb, rc, (uint8_t*) pl->d_symbols.p, (uint8_t*) pl->d_scratch.p,
+			(EncResult*) pl->d_results.p, (uint32_t*) pl->d_rates.p, (double*) pl->d_dists.p, ctx->stream);
 	launch_t1_gather((const EncBlock*) pl->d_blocks.p, (EncResult*) pl->d_results.p, nb, (const uint8_t*) pl->d_scratch.p,
 			(uint8_t*) pl->d_data.p, ctx->stream);
-	return launch_check(ctx, 3);
+	return launch_check(ctx, 4);
 }
 
 int gb200_encode_run_stage(gb200_plan *pl, int stage) {
@@ -891,9 +895,9 @@ int gb200_t1_encode_blocks(gb200_ctx *ctx, const int32_t *plane, uint32_t width,
 	CK(cudaSetDevice(ctx->device));
 	cudaStream_t s = ctx->stream;
 	std::vector<EncBlock> eb(nblocks);
-	uint64_t off = 0;
-	DevBuf d_plane, d_blocks, d_results, d_rates, d_dists, d_scratch, d_data;
-	auto freeall = [&]() { d_plane.release(); d_blocks.release(); d_results.release(); d_rates.release(); d_dists.release(); d_scratch.release(); d_data.release(); };
+	uint64_t off = 0, soff = 0;
+	DevBuf d_plane, d_blocks, d_results, d_rates, d_dists, d_scratch, d_data, d_symbols;
+	auto freeall = [&]() { d_plane.release(); d_blocks.release(); d_results.release(); d_rates.release(); d_dists.release(); d_scratch.release(); d_data.release(); d_symbols.release(); };
 	if (d_plane.alloc(std::max<size_t>((size_t) width * height * 4, 16))) FAIL(GB200_ERR_NOMEM, "cudaMalloc failed");
 	for (uint32_t i = 0; i < nblocks; ++i) {
 		const gb200_t1_block &b = blocks[i];
@@ -906,21 +910,24 @@ int gb200_t1_encode_blocks(gb200_ctx *ctx, const int32_t *plane, uint32_t width,
 		e.pass_offset = i * max_passes; e.max_passes = max_passes;
 		e.scratch_cap = (uint32_t) align_up((uint64_t) b.w * b.h * 4 + 2, 16);
 		e.scratch_off = off; e.rd_weight = b.rd_weight;
+		e.sym_off = soff;
+		e.sym_cap = t1_symbol_capacity(b.w, b.h, (max_passes + 2) / 3);
+		soff += e.sym_cap;
 		off += e.scratch_cap;
 	}
 	size_t np = (size_t) nblocks * max_passes;
 	if (d_blocks.alloc(std::max<size_t>(nblocks, 1) * sizeof(EncBlock)) || d_results.alloc(std::max<size_t>(nblocks, 1) * sizeof(EncResult))
 			|| d_rates.alloc(std::max<size_t>(np, 1) * 4) || d_dists.alloc(std::max<size_t>(np, 1) * 8) || d_scratch.alloc(std::max<uint64_t>(off, 16))
-			|| d_data.alloc(std::max<uint64_t>(off, 16))) { freeall(); FAIL(GB200_ERR_NOMEM, "cudaMalloc failed"); }
+			|| d_data.alloc(std::max<uint64_t>(off, 16)) || d_symbols.alloc(std::max<uint64_t>(soff, 16) + 64)) { freeall(); FAIL(GB200_ERR_NOMEM, "cudaMalloc failed"); }
 	cudaMemcpyAsync(d_plane.p, plane, (size_t) width * height * 4, cudaMemcpyHostToDevice, s);
 	cudaMemcpyAsync(d_blocks.p, eb.data(), nblocks * sizeof(EncBlock), cudaMemcpyHostToDevice, s);
 	cudaMemsetAsync(d_scratch.p, 0, d_scratch.bytes, s);
 	cudaMemsetAsync(d_rates.p, 0, d_rates.bytes, s);
 	cudaMemsetAsync(d_dists.p, 0, d_dists.bytes, s);
-	launch_t1_encode((const EncBlock*) d_blocks.p, nblocks, rate_control, (uint8_t*) d_scratch.p, (EncResult*) d_results.p,
-			(uint32_t*) d_rates.p, (double*) d_dists.p, s);
+	launch_t1_encode((const EncBlock*) d_blocks.p, nblocks, rate_control, (uint8_t*) d_symbols.p, (uint8_t*) d_scratch.p,
+			(EncResult*) d_results.p, (uint32_t*) d_rates.p, (double*) d_dists.p, s);
 	launch_t1_gather((const EncBlock*) d_blocks.p, (EncResult*) d_results.p, nblocks, (const uint8_t*) d_scratch.p, (uint8_t*) d_data.p, s);
-	int rc = launch_check(ctx, 3);
+	int rc = launch_check(ctx, 4);
 	if (!rc && nblocks) {
 		cudaMemcpyAsync(results, d_results.p, nblocks * sizeof(EncResult), cudaMemcpyDeviceToHost, s);
 		cudaMemcpyAsync(rates, d_rates.p, np * 4, cudaMemcpyDeviceToHost, s);

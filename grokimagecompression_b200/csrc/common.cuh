@@ -32,6 +32,9 @@ struct EncBlock {
 	uint32_t scratch_cap; // byte capacity reserved for this block
 	uint64_t scratch_off; // byte offset of the block's scratch area (one pad byte precedes the stream)
 	double rd_weight;
+	uint64_t sym_off;     // byte offset of the block's (context, decision) stream, 16-byte aligned
+	uint32_t sym_cap;     // bytes reserved for it (t1_symbol_capacity)
+	uint32_t pad2;
 };
 
 struct EncResult { // == gb200_cblk_enc
@@ -74,8 +77,9 @@ void launch_dwt_inv(const DwtPlane *planes_dev, const uint32_t *cta_plane_dev, u
 void dwt_tile_shape(int reversible, uint32_t *tw); // valid columns per CTA
 
 // t1_enc.cu / t1_dec.cu : one warp per code block.
-void launch_t1_encode(const EncBlock *blocks, uint32_t nblocks, int rate_control, uint8_t *scratch, EncResult *results,
-		uint32_t *rates, double *dists, cudaStream_t s);
+uint32_t t1_symbol_capacity(uint32_t w, uint32_t h, uint32_t planes);
+void launch_t1_encode(const EncBlock *blocks, uint32_t nblocks, int rate_control, uint8_t *symbols, uint8_t *scratch,
+		EncResult *results, uint32_t *rates, double *dists, cudaStream_t s);
 void launch_t1_gather(const EncBlock *blocks, EncResult *results, uint32_t nblocks, const uint8_t *scratch,
 		uint8_t *data, cudaStream_t s);
 // plane_scratch: t1_decode_scratch_bytes() of device memory (512 B per bit-plane per block)

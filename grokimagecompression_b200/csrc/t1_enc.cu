@@ -1,11 +1,13 @@
-// K4 (+K6): EBCOT Tier-1 encoder, one warp per code block, quantisation fused into the load.
+// K4 (+K6): EBCOT Tier-1 encoder in two kernels, quantisation fused into the load.
 //
 //   T1Part1::preEncode   T1Part1.cpp:58-95    quantise (x64 or fixed-point multiply), block max
 //   t1_encode_cblk       t1.cpp:1182-1326     plane loop, pass order, rates, distortion
 //   sig / ref / cln pass t1.cpp:287-338, 498-555, 739-782 (steps 197-231, 443-463, 639-699)
 //   MQ encoder           mqc_enc.cpp:168-287
 //
-// Design (not the reference's column-serial flag-word walk):
+// Context modelling and arithmetic coding have opposite shapes, so they are separate kernels:
+//
+// t1_model_kernel -- one WARP per code block (not the reference's column-serial flag-word walk):
 //  * Block state is five 64-bit row masks per row in shared memory (significant, negative,
 //    visited, refined, current bit-plane), built with warp ballots; a 64-bit word is one row.
 //  * Which samples a pass codes is computed BIT-PARALLEL for a whole stripe (4 rows x 64 columns)
@@ -13,10 +15,17 @@
 //    significant earlier in the same pass; because the encoder knows every bit in advance this is
 //    a monotone fixed point over the stripe's masks, reached in a few iterations.
 //  * The 32 lanes then form contexts for 32 columns at once (8-neighbour windows cut from the
-//    masks, the scan-order visibility of newly significant neighbours applied with masks), and
-//    write (context, decision) symbols in scan order into a shared-memory queue (warp prefix sum).
-//  * The MQ coder consumes the queue; A/C/CT live in registers, identical in all lanes, so the
-//    serial part is divergence free.  Bytes leave through lane 0 with a one-byte carry delay.
+//    masks, the scan-order visibility of newly significant neighbours applied with masks) and
+//    append (context, decision) bytes in scan order to the block's symbol stream (warp prefix sum,
+//    coalesced stores); a marker byte closes every coding pass.  Distortion estimates are summed
+//    here (they do not depend on the arithmetic coder).
+//
+// t1_mq_kernel -- one THREAD per code block, 32 independent MQ coders per warp: the coder is a
+//  strictly serial state machine, so the only parallelism is across blocks; run this way a warp
+//  instruction advances 32 streams instead of one.  Context states sit in shared memory as packed
+//  Table C.2 rows ([context][thread], conflict free), symbols arrive eight at a time with the next
+//  load already in flight, bytes leave with a one-byte carry delay.  Pass rates (t1.cpp:1255-1324)
+//  are produced here.
 #include "common.cuh"
 #include "t1_tables.cuh"
 
@@ -46,68 +55,14 @@ __device__ __forceinline__ uint32_t win3(uint64_t m, int x) {
 	return (uint32_t) (x == 0 ? (m << 1) : (m >> (x - 1))) & 7u;
 }
 
-struct Mq {
-	uint32_t a, c;
-	int ct;
-	int pos;        // index of the byte held in `last`; -1 = the pad byte in front of the stream
-	uint32_t last;
-	uint8_t *out;   // stream start (out[-1] is the pad)
-	uint32_t cap;
+constexpr uint32_t SYM_PASS_END = 0x80;   // marker: end of a coding pass
+constexpr uint32_t SYM_FLUSH_END = 0x81;  // marker: end of the last pass, terminate the codeword
+
+struct SymOut {
+	uint8_t *base;   // symbol stream of this block
+	uint32_t pos, cap;
 	uint32_t overflow;
-	uint32_t nsym;
-	uint32_t cst;   // MQ context `lane`: state index << 1 | mps (lanes 0..18), read with a shuffle
 };
-
-__device__ __forceinline__ void mq_byteout(Mq &q, int lane) {
-	if (q.last != 0xFF && (q.c & 0x8000000u)) { // carry into the delayed byte
-		q.last++;
-		q.c &= 0x7FFFFFFu;
-	}
-	if (q.pos >= 0) {
-		if ((uint32_t) q.pos < q.cap) { if (lane == 0) q.out[q.pos] = (uint8_t) q.last; }
-		else q.overflow = 1;
-	}
-	q.pos++;
-	if (q.last == 0xFF) { q.last = (q.c >> 20) & 0xFF; q.c &= 0xFFFFFu; q.ct = 7; }
-	else { q.last = (q.c >> 19) & 0xFF; q.c &= 0x7FFFFu; q.ct = 8; }
-}
-
-__device__ __forceinline__ void mq_encode(Mq &q, uint32_t sym, int lane) {
-	uint32_t cx = sym >> 1, d = sym & 1;
-	uint32_t st = __shfl_sync(0xffffffffu, q.cst, cx);
-	uint32_t row = c_mq[st >> 1];
-	uint32_t qe = row & 0xFFFFu;
-	q.nsym++;
-	q.a -= qe;
-	if (d == (st & 1)) {
-		if (q.a & 0x8000u) { q.c += qe; return; }
-		if (q.a < qe) q.a = qe; else q.c += qe;
-		st = (((row >> 16) & 63u) << 1) | (st & 1);
-	} else {
-		if (q.a < qe) q.c += qe; else q.a = qe;
-		st = (((row >> 22) & 63u) << 1) | ((st & 1) ^ (row >> 28));
-	}
-	if (lane == (int) cx) q.cst = st;
-	int sh = __clz(q.a) - 16; // bits to bring A back to >= 0x8000
-	while (sh > 0) {
-		int n = sh < q.ct ? sh : q.ct;
-		q.a <<= n; q.c <<= n; q.ct -= n; sh -= n;
-		if (q.ct == 0) mq_byteout(q, lane);
-	}
-}
-
-__device__ __forceinline__ void mq_flush(Mq &q, int lane) {
-	uint32_t t = q.c + q.a;
-	q.c |= 0xFFFFu;
-	if (q.c >= t) q.c -= 0x8000u;
-	q.c <<= q.ct; mq_byteout(q, lane);
-	q.c <<= q.ct; mq_byteout(q, lane);
-	if (q.last != 0xFF) {
-		if ((uint32_t) q.pos < q.cap) { if (lane == 0) q.out[q.pos] = (uint8_t) q.last; }
-		else q.overflow = 1;
-		q.pos++;
-	}
-}
 
 // quantised magnitude with 6 fractional bits and sign (T1Part1.cpp:45-56, 75, 85)
 __device__ __forceinline__ int32_t quantise(int32_t x, bool rev, int32_t inv_step) {
@@ -115,32 +70,40 @@ __device__ __forceinline__ int32_t quantise(int32_t x, bool rev, int32_t inv_ste
 }
 
 // warp-wide: lanes hand in `cnt` symbols each (packed 8 bits per symbol, first symbol lowest);
-// they are appended to the queue in lane order and then MQ-coded by the whole warp.
-__device__ __forceinline__ void emit_and_code(EncWarp &W, Mq &q, uint64_t lo, uint32_t hi, int cnt, int lane) {
+// they are appended to the block's symbol stream in lane order (staged in shared memory so that the
+// global stores are runs of consecutive bytes).
+__device__ __forceinline__ void emit(EncWarp &W, SymOut &o, uint64_t lo, uint32_t hi, int cnt, int lane) {
 	int incl = cnt;
 	#pragma unroll
-	for (int o = 1; o < 32; o <<= 1) {
-		int t = __shfl_up_sync(0xffffffffu, incl, o);
-		if (lane >= o) incl += t;
+	for (int d = 1; d < 32; d <<= 1) {
+		int t = __shfl_up_sync(0xffffffffu, incl, d);
+		if (lane >= d) incl += t;
 	}
-	int total = __shfl_sync(0xffffffffu, incl, 31);
+	const int total = __shfl_sync(0xffffffffu, incl, 31);
 	if (total == 0) return;
-	int off = incl - cnt;
+	const int off = incl - cnt;
 	for (int j = 0; j < cnt; ++j) {
 		uint32_t s = j < 8 ? (uint32_t) (lo >> (8 * j)) & 0xFF : (hi >> (8 * (j - 8))) & 0xFF;
 		W.queue[off + j] = (uint8_t) s;
 	}
 	__syncwarp();
-	for (int i = 0; i < total; ++i)
-		mq_encode(q, W.queue[i], lane);
+	if (o.pos + (uint32_t) total <= o.cap) {
+		for (int i = lane; i < total; i += 32) o.base[o.pos + i] = W.queue[i];
+	} else o.overflow = 1;
+	o.pos += (uint32_t) total;
 	__syncwarp();
+}
+
+__device__ __forceinline__ void emit_marker(SymOut &o, uint32_t m, int lane) {
+	if (o.pos < o.cap) { if (lane == 0) o.base[o.pos] = (uint8_t) m; }
+	else o.overflow = 1;
+	o.pos++;
 }
 
 #define PUSH(sym) do { uint32_t s_ = (sym); if (cnt < 8) lo |= (uint64_t) s_ << (8 * cnt); else hi |= s_ << (8 * (cnt - 8)); cnt++; } while (0)
 
-__global__ void __launch_bounds__(ENC_WARPS * 32, ENC_MIN_CTAS) t1_encode_kernel(const EncBlock *__restrict__ blocks, uint32_t nblocks,
-		int rate_control, uint8_t *__restrict__ scratch, EncResult *__restrict__ results, uint32_t *__restrict__ rates,
-		double *__restrict__ dists) {
+__global__ void __launch_bounds__(ENC_WARPS * 32, ENC_MIN_CTAS) t1_model_kernel(const EncBlock *__restrict__ blocks, uint32_t nblocks,
+		int rate_control, uint8_t *__restrict__ symbols, EncResult *__restrict__ results, double *__restrict__ dists) {
 	__shared__ EncWarp warps[ENC_WARPS];
 	__shared__ EncLuts L;
 	for (int i = threadIdx.x; i < 1024; i += blockDim.x) L.zc[i >> 8][i & 255] = c_zc[i >> 8][i & 255];
@@ -180,13 +143,10 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, ENC_MIN_CTAS) t1_encode_kernel
 		return;
 	}
 
-	Mq q;
-	q.a = 0x8000; q.c = 0; q.ct = 12; q.pos = -1; q.last = 0; q.overflow = 0; q.nsym = 0;
-	q.out = scratch + B.scratch_off + 1;
-	q.cap = B.scratch_cap - 1;
-	q.cst = lane == CTX_ZC0 ? (4 << 1) : lane == CTX_AGG ? (3 << 1) : lane == CTX_UNI ? (46 << 1) : 0; // mqc_dec.cpp:207-214
+	SymOut q;
+	q.base = symbols + B.sym_off;
+	q.pos = 0; q.cap = B.sym_cap; q.overflow = 0;
 
-	uint32_t *my_rates = rates + B.pass_offset;
 	double *my_dists = dists + B.pass_offset;
 	int npass = 0;
 	double cum = 0.0;
@@ -312,7 +272,7 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, ENC_MIN_CTAS) t1_encode_kernel
 								}
 							}
 						}
-						emit_and_code(W, q, lo, hi, cnt, lane);
+						emit(W, q, lo, hi, cnt, lane);
 					}
 				}
 				// commit the stripe
@@ -338,35 +298,144 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, ENC_MIN_CTAS) t1_encode_kernel
 				x = __dmul_rn(x, __ddiv_rn(__dmul_rn(x, (double) nmsedec), 8192.0));
 				cum = __dadd_rn(cum, x);
 			}
-			uint32_t rate;
-			if (type == 2 && bp == 0) { mq_flush(q, lane); rate = (uint32_t) q.pos; }
-			else rate = (uint32_t) q.pos + (q.ct < 5 ? 6 : 5);
-			if (lane == 0 && (uint32_t) npass < B.max_passes) { my_rates[npass] = rate; my_dists[npass] = rate_control ? cum : 0.0; }
+			emit_marker(q, type == 2 && bp == 0 ? SYM_FLUSH_END : SYM_PASS_END, lane);
+			if (lane == 0 && (uint32_t) npass < B.max_passes) my_dists[npass] = rate_control ? cum : 0.0;
 			npass++;
 		}
 	}
-	__syncwarp();
-	// ---- rate fix-ups (t1.cpp:1300-1324): non-increasing from the end, no trailing 0xFF ------
 	if (lane == 0) {
-		int np = min(npass, (int) B.max_passes);
-		uint32_t lastr = (uint32_t) q.pos;
-		for (int i = np - 1; i >= 0; --i) {
-			uint32_t r = my_rates[i];
-			if (r > lastr) { r = lastr; my_rates[i] = r; } else lastr = r;
-		}
-		for (int i = 0; i < np; ++i) {
-			uint32_t r = my_rates[i];
-			uint8_t prev = r >= 1 && r - 1 < q.cap ? q.out[r - 1] : 0;
-			if (prev == 0xFF) my_rates[i] = r - 1;
-		}
 		EncResult res;
 		res.numbps = (uint32_t) numbps;
 		res.numpasses = (q.overflow || npass > (int) B.max_passes) ? 0xFFFFFFFFu : (uint32_t) npass;
-		res.data_len = np ? my_rates[np - 1] : 0;
-		res.decisions = q.nsym;
+		res.data_len = 0;
+		res.decisions = 0;
 		res.data_offset = 0;
 		results[bid] = res;
 	}
+}
+
+// ---- MQ coder: one thread per code block ------------------------------------------------------------
+
+constexpr int MQ_THREADS = 32;
+
+struct MqT {
+	uint32_t a, c;     // A kept in the high half-word (a << 16) so that the renormalisation shift is clz(a)
+	int ct;
+	int pos;           // index of the byte held in `last`; -1 = the pad byte in front of the stream
+	uint32_t last;
+};
+
+__device__ __forceinline__ void mqt_byteout(MqT &q, uint8_t *out, uint32_t cap, uint32_t &overflow) {
+	if (q.last != 0xFF && (q.c & 0x8000000u)) { // carry into the delayed byte
+		q.last++;
+		q.c &= 0x7FFFFFFu;
+	}
+	if (q.pos >= 0) {
+		if ((uint32_t) q.pos < cap) out[q.pos] = (uint8_t) q.last; else overflow = 1;
+	}
+	q.pos++;
+	if (q.last == 0xFF) { q.last = (q.c >> 20) & 0xFF; q.c &= 0xFFFFFu; q.ct = 7; }
+	else { q.last = (q.c >> 19) & 0xFF; q.c &= 0x7FFFFu; q.ct = 8; }
+}
+
+__global__ void __launch_bounds__(MQ_THREADS) t1_mq_kernel(const EncBlock *__restrict__ blocks, uint32_t nblocks,
+		const uint8_t *__restrict__ symbols, uint8_t *__restrict__ scratch, EncResult *__restrict__ results,
+		uint32_t *__restrict__ rates) {
+	// packed Table C.2 rows: qe << 16 | switch << 13 | nlps << 6 | nmps ; bit 12 of a context entry = its MPS
+	__shared__ uint32_t tab[47];
+	__shared__ uint32_t ctx[NCTX][MQ_THREADS];
+	for (int i = threadIdx.x; i < 47; i += MQ_THREADS) {
+		const uint32_t r = c_mq[i];
+		tab[i] = (r << 16) | ((r >> 28) & 1u) << 13 | ((r >> 22) & 63u) << 6 | ((r >> 16) & 63u);
+	}
+	__syncthreads();
+	const int tid = threadIdx.x;
+	const uint32_t bid = blockIdx.x * MQ_THREADS + tid;
+	if (bid >= nblocks) return;
+	EncResult res = results[bid];
+	if (res.numbps == 0 || res.numpasses == 0 || res.numpasses == 0xFFFFFFFFu) return;
+	const EncBlock B = blocks[bid];
+	#pragma unroll
+	for (int i = 0; i < NCTX; ++i) ctx[i][tid] = tab[i == CTX_ZC0 ? 4 : i == CTX_AGG ? 3 : i == CTX_UNI ? 46 : 0]; // mqc_dec.cpp:207-214
+	uint8_t *out = scratch + B.scratch_off + 1;
+	const uint32_t cap = B.scratch_cap - 1;
+	uint32_t *my_rates = rates + B.pass_offset;
+	uint32_t overflow = 0, nsym = 0;
+	MqT q;
+	q.a = 0x80000000u; q.c = 0; q.ct = 12; q.pos = -1; q.last = 0;
+
+	const uint2 *sp = reinterpret_cast<const uint2*>(symbols + B.sym_off); // sym_off is 16-byte aligned
+	uint2 cur = sp[0], nxt = sp[1];
+	int have = 8, word = 2, npass = 0;
+	uint64_t buf = (uint64_t) cur.x | ((uint64_t) cur.y << 32);
+	bool done = false;
+	while (!done) {
+		if (have == 0) { // next eight symbols; the load after them is already in flight
+			buf = (uint64_t) nxt.x | ((uint64_t) nxt.y << 32);
+			nxt = sp[word++];
+			have = 8;
+		}
+		const uint32_t sym = (uint32_t) buf & 0xFFu;
+		buf >>= 8;
+		have--;
+		if (sym & 0x80u) { // end of a coding pass (t1.cpp:1255-1290)
+			uint32_t rate;
+			if (sym == SYM_FLUSH_END) { // FLUSH, mqc_enc.cpp:235-243, 274-287
+				const uint32_t areg = q.a >> 16;
+				const uint32_t t = q.c + areg;
+				q.c |= 0xFFFFu;
+				if (q.c >= t) q.c -= 0x8000u;
+				q.c <<= q.ct; mqt_byteout(q, out, cap, overflow);
+				q.c <<= q.ct; mqt_byteout(q, out, cap, overflow);
+				if (q.last != 0xFF) {
+					if ((uint32_t) q.pos < cap) out[q.pos] = (uint8_t) q.last; else overflow = 1;
+					q.pos++;
+				}
+				rate = (uint32_t) q.pos;
+				done = true;
+			} else rate = (uint32_t) q.pos + (q.ct < 5 ? 6 : 5);
+			if ((uint32_t) npass < B.max_passes) my_rates[npass] = rate;
+			npass++;
+			continue;
+		}
+		nsym++;
+		const uint32_t cx = sym >> 1, d = sym & 1u;
+		const uint32_t row = ctx[cx][tid];
+		const uint32_t qs = row & 0xFFFF0000u, qe = row >> 16;
+		const bool ismps = d == ((row >> 12) & 1u);
+		q.a -= qs;
+		if (ismps && (q.a & 0x80000000u)) { q.c += qe; continue; }
+		const bool small = q.a < qs;
+		if (ismps == small) q.a = qs; else q.c += qe; // MPS: A<Qe ? A=Qe : C+=Qe ; LPS: A<Qe ? C+=Qe : A=Qe
+		const uint32_t next = ismps ? row & 63u : (row >> 6) & 63u;
+		const uint32_t mps = ((row >> 12) & 1u) ^ (ismps ? 0u : (row >> 13) & 1u);
+		ctx[cx][tid] = tab[next] | (mps << 12);
+		int sh = __clz(q.a);
+		q.a <<= sh;
+		while (sh >= q.ct) { // a byte is completed inside this shift
+			q.c <<= q.ct;
+			sh -= q.ct;
+			mqt_byteout(q, out, cap, overflow);
+		}
+		q.c <<= sh;
+		q.ct -= sh;
+	}
+	// ---- rate fix-ups (t1.cpp:1300-1324): non-increasing from the end, no trailing 0xFF ------
+	const int np = min(npass, (int) B.max_passes);
+	uint32_t lastr = (uint32_t) q.pos;
+	for (int i = np - 1; i >= 0; --i) {
+		uint32_t r = my_rates[i];
+		if (r > lastr) { r = lastr; my_rates[i] = r; } else lastr = r;
+	}
+	for (int i = 0; i < np; ++i) {
+		const uint32_t r = my_rates[i];
+		const uint8_t prev = r >= 1 && r - 1 < cap ? out[r - 1] : 0;
+		if (prev == 0xFF) my_rates[i] = r - 1;
+	}
+	res.numpasses = (overflow || npass > (int) B.max_passes || npass != (int) res.numpasses) ? 0xFFFFFFFFu : (uint32_t) npass;
+	res.data_len = np ? my_rates[np - 1] : 0;
+	res.decisions = nsym;
+	results[bid] = res;
 }
 
 // ---- compaction: exclusive prefix sum of the block lengths, then one warp copies each block ----
@@ -400,12 +469,20 @@ __global__ void __launch_bounds__(256) t1_gather_kernel(const EncBlock *__restri
 
 static bool g_tables_ready = false;
 
-void launch_t1_encode(const EncBlock *blocks, uint32_t nblocks, int rate_control, uint8_t *scratch, EncResult *results,
-		uint32_t *rates, double *dists, cudaStream_t s) {
+void launch_t1_encode(const EncBlock *blocks, uint32_t nblocks, int rate_control, uint8_t *symbols, uint8_t *scratch,
+		EncResult *results, uint32_t *rates, double *dists, cudaStream_t s) {
 	if (!nblocks) return;
 	if (!g_tables_ready) { build_and_upload_t1_tables(); g_tables_ready = true; }
-	t1_encode_kernel<<<(nblocks + ENC_WARPS - 1) / ENC_WARPS, ENC_WARPS * 32, 0, s>>>(blocks, nblocks, rate_control, scratch,
-			results, rates, dists);
+	t1_model_kernel<<<(nblocks + ENC_WARPS - 1) / ENC_WARPS, ENC_WARPS * 32, 0, s>>>(blocks, nblocks, rate_control, symbols, results, dists);
+	t1_mq_kernel<<<(nblocks + MQ_THREADS - 1) / MQ_THREADS, MQ_THREADS, 0, s>>>(blocks, nblocks, symbols, scratch, results, rates);
+}
+
+// bytes of symbol stream to reserve for a w x h block with at most `planes` coded bit-planes: every sample
+// yields at most one decision per plane plus one sign, run-length mode adds at most two per stripe column,
+// one marker per pass; rounded up so that streams stay 16-byte aligned and 16 bytes can be read past the end
+uint32_t t1_symbol_capacity(uint32_t w, uint32_t h, uint32_t planes) {
+	uint64_t n = (uint64_t) planes * (w * h + ((h + 3) / 4) * w * 2) + (uint64_t) w * h + 3 * planes + 8;
+	return (uint32_t) ((n + 16 + 15) / 16 * 16);
 }
 
 void launch_t1_gather(const EncBlock *blocks, EncResult *results, uint32_t nblocks, const uint8_t *scratch, uint8_t *data,
