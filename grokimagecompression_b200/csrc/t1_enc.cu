@@ -364,20 +364,33 @@ __global__ void __launch_bounds__(MQ_THREADS) t1_mq_kernel(const EncBlock *__res
 	MqT q;
 	q.a = 0x80000000u; q.c = 0; q.ct = 12; q.pos = -1; q.last = 0;
 
+	// Symbols arrive eight at a time (the load after them already in flight); the context row of the NEXT
+	// symbol is fetched before the current one is coded, and patched if the current one changes that very
+	// context.  The step itself is branch free (selects) so that the short A-register recurrence
+	// (subtract, compare, select, clz, shift) is not serialised behind the table and C-register work;
+	// only the completion of an output byte branches.
 	const uint2 *sp = reinterpret_cast<const uint2*>(symbols + B.sym_off); // sym_off is 16-byte aligned
-	uint2 cur = sp[0], nxt = sp[1];
-	int have = 8, word = 2, npass = 0;
-	uint64_t buf = (uint64_t) cur.x | ((uint64_t) cur.y << 32);
+	uint2 nxt = sp[1];
+	int word = 2, npass = 0;
+	uint64_t buf;
+	{ const uint2 cur = sp[0]; buf = (uint64_t) cur.x | ((uint64_t) cur.y << 32); }
+	int have = 7;
+	uint32_t sym = (uint32_t) buf & 0xFFu;
+	buf >>= 8;
+	uint32_t row = (sym & 0x80u) ? 0u : ctx[sym >> 1][tid];
 	bool done = false;
 	while (!done) {
-		if (have == 0) { // next eight symbols; the load after them is already in flight
+		// fetch the following symbol and its context row
+		if (have == 0) {
 			buf = (uint64_t) nxt.x | ((uint64_t) nxt.y << 32);
 			nxt = sp[word++];
 			have = 8;
 		}
-		const uint32_t sym = (uint32_t) buf & 0xFFu;
+		const uint32_t symn = (uint32_t) buf & 0xFFu;
 		buf >>= 8;
 		have--;
+		const uint32_t cxn = (symn & 0x80u) ? 0u : symn >> 1;
+		uint32_t rown = ctx[cxn][tid];
 		if (sym & 0x80u) { // end of a coding pass (t1.cpp:1255-1290)
 			uint32_t rate;
 			if (sym == SYM_FLUSH_END) { // FLUSH, mqc_enc.cpp:235-243, 274-287
@@ -396,29 +409,36 @@ __global__ void __launch_bounds__(MQ_THREADS) t1_mq_kernel(const EncBlock *__res
 			} else rate = (uint32_t) q.pos + (q.ct < 5 ? 6 : 5);
 			if ((uint32_t) npass < B.max_passes) my_rates[npass] = rate;
 			npass++;
-			continue;
+		} else {
+			nsym++;
+			const uint32_t cx = sym >> 1, d = sym & 1u;
+			const uint32_t qs = row & 0xFFFF0000u, qe = row >> 16, mpsbit = (row >> 12) & 1u;
+			const bool ismps = d == mpsbit;
+			const uint32_t a1 = q.a - qs;
+			const bool norenorm = ismps && (a1 & 0x80000000u);
+			const bool small = a1 < qs;
+			const bool takeq = !norenorm && (ismps == small); // MPS: A<Qe ? A=Qe : C+=Qe ; LPS: A<Qe ? C+=Qe : A=Qe
+			const uint32_t a2 = takeq ? qs : a1;
+			q.c += takeq ? 0u : qe;
+			const uint32_t next = ismps ? row & 63u : (row >> 6) & 63u;
+			const uint32_t mps = mpsbit ^ (ismps ? 0u : (row >> 13) & 1u);
+			const uint32_t newrow = norenorm ? row : (tab[next] | (mps << 12));
+			ctx[cx][tid] = newrow;
+			if (cxn == cx) rown = newrow;
+			int sh = __clz(a2); // 0 when no renormalisation is due
+			q.a = a2 << sh;
+			if (sh >= q.ct) { // a byte is completed inside this shift
+				do {
+					q.c <<= q.ct;
+					sh -= q.ct;
+					mqt_byteout(q, out, cap, overflow);
+				} while (sh >= q.ct);
+			}
+			q.c <<= sh;
+			q.ct -= sh;
 		}
-		nsym++;
-		const uint32_t cx = sym >> 1, d = sym & 1u;
-		const uint32_t row = ctx[cx][tid];
-		const uint32_t qs = row & 0xFFFF0000u, qe = row >> 16;
-		const bool ismps = d == ((row >> 12) & 1u);
-		q.a -= qs;
-		if (ismps && (q.a & 0x80000000u)) { q.c += qe; continue; }
-		const bool small = q.a < qs;
-		if (ismps == small) q.a = qs; else q.c += qe; // MPS: A<Qe ? A=Qe : C+=Qe ; LPS: A<Qe ? C+=Qe : A=Qe
-		const uint32_t next = ismps ? row & 63u : (row >> 6) & 63u;
-		const uint32_t mps = ((row >> 12) & 1u) ^ (ismps ? 0u : (row >> 13) & 1u);
-		ctx[cx][tid] = tab[next] | (mps << 12);
-		int sh = __clz(q.a);
-		q.a <<= sh;
-		while (sh >= q.ct) { // a byte is completed inside this shift
-			q.c <<= q.ct;
-			sh -= q.ct;
-			mqt_byteout(q, out, cap, overflow);
-		}
-		q.c <<= sh;
-		q.ct -= sh;
+		sym = symn;
+		row = rown;
 	}
 	// ---- rate fix-ups (t1.cpp:1300-1324): non-increasing from the end, no trailing 0xFF ------
 	const int np = min(npass, (int) B.max_passes);
