@@ -46,13 +46,13 @@ struct DecWarp {
 };
 
 struct MqD {
-	uint32_t a, c;
+	uint32_t a, c;   // A is kept in the high half-word (A << 16), like the Chigh half of C it is compared with
 	int ct;
 	uint32_t pos, len;
 	const uint8_t *buf;
 	uint32_t wbase;  // first byte index of the register window
 	uint32_t word;   // this lane's 4 bytes of the window
-	uint32_t crow;   // context `lane`: Table C.2 row (qe | nmps<<16 | nlps<<22 | switch<<28) | mps << 29
+	uint32_t crow;   // context `lane`: qe << 16 | switch << 13 | mps << 12 | nlps << 6 | nmps   (Table C.2 row + MPS)
 };
 
 __device__ __forceinline__ void mqd_fill(MqD &q, uint32_t base, int lane) {
@@ -84,30 +84,46 @@ __device__ __forceinline__ void mqd_bytein(MqD &q, int lane) {
 	} else { q.pos++; q.c += next << 8; q.ct = 8; }
 }
 
-__device__ __forceinline__ uint32_t mqd_decode(MqD &q, uint32_t cx, int lane) {
+// packed Table C.2 rows in shared memory (same format as MqD::crow, MPS bit clear)
+struct DecTab { uint32_t row[47]; };
+
+__device__ __forceinline__ uint32_t mqd_decode(MqD &q, const DecTab &T, uint32_t cx, int lane) {
 	const uint32_t row = __shfl_sync(0xffffffffu, q.crow, cx);
-	const uint32_t qe = row & 0xFFFFu, mps = (row >> 29) & 1u;
-	q.a -= qe;
+	const uint32_t qs = row & 0xFFFF0000u, mps = (row >> 12) & 1u;
+	q.a -= qs;
 	bool lps;
-	if ((q.c >> 16) < qe) {
-		lps = q.a >= qe; // conditional exchange
-		q.a = qe;
+	if (q.c < qs) { // (C >> 16) < Qe : the LPS sub-interval
+		lps = q.a >= qs; // conditional exchange
+		q.a = qs;
 	} else {
-		q.c -= qe << 16;
-		if (q.a & 0x8000u) return mps;
-		lps = q.a < qe;
+		q.c -= qs;
+		if (q.a & 0x80000000u) return mps;
+		lps = q.a < qs;
 	}
-	const uint32_t next = lps ? (row >> 22) & 63u : (row >> 16) & 63u;
-	const uint32_t nmps = lps ? mps ^ ((row >> 28) & 1u) : mps;
-	const uint32_t nrow = c_mq[next] | (nmps << 29);
+	const uint32_t next = lps ? (row >> 6) & 63u : row & 63u;
+	const uint32_t nmps = lps ? mps ^ ((row >> 13) & 1u) : mps;
+	const uint32_t nrow = T.row[next] | (nmps << 12);
 	if (lane == (int) cx) q.crow = nrow;
-	int sh = __clz(q.a) - 16;
-	while (sh > 0) {
-		if (q.ct == 0) mqd_bytein(q, lane);
-		int n = sh < q.ct ? sh : q.ct;
-		q.a <<= n; q.c <<= n; q.ct -= n; sh -= n;
+	int sh = __clz(q.a);
+	q.a <<= sh;
+	if (sh <= q.ct) { q.c <<= sh; q.ct -= sh; }
+	else {
+		do { // RENORMD with BYTEIN whenever the bit counter runs out (mqc_dec_inl.h:136-147)
+			if (q.ct == 0) mqd_bytein(q, lane);
+			const int n = sh < q.ct ? sh : q.ct;
+			q.c <<= n; q.ct -= n; sh -= n;
+		} while (sh > 0);
 	}
 	return lps ? mps ^ 1u : mps;
+}
+
+// bits 4,7,10,13 (significance of the own column, rows 0..3) gathered into a nibble
+__device__ __forceinline__ uint32_t own_sig4(uint32_t f) {
+	return ((f >> 4) & 1u) | ((f >> 6) & 2u) | ((f >> 8) & 4u) | ((f >> 10) & 8u);
+}
+// rows whose 8-neighbourhood holds a significant sample
+__device__ __forceinline__ uint32_t nbr4(uint32_t f) {
+	return ((f & 0x1EFu) ? 1u : 0u) | ((f & (0x1EFu << 3)) ? 2u : 0u) | ((f & (0x1EFu << 6)) ? 4u : 0u) | ((f & (0x1EFu << 9)) ? 8u : 0u);
 }
 
 __global__ void __launch_bounds__(DEC_WARPS * 32, DEC_MIN_CTAS) t1_decode_kernel(const DecBlock *__restrict__ blocks,
@@ -116,6 +132,11 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, DEC_MIN_CTAS) t1_decode_kernel
 	__shared__ DecWarp warps[DEC_WARPS];
 	__shared__ uint8_t Lzc[4][512]; // zero-coding context by the 9 neighbourhood bits of a stripe-column word
 	__shared__ uint8_t Lsc[256];
+	__shared__ DecTab T;
+	for (int i = threadIdx.x; i < 47; i += blockDim.x) {
+		const uint32_t r = c_mq[i];
+		T.row[i] = (r << 16) | ((r >> 28) & 1u) << 13 | ((r >> 22) & 63u) << 6 | ((r >> 16) & 63u);
+	}
 	for (int i = threadIdx.x; i < 2048; i += blockDim.x) {
 		int o = i >> 9, n9 = i & 511;
 		int idx8 = (n9 & 7) | ((n9 >> 3) & 1) << 3 | ((n9 >> 5) & 1) << 4 | ((n9 >> 6) & 7) << 5;
@@ -152,13 +173,13 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, DEC_MIN_CTAS) t1_decode_kernel
 	q.buf = data + I.data_offset;
 	q.len = I.data_len;
 	q.pos = 0;
-	q.crow = c_mq[lane == CTX_ZC0 ? 4 : lane == CTX_AGG ? 3 : lane == CTX_UNI ? 46 : 0]; // mqc_dec.cpp:207-214, mps = 0
+	q.crow = T.row[lane == CTX_ZC0 ? 4 : lane == CTX_AGG ? 3 : lane == CTX_UNI ? 46 : 0]; // mqc_dec.cpp:207-214, mps = 0
 	mqd_fill(q, 0, lane);
 	q.c = mqd_byte(q, 0, lane) << 16; // INITDEC, mqc_dec.cpp:179-201
 	mqd_bytein(q, lane);
 	q.c <<= 7;
 	q.ct -= 7;
-	q.a = 0x8000;
+	q.a = 0x80000000u;
 
 	// plane of the last pass that will run: passes go cln(numbps), then sig/ref/cln per lower plane
 	const int npass_eff = min((int) I.numpasses, 3 * numbps - 2);
@@ -172,19 +193,15 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, DEC_MIN_CTAS) t1_decode_kernel
 			const int nk = min(4, h - 4 * s);
 			uint32_t f0 = W.F[s + 1][lane], f1 = two ? W.F[s + 1][lane + 32] : 0u;
 			// which columns hold a sample this pass can code (ballot of a per-lane test)
-			auto wants = [&](uint32_t f) -> bool {
-				bool any = false;
-				#pragma unroll
-				for (int k = 0; k < 4; ++k) {
-					if (k >= nk) break;
-					const bool sig = f & fsig(k + 1, 1), vis = f & (1u << (24 + k));
-					const bool nbr = (f >> (3 * k)) & 0x1EFu;
-					if (type == 0) any |= !sig && !vis && nbr;
-					else if (type == 1) any |= sig && !vis;
-					else any |= !sig && !vis;
-				}
-				return any;
+			const uint32_t rows = (1u << nk) - 1u;
+			// rows of a column this pass can code, from its word
+			auto todo = [&](uint32_t f) -> uint32_t {
+				const uint32_t sig = own_sig4(f), vis = (f >> 24) & 0xFu;
+				if (type == 0) return ~sig & ~vis & nbr4(f) & rows;
+				if (type == 1) return sig & ~vis & rows;
+				return ~sig & ~vis & rows;
 			};
+			auto wants = [&](uint32_t f) -> bool { return todo(f) != 0; };
 			uint64_t cols = (uint64_t) __ballot_sync(0xffffffffu, valid0 && wants(f0));
 			if (two) cols |= (uint64_t) __ballot_sync(0xffffffffu, valid1 && wants(f1)) << 32;
 			uint32_t mb0 = 0, mb1 = 0, lc0 = 0, lc1 = 0; // per-lane nibbles: magnitude bit decoded / sample coded
@@ -195,33 +212,33 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, DEC_MIN_CTAS) t1_decode_kernel
 				const bool hi = x >= 32;
 				uint32_t f = __shfl_sync(0xffffffffu, hi ? f1 : f0, src);
 				uint32_t mb = 0, lc = 0;
+				uint32_t cand = todo(f);
 				if (type == 1) {
-					#pragma unroll 1
-					for (int k = 0; k < nk; ++k) {
-						if (!(f & fsig(k + 1, 1)) || (f & (1u << (24 + k)))) continue;
+					while (cand) {
+						const int k = __ffs(cand) - 1;
+						cand &= cand - 1;
 						const uint32_t ctx = (f & (1u << (28 + k))) ? CTX_MR0 + 2 : ((f >> (3 * k)) & 0x1EFu) ? CTX_MR0 + 1 : CTX_MR0;
-						if (mqd_decode(q, ctx, lane)) mb |= 1u << k;
-						f |= 1u << (28 + k);
-						lc |= 1u << k;
+						if (mqd_decode(q, T, ctx, lane)) mb |= 1u << k;
 					}
+					const uint32_t done4 = todo(f);
+					f |= done4 << 28;
+					lc = done4;
 				} else {
-					int k0 = 0;
-					bool implied = false;
+					int kimp = -1; // row whose 1 is implied by the run-length code
 					if (type == 2 && nk == 4 && (f & 0x0F03FFFFu) == 0) { // run-length mode: nothing significant or visited around
-						if (!mqd_decode(q, CTX_AGG, lane)) continue;
-						k0 = (int) mqd_decode(q, CTX_UNI, lane) << 1;
-						k0 |= (int) mqd_decode(q, CTX_UNI, lane);
-						implied = true;
+						if (!mqd_decode(q, T, CTX_AGG, lane)) continue;
+						kimp = (int) mqd_decode(q, T, CTX_UNI, lane) << 1;
+						kimp |= (int) mqd_decode(q, T, CTX_UNI, lane);
+						cand &= ~((1u << kimp) - 1u);
 					}
 					uint32_t fW = 0, fE = 0;
 					bool have_nb = false;
-					#pragma unroll 1
-					for (int k = k0; k < nk; ++k) {
-						if (f & (fsig(k + 1, 1) | (1u << (24 + k)))) continue;
+					while (cand) {
+						const int k = __ffs(cand) - 1;
+						cand &= cand - 1;
 						const uint32_t n9 = (f >> (3 * k)) & 0x1FFu;
-						if (type == 0 && !(n9 & 0x1EFu)) continue;
 						uint32_t d = 1;
-						if (!(implied && k == k0)) d = mqd_decode(q, zc[n9], lane);
+						if (k != kimp) d = mqd_decode(q, T, zc[n9], lane);
 						if (type == 0) f |= 1u << (24 + k);
 						if (!d) continue;
 						if (!have_nb) { // signs of the west / east columns live in their owners' words
@@ -236,10 +253,12 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, DEC_MIN_CTAS) t1_decode_kernel
 						const uint32_t gN = f >> (18 + k) & 1, gS = f >> (20 + k) & 1, gW = fW >> (19 + k) & 1, gE = fE >> (19 + k) & 1;
 						const uint32_t idx = sN | sW << 1 | sE << 2 | sS << 3 | (gN & sN) << 4 | (gW & sW) << 5 | (gE & sE) << 6 | (gS & sS) << 7;
 						const uint32_t v = Lsc[idx];
-						const uint32_t neg = mqd_decode(q, v & 31u, lane) ^ (v >> 5);
+						const uint32_t neg = mqd_decode(q, T, v & 31u, lane) ^ (v >> 5);
 						f |= fsig(k + 1, 1) | (neg << (19 + k));
 						mb |= 1u << k;
 						lc |= 1u << k;
+						// in the significance pass the row below may have become codable through this sample
+						if (type == 0 && k + 1 < nk && !(f & (fsig(k + 2, 1) | (1u << (25 + k))))) cand |= 2u << k;
 						// the sample is the east neighbour of column x-1 and the west neighbour of column x+1
 						if (x > 0 && lane == ((x - 1) & 31)) { if (x - 1 >= 32) f1 |= fsig(k + 1, 2); else f0 |= fsig(k + 1, 2); }
 						if (x + 1 < w) {
