@@ -175,7 +175,9 @@ static void enumerate_blocks(const gb200_comp_params &p, uint32_t numres_limit, 
 				const uint32_t cx0 = gx0 + (prc % pw) * (1u << gwe), cy0 = gy0 + (prc / pw) * (1u << ghe);
 				const uint32_t qx0 = std::max(cx0, bx0), qy0 = std::max(cy0, by0);
 				const uint32_t qx1 = std::min(cx0 + (1u << gwe), bx1), qy1 = std::min(cy0 + (1u << ghe), by1);
-				if (qx1 <= qx0 || qy1 <= qy0) continue;
+				// an empty band still yields (zero-area) code blocks when its edge is not block aligned
+				// (TileComponent.cpp:384-404); they must stay in the table to keep the host's block order
+				if (qx1 < qx0 || qy1 < qy0) continue;
 				const uint32_t kx0 = (qx0 >> cwe) << cwe, ky0 = (qy0 >> che) << che;
 				const uint32_t kx1 = cdiv2n(qx1, cwe) << cwe, ky1 = cdiv2n(qy1, che) << che;
 				const uint32_t cw = (kx1 - kx0) >> cwe, ch = (ky1 - ky0) >> che;
@@ -901,7 +903,7 @@ int gb200_t1_encode_blocks(gb200_ctx *ctx, const int32_t *plane, uint32_t width,
 	if (d_plane.alloc(std::max<size_t>((size_t) width * height * 4, 16))) FAIL(GB200_ERR_NOMEM, "cudaMalloc failed");
 	for (uint32_t i = 0; i < nblocks; ++i) {
 		const gb200_t1_block &b = blocks[i];
-		if (b.w > 64 || b.h > 64 || !b.w || !b.h || b.x + b.w > width || b.y + b.h > height || b.orient > 3) { freeall(); FAIL(GB200_ERR_PARAM, "bad block"); }
+		if (b.w > 64 || b.h > 64 || b.x + b.w > width || b.y + b.h > height || b.orient > 3) { freeall(); FAIL(GB200_ERR_PARAM, "bad block"); }
 		EncBlock &e = eb[i];
 		memset(&e, 0, sizeof(e));
 		e.src = (const int32_t*) d_plane.p + (size_t) b.y * width + b.x;
@@ -964,7 +966,7 @@ int gb200_t1_decode_blocks(gb200_ctx *ctx, int32_t *plane, uint32_t width, uint3
 	uint32_t maxp = 1;
 	for (uint32_t i = 0; i < nblocks; ++i) {
 		const gb200_t1_block &b = blocks[i];
-		if (b.w > 64 || b.h > 64 || !b.w || !b.h || b.x + b.w > width || b.y + b.h > height || b.orient > 3) { freeall(); FAIL(GB200_ERR_PARAM, "bad block"); }
+		if (b.w > 64 || b.h > 64 || b.x + b.w > width || b.y + b.h > height || b.orient > 3) { freeall(); FAIL(GB200_ERR_PARAM, "bad block"); }
 		if (inputs[i].data_len && inputs[i].data_offset + inputs[i].data_len > data_len) { freeall(); FAIL(GB200_ERR_PARAM, "block bytes outside the data buffer"); }
 		if (inputs[i].numbps > 30) { freeall(); FAIL(GB200_ERR_UNSUPPORTED, "more than 30 bit planes (t1.cpp:1056)"); }
 		DecBlock &d = db[i];

@@ -917,7 +917,7 @@ GBO_API int gbo_enumerate_blocks(uint32_t tx0, uint32_t ty0, uint32_t tx1, uint3
 				uint32_t cx0 = gx0 + (p % pw) * (1u << gwe), cy0 = gy0 + (p / pw) * (1u << ghe);
 				uint32_t qx0 = umax(cx0, bx0), qy0 = umax(cy0, by0);
 				uint32_t qx1 = umin(cx0 + (1u << gwe), bx1), qy1 = umin(cy0 + (1u << ghe), by1);
-				if (qx1 <= qx0 || qy1 <= qy0)
+				if (qx1 < qx0 || qy1 < qy0) /* zero-area blocks of an empty band stay (TileComponent.cpp:384-404) */
 					continue;
 				uint32_t kx0 = fdiv2n(qx0, cwe) << cwe, ky0 = fdiv2n(qy0, che) << che;
 				uint32_t kx1 = cdiv2n(qx1, cwe) << cwe, ky1 = cdiv2n(qy1, che) << che;

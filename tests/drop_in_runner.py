@@ -24,6 +24,18 @@ CASES = {
     "c1_full": (2048, 2048, 1, 8, True, (0, 0), 6, (64, 64), (), 0),
     "c2_crop": (2048, 1080, 3, 8, False, (1024, 1024), 6, (64, 64), (40, 20, 10, 5), 0),
     "c4_frame": (2048, 1080, 3, 12, False, (0, 0), 6, (32, 32), (10,), 0),
+    # stress variants: uniform random = worst case for Tier-1, constant = zero-pass blocks
+    "random53": (300, 200, 3, 8, True, (128, 128), 5, (64, 64), (), 1, "random"),
+    "constant53": (256, 256, 1, 8, True, (0, 0), 6, (64, 64), (), 0, "constant"),
+    "random97": (256, 192, 3, 8, False, (0, 0), 5, (32, 32), (30, 5), 0, "random"),
+    # ragged geometry: prime sizes, tiles that do not divide the image, tiny images
+    "ragged53": (211, 157, 3, 8, True, (97, 61), 4, (16, 32), (), 1),
+    "ragged97": (173, 131, 1, 12, False, (80, 80), 6, (32, 16), (12, 4), 2),
+    "tiny": (5, 3, 1, 8, True, (0, 0), 3, (64, 64), (), 0),
+    "onepixel": (1, 1, 3, 8, True, (0, 0), 2, (64, 64), (), 0),
+    # configs[4]-style decode sweep: tiled 5/3 and 9/7 streams at every reduction, and a layer-limited decode
+    "sweep53": (1536, 1280, 3, 8, True, (512, 512), 6, (64, 64), (), "sweep"),
+    "sweep97": (1536, 1280, 3, 8, False, (512, 512), 6, (64, 64), (10,), "sweep"),
 }
 
 
@@ -37,13 +49,20 @@ def main():
     from grokimagecompression_b200.synth import synthetic_planes
     res = {}
     for name in names:
-        w, h, nc, prec, rev, tile, numres, cblk, rates, reduce = CASES[name]
-        img = synthetic_planes(w, h, nc, prec, seed=len(name) + w)
+        case = CASES[name]
+        w, h, nc, prec, rev, tile, numres, cblk, rates, reduce = case[:10]
+        kind = case[10] if len(case) > 10 else "smooth"
+        img = synthetic_planes(w, h, nc, prec, seed=len(name) + w, kind=kind)
         # rate-control algorithm 1 so that a single lossless layer is formed from the synced pass data
         cs = _libs.ref_encode_image(img, prec, tile=tile, numres=numres, cblk=cblk, irreversible=not rev, rates=rates, rc_algorithm=1)
         res[name + "_cs"] = np.frombuffer(cs, np.uint8)
         res[name + "_dec"] = np.stack(_libs.ref_decode_image(cs, nc, w, h))
-        if reduce:
+        if reduce == "sweep":
+            for r in (1, 2, 3, 4):
+                res[name + f"_dec_r{r}"] = np.stack(_libs.ref_decode_image(cs, nc, w, h, reduce=r))
+            if len(rates) > 0 or True:
+                res[name + "_dec_l1"] = np.stack(_libs.ref_decode_image(cs, nc, w, h, layers=1))
+        elif reduce:
             res[name + "_dec_r"] = np.stack(_libs.ref_decode_image(cs, nc, w, h, reduce=reduce))
         res[name + "_img"] = np.stack(img)
     if shim is not None:
