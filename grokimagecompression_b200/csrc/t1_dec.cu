@@ -37,7 +37,6 @@ constexpr int DEC_WARPS = 4;
 // bit 18+r = sign of own column row r-1; bit 24+k = visited (k = 0..3); bit 28+k = refined before
 __device__ __forceinline__ constexpr uint32_t fsig(int r, int j) { return 1u << (3 * r + j); }
 constexpr uint32_t F_PI_ALL = 0xFu << 24;
-constexpr uint32_t F_SIG_OWN4 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 13);
 
 struct DecWarp {
 	uint32_t F[18][64];   // [stripe + 1][column]; stripes -1 and 16 are never read as a current stripe

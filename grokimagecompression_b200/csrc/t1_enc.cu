@@ -317,6 +317,9 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, ENC_MIN_CTAS) t1_model_kernel(
 // ---- MQ coder: one thread per code block ------------------------------------------------------------
 
 constexpr int MQ_THREADS = 32;
+#ifndef MQ_LANES
+#define MQ_LANES 8   // active lanes (code blocks) per warp: fewer lanes = fewer distinct paths per step (measured 1..32)
+#endif
 
 struct MqT {
 	uint32_t a, c;     // A kept in the high half-word (a << 16) so that the renormalisation shift is clz(a)
@@ -350,7 +353,8 @@ __global__ void __launch_bounds__(MQ_THREADS) t1_mq_kernel(const EncBlock *__res
 	}
 	__syncthreads();
 	const int tid = threadIdx.x;
-	const uint32_t bid = blockIdx.x * MQ_THREADS + tid;
+	if (tid >= MQ_LANES) return;
+	const uint32_t bid = blockIdx.x * MQ_LANES + tid;
 	if (bid >= nblocks) return;
 	EncResult res = results[bid];
 	if (res.numbps == 0 || res.numpasses == 0 || res.numpasses == 0xFFFFFFFFu) return;
@@ -494,7 +498,7 @@ void launch_t1_encode(const EncBlock *blocks, uint32_t nblocks, int rate_control
 	if (!nblocks) return;
 	if (!g_tables_ready) { build_and_upload_t1_tables(); g_tables_ready = true; }
 	t1_model_kernel<<<(nblocks + ENC_WARPS - 1) / ENC_WARPS, ENC_WARPS * 32, 0, s>>>(blocks, nblocks, rate_control, symbols, results, dists);
-	t1_mq_kernel<<<(nblocks + MQ_THREADS - 1) / MQ_THREADS, MQ_THREADS, 0, s>>>(blocks, nblocks, symbols, scratch, results, rates);
+	t1_mq_kernel<<<(nblocks + MQ_LANES - 1) / MQ_LANES, MQ_THREADS, 0, s>>>(blocks, nblocks, symbols, scratch, results, rates);
 }
 
 // bytes of symbol stream to reserve for a w x h block with at most `planes` coded bit-planes: every sample
