@@ -52,6 +52,12 @@ __device__ __forceinline__ int reflect(int i, int len) {
 	return i >= len ? p - i : i;
 }
 
+// same, for an index at most len-1 outside [0,len) (one reflection is enough)
+__device__ __forceinline__ int reflect1(int i, int len) {
+	i = i < 0 ? -i : i;
+	return i >= len ? 2 * (len - 1) - i : i;
+}
+
 __device__ __forceinline__ int32_t fix13(int32_t a, int32_t b) {
 	return (int32_t) (((int64_t) a * (int64_t) b + 4096) >> 13);
 }
@@ -155,6 +161,9 @@ __global__ void __launch_bounds__(NCOL) dwt_fwd_kernel(const DwtPlane *__restric
 			const int32_t *p = col + (size_t) (Y0 - H) * P.src_stride;
 			#pragma unroll
 			for (int r = 0; r < NR; ++r) v[r] = p[(size_t) r * P.src_stride];
+		} else if (rh > 2 * H) { // border tile of a line longer than the halo: a single reflection
+			#pragma unroll
+			for (int r = 0; r < NR; ++r) v[r] = col[(size_t) reflect1(min(Y0 - H + r, rh + H - 1), rh) * P.src_stride];
 		} else {
 			#pragma unroll
 			for (int r = 0; r < NR; ++r) v[r] = col[(size_t) reflect(Y0 - H + r, rh) * P.src_stride];
@@ -189,14 +198,20 @@ __global__ void __launch_bounds__(NCOL) dwt_fwd_kernel(const DwtPlane *__restric
 	// number of valid low/high columns of this tile
 	const int vw = min(TW, rw - X0), vh = min(TH, rh - Y0);
 	const int nlow_x = (vw + (hpx ? 1 : 0)) >> 1, nhigh_x = vw - nlow_x;
-	// warp w stores tile rows w, w+4, ...; lanes walk the row: low-pass part, then high-pass part
+	// warp w stores tile rows w, w+4, ...; a lane owns low-pass columns lane, lane+32 and the same two
+	// high-pass columns: four predicated stores per row, predicates and offsets fixed per lane
 	const int lane = t & 31, warp = t >> 5;
+	const bool l0 = lane < nlow_x, l1 = lane + 32 < nlow_x, h0 = lane < nhigh_x, h1 = lane + 32 < nhigh_x;
+	const int hoff = (int) P.sw + lane;
+	#pragma unroll 4
 	for (int r = warp; r < vh; r += NCOL / 32) {
 		const bool hy = (r & 1) == hpy;
 		int32_t *orow = P.dst + (size_t) (lowy + (r >> 1) + (hy ? (int) P.sh : 0)) * P.dst_stride + lowx;
 		const int32_t *srow = sm + r * PITCH;
-		for (int k = lane; k < nlow_x; k += 32) orow[k] = srow[k];
-		for (int k = lane; k < nhigh_x; k += 32) orow[P.sw + k] = srow[TW / 2 + k];
+		if (l0) orow[lane] = srow[lane];
+		if (l1) orow[lane + 32] = srow[lane + 32];
+		if (h0) orow[hoff] = srow[TW / 2 + lane];
+		if (h1) orow[hoff + 32] = srow[TW / 2 + lane + 32];
 	}
 }
 
@@ -218,9 +233,11 @@ __global__ void __launch_bounds__(NCOL) dwt_inv_kernel(const DwtPlane *__restric
 		const int gx = reflect(X0 - H + t, rw);
 		const bool hx = (gx & 1) == hpx;
 		const int sx = (gx >> 1) + (hx ? (int) P.sw : 0);
+		const bool interior = Y0 - H >= 0 && Y0 - H + NR <= rh, simple = rh > 2 * H;
 		#pragma unroll 8
 		for (int r = 0; r < NR; ++r) {
-			const int gy = reflect(Y0 - H + r, rh);
+			const int y = Y0 - H + r;
+			const int gy = interior ? y : (simple ? reflect1(min(y, rh + H - 1), rh) : reflect(y, rh));
 			const bool hy = (gy & 1) == hpy;
 			const int sy = (gy >> 1) + (hy ? (int) P.sh : 0);
 			const int32_t *p = (!hx && !hy) ? P.src + (size_t) sy * P.src_stride : P.band + (size_t) sy * P.band_stride;
