@@ -84,9 +84,9 @@ struct gb200_plan {
 	// Tier-1
 	std::vector<EncBlock> encblocks;
 	std::vector<DecBlock> decblocks;
-	DevBuf d_blocks, d_results, d_rates, d_dists, d_scratch, d_data, d_inputs, d_planes, d_symbols;
+	DevBuf d_blocks, d_results, d_rates, d_dists, d_scratch, d_data, d_inputs, d_symbols;
 	uint64_t d_data_len = 0;
-	uint32_t max_planes = 1;
+	uint32_t max_bw = 1, max_bh = 1; // largest code block of the table
 	bool uniform = true; // every tile shares mct / qmfbid / shift / range parameters
 	std::vector<EncResult> h_results;
 	// where each tile-component's final decoded plane lives (0 A, 1 B, 2 C)
@@ -222,7 +222,7 @@ void gb200_plan_destroy(gb200_plan *pl) {
 	for (auto &b : pl->stash) b.release();
 	for (int r = 0; r < 2; ++r) for (auto &l : pl->lvl[r]) { l.dev.release(); l.map.release(); }
 	pl->d_blocks.release(); pl->d_results.release(); pl->d_rates.release(); pl->d_dists.release();
-	pl->d_scratch.release(); pl->d_data.release(); pl->d_inputs.release(); pl->d_planes.release(); pl->d_symbols.release();
+	pl->d_scratch.release(); pl->d_data.release(); pl->d_inputs.release(); pl->d_symbols.release();
 	delete pl;
 }
 
@@ -400,9 +400,9 @@ int gb200_plan_create(gb200_ctx *ctx, uint32_t ntiles, const gb200_tile_params *
 				bi.max_passes = std::max<uint32_t>(1, 3 * std::max<uint32_t>(p.band_numbps[g.band_index], 1) - 2);
 				bi.pass_offset = (uint32_t) pl->pass_slots;
 				pl->pass_slots += bi.max_passes;
-				pl->max_planes = std::max(pl->max_planes, p.band_numbps[g.band_index]);
 				pl->blocks.push_back(bi);
 				const uint32_t bw = g.x1 - g.x0, bh = g.y1 - g.y0;
+				pl->max_bw = std::max(pl->max_bw, bw); pl->max_bh = std::max(pl->max_bh, bh);
 				if (pl->encoder) {
 					// which ping-pong plane holds this sub-band: the output of the launch that produced it
 					int role = 0;
@@ -456,8 +456,7 @@ int gb200_plan_create(gb200_ctx *ctx, uint32_t ntiles, const gb200_tile_params *
 		cudaMemsetAsync(pl->d_scratch.p, 0, pl->d_scratch.bytes, ctx->stream);
 		pl->h_results.resize(nb);
 	} else {
-		if (pl->d_blocks.alloc(std::max<size_t>(nb, 1) * sizeof(DecBlock)) || pl->d_inputs.alloc(std::max<size_t>(nb, 1) * sizeof(DecInput))
-				|| pl->d_planes.alloc(std::max<size_t>(t1_decode_scratch_bytes((uint32_t) nb, pl->max_planes), 16)))
+		if (pl->d_blocks.alloc(std::max<size_t>(nb, 1) * sizeof(DecBlock)) || pl->d_inputs.alloc(std::max<size_t>(nb, 1) * sizeof(DecInput)))
 			return bail(GB200_ERR_NOMEM, "cudaMalloc failed for the Tier-1 buffers");
 		if (nb && cudaMemcpyAsync(pl->d_blocks.p, pl->decblocks.data(), nb * sizeof(DecBlock), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
 			return bail(GB200_ERR_CUDA, "upload of the block table failed");
@@ -659,8 +658,8 @@ int gb200_decode_upload(gb200_plan *pl, const gb200_cblk_dec *blocks, const uint
 	for (size_t i = 0; i < nb; ++i)
 		if (blocks[i].data_len && blocks[i].data_offset + blocks[i].data_len > data_len)
 			FAIL(GB200_ERR_PARAM, "code block bytes lie outside the data buffer");
-	if (pl->d_data.bytes < data_len + 16) {
-		if (pl->d_data.alloc(align_up(data_len + 16, 256))) FAIL(GB200_ERR_NOMEM, "cudaMalloc failed for the compressed data");
+	if (pl->d_data.bytes < data_len + T1_DEC_DATA_SLACK) {
+		if (pl->d_data.alloc(align_up(data_len + T1_DEC_DATA_SLACK, 256))) FAIL(GB200_ERR_NOMEM, "cudaMalloc failed for the compressed data");
 	}
 	pl->d_data_len = data_len;
 	if (nb) CK(cudaMemcpyAsync(pl->d_inputs.p, blocks, nb * sizeof(DecInput), cudaMemcpyHostToDevice, s));
@@ -671,9 +670,10 @@ int gb200_decode_upload(gb200_plan *pl, const gb200_cblk_dec *blocks, const uint
 static int run_t1_dec(gb200_plan *pl) {
 	const uint32_t nb = (uint32_t) pl->blocks.size();
 	if (!nb) return GB200_OK;
-	launch_t1_decode((const DecBlock*) pl->d_blocks.p, (const DecInput*) pl->d_inputs.p, nb, (const uint8_t*) pl->d_data.p,
-			pl->max_planes, (uint64_t*) pl->d_planes.p, pl->ctx->stream);
-	return launch_check(pl->ctx, 1);
+	if (launch_t1_decode((const DecBlock*) pl->d_blocks.p, (const DecInput*) pl->d_inputs.p, nb, (const uint8_t*) pl->d_data.p,
+			pl->max_bw, pl->max_bh, pl->ctx->stream))
+		FAIL(GB200_ERR_UNSUPPORTED, "Tier-1 decode: code block state does not fit in shared memory");
+	return launch_check(pl->ctx, T1_DEC_LAUNCHES);
 }
 
 static int run_mct_dc_inv(gb200_plan *pl) {
@@ -960,10 +960,10 @@ int gb200_t1_decode_blocks(gb200_ctx *ctx, int32_t *plane, uint32_t width, uint3
 	CK(cudaSetDevice(ctx->device));
 	cudaStream_t s = ctx->stream;
 	std::vector<DecBlock> db(nblocks);
-	DevBuf d_plane, d_blocks, d_inputs, d_data, d_planes;
-	auto freeall = [&]() { d_plane.release(); d_blocks.release(); d_inputs.release(); d_data.release(); d_planes.release(); };
+	DevBuf d_plane, d_blocks, d_inputs, d_data;
+	auto freeall = [&]() { d_plane.release(); d_blocks.release(); d_inputs.release(); d_data.release(); };
 	if (d_plane.alloc(std::max<size_t>((size_t) width * height * 4, 16))) FAIL(GB200_ERR_NOMEM, "cudaMalloc failed");
-	uint32_t maxp = 1;
+	uint32_t maxw = 1, maxh = 1;
 	for (uint32_t i = 0; i < nblocks; ++i) {
 		const gb200_t1_block &b = blocks[i];
 		if (b.w > 64 || b.h > 64 || b.x + b.w > width || b.y + b.h > height || b.orient > 3) { freeall(); FAIL(GB200_ERR_PARAM, "bad block"); }
@@ -974,16 +974,19 @@ int gb200_t1_decode_blocks(gb200_ctx *ctx, int32_t *plane, uint32_t width, uint3
 		d.dst = (int32_t*) d_plane.p + (size_t) b.y * width + b.x;
 		d.stride = width; d.w = (uint16_t) b.w; d.h = (uint16_t) b.h; d.orient = (uint8_t) b.orient;
 		d.reversible = b.qmfbid == 1; d.stepsize = b.stepsize;
-		maxp = std::max(maxp, inputs[i].numbps);
+		maxw = std::max(maxw, b.w); maxh = std::max(maxh, b.h);
 	}
 	if (d_blocks.alloc(std::max<size_t>(nblocks, 1) * sizeof(DecBlock)) || d_inputs.alloc(std::max<size_t>(nblocks, 1) * sizeof(DecInput))
-			|| d_data.alloc(align_up(data_len + 16, 256)) || d_planes.alloc(std::max<size_t>(t1_decode_scratch_bytes(nblocks, maxp), 16))) { freeall(); FAIL(GB200_ERR_NOMEM, "cudaMalloc failed"); }
+			|| d_data.alloc(align_up(data_len + T1_DEC_DATA_SLACK, 256))) { freeall(); FAIL(GB200_ERR_NOMEM, "cudaMalloc failed"); }
 	cudaMemcpyAsync(d_plane.p, plane, (size_t) width * height * 4, cudaMemcpyHostToDevice, s);
 	cudaMemcpyAsync(d_blocks.p, db.data(), nblocks * sizeof(DecBlock), cudaMemcpyHostToDevice, s);
 	cudaMemcpyAsync(d_inputs.p, inputs, nblocks * sizeof(DecInput), cudaMemcpyHostToDevice, s);
 	if (data_len) cudaMemcpyAsync(d_data.p, data, data_len, cudaMemcpyHostToDevice, s);
-	launch_t1_decode((const DecBlock*) d_blocks.p, (const DecInput*) d_inputs.p, nblocks, (const uint8_t*) d_data.p, maxp, (uint64_t*) d_planes.p, s);
-	int rc = launch_check(ctx, 1);
+	int rc = GB200_OK;
+	if (launch_t1_decode((const DecBlock*) d_blocks.p, (const DecInput*) d_inputs.p, nblocks, (const uint8_t*) d_data.p, maxw, maxh, s)) {
+		g_err = "Tier-1 decode: code block state does not fit in shared memory";
+		rc = GB200_ERR_UNSUPPORTED;
+	} else rc = launch_check(ctx, T1_DEC_LAUNCHES);
 	cudaMemcpyAsync(plane, d_plane.p, (size_t) width * height * 4, cudaMemcpyDeviceToHost, s);
 	cudaError_t e = cudaStreamSynchronize(s);
 	if (!rc && e != cudaSuccess) { g_err = std::string("t1 decode: ") + cudaGetErrorString(e); rc = GB200_ERR_CUDA; }

@@ -76,15 +76,17 @@ void launch_dwt_inv(const DwtPlane *planes_dev, const uint32_t *cta_plane_dev, u
 		cudaStream_t s);
 void dwt_tile_shape(int reversible, uint32_t *tw); // valid columns per CTA
 
-// t1_enc.cu / t1_dec.cu : one warp per code block.
+// t1_enc.cu / t1_dec.cu
 uint32_t t1_symbol_capacity(uint32_t w, uint32_t h, uint32_t planes);
 void launch_t1_encode(const EncBlock *blocks, uint32_t nblocks, int rate_control, uint8_t *symbols, uint8_t *scratch,
 		EncResult *results, uint32_t *rates, double *dists, cudaStream_t s);
 void launch_t1_gather(const EncBlock *blocks, EncResult *results, uint32_t nblocks, const uint8_t *scratch,
 		uint8_t *data, cudaStream_t s);
-// plane_scratch: t1_decode_scratch_bytes() of device memory (512 B per bit-plane per block)
-size_t t1_decode_scratch_bytes(uint32_t nblocks, uint32_t max_planes);
-void launch_t1_decode(const DecBlock *blocks, const DecInput *inputs, uint32_t nblocks, const uint8_t *data,
-		uint32_t max_planes, uint64_t *plane_scratch, cudaStream_t s);
+// three launches (clear, decode, de-quantise); max_w / max_h: largest block of the table; `data` must stay
+// readable for T1_DEC_DATA_SLACK bytes past the last segment.  Returns non-zero if a block cannot be placed.
+constexpr int T1_DEC_LAUNCHES = 3;
+constexpr size_t T1_DEC_DATA_SLACK = 64;
+int launch_t1_decode(const DecBlock *blocks, const DecInput *inputs, uint32_t nblocks, const uint8_t *data,
+		uint32_t max_w, uint32_t max_h, cudaStream_t s);
 
 } // namespace gb

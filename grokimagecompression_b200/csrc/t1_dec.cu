@@ -1,26 +1,34 @@
-// K5: EBCOT Tier-1 decoder with fused de-quantisation and scatter, one warp per code block.
+// K5: EBCOT Tier-1 decoder, one THREAD per code block, de-quantisation in a following pass.
 //
 //   T1Part1::decode / post_decode   T1Part1.cpp:135-329   segment concat, /2 or x stepsize, scatter
 //   t1_decode_cblk                  t1.cpp:1038-1130      plane loop, pass order
 //   sig / ref / cln pass            t1.cpp:381-441, 588-637, 784-870
 //   MQ decoder                      mqc_dec.cpp:161-214, mqc_dec_inl.h:60-189
 //
-// Decoding is serial by nature (each decision selects the next context), so the warp runs the scan
-// as ONE uniform instruction stream and the design goal is the shortest possible dependent chain
-// per decision with few live registers (occupancy hides the rest):
-//  * State of a stripe column is one 32-bit word: significance of the 3x6 neighbourhood, signs of
-//    the own column, visited and refined bits.  The 64 words of the current stripe live in the
-//    lanes' registers (lane l owns columns l and l+32); the scan fetches a column's word with one
-//    shuffle, works on it with 32-bit logic, and the lanes owning the west/east columns update
-//    their own copies when a sample turns significant.  Other stripes wait in shared memory.
-//  * Warp ballots turn the per-lane words into the list of columns that can be coded in this pass
-//    at all; the scan jumps between them with find-first-set instead of visiting 64 x 4 positions.
-//  * The MQ probability state of context i lives in lane i as the packed table row, so a decision
-//    costs one shuffle and no table access on its critical path; compressed bytes are held as a
-//    128-byte register window across the lanes.
-//  * Decoded magnitude bits are collected as per-lane nibbles, turned into row masks with ballots
-//    at the end of a stripe, kept per bit-plane, and only at the very end expanded to samples,
-//    de-quantised and written coalesced (no read-modify-write of the coefficient plane).
+// Decoding a block is one serial chain: every decision selects the next context.  A warp that
+// works on ONE block spends 32 issue slots per step of that chain, and the machine runs out of
+// issue bandwidth long before it runs out of blocks (round-1 kernel: 125 warp instructions per
+// decision, 19 ms for configs[1]).  Here a block belongs to one thread, so a warp instruction
+// advances up to DT_LANES chains, and what bounds the kernel is the latency of one chain:
+//  * The whole state of a block lives on chip.  One 32-bit word per stripe column holds the
+//    significance of its 3x6 neighbourhood, the signs of its own column, the visited and refined
+//    bits (the reference's flag word, t1.h:97-168, re-laid row major); a 64x64 block takes 4.2 KB
+//    of shared memory, so ~48 blocks are resident per SM and configs[1] (6804 blocks) is a single
+//    wave over 148 SMs.  The MQ probability state of the 19 contexts is kept as packed Table C.2
+//    rows (Qe, both transitions, MPS) so a decision costs one shared load before the interval
+//    arithmetic starts.
+//  * Threads of a warp sit in different blocks and in different coding passes.  To keep them on
+//    one instruction stream the column scan is a small state machine (zero coding / refinement,
+//    sign, run-length AGG, two UNI bits) around a SINGLE inlined MQ decode, so the expensive part
+//    of every step is shared by all lanes whatever pass each one is in.
+//  * A sample that turns significant updates its neighbours' words with shared-memory atomics
+//    that return nothing; magnitudes go straight to the coefficient plane: a store of the
+//    mid-point value when the sample turns significant, a fire-and-forget RED.ADD of +-half a
+//    step per refinement (t1.cpp:392-394, 485).  Nothing on the critical chain waits for memory
+//    further away than shared.
+//  * Compressed bytes are pulled through a 64-bit window with the next 8 bytes already in flight.
+// t1_dec_clear_kernel zeroes the block areas first (the reference decodes into a zeroed tile
+// buffer); t1_dec_finish_kernel applies /2 or x stepsize (T1Part1.cpp:300-327), one warp per block.
 // The reference's artificial FF FF end marker (mqc_dec.cpp:161-177) is emulated by reading 0xFF
 // past the end of the segment.
 #include "common.cuh"
@@ -28,93 +36,19 @@
 
 namespace gb {
 
-constexpr int DEC_WARPS = 4;
-#ifndef DEC_MIN_CTAS
-#define DEC_MIN_CTAS 8
+#ifndef DT_LANES
+#define DT_LANES 8          // code blocks (active lanes) per warp
 #endif
+constexpr int DT_MAX_THREADS = DT_LANES <= 2 ? 1024 : 512;
+constexpr int DT_MAX_SLOTS = DT_MAX_THREADS / 32 * DT_LANES;
+constexpr int DT_FIXED_WORDS = 96 + 512 + 64; // MQ table, zero-coding table (4 x 512 B), sign table (256 B)
+constexpr int DT_NZ_WORDS = 32;                // 16 stripes x 64-bit column masks per block
 
 // stripe-column word: bit 3r+j = significance of row r-1 (r = 0..5), column j-1 (j = 0 west, 1 own, 2 east);
 // bit 18+r = sign of own column row r-1; bit 24+k = visited (k = 0..3); bit 28+k = refined before
 __device__ __forceinline__ constexpr uint32_t fsig(int r, int j) { return 1u << (3 * r + j); }
 constexpr uint32_t F_PI_ALL = 0xFu << 24;
-
-struct DecWarp {
-	uint32_t F[18][64];   // [stripe + 1][column]; stripes -1 and 16 are never read as a current stripe
-	uint64_t pcur[64];    // magnitude bits of the current bit-plane, one row mask per row
-	uint64_t lastc[64];   // samples coded in the final (possibly partial) plane
-};
-
-struct MqD {
-	uint32_t a, c;   // A is kept in the high half-word (A << 16), like the Chigh half of C it is compared with
-	int ct;
-	uint32_t pos, len;
-	const uint8_t *buf;
-	uint32_t wbase;  // first byte index of the register window
-	uint32_t word;   // this lane's 4 bytes of the window
-	uint32_t crow;   // context `lane`: qe << 16 | switch << 13 | mps << 12 | nlps << 6 | nmps   (Table C.2 row + MPS)
-};
-
-__device__ __forceinline__ void mqd_fill(MqD &q, uint32_t base, int lane) {
-	q.wbase = base;
-	uint32_t w = 0;
-	#pragma unroll
-	for (int j = 0; j < 4; ++j) {
-		uint32_t i = base + 4 * lane + j;
-		uint32_t b = i < q.len ? q.buf[i] : 0xFFu;
-		w |= b << (8 * j);
-	}
-	q.word = w;
-}
-
-__device__ __forceinline__ uint32_t mqd_byte(MqD &q, uint32_t i, int lane) {
-	if (i >= q.len) return 0xFFu;
-	if (i - q.wbase >= 128u) mqd_fill(q, i, lane);
-	uint32_t o = i - q.wbase;
-	uint32_t w = __shfl_sync(0xffffffffu, q.word, o >> 2);
-	return (w >> (8 * (o & 3))) & 0xFFu;
-}
-
-__device__ __forceinline__ void mqd_bytein(MqD &q, int lane) {
-	uint32_t cur = mqd_byte(q, q.pos, lane);
-	uint32_t next = mqd_byte(q, q.pos + 1, lane);
-	if (cur == 0xFF) {
-		if (next > 0x8F) { q.c += 0xFF00u; q.ct = 8; }
-		else { q.pos++; q.c += next << 9; q.ct = 7; }
-	} else { q.pos++; q.c += next << 8; q.ct = 8; }
-}
-
-// packed Table C.2 rows in shared memory (same format as MqD::crow, MPS bit clear)
-struct DecTab { uint32_t row[47]; };
-
-__device__ __forceinline__ uint32_t mqd_decode(MqD &q, const DecTab &T, uint32_t cx, int lane) {
-	const uint32_t row = __shfl_sync(0xffffffffu, q.crow, cx);
-	const uint32_t qs = row & 0xFFFF0000u, mps = (row >> 12) & 1u;
-	q.a -= qs;
-	bool lps;
-	if (q.c < qs) { // (C >> 16) < Qe : the LPS sub-interval
-		lps = q.a >= qs; // conditional exchange
-		q.a = qs;
-	} else {
-		q.c -= qs;
-		if (q.a & 0x80000000u) return mps;
-		lps = q.a < qs;
-	}
-	const uint32_t next = lps ? (row >> 6) & 63u : row & 63u;
-	const uint32_t nmps = lps ? mps ^ ((row >> 13) & 1u) : mps;
-	const uint32_t nrow = T.row[next] | (nmps << 12);
-	if (lane == (int) cx) q.crow = nrow;
-	int sh = __clz(q.a);
-	q.a <<= sh;
-	if (sh <= q.ct) { q.c <<= sh; q.ct -= sh; }
-	else {
-		do { // RENORMD with BYTEIN whenever the bit counter runs out (mqc_dec_inl.h:136-147)
-			if (q.ct == 0) mqd_bytein(q, lane);
-			const int n = sh < q.ct ? sh : q.ct;
-			q.c <<= n; q.ct -= n; sh -= n;
-		} while (sh > 0);
-	}
-	return lps ? mps ^ 1u : mps;
-}
+constexpr uint32_t F_SIGMA_ALL = 0x3FFFFu;
 
 // bits 4,7,10,13 (significance of the own column, rows 0..3) gathered into a nibble
 __device__ __forceinline__ uint32_t own_sig4(uint32_t f) {
@@ -125,233 +59,325 @@ __device__ __forceinline__ uint32_t nbr4(uint32_t f) {
 	return ((f & 0x1EFu) ? 1u : 0u) | ((f & (0x1EFu << 3)) ? 2u : 0u) | ((f & (0x1EFu << 6)) ? 4u : 0u) | ((f & (0x1EFu << 9)) ? 8u : 0u);
 }
 
-__global__ void __launch_bounds__(DEC_WARPS * 32, DEC_MIN_CTAS) t1_decode_kernel(const DecBlock *__restrict__ blocks,
-		const DecInput *__restrict__ inputs, uint32_t nblocks, const uint8_t *__restrict__ data, uint32_t max_planes,
-		uint64_t *__restrict__ plane_scratch) {
-	__shared__ DecWarp warps[DEC_WARPS];
-	__shared__ uint8_t Lzc[4][512]; // zero-coding context by the 9 neighbourhood bits of a stripe-column word
-	__shared__ uint8_t Lsc[256];
-	__shared__ DecTab T;
-	for (int i = threadIdx.x; i < 47; i += blockDim.x) {
-		const uint32_t r = c_mq[i];
-		T.row[i] = (r << 16) | ((r >> 28) & 1u) << 13 | ((r >> 22) & 63u) << 6 | ((r >> 16) & 63u);
+// ---- MQ decoder of one thread ------------------------------------------------------------------------
+struct MqT {
+	uint32_t a, c;   // A is kept in the high half-word (A << 16), like the Chigh half of C it is compared with
+	int ct;
+	uint32_t cur;    // byte at the read position
+	uint64_t win;    // the bytes that follow it, next one lowest
+	int nwin;        // bytes left in win (never 0 between calls)
+	uint64_t pre;    // the 8 bytes after the window, already loaded
+	const unsigned long long *base8; // 8-byte aligned address at or below the first byte
+	uint32_t wi;     // index of the next aligned word to load
+	uint32_t endoff; // offset of the end of the segment relative to base8
+};
+
+// aligned word j of the segment; bytes at or beyond its end read as 0xFF
+__device__ __forceinline__ uint64_t mq_word(const MqT &q, uint32_t j) {
+	const uint32_t lo = 8u * j;
+	if (lo >= q.endoff) return ~0ull;
+	uint64_t w = __ldg(q.base8 + j);
+	const uint32_t valid = q.endoff - lo;
+	if (valid < 8u) w |= ~0ull << (8u * valid);
+	return w;
+}
+
+__device__ __forceinline__ void mq_advance(MqT &q) {
+	q.win >>= 8;
+	if (--q.nwin == 0) {
+		q.win = q.pre;
+		q.nwin = 8;
+		q.pre = mq_word(q, q.wi++);
+	}
+}
+
+// BYTEIN, mqc_dec_inl.h:114-134
+__device__ __forceinline__ void mq_bytein(MqT &q) {
+	const uint32_t next = (uint32_t) q.win & 0xFFu;
+	if (q.cur == 0xFFu && next > 0x8Fu) { q.c += 0xFF00u; q.ct = 8; }
+	else {
+		const uint32_t ff = q.cur == 0xFFu ? 1u : 0u;
+		q.c += next << (8 + ff);
+		q.ct = 8 - (int) ff;
+		q.cur = next;
+		mq_advance(q);
+	}
+}
+
+// INITDEC, mqc_dec.cpp:179-201
+__device__ __forceinline__ void mq_init(MqT &q, const uint8_t *buf, uint32_t len) {
+	const uint32_t off0 = (uint32_t) (reinterpret_cast<uintptr_t>(buf) & 7u);
+	q.base8 = reinterpret_cast<const unsigned long long*>(buf - off0);
+	q.endoff = off0 + len;
+	q.win = mq_word(q, 0) >> (8u * off0);
+	q.nwin = 8 - (int) off0;
+	q.pre = mq_word(q, 1);
+	q.wi = 2;
+	q.cur = (uint32_t) q.win & 0xFFu;
+	mq_advance(q);
+	q.c = q.cur << 16;
+	mq_bytein(q);
+	q.c <<= 7;
+	q.ct -= 7;
+	q.a = 0x80000000u;
+}
+
+// context rows: qe << 16 | mps << 15 | next(LPS) << 8 | next(MPS); the successors index the 94-entry table
+// of (state, mps) pairs, so the SWITCH column of Table C.2 is folded into them.
+// DECODE + RENORMD, mqc_dec_inl.h:60-86, 136-169
+__device__ __forceinline__ uint32_t mq_decode(MqT &q, uint32_t *crow, const uint32_t *tab) {
+	const uint32_t row = *crow;
+	const uint32_t qs = row & 0xFFFF0000u, mps = (row >> 15) & 1u;
+	q.a -= qs;
+	bool lps;
+	if (q.c < qs) { // (C >> 16) < Qe : the LPS sub-interval
+		lps = q.a >= qs; // conditional exchange
+		q.a = qs;
+	} else {
+		q.c -= qs;
+		if (q.a & 0x80000000u) return mps;
+		lps = q.a < qs;
+	}
+	*crow = tab[lps ? (row >> 8) & 0x7Fu : row & 0x7Fu];
+	int sh = __clz(q.a);
+	q.a <<= sh;
+	while (sh > q.ct) { // RENORMD with BYTEIN whenever the bit counter runs out
+		q.c <<= q.ct;
+		sh -= q.ct;
+		mq_bytein(q);
+	}
+	q.c <<= sh;
+	q.ct -= sh;
+	return mps ^ (lps ? 1u : 0u);
+}
+
+enum { PH_FETCH = 0, PH_NORMAL = 1, PH_SIGN = 2, PH_AGG = 3, PH_UNI1 = 4, PH_UNI2 = 5 };
+
+// The scan of one block as a flat state machine: every trip of the single loop either moves to the next
+// stripe column that can hold work (PH_FETCH) or takes exactly one MQ decision, so the lanes of a warp
+// (different blocks, different passes) stay on one instruction stream and share the decoder.
+__global__ void __launch_bounds__(DT_MAX_THREADS, 1) t1_decode_kernel(const DecBlock *__restrict__ blocks,
+		const DecInput *__restrict__ inputs, uint32_t nblocks, const uint8_t *__restrict__ data, int fw, int fwords, int nslots) {
+	extern __shared__ __align__(16) uint32_t sm[];
+	uint32_t *tab = sm;                                        // 94 (state, mps) rows
+	uint8_t *Lzc = reinterpret_cast<uint8_t*>(sm + 96);        // zero-coding context by the 9 neighbourhood bits of a word
+	uint8_t *Lsc = Lzc + 2048;                                 // sign context | xor bit << 5
+	uint32_t *flags = sm + DT_FIXED_WORDS;                     // [slot][fwords]; the last DT_NZ_WORDS words of a slot hold nz[]
+	uint32_t *ctxrows = flags + (size_t) nslots * fwords;      // [context][slot]
+	for (int i = threadIdx.x; i < 94; i += blockDim.x) {
+		const uint32_t r = c_mq[i >> 1], mps = i & 1u, sw = (r >> 28) & 1u;
+		const uint32_t nm = ((r >> 16) & 63u) * 2u + mps, nl = ((r >> 22) & 63u) * 2u + (mps ^ sw);
+		tab[i] = (r << 16) | (mps << 15) | (nl << 8) | nm;
 	}
 	for (int i = threadIdx.x; i < 2048; i += blockDim.x) {
-		int o = i >> 9, n9 = i & 511;
-		int idx8 = (n9 & 7) | ((n9 >> 3) & 1) << 3 | ((n9 >> 5) & 1) << 4 | ((n9 >> 6) & 7) << 5;
-		Lzc[o][n9] = c_zc[o][idx8];
+		const int o = i >> 9, n9 = i & 511;
+		const int idx8 = (n9 & 7) | ((n9 >> 3) & 1) << 3 | ((n9 >> 5) & 1) << 4 | ((n9 >> 6) & 7) << 5;
+		Lzc[i] = c_zc[o][idx8];
 	}
 	for (int i = threadIdx.x; i < 256; i += blockDim.x) Lsc[i] = c_sc[i];
 	__syncthreads();
 
-	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-	const uint32_t bid = blockIdx.x * DEC_WARPS + wid;
-	if (bid >= nblocks) return;
-	DecWarp &W = warps[wid];
-	uint64_t *planes = plane_scratch + (size_t) bid * max_planes * 64; // [plane-1][row], global scratch
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	if (lane >= DT_LANES) return;
+	const int slot = warp * DT_LANES + lane;
+	const uint32_t bid = blockIdx.x * (uint32_t) nslots + (uint32_t) slot;
+	if (slot >= nslots || bid >= nblocks) return;
 	const DecBlock B = blocks[bid];
 	const DecInput I = inputs[bid];
 	const int w = B.w, h = B.h;
-	const uint8_t *zc = Lzc[B.orient];
 	const int numbps = (int) I.numbps;
-	const bool two = w > 32;
-	const bool valid0 = lane < w, valid1 = lane + 32 < w;
+	// T1Part1.cpp:139, t1.cpp:1056: nothing to decode; the cleared block area stays zero
+	if (I.numpasses == 0 || I.data_len == 0 || numbps == 0 || numbps > 30 || w == 0 || h == 0) return;
 
-	const bool empty = I.numpasses == 0 || I.data_len == 0 || numbps == 0 || numbps > (int) max_planes; // T1Part1.cpp:139
-	if (empty) {
-		// nothing decoded: the reference leaves the zero-initialised tile buffer untouched
-		for (int y = 0; y < h; ++y)
-			for (int x = lane; x < w; x += 32) B.dst[(size_t) y * B.stride + x] = 0;
-		return;
-	}
-	for (int i = lane; i < 18 * 64; i += 32) (&W.F[0][0])[i] = 0;
-	for (int i = lane; i < 64; i += 32) { W.pcur[i] = 0; W.lastc[i] = 0; }
-	__syncwarp();
-
-	MqD q;
-	q.buf = data + I.data_offset;
-	q.len = I.data_len;
-	q.pos = 0;
-	q.crow = T.row[lane == CTX_ZC0 ? 4 : lane == CTX_AGG ? 3 : lane == CTX_UNI ? 46 : 0]; // mqc_dec.cpp:207-214, mps = 0
-	mqd_fill(q, 0, lane);
-	q.c = mqd_byte(q, 0, lane) << 16; // INITDEC, mqc_dec.cpp:179-201
-	mqd_bytein(q, lane);
-	q.c <<= 7;
-	q.ct -= 7;
-	q.a = 0x80000000u;
-
-	// plane of the last pass that will run: passes go cln(numbps), then sig/ref/cln per lower plane
-	const int npass_eff = min((int) I.numpasses, 3 * numbps - 2);
-	const int finalplane = numbps - (npass_eff + 1) / 3;
 	const int nstripes = (h + 3) >> 2;
+	uint32_t *F = flags + (size_t) slot * fwords; // word of stripe s, column x: F[s * fw + x + 1]
+	for (int i = 0; i < fwords; ++i) F[i] = 0;
+	// nz[s]: columns of stripe s whose word holds any significance bit (own or neighbour)
+	unsigned long long *nz = reinterpret_cast<unsigned long long*>(F + fwords - DT_NZ_WORDS);
+	uint32_t *C = ctxrows + slot;
+	#pragma unroll
+	for (int i = 0; i < NCTX; ++i) C[i * nslots] = tab[2 * (i == CTX_ZC0 ? 4 : i == CTX_AGG ? 3 : i == CTX_UNI ? 46 : 0)]; // mqc_dec.cpp:207-214
+	const uint8_t *zc = Lzc + 512 * B.orient;
+	const uint64_t wmask = w >= 64 ? ~0ull : (1ull << w) - 1ull;
 
-	int bp1 = numbps, type = 2;
-	for (int pass = 0; pass < npass_eff; ++pass) {
-		const bool track_last = bp1 == finalplane;
-		for (int s = 0; s < nstripes; ++s) {
-			const int nk = min(4, h - 4 * s);
-			uint32_t f0 = W.F[s + 1][lane], f1 = two ? W.F[s + 1][lane + 32] : 0u;
-			// which columns hold a sample this pass can code (ballot of a per-lane test)
-			const uint32_t rows = (1u << nk) - 1u;
-			// rows of a column this pass can code, from its word
-			auto todo = [&](uint32_t f) -> uint32_t {
-				const uint32_t sig = own_sig4(f), vis = (f >> 24) & 0xFu;
-				if (type == 0) return ~sig & ~vis & nbr4(f) & rows;
-				if (type == 1) return sig & ~vis & rows;
-				return ~sig & ~vis & rows;
-			};
-			auto wants = [&](uint32_t f) -> bool { return todo(f) != 0; };
-			uint64_t cols = (uint64_t) __ballot_sync(0xffffffffu, valid0 && wants(f0));
-			if (two) cols |= (uint64_t) __ballot_sync(0xffffffffu, valid1 && wants(f1)) << 32;
-			uint32_t mb0 = 0, mb1 = 0, lc0 = 0, lc1 = 0; // per-lane nibbles: magnitude bit decoded / sample coded
-			while (cols) {
-				const int x = __ffsll((long long) cols) - 1;
-				cols &= cols - 1;
-				const int src = x & 31;
-				const bool hi = x >= 32;
-				uint32_t f = __shfl_sync(0xffffffffu, hi ? f1 : f0, src);
-				uint32_t mb = 0, lc = 0;
-				uint32_t cand = todo(f);
-				if (type == 1) {
-					while (cand) {
-						const int k = __ffs(cand) - 1;
-						cand &= cand - 1;
-						const uint32_t ctx = (f & (1u << (28 + k))) ? CTX_MR0 + 2 : ((f >> (3 * k)) & 0x1EFu) ? CTX_MR0 + 1 : CTX_MR0;
-						if (mqd_decode(q, T, ctx, lane)) mb |= 1u << k;
-					}
-					const uint32_t done4 = todo(f);
-					f |= done4 << 28;
-					lc = done4;
+	MqT q;
+	mq_init(q, data + I.data_offset, I.data_len);
+
+	// passes go cln(numbps), then sig / ref / cln per lower plane
+	int passes_left = min((int) I.numpasses, 3 * numbps - 2);
+	int bp1 = numbps, type = 2, s = -1;
+	int phase = PH_FETCH, x = 0, k = 0, nk = 4;
+	uint32_t f = 0, cand = 0, cand0 = 0, cx = 0, xorbit = 0, r = 0, rows = 0xFu;
+	uint64_t colmask = 0;
+	uint32_t *rowF = F + 1;
+	int32_t *drow = B.dst;
+	for (;;) {
+		if (phase == PH_FETCH) {
+			if (colmask == 0) { // next stripe, next pass
+				if (++s == nstripes) {
+					if (--passes_left == 0) break;
+					s = 0;
+					if (++type == 3) { type = 0; bp1--; }
+				}
+				nk = min(4, h - 4 * s);
+				rows = (1u << nk) - 1u;
+				rowF = F + s * fw + 1;
+				drow = B.dst + (size_t) (4 * s) * B.stride;
+				colmask = type == 2 ? wmask : nz[s];
+			}
+			if (colmask != 0) {
+				x = __ffsll((long long) colmask) - 1;
+				colmask &= colmask - 1;
+				f = rowF[x];
+				const uint32_t sig4 = own_sig4(f);
+				cand = (type == 1 ? sig4 : ~sig4) & ~(f >> 24) & rows;
+				if (type == 0) cand &= nbr4(f);
+				cand0 = cand;
+				if (cand) {
+					phase = PH_NORMAL;
+					if (type == 2 && nk == 4 && (f & (F_PI_ALL | F_SIGMA_ALL)) == 0) { phase = PH_AGG; cx = CTX_AGG; } // run-length mode, t1.cpp:749
+				} else if (type == 2 && (f & F_PI_ALL)) rowF[x] = f & ~F_PI_ALL;
+			}
+		}
+		if (phase != PH_FETCH) {
+			if (phase == PH_NORMAL) {
+				k = __ffs(cand) - 1;
+				cand &= cand - 1;
+				const uint32_t n9 = (f >> (3 * k)) & 0x1FFu;
+				if (type == 1) cx = (f >> (28 + k) & 1u) ? CTX_MR0 + 2 : (n9 & 0x1EFu) ? CTX_MR0 + 1 : CTX_MR0;
+				else cx = zc[n9];
+			}
+			const uint32_t d = mq_decode(q, C + cx * nslots, tab);
+			bool to_sign = false;
+			if (phase == PH_NORMAL) {
+				if (type == 1) { // refinement: +-half a step towards the decoded bit (t1.cpp:476-496)
+					const uint32_t neg = (f >> (19 + k)) & 1u;
+					const int32_t half = (1 << bp1) >> 1;
+					atomicAdd(drow + (size_t) k * B.stride + x, (d ^ neg) ? half : -half);
 				} else {
-					int kimp = -1; // row whose 1 is implied by the run-length code
-					if (type == 2 && nk == 4 && (f & 0x0F03FFFFu) == 0) { // run-length mode: nothing significant or visited around
-						if (!mqd_decode(q, T, CTX_AGG, lane)) continue;
-						kimp = (int) mqd_decode(q, T, CTX_UNI, lane) << 1;
-						kimp |= (int) mqd_decode(q, T, CTX_UNI, lane);
-						cand &= ~((1u << kimp) - 1u);
-					}
-					uint32_t fW = 0, fE = 0;
-					bool have_nb = false;
-					while (cand) {
-						const int k = __ffs(cand) - 1;
-						cand &= cand - 1;
-						const uint32_t n9 = (f >> (3 * k)) & 0x1FFu;
-						uint32_t d = 1;
-						if (k != kimp) d = mqd_decode(q, T, zc[n9], lane);
-						if (type == 0) f |= 1u << (24 + k);
-						if (!d) continue;
-						if (!have_nb) { // signs of the west / east columns live in their owners' words
-							const int xm = x - 1, xp = x + 1;
-							const uint32_t a0 = __shfl_sync(0xffffffffu, xm >= 32 ? f1 : f0, xm & 31);
-							const uint32_t a1 = __shfl_sync(0xffffffffu, xp >= 32 ? f1 : f0, xp & 31);
-							fW = xm >= 0 ? a0 : 0u;
-							fE = xp < w ? a1 : 0u;
-							have_nb = true;
-						}
-						const uint32_t sN = n9 >> 1 & 1, sW = n9 >> 3 & 1, sE = n9 >> 5 & 1, sS = n9 >> 7 & 1;
-						const uint32_t gN = f >> (18 + k) & 1, gS = f >> (20 + k) & 1, gW = fW >> (19 + k) & 1, gE = fE >> (19 + k) & 1;
-						const uint32_t idx = sN | sW << 1 | sE << 2 | sS << 3 | (gN & sN) << 4 | (gW & sW) << 5 | (gE & sE) << 6 | (gS & sS) << 7;
-						const uint32_t v = Lsc[idx];
-						const uint32_t neg = mqd_decode(q, T, v & 31u, lane) ^ (v >> 5);
-						f |= fsig(k + 1, 1) | (neg << (19 + k));
-						mb |= 1u << k;
-						lc |= 1u << k;
-						// in the significance pass the row below may have become codable through this sample
-						if (type == 0 && k + 1 < nk && !(f & (fsig(k + 2, 1) | (1u << (25 + k))))) cand |= 2u << k;
-						// the sample is the east neighbour of column x-1 and the west neighbour of column x+1
-						if (x > 0 && lane == ((x - 1) & 31)) { if (x - 1 >= 32) f1 |= fsig(k + 1, 2); else f0 |= fsig(k + 1, 2); }
-						if (x + 1 < w) {
-							if (lane == ((x + 1) & 31)) { if (x + 1 >= 32) f1 |= fsig(k + 1, 0); else f0 |= fsig(k + 1, 0); }
-							if (type == 0) cols |= 1ull << (x + 1); // may have become codable in this pass
-						}
-						// rows -1 / 4 of the stripes below / above
-						if ((k == 0 && s > 0) || (k == 3 && s + 1 < nstripes)) {
-							const int ts = k == 0 ? s : s + 2; // index into F (stripe + 1)
-							const int r = k == 0 ? 5 : 0;
-							if (lane < 3) {
-								const int cc = x + lane - 1;
-								if (cc >= 0 && cc < w)
-									atomicOr(&W.F[ts][cc], fsig(r, 2 - lane) | (lane == 1 ? neg << (18 + r) : 0u));
-							}
-						}
-					}
+					if (type == 0) f |= 1u << (24 + k);
+					to_sign = d != 0;
 				}
-				if (lane == src) {
-					if (hi) { f1 = f; mb1 |= mb; lc1 |= lc; } else { f0 = f; mb0 |= mb; lc0 |= lc; }
+			} else if (phase == PH_SIGN) {
+				const uint32_t neg = d ^ xorbit;
+				const int32_t oph = (1 << bp1) | ((1 << bp1) >> 1); // values carry one extra low bit: mid-point of the plane
+				f |= fsig(k + 1, 1) | (neg << (19 + k));
+				drow[(size_t) k * B.stride + x] = neg ? -oph : oph;
+				// the sample is the east neighbour of column x-1 and the west neighbour of column x+1
+				atomicOr(rowF + x - 1, fsig(k + 1, 2));
+				atomicOr(rowF + x + 1, fsig(k + 1, 0));
+				const unsigned long long three = (x ? 7ull << (x - 1) : 3ull) & wmask; // columns x-1, x, x+1
+				nz[s] |= three; // the block's state belongs to this thread alone
+				if (k == 0 && s > 0) { // row 4 of the stripe above
+					uint32_t *up = rowF - fw + x;
+					atomicOr(up - 1, fsig(5, 2));
+					atomicOr(up, fsig(5, 1) | (neg << 23));
+					atomicOr(up + 1, fsig(5, 0));
+					nz[s - 1] |= three;
 				}
+				if (k == 3 && s + 1 < nstripes) { // row -1 of the stripe below
+					uint32_t *dn = rowF + fw + x;
+					atomicOr(dn - 1, fsig(0, 2));
+					atomicOr(dn, fsig(0, 1) | (neg << 18));
+					atomicOr(dn + 1, fsig(0, 0));
+					nz[s + 1] |= three;
+				}
+				if (type == 0) {
+					// the row below and the next column may have become codable in this pass through this sample
+					if (k + 1 < nk && !(f & (fsig(k + 2, 1) | (1u << (25 + k))))) cand |= 2u << k;
+					colmask |= (2ull << x) & wmask;
+				}
+				phase = PH_NORMAL;
+			} else if (phase == PH_AGG) {
+				if (d) { phase = PH_UNI1; cx = CTX_UNI; }
+				else { phase = PH_NORMAL; cand = 0; }
+			} else if (phase == PH_UNI1) {
+				r = d << 1;
+				phase = PH_UNI2;
+			} else { // the row of the first 1 of the column; its significance is implied, its sign follows
+				k = (int) (r | d);
+				cand &= ~((2u << k) - 1u);
+				to_sign = true;
 			}
-			if (type == 2) { f0 &= ~F_PI_ALL; f1 &= ~F_PI_ALL; }
-			W.F[s + 1][lane] = f0;
-			if (two) W.F[s + 1][lane + 32] = f1;
-			// per-lane nibbles -> row masks of the current plane
-			if (__any_sync(0xffffffffu, (mb0 | mb1 | lc0 | lc1) != 0)) {
-				#pragma unroll
-				for (int k = 0; k < 4; ++k) {
-					const uint64_t m = (uint64_t) __ballot_sync(0xffffffffu, mb0 >> k & 1) | (uint64_t) __ballot_sync(0xffffffffu, mb1 >> k & 1) << 32;
-					const uint64_t l = (uint64_t) __ballot_sync(0xffffffffu, lc0 >> k & 1) | (uint64_t) __ballot_sync(0xffffffffu, lc1 >> k & 1) << 32;
-					if (lane == k && k < nk) {
-						W.pcur[4 * s + k] |= m;
-						if (track_last) W.lastc[4 * s + k] |= l;
-					}
-				}
+			if (to_sign) { // sign context from the 4 neighbours' significance and signs (t1.cpp:115-140)
+				const uint32_t n9 = (f >> (3 * k)) & 0x1FFu;
+				const uint32_t fW = rowF[x - 1], fE = rowF[x + 1];
+				const uint32_t idx = (n9 >> 1 & 1u) | (n9 >> 3 & 1u) << 1 | (n9 >> 5 & 1u) << 2 | (n9 >> 7 & 1u) << 3
+						| (f >> (18 + k) & 1u) << 4 | (fW >> (19 + k) & 1u) << 5 | (fE >> (19 + k) & 1u) << 6 | (f >> (20 + k) & 1u) << 7;
+				const uint32_t v = Lsc[idx];
+				cx = v & 31u;
+				xorbit = v >> 5;
+				phase = PH_SIGN;
+			} else if (phase == PH_NORMAL && cand == 0) { // column finished
+				if (type == 1) f |= cand0 << 28;
+				if (type == 2) f &= ~F_PI_ALL;
+				rowF[x] = f;
+				phase = PH_FETCH;
 			}
-			__syncwarp();
-		}
-		if (++type == 3) {
-			// plane finished: park its magnitude bits in the scratch area
-			for (int i = lane; i < 64; i += 32) { planes[(size_t) (bp1 - 1) * 64 + i] = W.pcur[i]; W.pcur[i] = 0; }
-			__syncwarp();
-			type = 0;
-			bp1--;
 		}
 	}
-	const int lastplane = finalplane;
-	if (type != 0) { // the last plane was left unfinished (no cleanup pass): park what there is
-		for (int i = lane; i < 64; i += 32) planes[(size_t) (lastplane - 1) * 64 + i] = W.pcur[i];
-	}
-	__syncwarp();
-	// ---- reconstruct, de-quantise, scatter (T1Part1.cpp:216-329) -----------------------------
-	for (int y = 0; y < h; ++y) {
-		const int s = y >> 2, k = y & 3;
-		const uint64_t lrow = W.lastc[y];
-		uint32_t mag0 = 0, mag1 = 0;
-		for (int p = lastplane; p <= numbps; ++p) {
-			const uint64_t m = planes[(size_t) (p - 1) * 64 + y];
-			mag0 |= (uint32_t) (m >> lane & 1) << p;
-			mag1 |= (uint32_t) (m >> (lane + 32) & 1) << p;
+}
+
+// ---- before / after: one warp per block, coalesced ---------------------------------------------------
+__global__ void __launch_bounds__(256) t1_dec_clear_kernel(const DecBlock *__restrict__ blocks, uint32_t nblocks) {
+	const uint32_t bid = blockIdx.x * 8 + (threadIdx.x >> 5);
+	if (bid >= nblocks) return;
+	const int lane = threadIdx.x & 31;
+	const DecBlock B = blocks[bid];
+	for (int y = 0; y < B.h; ++y)
+		for (int x = lane; x < B.w; x += 32) B.dst[(size_t) y * B.stride + x] = 0;
+}
+
+// T1Part1.cpp:300-327: reversible /2 (C division), irreversible float(value) * stepsize
+__global__ void __launch_bounds__(256) t1_dec_finish_kernel(const DecBlock *__restrict__ blocks, uint32_t nblocks) {
+	const uint32_t bid = blockIdx.x * 8 + (threadIdx.x >> 5);
+	if (bid >= nblocks) return;
+	const int lane = threadIdx.x & 31;
+	const DecBlock B = blocks[bid];
+	for (int y = 0; y < B.h; ++y)
+		for (int x = lane; x < B.w; x += 32) {
+			int32_t *p = B.dst + (size_t) y * B.stride + x;
+			const int32_t v = *p;
+			*p = B.reversible ? v / 2 : __float_as_int(__fmul_rn((float) v, B.stepsize));
 		}
-		#pragma unroll
-		for (int half = 0; half < 2; ++half) {
-			const int x = lane + 32 * half;
-			if (x >= w) continue;
-			const uint32_t f = W.F[s + 1][x];
-			int32_t v = 0;
-			if (f & fsig(k + 1, 1)) {
-				uint32_t mag = half ? mag1 : mag0;
-				mag |= (lrow >> x & 1) ? (1u << lastplane) >> 1 : 1u << lastplane;
-				v = (f >> (19 + k) & 1) ? -(int32_t) mag : (int32_t) mag;
-			}
-			int32_t o;
-			if (B.reversible) o = v / 2;
-			else o = __float_as_int(__fmul_rn((float) v, B.stepsize));
-			B.dst[(size_t) y * B.stride + x] = o;
-		}
-	}
 }
 
 static bool g_dec_tables_ready = false;
 
-size_t t1_decode_scratch_bytes(uint32_t nblocks, uint32_t max_planes) {
-	return (size_t) nblocks * (max_planes < 1 ? 1 : max_planes) * 64 * sizeof(uint64_t);
-}
-
-void launch_t1_decode(const DecBlock *blocks, const DecInput *inputs, uint32_t nblocks, const uint8_t *data,
-		uint32_t max_planes, uint64_t *plane_scratch, cudaStream_t s) {
-	if (!nblocks) return;
+int launch_t1_decode(const DecBlock *blocks, const DecInput *inputs, uint32_t nblocks, const uint8_t *data,
+		uint32_t max_w, uint32_t max_h, cudaStream_t s) {
+	if (!nblocks) return 0;
 	if (!g_dec_tables_ready) { build_and_upload_t1_tables(); g_dec_tables_ready = true; }
-	if (max_planes < 1) max_planes = 1;
-	t1_decode_kernel<<<(nblocks + DEC_WARPS - 1) / DEC_WARPS, DEC_WARPS * 32, 0, s>>>(blocks, inputs, nblocks, data, max_planes,
-			plane_scratch);
+	int dev = 0, sms = 148, smem_max = 0;
+	cudaGetDevice(&dev);
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+	if (max_w < 1) max_w = 1;
+	if (max_h < 1) max_h = 1;
+	const int fw = (int) max_w + 2;
+	int fwords = (int) ((max_h + 3) / 4) * fw;
+	fwords += fwords & 1;      // the column masks that follow are 64-bit
+	fwords += DT_NZ_WORDS;
+	// slots of one warp start 32 / DT_LANES banks apart
+	int bank0 = 32 / DT_LANES % 32;
+	if (bank0 & 1) bank0 = 2;
+	while (fwords % 32 != bank0) fwords += 2;
+	const int per_slot = (fwords + NCTX) * 4;
+	int cap = (smem_max - DT_FIXED_WORDS * 4) / per_slot;
+	int want = (int) ((nblocks + (uint32_t) sms - 1) / (uint32_t) sms); // spread a small job over every SM
+	int nslots = cap < want ? cap : want;
+	if (nslots > DT_MAX_SLOTS) nslots = DT_MAX_SLOTS;
+	nslots = (nslots + DT_LANES - 1) / DT_LANES * DT_LANES;
+	while (nslots > cap) nslots -= DT_LANES;
+	if (nslots < DT_LANES) nslots = cap; // a partial warp: blocks too large for DT_LANES of them
+	if (nslots < 1) return 1;
+	const size_t smem = (size_t) DT_FIXED_WORDS * 4 + (size_t) nslots * per_slot;
+	if (cudaFuncSetAttribute(t1_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) != cudaSuccess) return 1;
+	const int threads = (nslots + DT_LANES - 1) / DT_LANES * 32;
+	t1_dec_clear_kernel<<<(nblocks + 7) / 8, 256, 0, s>>>(blocks, nblocks);
+	t1_decode_kernel<<<(nblocks + nslots - 1) / nslots, threads, smem, s>>>(blocks, inputs, nblocks, data, fw, fwords, nslots);
+	t1_dec_finish_kernel<<<(nblocks + 7) / 8, 256, 0, s>>>(blocks, nblocks);
+	return 0;
 }
 
 } // namespace gb
