@@ -37,12 +37,11 @@
 namespace gb {
 
 #ifndef DT_LANES
-#define DT_LANES 8          // code blocks (active lanes) per warp
+#define DT_LANES 2          // code blocks (active lanes) per warp
 #endif
 constexpr int DT_MAX_THREADS = DT_LANES <= 2 ? 1024 : 512;
 constexpr int DT_MAX_SLOTS = DT_MAX_THREADS / 32 * DT_LANES;
 constexpr int DT_FIXED_WORDS = 96 + 512 + 64; // MQ table, zero-coding table (4 x 512 B), sign table (256 B)
-constexpr int DT_NZ_WORDS = 32;                // 16 stripes x 64-bit column masks per block
 
 // stripe-column word: bit 3r+j = significance of row r-1 (r = 0..5), column j-1 (j = 0 west, 1 own, 2 east);
 // bit 18+r = sign of own column row r-1; bit 24+k = visited (k = 0..3); bit 28+k = refined before
@@ -151,18 +150,87 @@ __device__ __forceinline__ uint32_t mq_decode(MqT &q, uint32_t *crow, const uint
 	return mps ^ (lps ? 1u : 0u);
 }
 
-enum { PH_FETCH = 0, PH_NORMAL = 1, PH_SIGN = 2, PH_AGG = 3, PH_UNI1 = 4, PH_UNI2 = 5 };
+// ---- the three coding passes of one stripe column, rows unrolled with constant bit positions ---------
+struct Blk {
+	MqT q;
+	uint32_t *C;          // context rows of this block, C[cx * cs]
+	int cs;
+	const uint32_t *tab;  // 94 (state, mps) rows
+	const uint8_t *zc;    // zero-coding context by the 9 neighbourhood bits, this block's orientation
+	const uint8_t *sc;    // sign context | xor bit << 5, by (N W E S significance at bits 1 3 5 7, signs at bits 0 2 4 6)
+	int32_t *dst;
+	uint32_t stride;
+	int fw, nstripes;
+};
 
-// The scan of one block as a flat state machine: every trip of the single loop either moves to the next
-// stripe column that can hold work (PH_FETCH) or takes exactly one MQ decision, so the lanes of a warp
-// (different blocks, different passes) stay on one instruction stream and share the decoder.
+constexpr uint32_t F_OWNSIG = 0x2490u; // significance of the own column, rows 0..3
+
+// sign of a sample that just turned significant (t1.cpp:115-140), mid-point store, neighbour updates (t1.cpp:168-195)
+template<int K>
+__device__ __forceinline__ void sign_and_mark(Blk &b, uint32_t &f, uint32_t *cw, int s, uint32_t off, int32_t oph) {
+	const uint32_t fW = cw[-1], fE = cw[1];
+	const uint32_t idx = ((f >> (3 * K)) & 0xAAu) | ((f >> (18 + K)) & 1u) | ((fW >> (17 + K)) & 4u) | ((fE >> (15 + K)) & 0x10u)
+			| ((f >> (14 + K)) & 0x40u);
+	const uint32_t v = b.sc[idx];
+	const uint32_t neg = mq_decode(b.q, b.C + (v & 31u) * b.cs, b.tab) ^ (v >> 5);
+	f |= fsig(K + 1, 1) | (neg << (19 + K));
+	b.dst[off + K * b.stride] = neg ? -oph : oph;
+	// the sample is the east neighbour of column x-1 and the west neighbour of column x+1
+	atomicOr(cw - 1, fsig(K + 1, 2));
+	atomicOr(cw + 1, fsig(K + 1, 0));
+	if (K == 0 && s > 0) { // row 4 of the stripe above
+		uint32_t *up = cw - b.fw;
+		atomicOr(up - 1, fsig(5, 2));
+		atomicOr(up, fsig(5, 1) | (neg << 23));
+		atomicOr(up + 1, fsig(5, 0));
+	}
+	if (K == 3 && s + 1 < b.nstripes) { // row -1 of the stripe below
+		uint32_t *dn = cw + b.fw;
+		atomicOr(dn - 1, fsig(0, 2));
+		atomicOr(dn, fsig(0, 1) | (neg << 18));
+		atomicOr(dn + 1, fsig(0, 0));
+	}
+}
+
+// significance propagation, t1.cpp:381-441
+template<int K>
+__device__ __forceinline__ void sig_row(Blk &b, uint32_t &f, uint32_t *cw, int s, uint32_t off, int32_t oph) {
+	if ((f & (fsig(K + 1, 1) | (1u << (24 + K)))) == 0 && (f & (0x1EFu << (3 * K))) != 0) {
+		const uint32_t d = mq_decode(b.q, b.C + b.zc[(f >> (3 * K)) & 0x1FFu] * b.cs, b.tab);
+		f |= 1u << (24 + K);
+		if (d) sign_and_mark<K>(b, f, cw, s, off, oph);
+	}
+}
+
+// magnitude refinement: +-half a step towards the decoded bit, t1.cpp:476-496, 588-637
+template<int K>
+__device__ __forceinline__ void ref_row(Blk &b, uint32_t &f, uint32_t off, int32_t half) {
+	if ((f & (fsig(K + 1, 1) | (1u << (24 + K)))) == fsig(K + 1, 1)) {
+		const uint32_t cx = (f & (1u << (28 + K))) ? CTX_MR0 + 2 : (f & (0x1EFu << (3 * K))) ? CTX_MR0 + 1 : CTX_MR0;
+		const uint32_t d = mq_decode(b.q, b.C + cx * b.cs, b.tab);
+		const uint32_t neg = (f >> (19 + K)) & 1u;
+		atomicAdd(b.dst + off + K * b.stride, (d ^ neg) ? half : -half);
+		f |= 1u << (28 + K);
+	}
+}
+
+// cleanup, t1.cpp:784-870; start / implied: the row whose 1 the run-length code already delivered
+template<int K>
+__device__ __forceinline__ void cln_row(Blk &b, uint32_t &f, uint32_t *cw, int s, uint32_t off, int32_t oph, int start, bool implied) {
+	if (K >= start && (f & (fsig(K + 1, 1) | (1u << (24 + K)))) == 0) {
+		uint32_t d = 1;
+		if (!(implied && K == start)) d = mq_decode(b.q, b.C + b.zc[(f >> (3 * K)) & 0x1FFu] * b.cs, b.tab);
+		if (d) sign_and_mark<K>(b, f, cw, s, off, oph);
+	}
+}
+
 __global__ void __launch_bounds__(DT_MAX_THREADS, 1) t1_decode_kernel(const DecBlock *__restrict__ blocks,
 		const DecInput *__restrict__ inputs, uint32_t nblocks, const uint8_t *__restrict__ data, int fw, int fwords, int nslots) {
 	extern __shared__ __align__(16) uint32_t sm[];
 	uint32_t *tab = sm;                                        // 94 (state, mps) rows
 	uint8_t *Lzc = reinterpret_cast<uint8_t*>(sm + 96);        // zero-coding context by the 9 neighbourhood bits of a word
-	uint8_t *Lsc = Lzc + 2048;                                 // sign context | xor bit << 5
-	uint32_t *flags = sm + DT_FIXED_WORDS;                     // [slot][fwords]; the last DT_NZ_WORDS words of a slot hold nz[]
+	uint8_t *Lsc = Lzc + 2048;
+	uint32_t *flags = sm + DT_FIXED_WORDS;                     // [slot][fwords]
 	uint32_t *ctxrows = flags + (size_t) nslots * fwords;      // [context][slot]
 	for (int i = threadIdx.x; i < 94; i += blockDim.x) {
 		const uint32_t r = c_mq[i >> 1], mps = i & 1u, sw = (r >> 28) & 1u;
@@ -174,7 +242,11 @@ __global__ void __launch_bounds__(DT_MAX_THREADS, 1) t1_decode_kernel(const DecB
 		const int idx8 = (n9 & 7) | ((n9 >> 3) & 1) << 3 | ((n9 >> 5) & 1) << 4 | ((n9 >> 6) & 7) << 5;
 		Lzc[i] = c_zc[o][idx8];
 	}
-	for (int i = threadIdx.x; i < 256; i += blockDim.x) Lsc[i] = c_sc[i];
+	for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+		const int orig = (i >> 1 & 1) | (i >> 3 & 1) << 1 | (i >> 5 & 1) << 2 | (i >> 7 & 1) << 3
+				| (i & 1) << 4 | (i >> 2 & 1) << 5 | (i >> 4 & 1) << 6 | (i >> 6 & 1) << 7;
+		Lsc[i] = c_sc[orig];
+	}
 	__syncthreads();
 
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -189,132 +261,76 @@ __global__ void __launch_bounds__(DT_MAX_THREADS, 1) t1_decode_kernel(const DecB
 	// T1Part1.cpp:139, t1.cpp:1056: nothing to decode; the cleared block area stays zero
 	if (I.numpasses == 0 || I.data_len == 0 || numbps == 0 || numbps > 30 || w == 0 || h == 0) return;
 
-	const int nstripes = (h + 3) >> 2;
+	Blk b;
+	b.nstripes = (h + 3) >> 2;
+	b.fw = fw;
 	uint32_t *F = flags + (size_t) slot * fwords; // word of stripe s, column x: F[s * fw + x + 1]
-	for (int i = 0; i < fwords; ++i) F[i] = 0;
-	// nz[s]: columns of stripe s whose word holds any significance bit (own or neighbour)
-	unsigned long long *nz = reinterpret_cast<unsigned long long*>(F + fwords - DT_NZ_WORDS);
-	uint32_t *C = ctxrows + slot;
+	for (int i = 0; i < b.nstripes * fw; ++i) F[i] = 0;
+	// rows below the block in a partial last stripe count as visited for ever (t1.cpp:990-1003)
+	const uint32_t last_pi = (0xFu << (h - 4 * (b.nstripes - 1)) & 0xFu) << 24;
+	if (last_pi)
+		for (int x = 0; x < w; ++x) F[(b.nstripes - 1) * fw + 1 + x] = last_pi;
+	b.C = ctxrows + slot;
+	b.cs = nslots;
+	b.tab = tab;
 	#pragma unroll
-	for (int i = 0; i < NCTX; ++i) C[i * nslots] = tab[2 * (i == CTX_ZC0 ? 4 : i == CTX_AGG ? 3 : i == CTX_UNI ? 46 : 0)]; // mqc_dec.cpp:207-214
-	const uint8_t *zc = Lzc + 512 * B.orient;
-	const uint64_t wmask = w >= 64 ? ~0ull : (1ull << w) - 1ull;
-
-	MqT q;
-	mq_init(q, data + I.data_offset, I.data_len);
+	for (int i = 0; i < NCTX; ++i) b.C[i * nslots] = tab[2 * (i == CTX_ZC0 ? 4 : i == CTX_AGG ? 3 : i == CTX_UNI ? 46 : 0)]; // mqc_dec.cpp:207-214
+	b.zc = Lzc + 512 * B.orient;
+	b.sc = Lsc;
+	b.dst = B.dst;
+	b.stride = B.stride;
+	mq_init(b.q, data + I.data_offset, I.data_len);
 
 	// passes go cln(numbps), then sig / ref / cln per lower plane
-	int passes_left = min((int) I.numpasses, 3 * numbps - 2);
-	int bp1 = numbps, type = 2, s = -1;
-	int phase = PH_FETCH, x = 0, k = 0, nk = 4;
-	uint32_t f = 0, cand = 0, cand0 = 0, cx = 0, xorbit = 0, r = 0, rows = 0xFu;
-	uint64_t colmask = 0;
-	uint32_t *rowF = F + 1;
-	int32_t *drow = B.dst;
-	for (;;) {
-		if (phase == PH_FETCH) {
-			if (colmask == 0) { // next stripe, next pass
-				if (++s == nstripes) {
-					if (--passes_left == 0) break;
-					s = 0;
-					if (++type == 3) { type = 0; bp1--; }
+	const int npass = min((int) I.numpasses, 3 * numbps - 2);
+	int bp1 = numbps, type = 2;
+	for (int pass = 0; pass < npass; ++pass) {
+		// values carry one extra low bit: the plane weight is 1 << bp1, the mid-point sits half a step above
+		const int32_t half = (1 << bp1) >> 1, oph = (1 << bp1) | half;
+		for (int s = 0; s < b.nstripes; ++s) {
+			uint32_t *cw = F + s * fw + 1;
+			uint32_t off = (uint32_t) (4 * s) * B.stride;
+			if (type == 0) {
+				for (int x = 0; x < w; ++x, ++cw, ++off) {
+					uint32_t f = *cw;
+					if (!(f & F_SIGMA_ALL)) continue;
+					sig_row<0>(b, f, cw, s, off, oph);
+					sig_row<1>(b, f, cw, s, off, oph);
+					sig_row<2>(b, f, cw, s, off, oph);
+					sig_row<3>(b, f, cw, s, off, oph);
+					*cw = f;
 				}
-				nk = min(4, h - 4 * s);
-				rows = (1u << nk) - 1u;
-				rowF = F + s * fw + 1;
-				drow = B.dst + (size_t) (4 * s) * B.stride;
-				colmask = type == 2 ? wmask : nz[s];
-			}
-			if (colmask != 0) {
-				x = __ffsll((long long) colmask) - 1;
-				colmask &= colmask - 1;
-				f = rowF[x];
-				const uint32_t sig4 = own_sig4(f);
-				cand = (type == 1 ? sig4 : ~sig4) & ~(f >> 24) & rows;
-				if (type == 0) cand &= nbr4(f);
-				cand0 = cand;
-				if (cand) {
-					phase = PH_NORMAL;
-					if (type == 2 && nk == 4 && (f & (F_PI_ALL | F_SIGMA_ALL)) == 0) { phase = PH_AGG; cx = CTX_AGG; } // run-length mode, t1.cpp:749
-				} else if (type == 2 && (f & F_PI_ALL)) rowF[x] = f & ~F_PI_ALL;
-			}
-		}
-		if (phase != PH_FETCH) {
-			if (phase == PH_NORMAL) {
-				k = __ffs(cand) - 1;
-				cand &= cand - 1;
-				const uint32_t n9 = (f >> (3 * k)) & 0x1FFu;
-				if (type == 1) cx = (f >> (28 + k) & 1u) ? CTX_MR0 + 2 : (n9 & 0x1EFu) ? CTX_MR0 + 1 : CTX_MR0;
-				else cx = zc[n9];
-			}
-			const uint32_t d = mq_decode(q, C + cx * nslots, tab);
-			bool to_sign = false;
-			if (phase == PH_NORMAL) {
-				if (type == 1) { // refinement: +-half a step towards the decoded bit (t1.cpp:476-496)
-					const uint32_t neg = (f >> (19 + k)) & 1u;
-					const int32_t half = (1 << bp1) >> 1;
-					atomicAdd(drow + (size_t) k * B.stride + x, (d ^ neg) ? half : -half);
-				} else {
-					if (type == 0) f |= 1u << (24 + k);
-					to_sign = d != 0;
+			} else if (type == 1) {
+				for (int x = 0; x < w; ++x, ++cw, ++off) {
+					uint32_t f = *cw;
+					if (!(f & F_OWNSIG)) continue;
+					ref_row<0>(b, f, off, half);
+					ref_row<1>(b, f, off, half);
+					ref_row<2>(b, f, off, half);
+					ref_row<3>(b, f, off, half);
+					*cw = f;
 				}
-			} else if (phase == PH_SIGN) {
-				const uint32_t neg = d ^ xorbit;
-				const int32_t oph = (1 << bp1) | ((1 << bp1) >> 1); // values carry one extra low bit: mid-point of the plane
-				f |= fsig(k + 1, 1) | (neg << (19 + k));
-				drow[(size_t) k * B.stride + x] = neg ? -oph : oph;
-				// the sample is the east neighbour of column x-1 and the west neighbour of column x+1
-				atomicOr(rowF + x - 1, fsig(k + 1, 2));
-				atomicOr(rowF + x + 1, fsig(k + 1, 0));
-				const unsigned long long three = (x ? 7ull << (x - 1) : 3ull) & wmask; // columns x-1, x, x+1
-				nz[s] |= three; // the block's state belongs to this thread alone
-				if (k == 0 && s > 0) { // row 4 of the stripe above
-					uint32_t *up = rowF - fw + x;
-					atomicOr(up - 1, fsig(5, 2));
-					atomicOr(up, fsig(5, 1) | (neg << 23));
-					atomicOr(up + 1, fsig(5, 0));
-					nz[s - 1] |= three;
+			} else {
+				const uint32_t keep_pi = s == b.nstripes - 1 ? last_pi : 0u;
+				for (int x = 0; x < w; ++x, ++cw, ++off) {
+					uint32_t f = *cw;
+					int start = 0;
+					bool implied = false;
+					if ((f & (F_PI_ALL | F_SIGMA_ALL)) == 0) { // run-length mode, t1.cpp:749 (full stripes only: keep_pi)
+						if (!mq_decode(b.q, b.C + CTX_AGG * b.cs, tab)) continue;
+						start = (int) mq_decode(b.q, b.C + CTX_UNI * b.cs, tab) << 1;
+						start |= (int) mq_decode(b.q, b.C + CTX_UNI * b.cs, tab);
+						implied = true;
+					}
+					cln_row<0>(b, f, cw, s, off, oph, start, implied);
+					cln_row<1>(b, f, cw, s, off, oph, start, implied);
+					cln_row<2>(b, f, cw, s, off, oph, start, implied);
+					cln_row<3>(b, f, cw, s, off, oph, start, implied);
+					*cw = (f & ~F_PI_ALL) | keep_pi;
 				}
-				if (k == 3 && s + 1 < nstripes) { // row -1 of the stripe below
-					uint32_t *dn = rowF + fw + x;
-					atomicOr(dn - 1, fsig(0, 2));
-					atomicOr(dn, fsig(0, 1) | (neg << 18));
-					atomicOr(dn + 1, fsig(0, 0));
-					nz[s + 1] |= three;
-				}
-				if (type == 0) {
-					// the row below and the next column may have become codable in this pass through this sample
-					if (k + 1 < nk && !(f & (fsig(k + 2, 1) | (1u << (25 + k))))) cand |= 2u << k;
-					colmask |= (2ull << x) & wmask;
-				}
-				phase = PH_NORMAL;
-			} else if (phase == PH_AGG) {
-				if (d) { phase = PH_UNI1; cx = CTX_UNI; }
-				else { phase = PH_NORMAL; cand = 0; }
-			} else if (phase == PH_UNI1) {
-				r = d << 1;
-				phase = PH_UNI2;
-			} else { // the row of the first 1 of the column; its significance is implied, its sign follows
-				k = (int) (r | d);
-				cand &= ~((2u << k) - 1u);
-				to_sign = true;
-			}
-			if (to_sign) { // sign context from the 4 neighbours' significance and signs (t1.cpp:115-140)
-				const uint32_t n9 = (f >> (3 * k)) & 0x1FFu;
-				const uint32_t fW = rowF[x - 1], fE = rowF[x + 1];
-				const uint32_t idx = (n9 >> 1 & 1u) | (n9 >> 3 & 1u) << 1 | (n9 >> 5 & 1u) << 2 | (n9 >> 7 & 1u) << 3
-						| (f >> (18 + k) & 1u) << 4 | (fW >> (19 + k) & 1u) << 5 | (fE >> (19 + k) & 1u) << 6 | (f >> (20 + k) & 1u) << 7;
-				const uint32_t v = Lsc[idx];
-				cx = v & 31u;
-				xorbit = v >> 5;
-				phase = PH_SIGN;
-			} else if (phase == PH_NORMAL && cand == 0) { // column finished
-				if (type == 1) f |= cand0 << 28;
-				if (type == 2) f &= ~F_PI_ALL;
-				rowF[x] = f;
-				phase = PH_FETCH;
 			}
 		}
+		if (++type == 3) { type = 0; bp1--; }
 	}
 }
 
@@ -356,8 +372,7 @@ int launch_t1_decode(const DecBlock *blocks, const DecInput *inputs, uint32_t nb
 	if (max_h < 1) max_h = 1;
 	const int fw = (int) max_w + 2;
 	int fwords = (int) ((max_h + 3) / 4) * fw;
-	fwords += fwords & 1;      // the column masks that follow are 64-bit
-	fwords += DT_NZ_WORDS;
+	fwords += fwords & 1;
 	// slots of one warp start 32 / DT_LANES banks apart
 	int bank0 = 32 / DT_LANES % 32;
 	if (bank0 & 1) bank0 = 2;
