@@ -41,6 +41,7 @@ namespace gb {
 #endif
 constexpr int DT_MAX_THREADS = DT_LANES <= 2 ? 1024 : 512;
 constexpr int DT_MAX_SLOTS = DT_MAX_THREADS / 32 * DT_LANES;
+constexpr int DT_CTX_WORDS = 20;  // 19 context rows per block, padded
 constexpr int DT_FIXED_WORDS = 96 + 512 + 64; // MQ table, zero-coding table (4 x 512 B), sign table (256 B)
 
 // stripe-column word: bit 3r+j = significance of row r-1 (r = 0..5), column j-1 (j = 0 west, 1 own, 2 east);
@@ -153,8 +154,7 @@ __device__ __forceinline__ uint32_t mq_decode(MqT &q, uint32_t *crow, const uint
 // ---- the three coding passes of one stripe column, rows unrolled with constant bit positions ---------
 struct Blk {
 	MqT q;
-	uint32_t *C;          // context rows of this block, C[cx * cs]
-	int cs;
+	uint32_t *C;          // the 19 context rows of this block
 	const uint32_t *tab;  // 94 (state, mps) rows
 	const uint8_t *zc;    // zero-coding context by the 9 neighbourhood bits, this block's orientation
 	const uint8_t *sc;    // sign context | xor bit << 5, by (N W E S significance at bits 1 3 5 7, signs at bits 0 2 4 6)
@@ -172,7 +172,7 @@ __device__ __forceinline__ void sign_and_mark(Blk &b, uint32_t &f, uint32_t *cw,
 	const uint32_t idx = ((f >> (3 * K)) & 0xAAu) | ((f >> (18 + K)) & 1u) | ((fW >> (17 + K)) & 4u) | ((fE >> (15 + K)) & 0x10u)
 			| ((f >> (14 + K)) & 0x40u);
 	const uint32_t v = b.sc[idx];
-	const uint32_t neg = mq_decode(b.q, b.C + (v & 31u) * b.cs, b.tab) ^ (v >> 5);
+	const uint32_t neg = mq_decode(b.q, b.C + (v & 31u), b.tab) ^ (v >> 5);
 	f |= fsig(K + 1, 1) | (neg << (19 + K));
 	b.dst[off + K * b.stride] = neg ? -oph : oph;
 	// the sample is the east neighbour of column x-1 and the west neighbour of column x+1
@@ -196,7 +196,7 @@ __device__ __forceinline__ void sign_and_mark(Blk &b, uint32_t &f, uint32_t *cw,
 template<int K>
 __device__ __forceinline__ void sig_row(Blk &b, uint32_t &f, uint32_t *cw, int s, uint32_t off, int32_t oph) {
 	if ((f & (fsig(K + 1, 1) | (1u << (24 + K)))) == 0 && (f & (0x1EFu << (3 * K))) != 0) {
-		const uint32_t d = mq_decode(b.q, b.C + b.zc[(f >> (3 * K)) & 0x1FFu] * b.cs, b.tab);
+		const uint32_t d = mq_decode(b.q, b.C + b.zc[(f >> (3 * K)) & 0x1FFu], b.tab);
 		f |= 1u << (24 + K);
 		if (d) sign_and_mark<K>(b, f, cw, s, off, oph);
 	}
@@ -207,7 +207,7 @@ template<int K>
 __device__ __forceinline__ void ref_row(Blk &b, uint32_t &f, uint32_t off, int32_t half) {
 	if ((f & (fsig(K + 1, 1) | (1u << (24 + K)))) == fsig(K + 1, 1)) {
 		const uint32_t cx = (f & (1u << (28 + K))) ? CTX_MR0 + 2 : (f & (0x1EFu << (3 * K))) ? CTX_MR0 + 1 : CTX_MR0;
-		const uint32_t d = mq_decode(b.q, b.C + cx * b.cs, b.tab);
+		const uint32_t d = mq_decode(b.q, b.C + cx, b.tab);
 		const uint32_t neg = (f >> (19 + K)) & 1u;
 		atomicAdd(b.dst + off + K * b.stride, (d ^ neg) ? half : -half);
 		f |= 1u << (28 + K);
@@ -219,7 +219,7 @@ template<int K>
 __device__ __forceinline__ void cln_row(Blk &b, uint32_t &f, uint32_t *cw, int s, uint32_t off, int32_t oph, int start, bool implied) {
 	if (K >= start && (f & (fsig(K + 1, 1) | (1u << (24 + K)))) == 0) {
 		uint32_t d = 1;
-		if (!(implied && K == start)) d = mq_decode(b.q, b.C + b.zc[(f >> (3 * K)) & 0x1FFu] * b.cs, b.tab);
+		if (!(implied && K == start)) d = mq_decode(b.q, b.C + b.zc[(f >> (3 * K)) & 0x1FFu], b.tab);
 		if (d) sign_and_mark<K>(b, f, cw, s, off, oph);
 	}
 }
@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(DT_MAX_THREADS, 1) t1_decode_kernel(const DecB
 	uint8_t *Lzc = reinterpret_cast<uint8_t*>(sm + 96);        // zero-coding context by the 9 neighbourhood bits of a word
 	uint8_t *Lsc = Lzc + 2048;
 	uint32_t *flags = sm + DT_FIXED_WORDS;                     // [slot][fwords]
-	uint32_t *ctxrows = flags + (size_t) nslots * fwords;      // [context][slot]
+	uint32_t *ctxrows = flags + (size_t) nslots * fwords;      // [slot][DT_CTX_WORDS]
 	for (int i = threadIdx.x; i < 94; i += blockDim.x) {
 		const uint32_t r = c_mq[i >> 1], mps = i & 1u, sw = (r >> 28) & 1u;
 		const uint32_t nm = ((r >> 16) & 63u) * 2u + mps, nl = ((r >> 22) & 63u) * 2u + (mps ^ sw);
@@ -270,11 +270,10 @@ __global__ void __launch_bounds__(DT_MAX_THREADS, 1) t1_decode_kernel(const DecB
 	const uint32_t last_pi = (0xFu << (h - 4 * (b.nstripes - 1)) & 0xFu) << 24;
 	if (last_pi)
 		for (int x = 0; x < w; ++x) F[(b.nstripes - 1) * fw + 1 + x] = last_pi;
-	b.C = ctxrows + slot;
-	b.cs = nslots;
+	b.C = ctxrows + slot * DT_CTX_WORDS;
 	b.tab = tab;
 	#pragma unroll
-	for (int i = 0; i < NCTX; ++i) b.C[i * nslots] = tab[2 * (i == CTX_ZC0 ? 4 : i == CTX_AGG ? 3 : i == CTX_UNI ? 46 : 0)]; // mqc_dec.cpp:207-214
+	for (int i = 0; i < NCTX; ++i) b.C[i] = tab[2 * (i == CTX_ZC0 ? 4 : i == CTX_AGG ? 3 : i == CTX_UNI ? 46 : 0)]; // mqc_dec.cpp:207-214
 	b.zc = Lzc + 512 * B.orient;
 	b.sc = Lsc;
 	b.dst = B.dst;
@@ -293,7 +292,7 @@ __global__ void __launch_bounds__(DT_MAX_THREADS, 1) t1_decode_kernel(const DecB
 			if (type == 0) {
 				for (int x = 0; x < w; ++x, ++cw, ++off) {
 					uint32_t f = *cw;
-					if (!(f & F_SIGMA_ALL)) continue;
+					if (!(f & F_SIGMA_ALL) || (f & F_OWNSIG) == F_OWNSIG) continue; // nothing significant around / nothing left to find
 					sig_row<0>(b, f, cw, s, off, oph);
 					sig_row<1>(b, f, cw, s, off, oph);
 					sig_row<2>(b, f, cw, s, off, oph);
@@ -317,9 +316,9 @@ __global__ void __launch_bounds__(DT_MAX_THREADS, 1) t1_decode_kernel(const DecB
 					int start = 0;
 					bool implied = false;
 					if ((f & (F_PI_ALL | F_SIGMA_ALL)) == 0) { // run-length mode, t1.cpp:749 (full stripes only: keep_pi)
-						if (!mq_decode(b.q, b.C + CTX_AGG * b.cs, tab)) continue;
-						start = (int) mq_decode(b.q, b.C + CTX_UNI * b.cs, tab) << 1;
-						start |= (int) mq_decode(b.q, b.C + CTX_UNI * b.cs, tab);
+						if (!mq_decode(b.q, b.C + CTX_AGG, tab)) continue;
+						start = (int) mq_decode(b.q, b.C + CTX_UNI, tab) << 1;
+						start |= (int) mq_decode(b.q, b.C + CTX_UNI, tab);
 						implied = true;
 					}
 					cln_row<0>(b, f, cw, s, off, oph, start, implied);
@@ -377,7 +376,7 @@ int launch_t1_decode(const DecBlock *blocks, const DecInput *inputs, uint32_t nb
 	int bank0 = 32 / DT_LANES % 32;
 	if (bank0 & 1) bank0 = 2;
 	while (fwords % 32 != bank0) fwords += 2;
-	const int per_slot = (fwords + NCTX) * 4;
+	const int per_slot = (fwords + DT_CTX_WORDS) * 4;
 	int cap = (smem_max - DT_FIXED_WORDS * 4) / per_slot;
 	int want = (int) ((nblocks + (uint32_t) sms - 1) / (uint32_t) sms); // spread a small job over every SM
 	int nslots = cap < want ? cap : want;
