@@ -1,0 +1,359 @@
+/*
+ * grok_plugin_b200.cpp -- libgrok_plugin.so: Grok's official minpf plugin ABI ("B1" of SURVEY.md section 8(b))
+ * implemented on top of the C ABI of include/grok_b200.h.
+ *
+ * An unmodified Grok built with the plugin loader (src/lib/jp2/CMakeLists.txt:188-190) finds this library through
+ * grk_plugin_load / `grk_compress -g <dir>` (grok.cpp:834-861), resolves the entry points below by name with dlsym on
+ * every call (grok.cpp:862-1103) and, for an encode, hands over the whole front end of the tile coder:
+ *
+ *   plugin_encode(grk_cparameters*, callback)     plugin_interface.h:74, stub src/lib/jp2_plugin/Plugin.cpp:62-67
+ *     - the plugin reads parameters->infile itself (PNM here), runs level shift, RCT/ICT, DWT, quantisation and
+ *       Tier-1 on the B200 (gb200_encode_tiles) and describes the result as a grk_plugin_tile tree (grok.h:1223-1278)
+ *     - it then calls the host's callback ONCE, synchronously; inside it the host creates its codec and runs
+ *       grk_encode_with_plugin: TileProcessor::encode_tile skips its own DC shift / MCT / DWT / T1
+ *       (TileProcessor.cpp:994) and pcrd_bisect_* pulls every code block through encode_synch_with_plugin
+ *       (plugin_bridge.cpp:148-260), then does PCRD, Tier-2 and the codestream itself.
+ *
+ * Contract details honoured here (all read in plugin_bridge.cpp):
+ *   - the tree is indexed [comp][resno][band][precinct][block] in the host's traversal order;
+ *   - the host ALIASES compressedData (cblk->data = plugin_cblk->compressedData, owns_data = false), so every
+ *     buffer of the tree stays alive until the callback has returned;
+ *   - pass rates are reported one less than the reference's final rate: the host computes
+ *     min(rate + 1, total) and then drops a trailing 0xFF (plugin_bridge.cpp:236-244);
+ *   - distortionDecrease is cumulative (t1.cpp:1262);
+ *   - one grk_plugin_tile describes the whole image (j2k.cpp:2069 re-uses the pointer for every tile), so a
+ *     multi-tile request cannot be expressed: plugin_encode returns non-zero and the host falls back to its CPU
+ *     path (grk_compress.cpp:2215-2219).  Multi-tile images go through the TCD stage seam instead
+ *     (integration/grok_tcd_shim.cpp).
+ *
+ * Quantisation constants are derived with the host's own code (param_qcd::generate / pull as j2k.cpp:1839-2049
+ * does, the three formulas of Quantizer.cpp:65-105, dwt_utils::getnorm_*, mct::get_norms_*): this file is built
+ * against Grok's headers and links libgrok, it restates none of its tables.
+ * There is no CPU fallback in this layer: plugin_init fails without a CUDA device, and the host then keeps its own path.
+ */
+#include "grok_includes.h"
+#include "dwt_utils.h"
+#include "plugin/plugin_interface.h"
+#include "../include/grok_b200.h"
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+namespace {
+
+gb200_ctx *g_ctx = nullptr;
+bool g_verbose = false;
+uint64_t g_encodes = 0, g_blocks = 0;
+
+void say(const char *what) {
+	if (g_verbose) fprintf(stderr, "grok_plugin_b200: %s: %s\n", what, gb200_last_error());
+}
+
+/* ---- PNM (P5 / P6, 8 or 16 bit big endian): the only input format this adapter reads itself -------------- */
+bool pnm_token(FILE *f, uint32_t *v) {
+	int c = fgetc(f);
+	for (;;) {
+		while (c == ' ' || c == '\t' || c == '\n' || c == '\r') c = fgetc(f);
+		if (c != '#') break;
+		while (c != '\n' && c != EOF) c = fgetc(f);
+	}
+	if (c < '0' || c > '9') return false;
+	uint64_t x = 0;
+	while (c >= '0' && c <= '9') { x = x * 10 + (uint64_t) (c - '0'); if (x > 0xFFFFFFFFull) return false; c = fgetc(f); }
+	*v = (uint32_t) x; /* the single white-space byte after the token has been consumed */
+	return true;
+}
+
+grk_image *read_pnm(const grk_cparameters *p) {
+	FILE *f = fopen(p->infile, "rb");
+	if (!f) return nullptr;
+	grk_image *img = nullptr;
+	int m0 = fgetc(f), m1 = fgetc(f);
+	uint32_t w = 0, h = 0, maxval = 0;
+	if (m0 == 'P' && (m1 == '5' || m1 == '6') && pnm_token(f, &w) && pnm_token(f, &h) && pnm_token(f, &maxval) && w && h
+			&& maxval && maxval < 65536) {
+		const uint32_t nc = m1 == '6' ? 3 : 1;
+		uint32_t prec = 1;
+		while ((1u << prec) <= maxval) prec++;
+		const uint32_t dx = p->subsampling_dx ? p->subsampling_dx : 1, dy = p->subsampling_dy ? p->subsampling_dy : 1;
+		std::vector<grk_image_cmptparm> cp(nc);
+		for (auto &c : cp) {
+			memset(&c, 0, sizeof(c));
+			c.dx = dx; c.dy = dy; c.w = w; c.h = h; c.prec = prec; c.sgnd = 0;
+			c.x0 = p->image_offset_x0; c.y0 = p->image_offset_y0;
+		}
+		img = grk_image_create(nc, cp.data(), nc == 3 ? GRK_CLRSPC_SRGB : GRK_CLRSPC_GRAY);
+		if (img) {
+			/* image area on the reference grid, as the host's PNM reader sets it */
+			img->x0 = p->image_offset_x0; img->y0 = p->image_offset_y0;
+			img->x1 = img->x0 + (w - 1) * dx + 1; img->y1 = img->y0 + (h - 1) * dy + 1;
+			const size_t bps = maxval > 255 ? 2 : 1, row = (size_t) w * nc * bps;
+			std::vector<uint8_t> line(row);
+			bool ok = true;
+			for (uint32_t y = 0; y < h && ok; ++y) {
+				ok = fread(line.data(), 1, row, f) == row;
+				for (uint32_t x = 0; x < w && ok; ++x)
+					for (uint32_t c = 0; c < nc; ++c) {
+						const uint8_t *s = line.data() + ((size_t) x * nc + c) * bps;
+						img->comps[c].data[(size_t) y * w + x] = bps == 2 ? (s[0] << 8 | s[1]) : s[0];
+					}
+			}
+			if (!ok) { grk_image_destroy(img); img = nullptr; }
+		}
+	}
+	fclose(f);
+	return img;
+}
+
+/* ---- coding parameters of the single tile, derived the way j2k_setup_encoder + TileComponent::init do ------ */
+bool fill_comp(const grk_cparameters *p, const grk_image *img, uint32_t c, bool mct, gb200_comp_params &cp) {
+	using namespace grk;
+	memset(&cp, 0, sizeof(cp));
+	const grk_image_comp *ic = img->comps + c;
+	cp.x0 = ceildiv<uint32_t>(img->x0, ic->dx); cp.y0 = ceildiv<uint32_t>(img->y0, ic->dy);
+	cp.x1 = ceildiv<uint32_t>(img->x1, ic->dx); cp.y1 = ceildiv<uint32_t>(img->y1, ic->dy);
+	cp.numres = p->numresolution;
+	cp.cblkw_expn = uint_floorlog2(p->cblockw_init); cp.cblkh_expn = uint_floorlog2(p->cblockh_init);
+	const bool rev = !p->irreversible;
+	cp.qmfbid = rev ? 1 : 0;
+	cp.prec = ic->prec; cp.sgnd = ic->sgnd;
+	cp.dc_shift = ic->sgnd ? 0 : 1 << (ic->prec - 1); /* j2k.cpp:1972-1977 */
+	cp.cblk_sty = p->cblk_sty;
+	cp.roishift = ((int32_t) c == p->roi_compno) ? p->roi_shift : 0;
+	/* precinct sizes, j2k.cpp:2001-2048 */
+	if ((p->csty & J2K_CCP_CSTY_PRT) && p->res_spec) {
+		uint32_t k = 0;
+		for (int32_t r = (int32_t) cp.numres - 1; r >= 0; --r, ++k) {
+			uint32_t pw, ph;
+			if (k < p->res_spec) { pw = p->prcw_init[k]; ph = p->prch_init[k]; }
+			else { pw = p->prcw_init[p->res_spec - 1] >> (k - (p->res_spec - 1)); ph = p->prch_init[p->res_spec - 1] >> (k - (p->res_spec - 1)); }
+			cp.prcw_expn[r] = pw < 1 ? 1 : uint_floorlog2(pw);
+			cp.prch_expn[r] = ph < 1 ? 1 : uint_floorlog2(ph);
+		}
+	} else
+		for (uint32_t r = 0; r < cp.numres; ++r) cp.prcw_expn[r] = cp.prch_expn[r] = 15;
+	/* quantisation: QCD generated from component 0 (j2k.cpp:1839-1841), pulled into every component (:2049) */
+	const uint8_t numgbits = 2;
+	param_qcd qcd;
+	qcd.generate(numgbits, cp.numres - 1, rev, img->comps[0].prec, mct, img->comps[0].sgnd);
+	grk_stepsize steps[GRK_J2K_MAXBANDS];
+	memset(steps, 0, sizeof(steps));
+	qcd.pull(steps, rev);
+	const double *norms = mct ? (rev ? mct::get_norms_rev() : mct::get_norms_irrev()) : nullptr;
+	const double w1 = (norms && c < 3) ? norms[c] : 1.0;
+	for (uint32_t r = 0; r < cp.numres; ++r)
+		for (uint32_t b = 0; b < (r ? 3u : 1u); ++b) {
+			const uint32_t bi = r ? 3 * r - 2 + b : 0, orient = r ? b + 1 : 0;
+			const uint32_t gain = rev ? (orient == 0 ? 0 : orient < 3 ? 1 : 2) : 0;
+			const uint32_t numbps = ic->prec + gain;
+			/* Quantizer::setBandStepSizeAndBps, Quantizer.cpp:65-105 */
+			const float stepsize = (float) ((1.0 + steps[bi].mant / 2048.0) * pow(2.0, (int32_t) (numbps - steps[bi].expn)));
+			cp.stepsize[bi] = stepsize;
+			cp.band_numbps[bi] = cp.roishift + (uint32_t) (steps[bi].expn + numgbits) - 1;
+			cp.inv_step[bi] = (uint32_t) ((8192.0 / stepsize) + 0.5f);
+			const uint32_t level = cp.numres - 1 - r; /* T1Part1.cpp:114 */
+			const double w2 = rev ? dwt_utils::getnorm_53(level, (uint8_t) orient) : dwt_utils::getnorm_97(level, (uint8_t) orient);
+			cp.rd_weight[bi] = w1 * w2 * (double) stepsize; /* t1.cpp:912-932 */
+		}
+	return true;
+}
+
+/* the grk_plugin_tile tree over the encoder results; owns every node and the compressed bytes */
+struct Tree {
+	grk_plugin_tile tile;
+	std::vector<grk_plugin_tile_component> comps;
+	std::vector<grk_plugin_tile_component*> comp_ptrs;
+	std::vector<std::unique_ptr<grk_plugin_resolution[]>> res;
+	std::vector<std::vector<grk_plugin_resolution*>> res_ptrs;
+	std::vector<std::unique_ptr<grk_plugin_band[]>> bands;
+	std::vector<std::vector<grk_plugin_band*>> band_ptrs;
+	std::vector<std::unique_ptr<grk_plugin_precinct[]>> precs;
+	std::vector<std::vector<grk_plugin_precinct*>> prec_ptrs;
+	std::vector<std::vector<grk_plugin_code_block*>> blk_ptrs;
+	std::vector<grk_plugin_code_block> blocks;
+	std::vector<uint8_t> data;
+};
+
+} // namespace
+
+/* ---- minpf registration (minpf_plugin.h:24-57, loader minpf_plugin_manager.cpp:146-162) --------------------- */
+extern "C" PLUGIN_API int32_t grok_b200_plugin_exit() {
+	if (g_ctx) { gb200_destroy(g_ctx); g_ctx = nullptr; }
+	return 0;
+}
+static void *plugin_create(grk::minpf_object_params *) { return nullptr; }
+static int32_t plugin_destroy(void *) { return 0; }
+
+extern "C" PLUGIN_API grk::minpf_exit_func minpf_post_load_plugin(const char *, const grk::minpf_platform_services *services) {
+	grk::minpf_register_params rp;
+	rp.version.major = 1; /* must equal the host's, minpf_plugin_manager.cpp:59-61 */
+	rp.version.minor = 0;
+	rp.createFunc = plugin_create;
+	rp.destroyFunc = plugin_destroy;
+	if (!services || services->registerObject("GrokB200", &rp) < 0) return nullptr;
+	return grok_b200_plugin_exit;
+}
+
+extern "C" PLUGIN_API bool plugin_init(grk_plugin_init_info info) {
+	g_verbose = info.verbose;
+	if (g_ctx) return true;
+	const char *d = getenv("GROK_B200_DEVICE");
+	const int dev = d ? atoi(d) : (info.deviceId > 0 ? info.deviceId : 0);
+	if (gb200_create(dev, &g_ctx) != GB200_OK) { /* false => the host silently keeps its CPU path */
+		say("plugin_init");
+		g_ctx = nullptr;
+		return false;
+	}
+	return true;
+}
+
+/* counters for the parity tests: 0 = images encoded on the device, 1 = code blocks handed to the host */
+extern "C" PLUGIN_API uint64_t grok_b200_plugin_stat(int i) { return i == 0 ? g_encodes : g_blocks; }
+
+/* ---- encode -------------------------------------------------------------------------------------------------- */
+extern "C" PLUGIN_API int32_t plugin_encode(grk_cparameters *p, grk::PLUGIN_ENCODE_USER_CALLBACK callback) {
+	if (!g_ctx || !p || !callback) return -1;
+	/* what the single grk_plugin_tile of this ABI, or this build of the kernels, cannot express -> host CPU path */
+	if (p->isHT || p->cblk_sty != 0 || p->roi_compno >= 0 || p->decod_format != GRK_PXM_FMT) return 1;
+	grk_image *img = read_pnm(p);
+	if (!img) return 2;
+	struct ImgGuard { grk_image *i; ~ImgGuard() { grk_image_destroy(i); } } guard{img};
+	if (p->tile_size_on && (p->cp_tx0 + p->cp_tdx < img->x1 || p->cp_ty0 + p->cp_tdy < img->y1)) return 1; /* more than one tile */
+	const uint32_t nc = img->numcomps;
+	/* MCT decision of grk_compress.cpp:1996-1998 and j2k.cpp:1961-1970 */
+	bool mct = p->tcp_mct == 255 ? nc >= 3 : p->tcp_mct == 1;
+	if (p->tcp_mct > 1 && p->tcp_mct != 255) return 1; /* array based MCT */
+	if (mct && nc < 3) return 1;
+	std::vector<gb200_comp_params> cps(nc);
+	for (uint32_t c = 0; c < nc; ++c) fill_comp(p, img, c, mct, cps[c]);
+	gb200_tile_params tp;
+	memset(&tp, 0, sizeof(tp));
+	tp.numcomps = nc;
+	tp.mct = mct ? 1 : 0;
+	tp.rate_control = 1; /* the host decides later whether it uses the distortions (needs_rate_control) */
+	tp.comps = cps.data();
+	gb200_plan *plan = nullptr;
+	if (gb200_plan_create(g_ctx, 1, &tp, 1, &plan) != GB200_OK) { say("gb200_plan_create"); return 3; }
+	struct PlanGuard { gb200_plan *p; ~PlanGuard() { gb200_plan_destroy(p); } } pguard{plan};
+	const size_t nb = gb200_plan_num_blocks(plan);
+	std::vector<gb200_cblk_enc> enc(nb);
+	std::vector<uint32_t> rates(gb200_plan_num_pass_slots(plan) + 1);
+	std::vector<double> dists(gb200_plan_num_pass_slots(plan) + 1);
+	Tree T;
+	T.data.resize(gb200_plan_data_capacity(plan) + 16);
+	std::vector<const int32_t*> planes(nc);
+	for (uint32_t c = 0; c < nc; ++c) planes[c] = img->comps[c].data;
+	uint64_t len = 0;
+	if (gb200_encode_tiles(plan, planes.data(), enc.data(), rates.data(), dists.data(), T.data.data(), T.data.size(), &len) != GB200_OK) {
+		say("gb200_encode_tiles");
+		return 4;
+	}
+	/* ---- the tree, sized from the block table (host order: comp, resno, band, precinct, block) ---- */
+	const gb200_cblk_info *info = gb200_plan_blocks(plan);
+	T.blocks.resize(nb);
+	T.comps.resize(nc);
+	T.comp_ptrs.resize(nc);
+	for (uint32_t c = 0; c < nc; ++c) {
+		const uint32_t numres = cps[c].numres;
+		T.res.emplace_back(new grk_plugin_resolution[numres]);
+		T.res_ptrs.emplace_back(numres);
+		grk_plugin_resolution *res = T.res.back().get();
+		for (uint32_t r = 0; r < numres; ++r) {
+			const uint32_t nbands = r ? 3 : 1;
+			T.bands.emplace_back(new grk_plugin_band[nbands]);
+			T.band_ptrs.emplace_back(nbands);
+			grk_plugin_band *bands = T.bands.back().get();
+			for (uint32_t b = 0; b < nbands; ++b) {
+				const uint32_t orient = r ? b + 1 : 0, bi = r ? 3 * r - 2 + b : 0;
+				/* precincts and blocks of this band: highest indices present in the table */
+				size_t nprec = 0;
+				for (size_t i = 0; i < nb; ++i)
+					if (info[i].compno == c && info[i].resno == r && info[i].bandno == orient) nprec = std::max<size_t>(nprec, info[i].precno + 1);
+				T.precs.emplace_back(new grk_plugin_precinct[nprec ? nprec : 1]);
+				T.prec_ptrs.emplace_back(nprec);
+				grk_plugin_precinct *precs = T.precs.back().get();
+				std::vector<size_t> nblk(nprec, 0);
+				for (size_t i = 0; i < nb; ++i)
+					if (info[i].compno == c && info[i].resno == r && info[i].bandno == orient)
+						nblk[info[i].precno] = std::max<size_t>(nblk[info[i].precno], info[i].cblkno + 1);
+				for (size_t pr = 0; pr < nprec; ++pr) {
+					T.blk_ptrs.emplace_back(nblk[pr]);
+					precs[pr].numBlocks = nblk[pr];
+					precs[pr].blocks = T.blk_ptrs.back().data();
+					T.prec_ptrs.back()[pr] = precs + pr;
+				}
+				for (size_t i = 0; i < nb; ++i)
+					if (info[i].compno == c && info[i].resno == r && info[i].bandno == orient) precs[info[i].precno].blocks[info[i].cblkno] = &T.blocks[i];
+				bands[b].orient = orient;
+				bands[b].numPrecincts = nprec;
+				bands[b].precincts = T.prec_ptrs.back().data();
+				bands[b].stepsize = cps[c].stepsize[bi];
+				T.band_ptrs.back()[b] = bands + b;
+			}
+			res[r].level = r;
+			res[r].numBands = nbands;
+			res[r].bands = T.band_ptrs.back().data();
+			T.res_ptrs.back()[r] = res + r;
+		}
+		T.comps[c].numResolutions = numres;
+		T.comps[c].resolutions = T.res_ptrs.back().data();
+		T.comp_ptrs[c] = &T.comps[c];
+	}
+	for (size_t i = 0; i < nb; ++i) {
+		grk_plugin_code_block &B = T.blocks[i];
+		memset(&B, 0, sizeof(B));
+		const gb200_cblk_enc &e = enc[i];
+		B.x0 = info[i].x0; B.y0 = info[i].y0; B.x1 = info[i].x1; B.y1 = info[i].y1;
+		B.numPix = (size_t) (B.x1 - B.x0) * (B.y1 - B.y0);
+		B.compressedData = T.data.data() + e.data_offset;
+		B.compressedDataLength = e.data_len;
+		B.numBitPlanes = e.numbps;
+		B.numPasses = e.numpasses;
+		if (e.numpasses > 67) return 5;
+		const uint32_t po = info[i].pass_offset;
+		for (uint32_t k = 0; k < e.numpasses; ++k) {
+			const uint32_t r = rates[po + k];
+			B.passes[k].distortionDecrease = dists[po + k];
+			B.passes[k].rate = r ? r - 1 : 0; /* host: min(rate + 1, total), plugin_bridge.cpp:236 */
+			B.passes[k].length = r - (k ? rates[po + k - 1] : 0);
+		}
+		B.sortedIndex = (unsigned int) i;
+	}
+	T.tile.decode_flags = 0;
+	T.tile.numComponents = nc;
+	T.tile.tileComponents = T.comp_ptrs.data();
+	g_encodes++;
+	g_blocks += nb;
+
+	grk::plugin_encode_user_callback_info cbinfo;
+	memset(&cbinfo, 0, sizeof(cbinfo));
+	cbinfo.input_file_name = p->infile;
+	cbinfo.outputFileNameIsRelative = false;
+	cbinfo.output_file_name = p->outfile;
+	cbinfo.encoder_parameters = p;
+	cbinfo.image = img;
+	cbinfo.tile = &T.tile;
+	cbinfo.error_code = 0;
+	try {
+		callback(&cbinfo); /* synchronous: header + PCRD + Tier-2 + file write happen in here */
+	} catch (...) {
+		return 6; /* nothing in libgrok catches what its callback throws */
+	}
+	return cbinfo.error_code;
+}
+
+/* the batch / decode entry points of the ABI are exported so that the host's dlsym succeeds; they report
+ * "not handled" and the host keeps its own path (grk_compress.cpp:2215-2219, grk_decompress.cpp) */
+extern "C" PLUGIN_API int32_t plugin_batch_encode(const char *, const char *, grk_cparameters *, grk::PLUGIN_ENCODE_USER_CALLBACK) { return -1; }
+extern "C" PLUGIN_API bool plugin_is_batch_complete(void) { return true; }
+extern "C" PLUGIN_API void plugin_stop_batch_encode(void) {}
+extern "C" PLUGIN_API int32_t plugin_decode(grk_decompress_parameters *, grk::PLUGIN_DECODE_USER_CALLBACK) { return -1; }
+extern "C" PLUGIN_API int32_t plugin_init_batch_decode(const char *, const char *, grk_decompress_parameters *, grk::PLUGIN_DECODE_USER_CALLBACK) { return -1; }
+extern "C" PLUGIN_API int32_t plugin_batch_decode(void) { return -1; }
+extern "C" PLUGIN_API void plugin_stop_batch_decode(void) {}
+extern "C" PLUGIN_API uint32_t plugin_get_debug_state(void) { return GRK_PLUGIN_STATE_NO_DEBUG; }
+extern "C" PLUGIN_API void plugin_debug_mqc_next_cxd(grk::grk_plugin_debug_mqc *, uint32_t) {}
+extern "C" PLUGIN_API void plugin_debug_mqc_next_plane(grk::grk_plugin_debug_mqc *) {}

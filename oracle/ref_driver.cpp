@@ -322,4 +322,64 @@ int ref_decode_image(const uint8_t *buf, uint64_t len, uint32_t reduce, uint32_t
 	return rc;
 }
 
+/* ---- the official plugin path: grk_plugin_load / init / encode, exactly what `grk_compress -g <dir>` does
+ * (grk_compress.cpp:2205-2301), with a callback that mirrors plugin_compress_callback (grk_compress.cpp:1770-2160)
+ * but writes the codestream into memory.  Returns the codestream length; -1 = plugin not loaded / init failed
+ * (the CLI would fall back to the CPU), -2 = plugin_encode returned non-zero, -3 = the host side failed. */
+static uint8_t *g_cb_out = nullptr;
+static uint64_t g_cb_cap = 0;
+static int64_t g_cb_len = -1;
+
+static bool plugin_cb(grk_plugin_encode_user_callback_info *info) {
+	grk_cparameters *param = info->encoder_parameters;
+	grk_image *image = info->image;
+	g_cb_len = -3;
+	if (!image || !info->tile) return false;
+	if (param->tcp_mct == 255) param->tcp_mct = (image->numcomps >= 3) ? 1 : 0; /* grk_compress.cpp:1996-1998 */
+	grk_stream *stream = grk_stream_create_mem_stream(g_cb_out, g_cb_cap, false, false);
+	grk_codec *codec = stream ? grk_create_compress(GRK_CODEC_J2K, stream) : nullptr;
+	if (codec && grk_setup_encoder(codec, param, image) && grk_start_compress(codec, image)
+			&& grk_encode_with_plugin(codec, info->tile) && grk_end_compress(codec))
+		g_cb_len = (int64_t) grk_stream_get_write_mem_stream_length(stream);
+	if (stream) grk_stream_destroy(stream);
+	if (codec) grk_destroy_codec(codec);
+	return g_cb_len >= 0;
+}
+
+int64_t ref_plugin_encode_file(const char *plugin_dir, const char *infile, uint32_t tile_w, uint32_t tile_h, uint32_t numres,
+		uint32_t cblkw, uint32_t cblkh, int irreversible, uint32_t numlayers, const double *rates, uint32_t rc_algorithm,
+		uint8_t *out, uint64_t cap) {
+	grk_set_info_handler(quiet_cb, nullptr);
+	grk_set_warning_handler(quiet_cb, nullptr);
+	grk_set_error_handler(quiet_cb, nullptr);
+	grk_plugin_load_info li;
+	li.plugin_path = plugin_dir;
+	if (!grk_plugin_load(li)) return -1;
+	grk_plugin_init_info ii;
+	ii.deviceId = 0;
+	ii.verbose = true;
+	if (!grk_plugin_init(ii)) { grk_plugin_cleanup(); return -1; }
+	grk_cparameters param;
+	grk_set_default_encoder_parameters(&param);
+	strncpy(param.infile, infile, sizeof(param.infile) - 1);
+	param.decod_format = GRK_PXM_FMT;
+	param.cod_format = GRK_J2K_FMT;
+	param.numresolution = numres;
+	param.cblockw_init = cblkw;
+	param.cblockh_init = cblkh;
+	param.irreversible = irreversible != 0;
+	param.rateControlAlgorithm = rc_algorithm;
+	if (tile_w && tile_h) { param.tile_size_on = true; param.cp_tdx = tile_w; param.cp_tdy = tile_h; }
+	param.tcp_numlayers = numlayers ? numlayers : 1;
+	for (uint32_t i = 0; i < numlayers; ++i) param.tcp_rates[i] = rates[i];
+	if (!numlayers) param.tcp_rates[0] = 0;
+	param.cp_disto_alloc = 1;
+	param.tcp_mct = 255; /* "not set on the command line": decided from the component count, grk_compress.cpp:1996-1998 */
+	g_cb_out = out; g_cb_cap = cap; g_cb_len = -1;
+	int32_t rc = grk_plugin_encode(&param, plugin_cb);
+	int64_t len = rc ? -2 : g_cb_len;
+	grk_plugin_cleanup();
+	return len;
+}
+
 } /* extern "C" */

@@ -100,9 +100,35 @@ def ref():
                                    C.c_void_p, C.c_int, C.c_uint32, u8p, C.c_uint64]
     L.ref_encode_image.restype = C.c_int64
     L.ref_decode_image.argtypes = [u8p, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p), C.c_uint64, u32p]
+    L.ref_plugin_encode_file.argtypes = [C.c_char_p, C.c_char_p] + [C.c_uint32] * 5 + [C.c_int, C.c_uint32, C.c_void_p, C.c_uint32,
+                                         u8p, C.c_uint64]
+    L.ref_plugin_encode_file.restype = C.c_int64
     L.ref_init(int(os.environ.get("GRK_REF_THREADS", "0")) or (os.cpu_count() or 1))
     _ref = L
     return L
+
+
+def write_pnm(path, planes, prec):
+    """binary PGM / PPM (8 or 16 bit big endian), what grk_compress -i reads"""
+    h, w = planes[0].shape
+    nc = len(planes)
+    assert nc in (1, 3)
+    a = np.stack([np.asarray(p) for p in planes], axis=-1)
+    with open(path, "wb") as f:
+        f.write(b"P%d\n%d %d\n%d\n" % (5 if nc == 1 else 6, w, h, (1 << prec) - 1))
+        f.write(a.astype(">u2" if prec > 8 else np.uint8).tobytes())
+
+
+def ref_plugin_encode_file(infile, area, tile=(0, 0), numres=6, cblk=(64, 64), irreversible=False, rates=(), rc_algorithm=1):
+    """`grk_compress -g oracle/_ref -i infile`: grk_plugin_load / init / encode with libgrok_plugin.so (integration/
+    grok_plugin_b200.cpp).  Returns the codestream bytes, or the negative status of ref_plugin_encode_file."""
+    L = ref()
+    cap = area * 4 * 3 + (1 << 20)
+    out = np.zeros(cap, np.uint8)
+    r = np.ascontiguousarray(rates, np.float64)
+    n = L.ref_plugin_encode_file(os.path.join(ORACLE_DIR, "_ref").encode(), infile.encode(), tile[0] or 0, tile[1] or 0, numres,
+                                 cblk[0], cblk[1], int(irreversible), len(r), r.ctypes.data if len(r) else None, rc_algorithm, out, cap)
+    return bytes(out[:n]) if n > 0 else int(n)
 
 
 def ref_encode_image(planes, prec, sgnd=0, tile=(0, 0), numres=6, cblk=(64, 64), irreversible=False, rates=(),

@@ -60,3 +60,29 @@ def test_product_does_not_reference_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 txt = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "gb_oracle" not in txt and "libgrkref" not in txt and "oracle/" not in txt, f
+
+
+PLUGIN_SO = os.path.join(ROOT, "oracle", "_ref", "libgrok_plugin.so")
+# what the host resolves by name with dlsym: grok.cpp:810-822, plugin_bridge.cpp:302-303, minpf_plugin_manager.cpp:146-147
+PLUGIN_ABI = ["minpf_post_load_plugin", "plugin_init", "plugin_encode", "plugin_batch_encode", "plugin_is_batch_complete",
+              "plugin_stop_batch_encode", "plugin_decode", "plugin_init_batch_decode", "plugin_batch_decode", "plugin_stop_batch_decode",
+              "plugin_get_debug_state", "plugin_debug_mqc_next_cxd", "plugin_debug_mqc_next_plane"]
+
+
+@pytest.mark.skipif(not os.path.exists(PLUGIN_SO), reason="oracle/_ref not built")
+def test_plugin_adapter_exports_the_minpf_abi_and_host_falls_back_without_gpu(tmp_path):
+    out = subprocess.check_output(["nm", "-D", "--defined-only", PLUGIN_SO], text=True)
+    exported = set(re.findall(r" T (\w+)", out))
+    for n in PLUGIN_ABI:
+        assert n in exported, n
+    import torch
+    if torch.cuda.is_available():
+        return
+    # the reference's own loader finds, loads and registers the plugin; plugin_init says no (no device), so the host keeps
+    # its CPU path: that is status -1 of the driver, never a silently CPU-computed "plugin" result
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import numpy as np, _libs\n"
+            "_libs.write_pnm(%r, [np.arange(48 * 64, dtype=np.int32).reshape(48, 64) %% 251], 8)\n"
+            "r = _libs.ref_plugin_encode_file(%r, 48 * 64)\n"
+            "assert r == -1, r\n") % (os.path.join(ROOT, "tests"), ROOT, str(tmp_path / "a.pgm"), str(tmp_path / "a.pgm"))
+    subprocess.check_call([os.sys.executable, "-c", code], timeout=120)

@@ -1,0 +1,75 @@
+"""GPU: drop-in parity through Grok's official plugin ABI (SURVEY.md 8(b) "B1").  The unmodified reference is asked
+to encode a PNM file the way `grk_compress -g <dir>` does: grk_plugin_load finds oracle/_ref/libgrok_plugin.so
+(integration/grok_plugin_b200.cpp), plugin_encode runs DC shift + MCT + DWT + quantisation + Tier-1 on the B200 and hands
+the host a grk_plugin_tile; the host's own PCRD, Tier-2 and codestream writer finish the job.  The codestream must be
+byte-identical to a pure CPU run of the reference on the same pixels."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = os.path.join(ROOT, "oracle", "_ref")
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not os.path.exists(os.path.join(REF, "libgrok_plugin.so")), reason="oracle/_ref not built")]
+
+CASES = {
+    # name: (width, height, comps, prec, reversible, numres, cblk, rates)
+    "gray53": (200, 150, 1, 8, True, 5, (32, 32), ()),
+    "rgb53": (260, 200, 3, 8, True, 6, (64, 64), ()),
+    "rgb16_53": (130, 90, 3, 16, True, 3, (64, 64), ()),
+    "rgb97_layers": (256, 200, 3, 8, False, 6, (64, 64), (20, 8, 3)),
+    "gray12_97": (173, 131, 1, 12, False, 6, (32, 16), (12, 4)),
+    "c1_full": (2048, 2048, 1, 8, True, 6, (64, 64), ()),
+}
+
+RUNNER = r"""
+import os, sys
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.dirname(sys.argv[1]))
+import numpy as np, _libs
+from grokimagecompression_b200.synth import synthetic_planes
+from test_gpu_plugin import CASES
+out = {}
+for name in sys.argv[4:]:
+    w, h, nc, prec, rev, numres, cblk, rates = CASES[name]
+    img = synthetic_planes(w, h, nc, prec, seed=len(name) + w)
+    if sys.argv[2] == "plugin":
+        path = os.path.join(os.path.dirname(sys.argv[3]), name + (".pgm" if nc == 1 else ".ppm"))
+        _libs.write_pnm(path, img, prec)
+        cs = _libs.ref_plugin_encode_file(path, w * h * nc, numres=numres, cblk=cblk, irreversible=not rev, rates=rates)
+        assert not isinstance(cs, int), f"{name}: plugin path status {cs}"
+    else:
+        cs = _libs.ref_encode_image(img, prec, numres=numres, cblk=cblk, irreversible=not rev, rates=rates, rc_algorithm=1)
+    out[name] = np.frombuffer(cs, np.uint8)
+    out[name + "_dec"] = np.stack(_libs.ref_decode_image(cs, nc, w, h))
+    out[name + "_img"] = np.stack(img)
+np.savez_compressed(sys.argv[3], **out)
+"""
+
+
+def _run(mode, out, cases):
+    subprocess.check_call([sys.executable, "-c", RUNNER, HERE, mode, out] + cases, timeout=900)
+    return np.load(out)
+
+
+@pytest.mark.parametrize("cases", [["gray53", "rgb53", "rgb16_53"], ["rgb97_layers", "gray12_97"], ["c1_full"]])
+def test_plugin_encode_is_byte_identical(tmp_path, cases):
+    pure = _run("pure", str(tmp_path / "pure.npz"), cases)
+    plug = _run("plugin", str(tmp_path / "plugin.npz"), cases)
+    for name in cases:
+        assert pure[name].tobytes() == plug[name].tobytes(), f"{name}: codestream differs"
+        assert (pure[name + "_dec"] == plug[name + "_dec"]).all()
+        if CASES[name][4]:
+            assert (plug[name + "_dec"] == plug[name + "_img"]).all(), f"{name}: not lossless"
+
+
+def test_multi_tile_request_is_declined(tmp_path):
+    """one grk_plugin_tile describes the whole image (j2k.cpp:2069): the adapter must say no, not mis-encode"""
+    code = RUNNER.replace('cs = _libs.ref_plugin_encode_file(path, w * h * nc, numres=numres',
+                          'cs = _libs.ref_plugin_encode_file(path, w * h * nc, tile=(64, 64), numres=numres')
+    code = code.replace('assert not isinstance(cs, int), f"{name}: plugin path status {cs}"', 'assert cs == -2, cs; sys.exit(0)')
+    subprocess.check_call([sys.executable, "-c", code, HERE, "plugin", str(tmp_path / "x.npz"), "gray53"], timeout=300)
