@@ -315,11 +315,16 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, ENC_MIN_CTAS) t1_model_kernel(
 }
 
 // ---- MQ coder: one thread per code block ------------------------------------------------------------
+// Lean scalar code, MQ_LANES coders per warp: what bounds this kernel is the number of instructions of one
+// coder's serial chain, so the step is written the way the reference's CODEMPS / CODELPS / RENORME are
+// (mqc_enc.cpp:168-243), with the SWITCH column folded into a 94-entry (state, mps) table and A kept in the
+// high half-word so that one CLZ gives the renormalisation shift.
 
-constexpr int MQ_THREADS = 32;
+constexpr int MQ_WARPS = 4;
 #ifndef MQ_LANES
-#define MQ_LANES 8   // active lanes (code blocks) per warp: fewer lanes = fewer distinct paths per step (measured 1..32)
+#define MQ_LANES 2   // active lanes (code blocks) per warp
 #endif
+constexpr int MQ_CTX_WORDS = 20;
 
 struct MqT {
 	uint32_t a, c;     // A kept in the high half-word (a << 16) so that the renormalisation shift is clz(a)
@@ -341,108 +346,102 @@ __device__ __forceinline__ void mqt_byteout(MqT &q, uint8_t *out, uint32_t cap, 
 	else { q.last = (q.c >> 19) & 0xFF; q.c &= 0x7FFFFu; q.ct = 8; }
 }
 
-__global__ void __launch_bounds__(MQ_THREADS) t1_mq_kernel(const EncBlock *__restrict__ blocks, uint32_t nblocks,
+__global__ void __launch_bounds__(MQ_WARPS * 32) t1_mq_kernel(const EncBlock *__restrict__ blocks, uint32_t nblocks,
 		const uint8_t *__restrict__ symbols, uint8_t *__restrict__ scratch, EncResult *__restrict__ results,
 		uint32_t *__restrict__ rates) {
-	// packed Table C.2 rows: qe << 16 | switch << 13 | nlps << 6 | nmps ; bit 12 of a context entry = its MPS
-	__shared__ uint32_t tab[47];
-	__shared__ uint32_t ctx[NCTX][MQ_THREADS];
-	for (int i = threadIdx.x; i < 47; i += MQ_THREADS) {
-		const uint32_t r = c_mq[i];
-		tab[i] = (r << 16) | ((r >> 28) & 1u) << 13 | ((r >> 22) & 63u) << 6 | ((r >> 16) & 63u);
+	// context rows: qe << 16 | mps << 15 | next(LPS) << 8 | next(MPS); successors index the (state, mps) table
+	__shared__ uint32_t tab[96];
+	__shared__ uint32_t ctx[MQ_WARPS * MQ_LANES][MQ_CTX_WORDS];
+	for (int i = threadIdx.x; i < 94; i += blockDim.x) {
+		const uint32_t r = c_mq[i >> 1], mps = i & 1u, sw = (r >> 28) & 1u;
+		const uint32_t nm = ((r >> 16) & 63u) * 2u + mps, nl = ((r >> 22) & 63u) * 2u + (mps ^ sw);
+		tab[i] = (r << 16) | (mps << 15) | (nl << 8) | nm;
 	}
 	__syncthreads();
-	const int tid = threadIdx.x;
-	if (tid >= MQ_LANES) return;
-	const uint32_t bid = blockIdx.x * MQ_LANES + tid;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	if (lane >= MQ_LANES) return;
+	int slot = warp * MQ_LANES + lane;
+	const uint32_t bid = blockIdx.x * (MQ_WARPS * MQ_LANES) + (uint32_t) slot;
 	if (bid >= nblocks) return;
 	EncResult res = results[bid];
 	if (res.numbps == 0 || res.numpasses == 0 || res.numpasses == 0xFFFFFFFFu) return;
 	const EncBlock B = blocks[bid];
+	asm volatile("" : "+r"(slot)); // keep the context base in a register instead of re-deriving it from the thread index per symbol
+	uint32_t *C = ctx[slot];
 	#pragma unroll
-	for (int i = 0; i < NCTX; ++i) ctx[i][tid] = tab[i == CTX_ZC0 ? 4 : i == CTX_AGG ? 3 : i == CTX_UNI ? 46 : 0]; // mqc_dec.cpp:207-214
+	for (int i = 0; i < NCTX; ++i) C[i] = tab[2 * (i == CTX_ZC0 ? 4 : i == CTX_AGG ? 3 : i == CTX_UNI ? 46 : 0)]; // mqc_dec.cpp:207-214
 	uint8_t *out = scratch + B.scratch_off + 1;
 	const uint32_t cap = B.scratch_cap - 1;
 	uint32_t *my_rates = rates + B.pass_offset;
 	uint32_t overflow = 0, nsym = 0;
+	int npass = 0;
 	MqT q;
 	q.a = 0x80000000u; q.c = 0; q.ct = 12; q.pos = -1; q.last = 0;
 
-	// Symbols arrive eight at a time (the load after them already in flight); the context row of the NEXT
-	// symbol is fetched before the current one is coded, and patched if the current one changes that very
-	// context.  The step itself is branch free (selects) so that the short A-register recurrence
-	// (subtract, compare, select, clz, shift) is not serialised behind the table and C-register work;
-	// only the completion of an output byte branches.
+	// CODEMPS / CODELPS + RENORME for one (context, decision) byte
+	auto code = [&](uint32_t sym) {
+		uint32_t *cr = C + (sym >> 1);
+		const uint32_t row = *cr;
+		const uint32_t qs = row & 0xFFFF0000u;
+		q.a -= qs;
+		if (((row >> 15) ^ sym) & 1u) { // CODELPS
+			if (q.a < qs) q.c += qs >> 16; else q.a = qs;
+			*cr = tab[(row >> 8) & 0x7Fu];
+		} else {                        // CODEMPS
+			if (q.a & 0x80000000u) { q.c += qs >> 16; return; }
+			if (q.a < qs) q.a = qs; else q.c += qs >> 16;
+			*cr = tab[row & 0x7Fu];
+		}
+		int sh = __clz(q.a); // RENORME
+		q.a <<= sh;
+		while (sh >= q.ct) { // a byte is completed inside this shift
+			q.c <<= q.ct;
+			sh -= q.ct;
+			mqt_byteout(q, out, cap, overflow);
+		}
+		q.c <<= sh;
+		q.ct -= sh;
+	};
+
+	// one byte per symbol, 0x80 / 0x81 close a coding pass; eight symbols per load, the next eight already in flight.
+	// Groups without a marker (all but ~1 in 200) run fully unrolled.
 	const uint2 *sp = reinterpret_cast<const uint2*>(symbols + B.sym_off); // sym_off is 16-byte aligned
-	uint2 nxt = sp[1];
-	int word = 2, npass = 0;
-	uint64_t buf;
-	{ const uint2 cur = sp[0]; buf = (uint64_t) cur.x | ((uint64_t) cur.y << 32); }
-	int have = 7;
-	uint32_t sym = (uint32_t) buf & 0xFFu;
-	buf >>= 8;
-	uint32_t row = (sym & 0x80u) ? 0u : ctx[sym >> 1][tid];
+	uint2 nxt = sp[0];
+	uint32_t word = 1, consumed = 0;
 	bool done = false;
 	while (!done) {
-		// fetch the following symbol and its context row
-		if (have == 0) {
-			buf = (uint64_t) nxt.x | ((uint64_t) nxt.y << 32);
-			nxt = sp[word++];
-			have = 8;
-		}
-		const uint32_t symn = (uint32_t) buf & 0xFFu;
-		buf >>= 8;
-		have--;
-		const uint32_t cxn = (symn & 0x80u) ? 0u : symn >> 1;
-		uint32_t rown = ctx[cxn][tid];
-		if (sym & 0x80u) { // end of a coding pass (t1.cpp:1255-1290)
-			uint32_t rate;
-			if (sym == SYM_FLUSH_END) { // FLUSH, mqc_enc.cpp:235-243, 274-287
-				const uint32_t areg = q.a >> 16;
-				const uint32_t t = q.c + areg;
-				q.c |= 0xFFFFu;
-				if (q.c >= t) q.c -= 0x8000u;
-				q.c <<= q.ct; mqt_byteout(q, out, cap, overflow);
-				q.c <<= q.ct; mqt_byteout(q, out, cap, overflow);
-				if (q.last != 0xFF) {
-					if ((uint32_t) q.pos < cap) out[q.pos] = (uint8_t) q.last; else overflow = 1;
-					q.pos++;
-				}
-				rate = (uint32_t) q.pos;
-				done = true;
-			} else rate = (uint32_t) q.pos + (q.ct < 5 ? 6 : 5);
-			if ((uint32_t) npass < B.max_passes) my_rates[npass] = rate;
-			npass++;
+		const uint2 cur = nxt;
+		nxt = sp[word++];
+		if (((cur.x | cur.y) & 0x80808080u) == 0) {
+			#pragma unroll
+			for (int j = 0; j < 8; ++j) code(((j < 4 ? cur.x : cur.y) >> (8 * (j & 3))) & 0xFFu);
 		} else {
-			nsym++;
-			const uint32_t cx = sym >> 1, d = sym & 1u;
-			const uint32_t qs = row & 0xFFFF0000u, qe = row >> 16, mpsbit = (row >> 12) & 1u;
-			const bool ismps = d == mpsbit;
-			const uint32_t a1 = q.a - qs;
-			const bool norenorm = ismps && (a1 & 0x80000000u);
-			const bool small = a1 < qs;
-			const bool takeq = !norenorm && (ismps == small); // MPS: A<Qe ? A=Qe : C+=Qe ; LPS: A<Qe ? C+=Qe : A=Qe
-			const uint32_t a2 = takeq ? qs : a1;
-			q.c += takeq ? 0u : qe;
-			const uint32_t next = ismps ? row & 63u : (row >> 6) & 63u;
-			const uint32_t mps = mpsbit ^ (ismps ? 0u : (row >> 13) & 1u);
-			const uint32_t newrow = norenorm ? row : (tab[next] | (mps << 12));
-			ctx[cx][tid] = newrow;
-			if (cxn == cx) rown = newrow;
-			int sh = __clz(a2); // 0 when no renormalisation is due
-			q.a = a2 << sh;
-			if (sh >= q.ct) { // a byte is completed inside this shift
-				do {
-					q.c <<= q.ct;
-					sh -= q.ct;
-					mqt_byteout(q, out, cap, overflow);
-				} while (sh >= q.ct);
+			uint64_t grp = (uint64_t) cur.x | ((uint64_t) cur.y << 32);
+			#pragma unroll 1
+			for (uint32_t j = 0; j < 8 && !done; ++j, grp >>= 8) {
+				const uint32_t sym = (uint32_t) grp & 0xFFu;
+				if (!(sym & 0x80u)) { code(sym); continue; }
+				// end of a coding pass (t1.cpp:1255-1290)
+				uint32_t rate;
+				if (sym == SYM_FLUSH_END) { // FLUSH, mqc_enc.cpp:235-243, 274-287
+					const uint32_t t = q.c + (q.a >> 16);
+					q.c |= 0xFFFFu;
+					if (q.c >= t) q.c -= 0x8000u;
+					q.c <<= q.ct; mqt_byteout(q, out, cap, overflow);
+					q.c <<= q.ct; mqt_byteout(q, out, cap, overflow);
+					if (q.last != 0xFF) {
+						if ((uint32_t) q.pos < cap) out[q.pos] = (uint8_t) q.last; else overflow = 1;
+						q.pos++;
+					}
+					rate = (uint32_t) q.pos;
+					nsym = consumed + j - (uint32_t) npass;
+					done = true;
+				} else rate = (uint32_t) q.pos + (q.ct < 5 ? 6 : 5);
+				if ((uint32_t) npass < B.max_passes) my_rates[npass] = rate;
+				npass++;
 			}
-			q.c <<= sh;
-			q.ct -= sh;
 		}
-		sym = symn;
-		row = rown;
+		consumed += 8;
 	}
 	// ---- rate fix-ups (t1.cpp:1300-1324): non-increasing from the end, no trailing 0xFF ------
 	const int np = min(npass, (int) B.max_passes);
@@ -498,7 +497,7 @@ void launch_t1_encode(const EncBlock *blocks, uint32_t nblocks, int rate_control
 	if (!nblocks) return;
 	if (!g_tables_ready) { build_and_upload_t1_tables(); g_tables_ready = true; }
 	t1_model_kernel<<<(nblocks + ENC_WARPS - 1) / ENC_WARPS, ENC_WARPS * 32, 0, s>>>(blocks, nblocks, rate_control, symbols, results, dists);
-	t1_mq_kernel<<<(nblocks + MQ_LANES - 1) / MQ_LANES, MQ_THREADS, 0, s>>>(blocks, nblocks, symbols, scratch, results, rates);
+	t1_mq_kernel<<<(nblocks + MQ_WARPS * MQ_LANES - 1) / (MQ_WARPS * MQ_LANES), MQ_WARPS * 32, 0, s>>>(blocks, nblocks, symbols, scratch, results, rates);
 }
 
 // bytes of symbol stream to reserve for a w x h block with at most `planes` coded bit-planes: every sample
