@@ -379,6 +379,9 @@ __global__ void __launch_bounds__(MQ_WARPS * 32) t1_mq_kernel(const EncBlock *__
 	q.a = 0x80000000u; q.c = 0; q.ct = 12; q.pos = -1; q.last = 0;
 
 	// CODEMPS / CODELPS + RENORME for one (context, decision) byte
+	uint32_t tab_s = (uint32_t) __cvta_generic_to_shared(tab);
+	asm volatile("" : "+r"(tab_s)); // the shared-window address of the table stays in a register
+	auto tabrow = [&](uint32_t i) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(tab_s + 4u * i)); return v; };
 	auto code = [&](uint32_t sym) {
 		uint32_t *cr = C + (sym >> 1);
 		const uint32_t row = *cr;
@@ -386,11 +389,11 @@ __global__ void __launch_bounds__(MQ_WARPS * 32) t1_mq_kernel(const EncBlock *__
 		q.a -= qs;
 		if (((row >> 15) ^ sym) & 1u) { // CODELPS
 			if (q.a < qs) q.c += qs >> 16; else q.a = qs;
-			*cr = tab[(row >> 8) & 0x7Fu];
+			*cr = tabrow((row >> 8) & 0x7Fu);
 		} else {                        // CODEMPS
 			if (q.a & 0x80000000u) { q.c += qs >> 16; return; }
 			if (q.a < qs) q.a = qs; else q.c += qs >> 16;
-			*cr = tab[row & 0x7Fu];
+			*cr = tabrow(row & 0x7Fu);
 		}
 		int sh = __clz(q.a); // RENORME
 		q.a <<= sh;
