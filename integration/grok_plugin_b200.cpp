@@ -46,7 +46,7 @@ namespace {
 
 gb200_ctx *g_ctx = nullptr;
 bool g_verbose = false;
-uint64_t g_encodes = 0, g_blocks = 0;
+uint64_t g_encodes = 0, g_blocks = 0, g_decodes = 0;
 
 void say(const char *what) {
 	if (g_verbose) fprintf(stderr, "grok_plugin_b200: %s: %s\n", what, gb200_last_error());
@@ -177,83 +177,12 @@ struct Tree {
 	std::vector<uint8_t> data;
 };
 
-} // namespace
-
-/* ---- minpf registration (minpf_plugin.h:24-57, loader minpf_plugin_manager.cpp:146-162) --------------------- */
-extern "C" PLUGIN_API int32_t grok_b200_plugin_exit() {
-	if (g_ctx) { gb200_destroy(g_ctx); g_ctx = nullptr; }
-	return 0;
-}
-static void *plugin_create(grk::minpf_object_params *) { return nullptr; }
-static int32_t plugin_destroy(void *) { return 0; }
-
-extern "C" PLUGIN_API grk::minpf_exit_func minpf_post_load_plugin(const char *, const grk::minpf_platform_services *services) {
-	grk::minpf_register_params rp;
-	rp.version.major = 1; /* must equal the host's, minpf_plugin_manager.cpp:59-61 */
-	rp.version.minor = 0;
-	rp.createFunc = plugin_create;
-	rp.destroyFunc = plugin_destroy;
-	if (!services || services->registerObject("GrokB200", &rp) < 0) return nullptr;
-	return grok_b200_plugin_exit;
-}
-
-extern "C" PLUGIN_API bool plugin_init(grk_plugin_init_info info) {
-	g_verbose = info.verbose;
-	if (g_ctx) return true;
-	const char *d = getenv("GROK_B200_DEVICE");
-	const int dev = d ? atoi(d) : (info.deviceId > 0 ? info.deviceId : 0);
-	if (gb200_create(dev, &g_ctx) != GB200_OK) { /* false => the host silently keeps its CPU path */
-		say("plugin_init");
-		g_ctx = nullptr;
-		return false;
-	}
-	return true;
-}
-
-/* counters for the parity tests: 0 = images encoded on the device, 1 = code blocks handed to the host */
-extern "C" PLUGIN_API uint64_t grok_b200_plugin_stat(int i) { return i == 0 ? g_encodes : g_blocks; }
-
-/* ---- encode -------------------------------------------------------------------------------------------------- */
-extern "C" PLUGIN_API int32_t plugin_encode(grk_cparameters *p, grk::PLUGIN_ENCODE_USER_CALLBACK callback) {
-	if (!g_ctx || !p || !callback) return -1;
-	/* what the single grk_plugin_tile of this ABI, or this build of the kernels, cannot express -> host CPU path */
-	if (p->isHT || p->cblk_sty != 0 || p->roi_compno >= 0 || p->decod_format != GRK_PXM_FMT) return 1;
-	grk_image *img = read_pnm(p);
-	if (!img) return 2;
-	struct ImgGuard { grk_image *i; ~ImgGuard() { grk_image_destroy(i); } } guard{img};
-	if (p->tile_size_on && (p->cp_tx0 + p->cp_tdx < img->x1 || p->cp_ty0 + p->cp_tdy < img->y1)) return 1; /* more than one tile */
-	const uint32_t nc = img->numcomps;
-	/* MCT decision of grk_compress.cpp:1996-1998 and j2k.cpp:1961-1970 */
-	bool mct = p->tcp_mct == 255 ? nc >= 3 : p->tcp_mct == 1;
-	if (p->tcp_mct > 1 && p->tcp_mct != 255) return 1; /* array based MCT */
-	if (mct && nc < 3) return 1;
-	std::vector<gb200_comp_params> cps(nc);
-	for (uint32_t c = 0; c < nc; ++c) fill_comp(p, img, c, mct, cps[c]);
-	gb200_tile_params tp;
-	memset(&tp, 0, sizeof(tp));
-	tp.numcomps = nc;
-	tp.mct = mct ? 1 : 0;
-	tp.rate_control = 1; /* the host decides later whether it uses the distortions (needs_rate_control) */
-	tp.comps = cps.data();
-	gb200_plan *plan = nullptr;
-	if (gb200_plan_create(g_ctx, 1, &tp, 1, &plan) != GB200_OK) { say("gb200_plan_create"); return 3; }
-	struct PlanGuard { gb200_plan *p; ~PlanGuard() { gb200_plan_destroy(p); } } pguard{plan};
+/* the tree, sized from the block table of a plan (host order: comp, resno, band, precinct, block) */
+void build_tree(Tree &T, gb200_plan *plan, uint32_t nc, const gb200_comp_params *cps) {
 	const size_t nb = gb200_plan_num_blocks(plan);
-	std::vector<gb200_cblk_enc> enc(nb);
-	std::vector<uint32_t> rates(gb200_plan_num_pass_slots(plan) + 1);
-	std::vector<double> dists(gb200_plan_num_pass_slots(plan) + 1);
-	Tree T;
-	T.data.resize(gb200_plan_data_capacity(plan) + 16);
-	std::vector<const int32_t*> planes(nc);
-	for (uint32_t c = 0; c < nc; ++c) planes[c] = img->comps[c].data;
-	uint64_t len = 0;
-	if (gb200_encode_tiles(plan, planes.data(), enc.data(), rates.data(), dists.data(), T.data.data(), T.data.size(), &len) != GB200_OK) {
-		say("gb200_encode_tiles");
-		return 4;
-	}
-	/* ---- the tree, sized from the block table (host order: comp, resno, band, precinct, block) ---- */
 	const gb200_cblk_info *info = gb200_plan_blocks(plan);
 	T.blocks.resize(nb);
+	for (auto &b : T.blocks) memset(&b, 0, sizeof(b));
 	T.comps.resize(nc);
 	T.comp_ptrs.resize(nc);
 	for (uint32_t c = 0; c < nc; ++c) {
@@ -304,10 +233,95 @@ extern "C" PLUGIN_API int32_t plugin_encode(grk_cparameters *p, grk::PLUGIN_ENCO
 	}
 	for (size_t i = 0; i < nb; ++i) {
 		grk_plugin_code_block &B = T.blocks[i];
-		memset(&B, 0, sizeof(B));
-		const gb200_cblk_enc &e = enc[i];
 		B.x0 = info[i].x0; B.y0 = info[i].y0; B.x1 = info[i].x1; B.y1 = info[i].y1;
 		B.numPix = (size_t) (B.x1 - B.x0) * (B.y1 - B.y0);
+		B.sortedIndex = (unsigned int) i;
+	}
+	T.tile.decode_flags = 0;
+	T.tile.numComponents = nc;
+	T.tile.tileComponents = T.comp_ptrs.data();
+}
+
+
+} // namespace
+
+/* ---- minpf registration (minpf_plugin.h:24-57, loader minpf_plugin_manager.cpp:146-162) --------------------- */
+extern "C" PLUGIN_API int32_t grok_b200_plugin_exit() {
+	if (g_ctx) { gb200_destroy(g_ctx); g_ctx = nullptr; }
+	return 0;
+}
+static void *plugin_create(grk::minpf_object_params *) { return nullptr; }
+static int32_t plugin_destroy(void *) { return 0; }
+
+extern "C" PLUGIN_API grk::minpf_exit_func minpf_post_load_plugin(const char *, const grk::minpf_platform_services *services) {
+	grk::minpf_register_params rp;
+	rp.version.major = 1; /* must equal the host's, minpf_plugin_manager.cpp:59-61 */
+	rp.version.minor = 0;
+	rp.createFunc = plugin_create;
+	rp.destroyFunc = plugin_destroy;
+	if (!services || services->registerObject("GrokB200", &rp) < 0) return nullptr;
+	return grok_b200_plugin_exit;
+}
+
+extern "C" PLUGIN_API bool plugin_init(grk_plugin_init_info info) {
+	g_verbose = info.verbose;
+	if (g_ctx) return true;
+	const char *d = getenv("GROK_B200_DEVICE");
+	const int dev = d ? atoi(d) : (info.deviceId > 0 ? info.deviceId : 0);
+	if (gb200_create(dev, &g_ctx) != GB200_OK) { /* false => the host silently keeps its CPU path */
+		say("plugin_init");
+		g_ctx = nullptr;
+		return false;
+	}
+	return true;
+}
+
+/* counters for the parity tests: 0 = images encoded on the device, 1 = code blocks handed to the host */
+extern "C" PLUGIN_API uint64_t grok_b200_plugin_stat(int i) { return i == 0 ? g_encodes : i == 1 ? g_blocks : g_decodes; }
+
+/* ---- encode -------------------------------------------------------------------------------------------------- */
+extern "C" PLUGIN_API int32_t plugin_encode(grk_cparameters *p, grk::PLUGIN_ENCODE_USER_CALLBACK callback) {
+	if (!g_ctx || !p || !callback) return -1;
+	/* what the single grk_plugin_tile of this ABI, or this build of the kernels, cannot express -> host CPU path */
+	if (p->isHT || p->cblk_sty != 0 || p->roi_compno >= 0 || p->decod_format != GRK_PXM_FMT) return 1;
+	grk_image *img = read_pnm(p);
+	if (!img) return 2;
+	struct ImgGuard { grk_image *i; ~ImgGuard() { grk_image_destroy(i); } } guard{img};
+	if (p->tile_size_on && (p->cp_tx0 + p->cp_tdx < img->x1 || p->cp_ty0 + p->cp_tdy < img->y1)) return 1; /* more than one tile */
+	const uint32_t nc = img->numcomps;
+	/* MCT decision of grk_compress.cpp:1996-1998 and j2k.cpp:1961-1970 */
+	bool mct = p->tcp_mct == 255 ? nc >= 3 : p->tcp_mct == 1;
+	if (p->tcp_mct > 1 && p->tcp_mct != 255) return 1; /* array based MCT */
+	if (mct && nc < 3) return 1;
+	std::vector<gb200_comp_params> cps(nc);
+	for (uint32_t c = 0; c < nc; ++c) fill_comp(p, img, c, mct, cps[c]);
+	gb200_tile_params tp;
+	memset(&tp, 0, sizeof(tp));
+	tp.numcomps = nc;
+	tp.mct = mct ? 1 : 0;
+	tp.rate_control = 1; /* the host decides later whether it uses the distortions (needs_rate_control) */
+	tp.comps = cps.data();
+	gb200_plan *plan = nullptr;
+	if (gb200_plan_create(g_ctx, 1, &tp, 1, &plan) != GB200_OK) { say("gb200_plan_create"); return 3; }
+	struct PlanGuard { gb200_plan *p; ~PlanGuard() { gb200_plan_destroy(p); } } pguard{plan};
+	const size_t nb = gb200_plan_num_blocks(plan);
+	std::vector<gb200_cblk_enc> enc(nb);
+	std::vector<uint32_t> rates(gb200_plan_num_pass_slots(plan) + 1);
+	std::vector<double> dists(gb200_plan_num_pass_slots(plan) + 1);
+	Tree T;
+	T.data.resize(gb200_plan_data_capacity(plan) + 16);
+	std::vector<const int32_t*> planes(nc);
+	for (uint32_t c = 0; c < nc; ++c) planes[c] = img->comps[c].data;
+	uint64_t len = 0;
+	if (gb200_encode_tiles(plan, planes.data(), enc.data(), rates.data(), dists.data(), T.data.data(), T.data.size(), &len) != GB200_OK) {
+		say("gb200_encode_tiles");
+		return 4;
+	}
+	build_tree(T, plan, nc, cps.data());
+	const gb200_cblk_info *info = gb200_plan_blocks(plan);
+	for (size_t i = 0; i < nb; ++i) {
+		grk_plugin_code_block &B = T.blocks[i];
+		const gb200_cblk_enc &e = enc[i];
 		B.compressedData = T.data.data() + e.data_offset;
 		B.compressedDataLength = e.data_len;
 		B.numBitPlanes = e.numbps;
@@ -320,11 +334,7 @@ extern "C" PLUGIN_API int32_t plugin_encode(grk_cparameters *p, grk::PLUGIN_ENCO
 			B.passes[k].rate = r ? r - 1 : 0; /* host: min(rate + 1, total), plugin_bridge.cpp:236 */
 			B.passes[k].length = r - (k ? rates[po + k - 1] : 0);
 		}
-		B.sortedIndex = (unsigned int) i;
 	}
-	T.tile.decode_flags = 0;
-	T.tile.numComponents = nc;
-	T.tile.tileComponents = T.comp_ptrs.data();
 	g_encodes++;
 	g_blocks += nb;
 
@@ -345,12 +355,160 @@ extern "C" PLUGIN_API int32_t plugin_encode(grk_cparameters *p, grk::PLUGIN_ENCO
 	return cbinfo.error_code;
 }
 
-/* the batch / decode entry points of the ABI are exported so that the host's dlsym succeeds; they report
- * "not handled" and the host keeps its own path (grk_compress.cpp:2215-2219, grk_decompress.cpp) */
+/* ---- decode --------------------------------------------------------------------------------------------------
+ * The staged protocol of grk_decompress.cpp:1336-1560 (decode_callback / pre_decode / post_decode):
+ *   1. callback(HEADER) with init_decoders_func set: the host opens its stream, reads the header and calls back
+ *      into decode_init below with the header info and the image -> geometry, tree, byte arena;
+ *   2. callback(T2) with the tree: the host parses packets and copies every block's segment bytes, bit-plane and
+ *      pass counts and the band step sizes into the tree (decode_synch_plugin_with_host, plugin_bridge.cpp:24-87),
+ *      then destroys its codec;
+ *   3. Tier-1 + de-quantisation + inverse DWT + inverse MCT + level shift/clamp run on the device
+ *      (gb200_decode_tiles) straight into image->comps[].data;
+ *   4. callback(POST_T1): the host stores the image; callback(CLEAN): it frees it. */
+namespace {
+
+struct DecodeJob {
+	uint32_t reduce = 0;
+	uint32_t nc = 0;
+	std::vector<gb200_comp_params> cps;
+	gb200_tile_params tp;
+	Tree T;
+	std::vector<uint64_t> offset; /* of each block in T.data */
+	bool ready = false;
+	int status = 0;
+};
+DecodeJob *g_job = nullptr;
+
+int decode_init(grk_header_info *h, grk_image *img) {
+	using namespace grk;
+	DecodeJob &J = *g_job;
+	J.status = 1;
+	if (!h || !img || !g_ctx) return 1;
+	/* what one grk_plugin_tile / this build of the kernels cannot express: the host decodes on its own */
+	if (h->cp_tw * h->cp_th != 1 || h->cblk_sty != 0 || h->mct > 1) return 1;
+	if (J.reduce >= h->numresolutions) return 1;
+	const uint32_t nc = img->numcomps;
+	J.nc = nc;
+	J.cps.assign(nc, gb200_comp_params());
+	for (uint32_t c = 0; c < nc; ++c) {
+		gb200_comp_params &cp = J.cps[c];
+		memset(&cp, 0, sizeof(cp));
+		const grk_image_comp *ic = img->comps + c;
+		cp.x0 = ceildiv<uint32_t>(img->x0, ic->dx); cp.y0 = ceildiv<uint32_t>(img->y0, ic->dy);
+		cp.x1 = ceildiv<uint32_t>(img->x1, ic->dx); cp.y1 = ceildiv<uint32_t>(img->y1, ic->dy);
+		cp.numres = h->numresolutions;
+		cp.cblkw_expn = uint_floorlog2(h->cblockw_init); cp.cblkh_expn = uint_floorlog2(h->cblockh_init);
+		for (uint32_t r = 0; r < cp.numres; ++r) { cp.prcw_expn[r] = uint_floorlog2(h->prcw_init[r]); cp.prch_expn[r] = uint_floorlog2(h->prch_init[r]); }
+		cp.qmfbid = h->irreversible ? 0 : 1;
+		cp.prec = ic->prec; cp.sgnd = ic->sgnd;
+		cp.dc_shift = ic->sgnd ? 0 : 1 << (ic->prec - 1);
+		for (uint32_t b = 0; b < 3 * cp.numres - 2; ++b) { cp.stepsize[b] = 1.0f; cp.inv_step[b] = 8192; cp.band_numbps[b] = 30; cp.rd_weight[b] = 1.0; }
+	}
+	memset(&J.tp, 0, sizeof(J.tp));
+	J.tp.numcomps = nc;
+	J.tp.mct = h->mct;
+	J.tp.numres_decode = 0; /* the tree spans every resolution; the decode plan is cut to numresolutions - reduce later */
+	J.tp.comps = J.cps.data();
+	gb200_plan *geo = nullptr; /* only for its block table */
+	if (gb200_plan_create(g_ctx, 1, &J.tp, 0, &geo) != GB200_OK) { say("gb200_plan_create"); return 1; }
+	build_tree(J.T, geo, nc, J.cps.data());
+	/* the host writes each block's bytes without a capacity field (plugin_bridge.cpp:71-78): give every block the
+	 * reference encoder's own worst case (TileProcessor.cpp:2003-2018) plus slack */
+	const size_t nb = J.T.blocks.size();
+	J.offset.resize(nb);
+	uint64_t total = 0;
+	for (size_t i = 0; i < nb; ++i) { J.offset[i] = total; total += (J.T.blocks[i].numPix * 4 + 64 + 15) / 16 * 16; }
+	J.T.data.assign(total + 64, 0);
+	for (size_t i = 0; i < nb; ++i) J.T.blocks[i].compressedData = J.T.data.data() + J.offset[i];
+	gb200_plan_destroy(geo);
+	J.ready = true;
+	J.status = 0;
+	return 0;
+}
+
+} // namespace
+
+extern "C" PLUGIN_API int32_t plugin_decode(grk_decompress_parameters *dp, grk::PLUGIN_DECODE_USER_CALLBACK callback) {
+	if (!g_ctx || !dp || !callback) return -1;
+	DecodeJob J;
+	J.reduce = dp->core.cp_reduce;
+	g_job = &J;
+	grk::PluginDecodeCallbackInfo info(dp->infile, dp->outfile, dp, dp->decod_format, GRK_DECODE_HEADER);
+	info.init_decoders_func = decode_init;
+	auto clean = [&](int32_t rc) {
+		info.decode_flags = GRK_PLUGIN_DECODE_CLEAN;
+		info.init_decoders_func = nullptr;
+		try { callback(&info); } catch (...) {}
+		g_job = nullptr;
+		return rc;
+	};
+	int32_t rc;
+	try { rc = callback(&info); } catch (...) { rc = 7; }
+	if (rc || !J.ready) return clean(rc ? rc : 1);
+	info.init_decoders_func = nullptr;
+	info.tile = &J.T.tile;
+	info.decode_flags = GRK_DECODE_T2;
+	try { rc = callback(&info); } catch (...) { rc = 7; } /* PluginDecodeUnsupportedException: multi-segment blocks etc. */
+	if (rc || !info.image) return clean(rc ? rc : 1);
+	/* ---- device decode ---- */
+	const size_t nb = J.T.blocks.size();
+	for (uint32_t c = 0; c < J.nc; ++c) {
+		const grk_plugin_tile_component *tc = J.T.tile.tileComponents[c];
+		for (uint32_t r = 0; r < tc->numResolutions; ++r)
+			for (uint32_t b = 0; b < tc->resolutions[r]->numBands; ++b)
+				J.cps[c].stepsize[r ? 3 * r - 2 + b : 0] = tc->resolutions[r]->bands[b]->stepsize; /* carries the decoder's x0.5 */
+	}
+	J.tp.numres_decode = J.cps[0].numres - J.reduce;
+	gb200_plan *plan = nullptr;
+	if (gb200_plan_create(g_ctx, 1, &J.tp, 0, &plan) != GB200_OK) { say("gb200_plan_create"); return clean(3); }
+	struct PlanGuard { gb200_plan *p; ~PlanGuard() { gb200_plan_destroy(p); } } pguard{plan};
+	const size_t nbd = gb200_plan_num_blocks(plan); /* blocks of the resolutions that are reconstructed */
+	const gb200_cblk_info *dinfo = gb200_plan_blocks(plan);
+	std::vector<gb200_cblk_dec> in(nbd);
+	{ /* the reduced table is the full one minus the blocks of the dropped resolutions, same order */
+		size_t i = 0;
+		const gb200_cblk_info *unused = nullptr; (void) unused;
+		gb200_plan *full = nullptr;
+		gb200_tile_params tpf = J.tp;
+		tpf.numres_decode = 0;
+		if (gb200_plan_create(g_ctx, 1, &tpf, 0, &full) != GB200_OK) return clean(3);
+		const gb200_cblk_info *finfo = gb200_plan_blocks(full);
+		for (size_t k = 0; k < nb && i < nbd; ++k) {
+			if (finfo[k].compno != dinfo[i].compno || finfo[k].resno != dinfo[i].resno || finfo[k].bandno != dinfo[i].bandno
+					|| finfo[k].precno != dinfo[i].precno || finfo[k].cblkno != dinfo[i].cblkno) continue;
+			const grk_plugin_code_block &B = J.T.blocks[k];
+			memset(&in[i], 0, sizeof(in[i]));
+			in[i].numbps = (uint32_t) B.numBitPlanes;
+			in[i].numpasses = (uint32_t) B.numPasses;
+			in[i].data_len = (uint32_t) B.compressedDataLength;
+			in[i].data_offset = J.offset[k];
+			++i;
+		}
+		gb200_plan_destroy(full);
+		if (i != nbd) return clean(5);
+	}
+	std::vector<int32_t*> planes(J.nc);
+	for (uint32_t c = 0; c < J.nc; ++c) {
+		grk_image_comp *ic = info.image->comps + c;
+		const uint32_t top = J.reduce;
+		const uint32_t w = grk::uint_ceildivpow2(J.cps[c].x1, top) - grk::uint_ceildivpow2(J.cps[c].x0, top);
+		const uint32_t hgt = grk::uint_ceildivpow2(J.cps[c].y1, top) - grk::uint_ceildivpow2(J.cps[c].y0, top);
+		if (ic->w != w || ic->h != hgt) return clean(5);
+		if (!ic->data && !grk_image_single_component_data_alloc(ic)) return clean(5);
+		planes[c] = ic->data;
+	}
+	if (gb200_decode_tiles(plan, in.data(), J.T.data.data(), J.T.data.size() - 64, planes.data()) != GB200_OK) { say("gb200_decode_tiles"); return clean(4); }
+	g_decodes++;
+	info.decode_flags = GRK_DECODE_POST_T1;
+	try { rc = callback(&info); } catch (...) { rc = 7; }
+	return clean(rc);
+}
+
+/* the batch entry points of the ABI are exported so that the host's dlsym succeeds; they report "not handled" and the
+ * host keeps its own frame loop (grk_compress.cpp:2215-2219, grk_decompress.cpp) */
 extern "C" PLUGIN_API int32_t plugin_batch_encode(const char *, const char *, grk_cparameters *, grk::PLUGIN_ENCODE_USER_CALLBACK) { return -1; }
 extern "C" PLUGIN_API bool plugin_is_batch_complete(void) { return true; }
 extern "C" PLUGIN_API void plugin_stop_batch_encode(void) {}
-extern "C" PLUGIN_API int32_t plugin_decode(grk_decompress_parameters *, grk::PLUGIN_DECODE_USER_CALLBACK) { return -1; }
 extern "C" PLUGIN_API int32_t plugin_init_batch_decode(const char *, const char *, grk_decompress_parameters *, grk::PLUGIN_DECODE_USER_CALLBACK) { return -1; }
 extern "C" PLUGIN_API int32_t plugin_batch_decode(void) { return -1; }
 extern "C" PLUGIN_API void plugin_stop_batch_decode(void) {}

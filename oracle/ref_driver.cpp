@@ -382,4 +382,102 @@ int64_t ref_plugin_encode_file(const char *plugin_dir, const char *infile, uint3
 	return len;
 }
 
+/* ---- the official plugin path, decode: grk_plugin_load / init / decode with a callback that mirrors decode_callback /
+ * pre_decode / post_decode of grk_decompress.cpp:1336-1560, reading the codestream from memory and handing the pixels
+ * back in memory instead of writing a file.  Returns 0; -1 = plugin not loaded / init failed (CLI: CPU path), -2 =
+ * plugin_decode returned non-zero (CLI: CPU path), -3 = host side failed. */
+static const uint8_t *g_dec_in = nullptr;
+static uint64_t g_dec_in_len = 0;
+static int32_t *const *g_dec_out = nullptr;
+static uint64_t g_dec_cap = 0;
+static uint32_t *g_dec_dims = nullptr;
+static int g_dec_stored = 0;
+
+static int32_t plugin_dec_cb(grk_plugin_decode_callback_info *info) {
+	int32_t rc = -1;
+	grk_decompress_parameters *param = info->decoder_parameters;
+	if (info->decode_flags & GRK_DECODE_T1) info->init_decoders_func = nullptr;
+	if (info->decode_flags & GRK_PLUGIN_DECODE_CLEAN) {
+		if (info->l_stream) grk_stream_destroy(info->l_stream);
+		info->l_stream = nullptr;
+		if (info->l_codec) grk_destroy_codec(info->l_codec);
+		info->l_codec = nullptr;
+		if (info->image && !info->plugin_owns_image) { grk_image_destroy(info->image); info->image = nullptr; }
+		rc = 0;
+	}
+	if (info->decode_flags & (GRK_DECODE_HEADER | GRK_DECODE_T1 | GRK_DECODE_T2)) { /* pre_decode */
+		bool failed = false;
+		if (!info->l_stream) {
+			info->l_stream = grk_stream_create_mem_stream(const_cast<uint8_t*>(g_dec_in), g_dec_in_len, false, true);
+			info->l_codec = info->l_stream ? grk_create_decompress(GRK_CODEC_J2K, info->l_stream) : nullptr;
+			if (!info->l_codec || !grk_setup_decoder(info->l_codec, &param->core)) failed = true;
+		}
+		if (!failed && (info->decode_flags & GRK_DECODE_HEADER)) {
+			if (!grk_read_header(info->l_codec, &info->header_info, &info->image)) failed = true;
+			else if (info->init_decoders_func) return info->init_decoders_func(&info->header_info, info->image);
+		}
+		if (!failed && info->decode_flags != GRK_DECODE_HEADER) {
+			if (info->tile) info->tile->decode_flags = info->decode_flags;
+			if (!grk_set_decode_area(info->l_codec, info->image, 0, 0, 0, 0)
+					|| !(grk_decode(info->l_codec, info->tile, info->image) && grk_end_decompress(info->l_codec)))
+				failed = true;
+		}
+		if (info->decode_flags != GRK_DECODE_HEADER || failed) {
+			if (info->l_stream) grk_stream_destroy(info->l_stream);
+			info->l_stream = nullptr;
+			if (info->l_codec) grk_destroy_codec(info->l_codec);
+			info->l_codec = nullptr;
+		}
+		if (failed) {
+			if (info->image) grk_image_destroy(info->image);
+			info->image = nullptr;
+			return 1;
+		}
+		rc = 0;
+	}
+	if (info->decode_flags & GRK_DECODE_POST_T1) { /* post_decode: "store" the image */
+		grk_image *image = info->image;
+		rc = 1;
+		if (image) {
+			rc = 0;
+			g_dec_dims[0] = image->comps[0].w; g_dec_dims[1] = image->comps[0].h; g_dec_dims[2] = image->numcomps;
+			for (uint32_t c = 0; c < image->numcomps; ++c) {
+				uint64_t n = (uint64_t) image->comps[c].w * image->comps[c].h;
+				if (n > g_dec_cap || !image->comps[c].data) { rc = 2; break; }
+				memcpy(g_dec_out[c], image->comps[c].data, n * sizeof(int32_t));
+			}
+			if (!rc) g_dec_stored = 1;
+		}
+	}
+	return rc;
+}
+
+int ref_plugin_decode(const char *plugin_dir, const uint8_t *buf, uint64_t len, uint32_t reduce, uint32_t layers,
+		int32_t *const *planes_out, uint64_t plane_capacity, uint32_t *dims) {
+	grk_set_info_handler(quiet_cb, nullptr);
+	grk_set_warning_handler(quiet_cb, nullptr);
+	grk_set_error_handler(quiet_cb, nullptr);
+	grk_plugin_load_info li;
+	li.plugin_path = plugin_dir;
+	if (!grk_plugin_load(li)) return -1;
+	grk_plugin_init_info ii;
+	ii.deviceId = 0;
+	ii.verbose = true;
+	if (!grk_plugin_init(ii)) { grk_plugin_cleanup(); return -1; }
+	grk_decompress_parameters param;
+	memset(&param, 0, sizeof(param));
+	grk_set_default_decoder_parameters(&param.core);
+	param.core.cp_reduce = reduce;
+	param.core.cp_layer = layers;
+	param.decod_format = GRK_J2K_FMT;
+	param.cod_format = GRK_PXM_FMT;
+	strcpy(param.infile, "memory.j2k");
+	strcpy(param.outfile, "memory.ppm");
+	g_dec_in = buf; g_dec_in_len = len; g_dec_out = planes_out; g_dec_cap = plane_capacity; g_dec_dims = dims; g_dec_stored = 0;
+	int32_t rc = grk_plugin_decode(&param, plugin_dec_cb);
+	grk_plugin_cleanup();
+	if (rc) return -2;
+	return g_dec_stored ? 0 : -3;
+}
+
 } /* extern "C" */

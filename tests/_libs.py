@@ -103,6 +103,7 @@ def ref():
     L.ref_plugin_encode_file.argtypes = [C.c_char_p, C.c_char_p] + [C.c_uint32] * 5 + [C.c_int, C.c_uint32, C.c_void_p, C.c_uint32,
                                          u8p, C.c_uint64]
     L.ref_plugin_encode_file.restype = C.c_int64
+    L.ref_plugin_decode.argtypes = [C.c_char_p, u8p, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p), C.c_uint64, u32p]
     L.ref_init(int(os.environ.get("GRK_REF_THREADS", "0")) or (os.cpu_count() or 1))
     _ref = L
     return L
@@ -156,6 +157,21 @@ def ref_decode_image(cs, numcomps, width, height, reduce=0, layers=0):
     dims = np.zeros(4, np.uint32)
     rc = L.ref_decode_image(buf, len(buf), reduce, layers, pa, planes[0].size, dims)
     assert rc == 0, f"reference decode failed rc={rc}"
+    assert (dims[0], dims[1], dims[2]) == (planes[0].shape[1], planes[0].shape[0], numcomps), dims
+    return planes
+
+
+def ref_plugin_decode(cs, numcomps, width, height, reduce=0, layers=0):
+    """`grk_decompress -g oracle/_ref`: grk_plugin_load / init / decode.  Returns the planes, or the negative status."""
+    L = ref()
+    buf = np.frombuffer(cs, np.uint8).copy()
+    cd = lambda v: (v + (1 << reduce) - 1) >> reduce
+    planes = [np.zeros((cd(height), cd(width)), np.int32) for _ in range(numcomps)]
+    pa = (C.c_void_p * numcomps)(*[p.ctypes.data for p in planes])
+    dims = np.zeros(4, np.uint32)
+    rc = L.ref_plugin_decode(os.path.join(ORACLE_DIR, "_ref").encode(), buf, len(buf), reduce, layers, pa, planes[0].size, dims)
+    if rc:
+        return int(rc)
     assert (dims[0], dims[1], dims[2]) == (planes[0].shape[1], planes[0].shape[0], numcomps), dims
     return planes
 

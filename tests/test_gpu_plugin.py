@@ -45,7 +45,16 @@ for name in sys.argv[4:]:
     else:
         cs = _libs.ref_encode_image(img, prec, numres=numres, cblk=cblk, irreversible=not rev, rates=rates, rc_algorithm=1)
     out[name] = np.frombuffer(cs, np.uint8)
-    out[name + "_dec"] = np.stack(_libs.ref_decode_image(cs, nc, w, h))
+    if sys.argv[2] == "plugin":
+        # decode through the plugin ABI as well: host T2 -> device T1 / IDWT / MCT -> host stores the image
+        for key, kw in (("_dec", {}), ("_dec_r1", {"reduce": 1}), ("_dec_l1", {"layers": 1})):
+            dec = _libs.ref_plugin_decode(cs, nc, w, h, **kw)
+            assert not isinstance(dec, int), f"{name}{key}: plugin decode status {dec}"
+            out[name + key] = np.stack(dec)
+    else:
+        out[name + "_dec"] = np.stack(_libs.ref_decode_image(cs, nc, w, h))
+        out[name + "_dec_r1"] = np.stack(_libs.ref_decode_image(cs, nc, w, h, reduce=1))
+        out[name + "_dec_l1"] = np.stack(_libs.ref_decode_image(cs, nc, w, h, layers=1))
     out[name + "_img"] = np.stack(img)
 np.savez_compressed(sys.argv[3], **out)
 """
@@ -57,12 +66,13 @@ def _run(mode, out, cases):
 
 
 @pytest.mark.parametrize("cases", [["gray53", "rgb53", "rgb16_53"], ["rgb97_layers", "gray12_97"], ["c1_full"]])
-def test_plugin_encode_is_byte_identical(tmp_path, cases):
+def test_plugin_encode_and_decode_match_the_reference(tmp_path, cases):
     pure = _run("pure", str(tmp_path / "pure.npz"), cases)
     plug = _run("plugin", str(tmp_path / "plugin.npz"), cases)
     for name in cases:
         assert pure[name].tobytes() == plug[name].tobytes(), f"{name}: codestream differs"
-        assert (pure[name + "_dec"] == plug[name + "_dec"]).all()
+        for key in ("_dec", "_dec_r1", "_dec_l1"):
+            assert (pure[name + key] == plug[name + key]).all(), f"{name}{key}: decoded pixels differ"
         if CASES[name][4]:
             assert (plug[name + "_dec"] == plug[name + "_img"]).all(), f"{name}: not lossless"
 
