@@ -170,3 +170,56 @@ def test_idempotent_and_deterministic(ctx):
     a = plan.encode(planes)
     b = plan.encode(planes)
     assert (a[0] == b[0]).all() and (a[1] == b[1]).all() and bytes(a[3]) == bytes(b[3])
+
+
+def test_c3_lossless_full_size(ctx):
+    # config 3 at its full size: 8192x8192, 3 x 16-bit, 5/3 + RCT, 64 tiles of 1024x1024, 49 728 code blocks
+    img, full, res, data = _roundtrip(ctx, 8192, 8192, 3, 16, True, (1024, 1024), 6, seed=3)
+    assert len(res) == 64 * 3 * 259
+    for c in range(3):
+        assert (full[c] == img[c]).all()
+
+
+@pytest.mark.parametrize("rev", [True, False])
+def test_c5_16k_decode_full_and_reduced(ctx, rev):
+    # config 5: 16384x16384 tiled codestream, full-resolution and reduced-resolution decode (one component keeps the host
+    # side of the test within a few GB).  5/3: the full decode is lossless and a decode at reduce r must equal the LL band
+    # of an r-level forward transform of the same image (+ level shift); 9/7: near-lossless at full size, and the reduced
+    # decode must match that low-pass band to within the quantisation of the coarser bands.
+    W = H = 16384
+    img = synthetic_planes(W, H, 1, 8, seed=16)
+    tiles = P.image_tiles(W, H, 1, 8, rev, (1024, 1024), 6, rate_control=False)
+    planes = P.split_planes(img, W, H, (1024, 1024))
+    plan = gb.Plan(ctx, tiles, encoder=True)
+    res, rates, dists, data = plan.encode(planes)
+    assert len(res) == 256 * 259
+    inp = _enc_to_dec_inputs(res)
+    for reduce in (0, 2):
+        tiles_d = P.image_tiles(W, H, 1, 8, rev, (1024, 1024), 6, encoder=False, numres_decode=6 - reduce)
+        dplan = gb.Plan(ctx, tiles_d, encoder=False)
+        keep = np.asarray(plan.blocks["resno"]) < 6 - reduce
+        got = dplan.decode(inp[keep], data)
+        dplan.close()
+        if reduce == 0:
+            full = P.join_planes(got, W, H, 1, (1024, 1024))[0]
+            if rev:
+                assert (full == img[0]).all()
+            else:
+                assert _psnr(full, img[0], 8) > 45.0
+        else:
+            ll_plan = gb.Plan(ctx, P.image_tiles(W, H, 1, 8, rev, (1024, 1024), 1 + reduce), encoder=True)
+            ll_plan.encode_upload(planes)
+            ll_plan.encode_run_stage(0)
+            ll_plan.encode_run_stage(1)
+            ctx.sync()
+            for t in (0, 100, 255):
+                co = ll_plan.coefficients(t, 0)
+                n = 1024 >> reduce
+                ll = co[:n, :n].astype(np.float64)
+                if not rev:
+                    ll = ll / 2048.0  # the 9/7 analysis carries 11 fractional bits
+                want = np.clip(np.rint(ll) + 128, 0, 255)
+                diff = np.abs(got[t].astype(np.float64) - want)
+                assert diff.max() <= (0 if rev else 2), (t, diff.max())
+            ll_plan.close()
+    plan.close()
