@@ -35,12 +35,15 @@ WORKLOADS = {
                rates=(40, 20, 10, 5)),
     "c3": dict(width=8192, height=8192, comps=3, prec=16, reversible=True, tile=(1024, 1024), numres=6, cblk=(6, 6), rates=()),
     "c4": dict(width=2048, height=1080, comps=3, prec=12, reversible=False, tile=(None, None), numres=6, cblk=(5, 5), rates=(10,)),
+    # 30 of the 240 frames of configs[3]: what one GPU of eight gets when the batch is sharded by frame; one plan, one launch per stage
+    "c4x30": dict(width=2048, height=1080, comps=3, prec=12, reversible=False, tile=(None, None), numres=6, cblk=(5, 5), rates=(10,), frames=30),
 }
 WORKLOAD_TEXT = {
     "c1": "configs[0]: 2048x2048 8-bit gray, lossless 5/3, 1 tile, 64x64 blocks, 5 levels",
     "c2": "configs[1]: 4096x2160 RGB 8-bit, irreversible 9/7 + ICT, quantised, 4 quality layers, 1024x1024 tiles",
     "c3": "configs[2]: 8192x8192 3x16-bit, lossless 5/3 + RCT, 1024x1024 tiles",
     "c4": "configs[3]: one DCI 2K frame 2048x1080 3x12-bit, 9/7 + ICT, 32x32 blocks",
+    "c4x30": "configs[3]: batch of 30 DCI 2K frames 2048x1080 3x12-bit (240 frames over 8 GPUs), 9/7 + ICT, 32x32 blocks",
 }
 
 
@@ -91,13 +94,16 @@ def make_workload(name, seed):
     from grokimagecompression_b200 import params as P
     from grokimagecompression_b200.synth import synthetic_planes
     w = WORKLOADS[name]
-    img = synthetic_planes(w["width"], w["height"], w["comps"], w["prec"], seed=seed)
     rc = len(w["rates"]) > 0
-    tiles_e = P.image_tiles(w["width"], w["height"], w["comps"], w["prec"], w["reversible"], w["tile"], w["numres"],
-                            rate_control=rc, cblk_expn=w["cblk"])
-    tiles_d = P.image_tiles(w["width"], w["height"], w["comps"], w["prec"], w["reversible"], w["tile"], w["numres"],
-                            cblk_expn=w["cblk"], encoder=False)
-    planes = P.split_planes(img, w["width"], w["height"], w["tile"])
+    img, tiles_e, tiles_d, planes = None, [], [], []
+    for f in range(w.get("frames", 1)):  # frames of a batch are independent images: more tiles of the same plan
+        fimg = synthetic_planes(w["width"], w["height"], w["comps"], w["prec"], seed=seed + f)
+        img = fimg if img is None else img  # the correctness gate looks at the first frame
+        tiles_e += P.image_tiles(w["width"], w["height"], w["comps"], w["prec"], w["reversible"], w["tile"], w["numres"],
+                                 rate_control=rc, cblk_expn=w["cblk"])
+        tiles_d += P.image_tiles(w["width"], w["height"], w["comps"], w["prec"], w["reversible"], w["tile"], w["numres"],
+                                 cblk_expn=w["cblk"], encoder=False)
+        planes += P.split_planes(fimg, w["width"], w["height"], w["tile"])
     return w, img, tiles_e, tiles_d, planes
 
 
@@ -227,7 +233,7 @@ def main():
     ctx = gb.Context(local_rank)
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
     w, img, tiles_e, tiles_d, planes = make_workload(args.workload, seed=1000 + rank)
-    pixels = w["width"] * w["height"]
+    pixels = w["width"] * w["height"] * w.get("frames", 1)
     eplan = gb.Plan(ctx, tiles_e, encoder=True)
     dplan = gb.Plan(ctx, tiles_d, encoder=False)
 
@@ -268,7 +274,8 @@ def main():
     h_data = data[:enc_bytes]
     dplan.decode(h_inp, h_data, h_out)
     from grokimagecompression_b200 import params as P
-    full = P.join_planes(h_out, w["width"], w["height"], w["comps"], w["tile"])
+    per_frame = len(h_out) // w.get("frames", 1)
+    full = P.join_planes(h_out[:per_frame], w["width"], w["height"], w["comps"], w["tile"])
     if w["reversible"]:
         assert all((a == b).all() for a, b in zip(full, img)), "lossless round trip failed"
         psnr = float("inf")
