@@ -37,10 +37,14 @@
 namespace gb {
 
 #ifndef DT_LANES
-#define DT_LANES 2          // code blocks (active lanes) per warp
+#define DT_LANES 2          // code blocks (active lanes) per warp when the launch fills the machine
 #endif
-constexpr int DT_MAX_THREADS = DT_LANES <= 2 ? 1024 : 512;
-constexpr int DT_MAX_SLOTS = DT_MAX_THREADS / 32 * DT_LANES;
+// a launch with few blocks per SM (one small image) is bound by the latency of one block's chain: then every block gets
+// a warp of its own, so that no two chains share an instruction stream
+#ifndef DT_SPARSE_BLOCKS_PER_SM
+#define DT_SPARSE_BLOCKS_PER_SM 16
+#endif
+constexpr int DT_MAX_THREADS = 1024;
 constexpr int DT_CTX_WORDS = 20;  // 19 context rows per block, padded
 constexpr int DT_FIXED_WORDS = 96 + 512 + 64; // MQ table, zero-coding table (4 x 512 B), sign table (256 B)
 
@@ -224,6 +228,7 @@ __device__ __forceinline__ void cln_row(Blk &b, uint32_t &f, uint32_t *cw, int s
 	}
 }
 
+template<int LANES>
 __global__ void __launch_bounds__(DT_MAX_THREADS, 1) t1_decode_kernel(const DecBlock *__restrict__ blocks,
 		const DecInput *__restrict__ inputs, uint32_t nblocks, const uint8_t *__restrict__ data, int fw, int fwords, int nslots) {
 	extern __shared__ __align__(16) uint32_t sm[];
@@ -250,8 +255,8 @@ __global__ void __launch_bounds__(DT_MAX_THREADS, 1) t1_decode_kernel(const DecB
 	__syncthreads();
 
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	if (lane >= DT_LANES) return;
-	const int slot = warp * DT_LANES + lane;
+	if (lane >= LANES) return;
+	const int slot = warp * LANES + lane;
 	const uint32_t bid = blockIdx.x * (uint32_t) nslots + (uint32_t) slot;
 	if (slot >= nslots || bid >= nblocks) return;
 	const DecBlock B = blocks[bid];
@@ -372,24 +377,27 @@ int launch_t1_decode(const DecBlock *blocks, const DecInput *inputs, uint32_t nb
 	const int fw = (int) max_w + 2;
 	int fwords = (int) ((max_h + 3) / 4) * fw;
 	fwords += fwords & 1;
-	// slots of one warp start 32 / DT_LANES banks apart
-	int bank0 = 32 / DT_LANES % 32;
+	int want = (int) ((nblocks + (uint32_t) sms - 1) / (uint32_t) sms); // spread a small job over every SM
+	const int lanes = want <= DT_SPARSE_BLOCKS_PER_SM ? 1 : DT_LANES;
+	// slots of one warp start 32 / lanes banks apart
+	int bank0 = 32 / lanes % 32;
 	if (bank0 & 1) bank0 = 2;
 	while (fwords % 32 != bank0) fwords += 2;
 	const int per_slot = (fwords + DT_CTX_WORDS) * 4;
 	int cap = (smem_max - DT_FIXED_WORDS * 4) / per_slot;
-	int want = (int) ((nblocks + (uint32_t) sms - 1) / (uint32_t) sms); // spread a small job over every SM
 	int nslots = cap < want ? cap : want;
-	if (nslots > DT_MAX_SLOTS) nslots = DT_MAX_SLOTS;
-	nslots = (nslots + DT_LANES - 1) / DT_LANES * DT_LANES;
-	while (nslots > cap) nslots -= DT_LANES;
-	if (nslots < DT_LANES) nslots = cap; // a partial warp: blocks too large for DT_LANES of them
+	const int max_slots = DT_MAX_THREADS / 32 * lanes;
+	if (nslots > max_slots) nslots = max_slots;
+	nslots = (nslots + lanes - 1) / lanes * lanes;
+	while (nslots > cap) nslots -= lanes;
+	if (nslots < lanes) nslots = cap; // a partial warp: blocks too large for `lanes` of them
 	if (nslots < 1) return 1;
 	const size_t smem = (size_t) DT_FIXED_WORDS * 4 + (size_t) nslots * per_slot;
-	if (cudaFuncSetAttribute(t1_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) != cudaSuccess) return 1;
-	const int threads = (nslots + DT_LANES - 1) / DT_LANES * 32;
+	auto kernel = lanes == 1 ? t1_decode_kernel<1> : t1_decode_kernel<DT_LANES>;
+	if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) != cudaSuccess) return 1;
+	const int threads = (nslots + lanes - 1) / lanes * 32;
 	t1_dec_clear_kernel<<<(nblocks + 7) / 8, 256, 0, s>>>(blocks, nblocks);
-	t1_decode_kernel<<<(nblocks + nslots - 1) / nslots, threads, smem, s>>>(blocks, inputs, nblocks, data, fw, fwords, nslots);
+	kernel<<<(nblocks + nslots - 1) / nslots, threads, smem, s>>>(blocks, inputs, nblocks, data, fw, fwords, nslots);
 	t1_dec_finish_kernel<<<(nblocks + 7) / 8, 256, 0, s>>>(blocks, nblocks);
 	return 0;
 }

@@ -324,6 +324,9 @@ constexpr int MQ_WARPS = 4;
 #ifndef MQ_LANES
 #define MQ_LANES 2   // active lanes (code blocks) per warp
 #endif
+#ifndef MQ_SPARSE_BLOCKS_PER_SM
+#define MQ_SPARSE_BLOCKS_PER_SM 16
+#endif
 constexpr int MQ_CTX_WORDS = 20;
 
 struct MqT {
@@ -346,12 +349,13 @@ __device__ __forceinline__ void mqt_byteout(MqT &q, uint8_t *out, uint32_t cap, 
 	else { q.last = (q.c >> 19) & 0xFF; q.c &= 0x7FFFFu; q.ct = 8; }
 }
 
+template<int LANES>
 __global__ void __launch_bounds__(MQ_WARPS * 32) t1_mq_kernel(const EncBlock *__restrict__ blocks, uint32_t nblocks,
 		const uint8_t *__restrict__ symbols, uint8_t *__restrict__ scratch, EncResult *__restrict__ results,
 		uint32_t *__restrict__ rates) {
 	// context rows: qe << 16 | mps << 15 | next(LPS) << 8 | next(MPS); successors index the (state, mps) table
 	__shared__ uint32_t tab[96];
-	__shared__ uint32_t ctx[MQ_WARPS * MQ_LANES][MQ_CTX_WORDS];
+	__shared__ uint32_t ctx[MQ_WARPS * LANES][MQ_CTX_WORDS];
 	for (int i = threadIdx.x; i < 94; i += blockDim.x) {
 		const uint32_t r = c_mq[i >> 1], mps = i & 1u, sw = (r >> 28) & 1u;
 		const uint32_t nm = ((r >> 16) & 63u) * 2u + mps, nl = ((r >> 22) & 63u) * 2u + (mps ^ sw);
@@ -359,9 +363,9 @@ __global__ void __launch_bounds__(MQ_WARPS * 32) t1_mq_kernel(const EncBlock *__
 	}
 	__syncthreads();
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	if (lane >= MQ_LANES) return;
-	int slot = warp * MQ_LANES + lane;
-	const uint32_t bid = blockIdx.x * (MQ_WARPS * MQ_LANES) + (uint32_t) slot;
+	if (lane >= LANES) return;
+	int slot = warp * LANES + lane;
+	const uint32_t bid = blockIdx.x * (MQ_WARPS * LANES) + (uint32_t) slot;
 	if (bid >= nblocks) return;
 	EncResult res = results[bid];
 	if (res.numbps == 0 || res.numpasses == 0 || res.numpasses == 0xFFFFFFFFu) return;
@@ -500,7 +504,14 @@ void launch_t1_encode(const EncBlock *blocks, uint32_t nblocks, int rate_control
 	if (!nblocks) return;
 	if (!g_tables_ready) { build_and_upload_t1_tables(); g_tables_ready = true; }
 	t1_model_kernel<<<(nblocks + ENC_WARPS - 1) / ENC_WARPS, ENC_WARPS * 32, 0, s>>>(blocks, nblocks, rate_control, symbols, results, dists);
-	t1_mq_kernel<<<(nblocks + MQ_WARPS * MQ_LANES - 1) / (MQ_WARPS * MQ_LANES), MQ_WARPS * 32, 0, s>>>(blocks, nblocks, symbols, scratch, results, rates);
+	// few blocks per SM: the launch is bound by the latency of one coder's chain, give every coder its own warp
+	int dev = 0, sms = 148;
+	cudaGetDevice(&dev);
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	if (nblocks <= (uint32_t) sms * MQ_SPARSE_BLOCKS_PER_SM)
+		t1_mq_kernel<1><<<(nblocks + MQ_WARPS - 1) / MQ_WARPS, MQ_WARPS * 32, 0, s>>>(blocks, nblocks, symbols, scratch, results, rates);
+	else
+		t1_mq_kernel<MQ_LANES><<<(nblocks + MQ_WARPS * MQ_LANES - 1) / (MQ_WARPS * MQ_LANES), MQ_WARPS * 32, 0, s>>>(blocks, nblocks, symbols, scratch, results, rates);
 }
 
 // bytes of symbol stream to reserve for a w x h block with at most `planes` coded bit-planes: every sample
