@@ -326,6 +326,7 @@ static const mq_row MQ[47] = {
 	{0x0001, 45, 43, 0}, {0x5601, 46, 46, 0}
 };
 
+enum { STY_LAZY = 1, STY_RESET = 2, STY_TERMALL = 4, STY_VSC = 8, STY_PTERM = 16, STY_SEGSYM = 32 };
 enum { CTX_ZC0 = 0, CTX_SC0 = 9, CTX_MR0 = 14, CTX_AGG = 17, CTX_UNI = 18, NCTX = 19 };
 
 typedef struct {
@@ -413,6 +414,67 @@ static void mqe_flush(mqe *q) {
 
 static inline uint32_t mqe_numbytes(const mqe *q) { return (uint32_t) (q->bp - q->start); }
 
+/* predictable termination (mqc_enc.cpp:396-407) */
+static void mqe_erterm(mqe *q) {
+	int k = 11 - q->ct + 1;
+	while (k > 0) {
+		q->c <<= q->ct;
+		q->ct = 0;
+		mqe_byteout(q);
+		k -= q->ct;
+	}
+	if (*q->bp != 0xFF) mqe_byteout(q);
+}
+
+/* INITENC again after a terminated pass: the last byte of the previous segment becomes the pending byte
+ * (mqc_enc.cpp:379-394) */
+static void mqe_restart(mqe *q) {
+	q->a = 0x8000;
+	q->c = 0;
+	q->ct = 12;
+	q->bp--;
+	if (*q->bp == 0xFF) q->ct = 13;
+}
+
+/* selective arithmetic coding bypass: raw bits with the same bit stuffing (mqc_enc.cpp:291-377) */
+#define MQE_BYPASS_CT_INIT 0x7FFFFFFF
+static void mqe_bypass_init(mqe *q) {
+	q->c = 0;
+	q->ct = MQE_BYPASS_CT_INIT; /* "no bit written yet" */
+}
+static void mqe_bypass(mqe *q, int d) {
+	if (q->ct == MQE_BYPASS_CT_INIT) q->ct = 8;
+	q->ct--;
+	q->c += (uint32_t) d << q->ct;
+	if (q->ct == 0) {
+		*q->bp = (uint8_t) q->c;
+		q->ct = 8;
+		if (*q->bp == 0xFF) q->ct = 7; /* the next byte keeps its MSB clear */
+		q->bp++;
+		q->c = 0;
+	}
+}
+static int mqe_bypass_pending(const mqe *q, int erterm) {
+	return q->ct < 7 || (q->ct == 7 && (erterm || q->bp[-1] != 0xFF));
+}
+static uint32_t mqe_bypass_extra_bytes(const mqe *q, int erterm) { return mqe_bypass_pending(q, erterm) ? 2 : 1; }
+static void mqe_bypass_flush(mqe *q, int erterm) {
+	if (mqe_bypass_pending(q, erterm)) {
+		int bit = 0;
+		while (q->ct > 0) { /* pad with 0,1,0,1,... */
+			q->ct--;
+			q->c += (uint32_t) bit << q->ct;
+			bit = 1 - bit;
+		}
+		*q->bp = (uint8_t) q->c;
+		q->bp++;
+	} else if (q->ct == 7 && q->bp[-1] == 0xFF) {
+		q->bp--; /* a trailing 0xFF is dropped */
+	} else if (q->ct == 8 && !erterm && q->bp[-1] == 0x7F && q->bp[-2] == 0xFF) {
+		q->bp -= 2; /* FF 7F reads the same as the end marker the decoder synthesises */
+	}
+}
+
 typedef struct {
 	uint32_t a, c;
 	int ct;
@@ -491,9 +553,12 @@ typedef struct {
 	int w, h, S; /* S = w+2 : row pitch of the state arrays */
 	uint8_t *sig, *neg, *vis, *refd; /* significant, negative, visited this plane, refined before */
 	int orient;
+	int vsc; /* vertically stripe-causal contexts: the row below a stripe counts as insignificant (t1.cpp:168-190) */
 } t1s;
 
 #define AT(p, x, y) ((p)[((y) + 1) * s->S + (x) + 1])
+/* significance of a neighbour in the row below sample row y: hidden when y is the last row of its stripe and VSC is on */
+#define BELOW(x, y) ((s->vsc && ((y) & 3) == 3) ? 0 : AT(s->sig, x, (y) + 1))
 
 static int t1s_alloc(t1s *s, int w, int h, int orient) {
 	s->w = w; s->h = h; s->S = w + 2; s->orient = orient;
@@ -508,8 +573,8 @@ static void t1s_free(t1s *s) { free(s->sig); }
 /* Table D.1 (t1_generate_luts.cpp:63-141); the HL band swaps the roles of h and v */
 static int ctx_zc(const t1s *s, int x, int y) {
 	int h = AT(s->sig, x - 1, y) + AT(s->sig, x + 1, y);
-	int v = AT(s->sig, x, y - 1) + AT(s->sig, x, y + 1);
-	int d = AT(s->sig, x - 1, y - 1) + AT(s->sig, x + 1, y - 1) + AT(s->sig, x - 1, y + 1) + AT(s->sig, x + 1, y + 1);
+	int v = AT(s->sig, x, y - 1) + BELOW(x, y);
+	int d = AT(s->sig, x - 1, y - 1) + AT(s->sig, x + 1, y - 1) + BELOW(x - 1, y) + BELOW(x + 1, y);
 	if (s->orient == 1) { int t = h; h = v; v = t; }
 	if (s->orient == 3) {
 		int hv = h + v;
@@ -526,15 +591,15 @@ static int ctx_zc(const t1s *s, int x, int y) {
 }
 
 static int any_sig_neighbour(const t1s *s, int x, int y) {
-	return AT(s->sig, x - 1, y) | AT(s->sig, x + 1, y) | AT(s->sig, x, y - 1) | AT(s->sig, x, y + 1)
-			| AT(s->sig, x - 1, y - 1) | AT(s->sig, x + 1, y - 1) | AT(s->sig, x - 1, y + 1) | AT(s->sig, x + 1, y + 1);
+	return AT(s->sig, x - 1, y) | AT(s->sig, x + 1, y) | AT(s->sig, x, y - 1) | BELOW(x, y)
+			| AT(s->sig, x - 1, y - 1) | AT(s->sig, x + 1, y - 1) | BELOW(x - 1, y) | BELOW(x + 1, y);
 }
 
 /* Tables D.2 / D.3 (t1_generate_luts.cpp:143-209): returns context, *xorbit = sign prediction */
 static int ctx_sc(const t1s *s, int x, int y, int *xorbit) {
 	#define CONTRIB(xx, yy) (AT(s->sig, xx, yy) ? (AT(s->neg, xx, yy) ? -1 : 1) : 0)
 	int hc = CONTRIB(x - 1, y) + CONTRIB(x + 1, y);
-	int vc = CONTRIB(x, y - 1) + CONTRIB(x, y + 1);
+	int vc = CONTRIB(x, y - 1) + (BELOW(x, y) ? (AT(s->neg, x, y + 1) ? -1 : 1) : 0);
 	#undef CONTRIB
 	hc = hc > 1 ? 1 : (hc < -1 ? -1 : hc);
 	vc = vc > 1 ? 1 : (vc < -1 ? -1 : vc);
@@ -609,8 +674,17 @@ typedef struct {
 	t1s s;
 	mqe q;
 	int nmsedec;
-	uint64_t nsym; /* MQ decisions coded: the algorithmic work unit of Tier-1 */
+	uint64_t nsym; /* MQ decisions (and raw bits) coded: the algorithmic work unit of Tier-1 */
+	int raw;       /* this pass bypasses the arithmetic coder (cblk_sty LAZY, t1.cpp:1229-1231) */
 } t1e;
+
+static void mqe_bypass(mqe *q, int d);
+
+/* one binary decision: MQ with its context, or a raw bit in a bypass pass (t1.cpp:208-211, 224-229, 456-460) */
+static void enc_emit(t1e *e, int cx, int d) {
+	if (e->raw) mqe_bypass(&e->q, d); else mqe_encode(&e->q, cx, d);
+	e->nsym++;
+}
 
 static inline uint32_t mag_at(const t1e *e, int x, int y) {
 	int32_t v = e->data[y * e->s.w + x];
@@ -622,8 +696,7 @@ static void enc_sign_and_mark(t1e *e, int x, int y, int bp) {
 	int xorbit, neg = e->data[y * s->w + x] < 0;
 	int cx = ctx_sc(s, x, y, &xorbit);
 	e->nmsedec += nmsedec_sig(mag_at(e, x, y), bp);
-	mqe_encode(&e->q, cx, neg ^ xorbit);
-	e->nsym++;
+	enc_emit(e, cx, e->raw ? neg : neg ^ xorbit); /* raw passes send the sign itself */
 	AT(s->sig, x, y) = 1;
 	AT(s->neg, x, y) = (uint8_t) neg;
 }
@@ -638,8 +711,7 @@ static void enc_sigpass(t1e *e, int bp) {
 				if (AT(s->sig, x, y) || !any_sig_neighbour(s, x, y))
 					continue;
 				int bit = (mag_at(e, x, y) >> (bp + 6)) & 1;
-				mqe_encode(&e->q, CTX_ZC0 + ctx_zc(s, x, y), bit);
-				e->nsym++;
+				enc_emit(e, CTX_ZC0 + ctx_zc(s, x, y), bit);
 				if (bit) enc_sign_and_mark(e, x, y, bp);
 				AT(s->vis, x, y) = 1;
 			}
@@ -655,8 +727,7 @@ static void enc_refpass(t1e *e, int bp) {
 				if (!AT(s->sig, x, y) || AT(s->vis, x, y))
 					continue;
 				e->nmsedec += nmsedec_ref(mag_at(e, x, y), bp);
-				mqe_encode(&e->q, ctx_mr(s, x, y), (mag_at(e, x, y) >> (bp + 6)) & 1);
-				e->nsym++;
+				enc_emit(e, ctx_mr(s, x, y), (mag_at(e, x, y) >> (bp + 6)) & 1);
 				AT(s->refd, x, y) = 1;
 			}
 }
@@ -762,19 +833,126 @@ GBO_API int gbo_t1_encode_block(const int32_t *data, int w, int h, int orient, i
 	return npass;
 }
 
+/* t1_enc_is_term_pass, t1.cpp:1131-1151 */
+static int enc_is_term_pass(int numbps, int sty, int bp, int type) {
+	if (type == 2 && bp == 0) return 1;
+	if (sty & STY_TERMALL) return 1;
+	if (sty & STY_LAZY) {
+		if (bp == numbps - 4 && type == 2) return 1;
+		if (bp < numbps - 4 && type > 0) return 1;
+	}
+	return 0;
+}
+
+/*
+ * Tier-1 encode of one block with code-block style switches (t1.cpp:1182-1326):
+ *   LAZY 0x01 bypass of the MQ coder for the significance / refinement passes below the fourth plane,
+ *   RESET 0x02 context reset after every pass, TERMALL 0x04 every pass terminated, VSC 0x08 stripe-causal
+ *   contexts, PTERM 0x10 predictable termination, SEGSYM 0x20 segmentation symbol after each cleanup pass.
+ * terms[i] = 1 when pass i ends a codeword segment.  Everything else as gbo_t1_encode_block.
+ */
+GBO_API int gbo_t1_encode_block_sty(const int32_t *data, int w, int h, int orient, int sty, int do_rd, double wbase,
+		uint8_t *out, uint32_t *numbps_out, uint32_t *rates, double *dists, uint8_t *terms, uint64_t *nsym_out) {
+	t1e e;
+	memset(&e, 0, sizeof(e));
+	e.data = data;
+	uint32_t mx = 0;
+	for (int i = 0; i < w * h; ++i) {
+		uint32_t a = (uint32_t) (data[i] < 0 ? -data[i] : data[i]);
+		if (a > mx) mx = a;
+	}
+	int nbits = 0;
+	while (mx >> nbits) nbits++;
+	int numbps = nbits > 6 ? nbits - 6 : 0;
+	*numbps_out = (uint32_t) numbps;
+	if (nsym_out) *nsym_out = 0;
+	if (numbps == 0)
+		return 0;
+	if (t1s_alloc(&e.s, w, h, orient))
+		return -1;
+	e.s.vsc = (sty & STY_VSC) != 0;
+	out[-1] = 0;
+	mqe_init(&e.q, out);
+	int npass = 0;
+	double cum = 0.0;
+	for (int bp = numbps - 1; bp >= 0; --bp)
+		for (int type = (bp == numbps - 1 ? 2 : 0); type < 3; ++type) {
+			e.raw = (bp < numbps - 4) && type < 2 && (sty & STY_LAZY);
+			if (npass > 0 && terms[npass - 1]) { /* the previous pass closed a segment */
+				if (e.raw) mqe_bypass_init(&e.q); else mqe_restart(&e.q);
+			}
+			if (type == 0) enc_sigpass(&e, bp);
+			else if (type == 1) enc_refpass(&e, bp);
+			else {
+				enc_clnpass(&e, bp);
+				if (sty & STY_SEGSYM) { /* mqc_segmark_enc, mqc_enc.cpp:409-413 */
+					for (int i = 1; i < 5; ++i) enc_emit(&e, CTX_UNI, i & 1);
+				}
+			}
+			if (do_rd) {
+				double x = wbase * (double) (1 << bp);
+				x *= x * e.nmsedec / 8192.0;
+				cum += x;
+				dists[npass] = cum;
+			} else
+				dists[npass] = 0.0;
+			if (enc_is_term_pass(numbps, sty, bp, type)) {
+				if (e.raw) mqe_bypass_flush(&e.q, sty & STY_PTERM);
+				else if (sty & STY_PTERM) mqe_erterm(&e.q);
+				else mqe_flush(&e.q);
+				terms[npass] = 1;
+				rates[npass] = mqe_numbytes(&e.q);
+			} else {
+				terms[npass] = 0;
+				rates[npass] = mqe_numbytes(&e.q) + (e.raw ? mqe_bypass_extra_bytes(&e.q, sty & STY_PTERM) : (e.q.ct < 5 ? 6u : 5u));
+			}
+			npass++;
+			if (sty & STY_RESET) mq_reset_ctx(e.q.st, e.q.mps);
+		}
+	uint32_t last = mqe_numbytes(&e.q);
+	for (int i = npass - 1; i >= 0; --i) {
+		if (rates[i] > last) rates[i] = last; else last = rates[i];
+	}
+	for (int i = 0; i < npass; ++i)
+		if (rates[i] > 0 && out[(int) rates[i] - 1] == 0xFF) rates[i]--;
+	if (nsym_out) *nsym_out = e.nsym;
+	t1s_free(&e.s);
+	return npass;
+}
+
 /* ---- decoder ------------------------------------------------------------------------------ */
 
 typedef struct {
 	int32_t *data;
 	t1s s;
 	mqd q;
+	int raw;           /* this segment bypasses the arithmetic coder */
+	uint32_t rc;       /* raw decoder: current byte, bits left in it (mqc_dec_inl.h:90-112) */
+	int rct;
 } t1d;
+
+/* mqc_raw_decode, mqc_dec_inl.h:90-112: bit-unstuffing reader; bytes past the segment read as 0xFF */
+static int raw_decode(t1d *d) {
+	mqd *q = &d->q;
+	if (d->rct == 0) {
+		uint32_t b = mqd_byte(q, q->pos);
+		if (d->rc == 0xFF) {
+			if (b > 0x8F) { d->rc = 0xFF; d->rct = 8; }
+			else { d->rc = b; q->pos++; d->rct = 7; }
+		} else { d->rc = b; q->pos++; d->rct = 8; }
+	}
+	d->rct--;
+	return (int) ((d->rc >> d->rct) & 1);
+}
+
+static int dec_get(t1d *d, int cx) { return d->raw ? raw_decode(d) : mqd_decode(&d->q, cx); }
 
 static void dec_sign_and_mark(t1d *d, int x, int y, int32_t oneplushalf) {
 	t1s *s = &d->s;
 	int xorbit;
 	int cx = ctx_sc(s, x, y, &xorbit);
-	int neg = mqd_decode(&d->q, cx) ^ xorbit;
+	int neg = dec_get(d, cx);
+	if (!d->raw) neg ^= xorbit; /* raw passes carry the sign itself */
 	d->data[y * s->w + x] = neg ? -oneplushalf : oneplushalf;
 	AT(s->sig, x, y) = 1;
 	AT(s->neg, x, y) = (uint8_t) neg;
@@ -789,7 +967,7 @@ static void dec_sigpass(t1d *d, int bp1) {
 			for (int y = y0; y < y0 + 4 && y < s->h; ++y) {
 				if (AT(s->sig, x, y) || !any_sig_neighbour(s, x, y))
 					continue;
-				if (mqd_decode(&d->q, CTX_ZC0 + ctx_zc(s, x, y)))
+				if (dec_get(d, CTX_ZC0 + ctx_zc(s, x, y)))
 					dec_sign_and_mark(d, x, y, oph);
 				AT(s->vis, x, y) = 1;
 			}
@@ -804,7 +982,7 @@ static void dec_refpass(t1d *d, int bp1) {
 			for (int y = y0; y < y0 + 4 && y < s->h; ++y) {
 				if (!AT(s->sig, x, y) || AT(s->vis, x, y))
 					continue;
-				int bit = mqd_decode(&d->q, ctx_mr(s, x, y));
+				int bit = dec_get(d, ctx_mr(s, x, y));
 				int32_t *p = &d->data[y * s->w + x];
 				*p += (bit ^ (*p < 0)) ? poshalf : -poshalf;
 				AT(s->refd, x, y) = 1;
@@ -863,6 +1041,51 @@ GBO_API int gbo_t1_decode_block(const uint8_t *bytes, uint32_t len, int numpasse
 		else if (type == 1) dec_refpass(&d, bp1);
 		else dec_clnpass(&d, bp1);
 		if (++type == 3) { type = 0; bp1--; }
+	}
+	t1s_free(&d.s);
+	return 0;
+}
+
+/*
+ * Tier-1 decode of one block from its codeword segments, with code-block style switches (t1.cpp:1038-1130).
+ * bytes = the segments back to back; seg_len[i] / seg_passes[i] as Tier-2 delivers them (T2.cpp:835-851: one pass per
+ * segment with TERMALL; 10, then 2, 1, 2, 1 ... with LAZY; otherwise a single segment).
+ */
+GBO_API int gbo_t1_decode_block_segs(const uint8_t *bytes, const uint32_t *seg_len, const uint32_t *seg_passes, int nsegs,
+		int numbps, int orient, int sty, int w, int h, int32_t *out) {
+	t1d d;
+	memset(&d, 0, sizeof(d));
+	memset(out, 0, sizeof(int32_t) * (size_t) w * h);
+	if (numbps >= 31)
+		return 1;
+	if (t1s_alloc(&d.s, w, h, orient))
+		return -1;
+	d.s.vsc = (sty & STY_VSC) != 0;
+	d.data = out;
+	mq_reset_ctx(d.q.st, d.q.mps);
+	int bp1 = numbps, type = 2;
+	uint32_t off = 0;
+	for (int sg = 0; sg < nsegs; ++sg) {
+		d.raw = (bp1 <= numbps - 4) && type < 2 && (sty & STY_LAZY);
+		uint8_t st[NCTX], mps[NCTX];
+		memcpy(st, d.q.st, NCTX);
+		memcpy(mps, d.q.mps, NCTX);
+		mqd_init(&d.q, bytes + off, seg_len[sg]); /* resets the contexts: put them back, only RESET clears them */
+		memcpy(d.q.st, st, NCTX);
+		memcpy(d.q.mps, mps, NCTX);
+		if (d.raw) { d.q.pos = 0; d.rc = 0; d.rct = 0; } /* mqc_raw_init_dec, mqc_dec.cpp:195-200 */
+		off += seg_len[sg];
+		for (uint32_t p = 0; p < seg_passes[sg] && bp1 >= 1; ++p) {
+			if (type == 0) dec_sigpass(&d, bp1);
+			else if (type == 1) dec_refpass(&d, bp1);
+			else {
+				dec_clnpass(&d, bp1);
+				if (sty & STY_SEGSYM) /* t1_dec_clnpass_check_segsym, t1.cpp:870-888: read, a mismatch only warns */
+					for (int i = 0; i < 4; ++i) mqd_decode(&d.q, CTX_UNI);
+			}
+			if ((sty & STY_RESET) && !d.raw) mq_reset_ctx(d.q.st, d.q.mps);
+			if (++type == 3) { type = 0; bp1--; }
+		}
 	}
 	t1s_free(&d.s);
 	return 0;

@@ -114,6 +114,9 @@ int ref_dwt_decode(int32_t *data, uint32_t x0, uint32_t y0, uint32_t x1, uint32_
 /* Tier-1 encode of one code block.  `data` holds w*h quantised coefficients WITH the 6 fractional
  * bits (what T1Part1::preEncode produces).  Returns total passes; fills numbps, per-pass rate/len/
  * distortion, and the byte stream (out must hold >= w*h*4+16 bytes). */
+static uint8_t *g_terms_out = nullptr; /* optional: per-pass termination flags of the next ref_t1_encode_cblk call */
+void ref_t1_want_terms(uint8_t *terms) { g_terms_out = terms; }
+
 int ref_t1_encode_cblk(const int32_t *data, uint32_t w, uint32_t h, uint32_t orient, uint32_t compno,
 		uint32_t level, uint32_t qmfbid, double stepsize, uint32_t cblksty, const double *mct_norms,
 		uint32_t mct_numcomps, int do_rate_control, uint8_t *out, uint32_t *numbps, uint32_t *rates,
@@ -144,7 +147,9 @@ int ref_t1_encode_cblk(const int32_t *data, uint32_t w, uint32_t h, uint32_t ori
 		rates[i] = cblk.passes[i].rate;
 		lens[i] = cblk.passes[i].len;
 		dists[i] = cblk.passes[i].distortiondec;
+		if (g_terms_out) g_terms_out[i] = (uint8_t) cblk.passes[i].term;
 	}
+	g_terms_out = nullptr;
 	if (np > 0)
 		memcpy(out, cblk.data, rates[np - 1]);
 	if (total_dist) *total_dist = d;
@@ -177,6 +182,38 @@ int ref_t1_decode_cblk(const uint8_t *bytes, uint32_t len, uint32_t numpasses, u
 	cblk.x0 = 0; cblk.y0 = 0; cblk.x1 = w; cblk.y1 = h;
 	cblk.real_num_segs = 1;
 	cblk.segs = &seg;
+	cblk.numbps = numbps;
+	bool ok = t1_decode_cblk(t1, &cblk, orient, roishift, cblksty, false);
+	if (ok)
+		memcpy(out, t1->data, (size_t) w * h * sizeof(int32_t));
+	grok_free(buf);
+	t1_destroy(t1);
+	return ok ? 0 : 1;
+}
+
+/* Tier-1 decode of a code block given as codeword segments (what Tier-2 delivers with TERMALL / LAZY) */
+int ref_t1_decode_cblk_segs(const uint8_t *bytes, const uint32_t *seg_len, const uint32_t *seg_passes, uint32_t nsegs,
+		uint32_t numbps, uint32_t orient, uint32_t roishift, uint32_t cblksty, uint32_t w, uint32_t h, int32_t *out) {
+	t1_info *t1 = t1_create(false);
+	if (!t1)
+		return -1;
+	uint64_t total = 0;
+	for (uint32_t i = 0; i < nsegs; ++i) total += seg_len[i];
+	uint8_t *buf = (uint8_t*) grk_calloc(1, (size_t) total + 16);
+	memcpy(buf, bytes, total);
+	tcd_seg_data_chunk_t chunk;
+	chunk.data = buf;
+	chunk.len = (uint32_t) total + GRK_FAKE_MARKER_BYTES;
+	std::vector<tcd_seg_t> segs(nsegs ? nsegs : 1);
+	memset(segs.data(), 0, segs.size() * sizeof(tcd_seg_t));
+	for (uint32_t i = 0; i < nsegs; ++i) { segs[i].len = seg_len[i]; segs[i].real_num_passes = seg_passes[i]; }
+	tcd_cblk_dec_t cblk;
+	memset(&cblk, 0, sizeof(cblk));
+	cblk.numchunks = 1;
+	cblk.chunks = &chunk;
+	cblk.x0 = 0; cblk.y0 = 0; cblk.x1 = w; cblk.y1 = h;
+	cblk.real_num_segs = nsegs;
+	cblk.segs = segs.data();
 	cblk.numbps = numbps;
 	bool ok = t1_decode_cblk(t1, &cblk, orient, roishift, cblksty, false);
 	if (ok)

@@ -61,6 +61,9 @@ def oracle():
     L.gbo_t1_encode_block.argtypes = [i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p,
                                       C.POINTER(C.c_uint32), u32p, f64p, C.POINTER(C.c_uint64)]
     L.gbo_t1_decode_block.argtypes = [u8p, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i32p]
+    L.gbo_t1_encode_block_sty.argtypes = [i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p,
+                                          C.POINTER(C.c_uint32), u32p, f64p, u8p, C.POINTER(C.c_uint64)]
+    L.gbo_t1_decode_block_segs.argtypes = [u8p, u32p, u32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i32p]
     L.gbo_nmsedec_tables.argtypes = [i16p] * 4
     L.gbo_context_tables.argtypes = [u8p, u8p, u8p]
     L.gbo_enumerate_blocks.argtypes = [C.c_uint32] * 7 + [u32p, C.c_void_p]
@@ -92,6 +95,9 @@ def ref():
                                      C.POINTER(C.c_uint32), u32p, u32p, f64p, C.POINTER(C.c_double)]
     L.ref_t1_decode_cblk.argtypes = [u8p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                      C.c_uint32, C.c_uint32, i32p]
+    L.ref_t1_want_terms.argtypes = [u8p]
+    L.ref_t1_decode_cblk_segs.argtypes = [u8p, u32p, u32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                          C.c_uint32, i32p]
     L.ref_qcd_generate.argtypes = [C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_int, C.c_int, u32p, u32p]
     L.ref_band_stepsize.argtypes = [C.c_uint32] * 5 + [C.c_int, C.c_uint32, C.c_uint32, C.c_float,
                                                        C.POINTER(C.c_float), C.POINTER(C.c_uint32),
@@ -213,6 +219,78 @@ def ref_t1_encode(blk, orient, compno=0, level=0, qmfbid=1, stepsize=1.0, mct_no
     assert n >= 0
     total = int(rates[n - 1]) if n else 0
     return bytes(buf[:total]), nb.value, rates[:n].copy(), dists[:n].copy()
+
+
+def oracle_t1_encode_sty(blk, orient, sty, do_rd=False, wbase=0.0):
+    """as oracle_t1_encode with a code-block style byte -> (bytes, numbps, rates, dists, terms, nsym)"""
+    L = oracle()
+    h, w = blk.shape
+    buf = np.zeros(w * h * 4 + 64, np.uint8)
+    rates = np.zeros(128, np.uint32)
+    dists = np.zeros(128, np.float64)
+    terms = np.zeros(128, np.uint8)
+    nb = C.c_uint32()
+    ns = C.c_uint64()
+    n = L.gbo_t1_encode_block_sty(np.ascontiguousarray(blk, np.int32).ravel(), w, h, orient, sty, int(do_rd), wbase,
+                                  buf.ctypes.data + 2, C.byref(nb), rates, dists, terms, C.byref(ns))
+    assert n >= 0
+    total = int(rates[n - 1]) if n else 0
+    return bytes(buf[2:2 + total]), nb.value, rates[:n].copy(), dists[:n].copy(), terms[:n].copy(), ns.value
+
+
+def ref_t1_encode_sty(blk, orient, sty, compno=0, level=0, qmfbid=1, stepsize=1.0, mct_norms=None, do_rd=False):
+    """-> (bytes, numbps, rates, dists, terms) from the unmodified reference"""
+    L = ref()
+    h, w = blk.shape
+    buf = np.zeros(w * h * 4 + 64, np.uint8)
+    rates = np.zeros(128, np.uint32)
+    lens = np.zeros(128, np.uint32)
+    dists = np.zeros(128, np.float64)
+    terms = np.zeros(128, np.uint8)
+    nb = C.c_uint32()
+    td = C.c_double()
+    if mct_norms is not None:
+        mn = np.ascontiguousarray(mct_norms, np.float64)
+        mp, nm = mn.ctypes.data, len(mn)
+    else:
+        mp, nm = None, 0
+    L.ref_t1_want_terms(terms)
+    n = L.ref_t1_encode_cblk(np.ascontiguousarray(blk, np.int32).ravel(), w, h, orient, compno, level, qmfbid,
+                             stepsize, sty, mp, nm, int(do_rd), buf, C.byref(nb), rates, lens, dists, C.byref(td))
+    assert n >= 0
+    total = int(rates[n - 1]) if n else 0
+    return bytes(buf[:total]), nb.value, rates[:n].copy(), dists[:n].copy(), terms[:n].copy()
+
+
+def segments_from_passes(rates, terms, npasses=None):
+    """codeword segments (len, passes) of the first `npasses` coding passes: a segment ends at every terminated pass"""
+    n = len(rates) if npasses is None else npasses
+    lens, cnts, start, cnt = [], [], 0, 0
+    for i in range(n):
+        cnt += 1
+        if terms[i] or i == n - 1:
+            lens.append(int(rates[i]) - start)
+            cnts.append(cnt)
+            start, cnt = int(rates[i]), 0
+    return np.array(lens, np.uint32), np.array(cnts, np.uint32)
+
+
+def oracle_t1_decode_segs(data, seg_len, seg_passes, numbps, orient, sty, w, h):
+    out = np.zeros((h, w), np.int32)
+    b = np.frombuffer(bytes(data) + b"\0\0", np.uint8).copy()
+    rc = oracle().gbo_t1_decode_block_segs(b, np.ascontiguousarray(seg_len, np.uint32), np.ascontiguousarray(seg_passes, np.uint32),
+                                           len(seg_len), numbps, orient, sty, w, h, out.ravel())
+    assert rc == 0
+    return out
+
+
+def ref_t1_decode_segs(data, seg_len, seg_passes, numbps, orient, sty, w, h):
+    out = np.zeros((h, w), np.int32)
+    b = np.frombuffer(bytes(data) + b"\0\0", np.uint8).copy()
+    rc = ref().ref_t1_decode_cblk_segs(b, np.ascontiguousarray(seg_len, np.uint32), np.ascontiguousarray(seg_passes, np.uint32),
+                                       len(seg_len), numbps, orient, 0, sty, w, h, out.ravel())
+    assert rc == 0
+    return out
 
 
 def oracle_t1_decode(data, numpasses, numbps, orient, w, h):

@@ -80,6 +80,37 @@ def test_t1_live_random_blocks():
     assert nsym > 500000
 
 
+def test_t1_code_block_styles_against_live_reference():
+    """every code-block style switch (LAZY, RESET, TERMALL, VSC, PTERM, SEGSYM) and random combinations of them:
+    bytes, bit planes, rates, termination flags and fp64 distortions of the restatement equal the reference's, and the
+    segment-wise decode of full and truncated streams agrees"""
+    from _libs import oracle_t1_encode_sty, ref_t1_encode_sty, segments_from_passes, oracle_t1_decode_segs, ref_t1_decode_segs
+    rng = np.random.default_rng(77)
+    stys = [1, 2, 4, 8, 16, 32, 1 | 4, 1 | 16, 4 | 16, 2 | 8 | 32, 63] + [int(v) for v in rng.integers(1, 64, 40)]
+    for it, sty in enumerate(stys):
+        w = int(rng.choice([64, 32, 17, 5, 64, 33]))
+        h = int(rng.choice([64, 32, 13, 4, 7, 64]))
+        amp = float(rng.choice([2, 20, 300, 5000, 60000]))
+        v = rng.laplace(0, amp, (h, w))
+        if it % 4 == 3:
+            v = v * (rng.random((h, w)) < 0.1)
+        q = (np.rint(v).astype(np.int64) * 64 + rng.integers(0, 64, (h, w)) * (it % 2)).astype(np.int32)
+        orient, do_rd = int(rng.integers(0, 4)), bool(it % 2)
+        step, lvl, comp, qm = float(rng.choice([1.0, 0.03125, 2.0])), int(rng.integers(0, 5)), int(rng.integers(0, 3)), int(rng.integers(0, 2))
+        norms = np.array([1.732, 1.805, 1.573]) if qm == 0 else np.array([1.732, .8292, .8292])
+        rb, rnb, rr, rd, rt = ref_t1_encode_sty(q, orient, sty, comp, lvl, qm, step, norms, do_rd)
+        wbase = (norms[comp] * ref().ref_dwt_norm(lvl, orient, qm)) * step
+        ob, onb, orr, od, ot, ns = oracle_t1_encode_sty(q, orient, sty, do_rd, wbase)
+        assert rnb == onb and (rr == orr).all() and (rt == ot).all() and rb == ob and (rd == od).all(), (it, sty)
+        if len(rr):
+            for k in sorted({len(rr), max(1, len(rr) // 2), 1}):
+                sl, sp = segments_from_passes(rr, rt, k)
+                ln = int(sl.sum())
+                a = ref_t1_decode_segs(rb[:ln], sl, sp, rnb, orient, sty, w, h)
+                b = oracle_t1_decode_segs(rb[:ln], sl, sp, rnb, orient, sty, w, h)
+                assert (a == b).all(), (it, sty, k)
+
+
 def test_tables_and_quantiser_constants():
     O, R = oracle(), ref()
     # step size / numbps / inv_step formula (Quantizer.cpp:65-105) against the E.1.1 restatement used by params.py
