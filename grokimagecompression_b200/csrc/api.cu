@@ -88,6 +88,7 @@ struct gb200_plan {
 	uint64_t d_data_len = 0;
 	uint32_t max_bw = 1, max_bh = 1; // largest code block of the table
 	bool uniform = true; // every tile shares mct / qmfbid / shift / range parameters
+	bool styles = false; // some component uses code-block style switches
 	std::vector<EncResult> h_results;
 	// where each tile-component's final decoded plane lives (0 A, 1 B, 2 C)
 	std::vector<int> final_role;
@@ -249,7 +250,8 @@ int gb200_plan_create(gb200_ctx *ctx, uint32_t ntiles, const gb200_tile_params *
 			cg.p = tp.comps[c];
 			const gb200_comp_params &p = cg.p;
 			if (p.numres < 1 || p.numres > GB200_MAX_RES || p.x1 < p.x0 || p.y1 < p.y0) return bail(GB200_ERR_PARAM, "bad component rectangle / numres");
-			if (p.cblk_sty != 0) return bail(GB200_ERR_UNSUPPORTED, "code-block style switches (LAZY/RESET/TERMALL/VSC/PTERM/SEGSYM) are not implemented");
+			if (p.cblk_sty & ~(uint32_t) STY_ALL) return bail(GB200_ERR_UNSUPPORTED, "HT code blocks (cblk_sty 0x40) are not implemented");
+			if (p.cblk_sty) pl->styles = true;
 			if (p.roishift != 0) return bail(GB200_ERR_UNSUPPORTED, "ROI shift is not implemented");
 			if (p.cblkw_expn > 6 || p.cblkh_expn > 6 || p.cblkw_expn < 2 || p.cblkh_expn < 2)
 				return bail(GB200_ERR_UNSUPPORTED, "code blocks larger than 64x64 are not implemented");
@@ -420,8 +422,10 @@ int gb200_plan_create(gb200_ctx *ctx, uint32_t ntiles, const gb200_tile_params *
 					eb.inv_step = (int32_t) p.inv_step[g.band_index];
 					eb.pass_offset = bi.pass_offset;
 					eb.max_passes = bi.max_passes;
-					eb.scratch_cap = (uint32_t) align_up((uint64_t) bw * bh * 4 + 2, 16);
+					// the reference's bound (TileProcessor.cpp:2003-2018); terminated passes add a few flush bytes each
+					eb.scratch_cap = (uint32_t) align_up((uint64_t) bw * bh * 4 + 2 + (p.cblk_sty ? 4 * bi.max_passes : 0), 16);
 					eb.scratch_off = scratch_off;
+					eb.sty = (uint8_t) p.cblk_sty;
 					eb.rd_weight = p.rd_weight[g.band_index];
 					eb.sym_off = sym_off;
 					eb.sym_cap = t1_symbol_capacity(bw, bh, std::max<uint32_t>(p.band_numbps[g.band_index], 1));
@@ -436,6 +440,7 @@ int gb200_plan_create(gb200_ctx *ctx, uint32_t ntiles, const gb200_tile_params *
 					db.w = (uint16_t) bw; db.h = (uint16_t) bh;
 					db.orient = (uint8_t) g.orient;
 					db.reversible = p.qmfbid == 1;
+					db.sty = (uint8_t) p.cblk_sty;
 					db.stepsize = p.stepsize[g.band_index];
 					pl->decblocks.push_back(db);
 				}
@@ -568,7 +573,7 @@ static int run_t1_enc(gb200_plan *pl) {
 	if (!nb) return GB200_OK;
 	int rc = 0;
 	for (auto &tg : pl->tiles) rc |= (int) tg.rate_control;
-	launch_t1_encode((const EncBlock*) pl->d_blocks.p, nb, rc, (uint8_t*) pl->d_symbols.p, (uint8_t*) pl->d_scratch.p,
+	launch_t1_encode((const EncBlock*) pl->d_blocks.p, nb, rc, pl->styles ? 1 : 0, (uint8_t*) pl->d_symbols.p, (uint8_t*) pl->d_scratch.p,
 			(EncResult*) pl->d_results.p, (uint32_t*) pl->d_rates.p, (double*) pl->d_dists.p, ctx->stream);
 	launch_t1_gather((const EncBlock*) pl->d_blocks.p, (EncResult*) pl->d_results.p, nb, (const uint8_t*) pl->d_scratch.p,
 			(uint8_t*) pl->d_data.p, ctx->stream);
@@ -898,6 +903,7 @@ int gb200_t1_encode_blocks(gb200_ctx *ctx, const int32_t *plane, uint32_t width,
 	cudaStream_t s = ctx->stream;
 	std::vector<EncBlock> eb(nblocks);
 	uint64_t off = 0, soff = 0;
+	bool styles = false;
 	DevBuf d_plane, d_blocks, d_results, d_rates, d_dists, d_scratch, d_data, d_symbols;
 	auto freeall = [&]() { d_plane.release(); d_blocks.release(); d_results.release(); d_rates.release(); d_dists.release(); d_scratch.release(); d_data.release(); d_symbols.release(); };
 	if (d_plane.alloc(std::max<size_t>((size_t) width * height * 4, 16))) FAIL(GB200_ERR_NOMEM, "cudaMalloc failed");
@@ -909,8 +915,11 @@ int gb200_t1_encode_blocks(gb200_ctx *ctx, const int32_t *plane, uint32_t width,
 		e.src = (const int32_t*) d_plane.p + (size_t) b.y * width + b.x;
 		e.stride = width; e.w = (uint16_t) b.w; e.h = (uint16_t) b.h; e.orient = (uint8_t) b.orient;
 		e.reversible = b.qmfbid == 1; e.inv_step = (int32_t) b.inv_step;
+		if (b.cblk_sty & ~(uint32_t) STY_ALL) { freeall(); FAIL(GB200_ERR_UNSUPPORTED, "HT code blocks are not implemented"); }
+		e.sty = (uint8_t) b.cblk_sty;
+		styles |= b.cblk_sty != 0;
 		e.pass_offset = i * max_passes; e.max_passes = max_passes;
-		e.scratch_cap = (uint32_t) align_up((uint64_t) b.w * b.h * 4 + 2, 16);
+		e.scratch_cap = (uint32_t) align_up((uint64_t) b.w * b.h * 4 + 2 + (b.cblk_sty ? 4 * max_passes : 0), 16);
 		e.scratch_off = off; e.rd_weight = b.rd_weight;
 		e.sym_off = soff;
 		e.sym_cap = t1_symbol_capacity(b.w, b.h, (max_passes + 2) / 3);
@@ -926,7 +935,7 @@ int gb200_t1_encode_blocks(gb200_ctx *ctx, const int32_t *plane, uint32_t width,
 	cudaMemsetAsync(d_scratch.p, 0, d_scratch.bytes, s);
 	cudaMemsetAsync(d_rates.p, 0, d_rates.bytes, s);
 	cudaMemsetAsync(d_dists.p, 0, d_dists.bytes, s);
-	launch_t1_encode((const EncBlock*) d_blocks.p, nblocks, rate_control, (uint8_t*) d_symbols.p, (uint8_t*) d_scratch.p,
+	launch_t1_encode((const EncBlock*) d_blocks.p, nblocks, rate_control, styles ? 1 : 0, (uint8_t*) d_symbols.p, (uint8_t*) d_scratch.p,
 			(EncResult*) d_results.p, (uint32_t*) d_rates.p, (double*) d_dists.p, s);
 	launch_t1_gather((const EncBlock*) d_blocks.p, (EncResult*) d_results.p, nblocks, (const uint8_t*) d_scratch.p, (uint8_t*) d_data.p, s);
 	int rc = launch_check(ctx, 4);

@@ -25,7 +25,7 @@ struct EncBlock {
 	const int32_t *src;  // top-left coefficient of the block inside its sub-band (DWT output)
 	uint32_t stride;
 	uint16_t w, h;
-	uint8_t orient, reversible, pad0, pad1;
+	uint8_t orient, reversible, sty /* code-block style switches, STY_* */, pad1;
 	int32_t inv_step;
 	uint32_t pass_offset; // first slot in rates/dists
 	uint32_t max_passes;
@@ -37,6 +37,9 @@ struct EncBlock {
 	uint32_t pad2;
 };
 
+// code-block style switches (tccp->cblk_sty, grok.h GRK_CBLKSTY_*)
+enum { STY_LAZY = 1, STY_RESET = 2, STY_TERMALL = 4, STY_VSC = 8, STY_PTERM = 16, STY_SEGSYM = 32, STY_ALL = 63 };
+
 struct EncResult { // == gb200_cblk_enc
 	uint32_t numbps, numpasses, data_len, decisions;
 	uint64_t data_offset;
@@ -47,7 +50,7 @@ struct DecBlock {
 	int32_t *dst;        // top-left of the block inside the coefficient plane
 	uint32_t stride;
 	uint16_t w, h;
-	uint8_t orient, reversible, pad0, pad1;
+	uint8_t orient, reversible, sty, pad1;
 	float stepsize;
 	uint32_t pad2;
 };
@@ -78,7 +81,8 @@ void dwt_tile_shape(int reversible, uint32_t *tw); // valid columns per CTA
 
 // t1_enc.cu / t1_dec.cu
 uint32_t t1_symbol_capacity(uint32_t w, uint32_t h, uint32_t planes);
-void launch_t1_encode(const EncBlock *blocks, uint32_t nblocks, int rate_control, uint8_t *symbols, uint8_t *scratch,
+// styles: non-zero when any block of the table has a code-block style switch set (selects the general MQ kernel)
+void launch_t1_encode(const EncBlock *blocks, uint32_t nblocks, int rate_control, int styles, uint8_t *symbols, uint8_t *scratch,
 		EncResult *results, uint32_t *rates, double *dists, cudaStream_t s);
 void launch_t1_gather(const EncBlock *blocks, EncResult *results, uint32_t nblocks, const uint8_t *scratch,
 		uint8_t *data, cudaStream_t s);

@@ -55,8 +55,10 @@ __device__ __forceinline__ uint32_t win3(uint64_t m, int x) {
 	return (uint32_t) (x == 0 ? (m << 1) : (m >> (x - 1))) & 7u;
 }
 
-constexpr uint32_t SYM_PASS_END = 0x80;   // marker: end of a coding pass
-constexpr uint32_t SYM_FLUSH_END = 0x81;  // marker: end of the last pass, terminate the codeword
+// marker bytes close every coding pass: 0x80 | terminated | last pass << 1 | next pass bypasses the MQ coder << 2
+constexpr uint32_t SYM_PASS_END = 0x80;   // not terminated
+constexpr uint32_t SYM_TERM = 1, SYM_LAST = 2, SYM_NEXT_RAW = 4;
+constexpr uint32_t SYM_FLUSH_END = 0x80 | SYM_TERM | SYM_LAST; // end of the block's last pass
 
 struct SymOut {
 	uint8_t *base;   // symbol stream of this block
@@ -120,6 +122,7 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, ENC_MIN_CTAS) t1_model_kernel(
 	const bool rev = B.reversible != 0;
 	const uint64_t wmask = w >= 64 ? ~0ull : ((1ull << w) - 1);
 	const uint8_t *zc = L.zc[B.orient];
+	const uint32_t sty = B.sty;
 
 	// ---- quantise, block maximum, sign masks ------------------------------------------------
 	for (int i = lane; i < 66; i += 32) { W.sig[i] = 0; W.neg[i] = 0; W.vis[i] = 0; W.refd[i] = 0; W.bit[i] = 0; }
@@ -164,11 +167,14 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, ENC_MIN_CTAS) t1_model_kernel(
 
 		for (int type = (bp == numbps - 1 ? 2 : 0); type < 3; ++type) {
 			int nmsedec = 0;
+			// selective arithmetic coding bypass: raw passes carry the sign itself (t1.cpp:224-229, 1229-1231)
+			const bool raw = (sty & STY_LAZY) && bp < numbps - 4 && type < 2;
 			for (int y0 = 0; y0 < h; y0 += 4) {
 				const int nk = min(4, h - y0);
 				uint64_t S[6], Bm[4], M[4], N[4], H0[4];
 				#pragma unroll
 				for (int j = 0; j < 6; ++j) S[j] = W.sig[y0 + j];
+				if (sty & STY_VSC) S[5] = 0; // stripe-causal contexts: the row below the stripe is invisible (t1.cpp:177-182)
 				#pragma unroll
 				for (int k = 0; k < 4; ++k) {
 					Bm[k] = W.bit[y0 + 1 + k];
@@ -263,7 +269,7 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, ENC_MIN_CTAS) t1_model_kernel(
 										uint32_t idx = sN | sW << 1 | sE << 2 | sS << 3 | (gN & sN) << 4 | (gW & sW) << 5 | (gE & sE) << 6 | (gS & sS) << 7;
 										uint32_t v = L.sc[idx];
 										uint32_t sgn = gw[k + 1] >> 1 & 1;
-										PUSH((v & 31) << 1 | (sgn ^ (v >> 5)));
+										PUSH((v & 31) << 1 | (raw ? sgn : sgn ^ (v >> 5)));
 										if (rate_control) {
 											uint32_t mag = (uint32_t) abs(quantise(B.src[(size_t) (y0 + k) * B.stride + gx], rev, B.inv_step));
 											nmsedec += L.nmsedec[bp > 0 ? 0 : 1][(mag >> bp) & 127];
@@ -289,6 +295,9 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, ENC_MIN_CTAS) t1_model_kernel(
 			if (type == 2) {
 				for (int i = lane; i < 66; i += 32) W.vis[i] = 0;
 				__syncwarp();
+				if (sty & STY_SEGSYM) // segmentation symbol 1010 in the UNIFORM context (mqc_enc.cpp:409-413)
+					emit(W, q, lane == 0 ? (uint64_t) (CTX_UNI << 1 | 1) | (uint64_t) (CTX_UNI << 1) << 8 | (uint64_t) (CTX_UNI << 1 | 1) << 16
+							| (uint64_t) (CTX_UNI << 1) << 24 : 0ull, 0u, lane == 0 ? 4 : 0, lane);
 			}
 			// ---- pass bookkeeping (t1.cpp:1255-1290) ----------------------------------------
 			if (rate_control) {
@@ -298,7 +307,14 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, ENC_MIN_CTAS) t1_model_kernel(
 				x = __dmul_rn(x, __ddiv_rn(__dmul_rn(x, (double) nmsedec), 8192.0));
 				cum = __dadd_rn(cum, x);
 			}
-			emit_marker(q, type == 2 && bp == 0 ? SYM_FLUSH_END : SYM_PASS_END, lane);
+			{ // t1_enc_is_term_pass, t1.cpp:1131-1151
+				const bool last = type == 2 && bp == 0;
+				bool term = last || (sty & STY_TERMALL);
+				if (sty & STY_LAZY) term = term || (bp == numbps - 4 && type == 2) || (bp < numbps - 4 && type > 0);
+				const int ntype = type == 2 ? 0 : type + 1, nbp = type == 2 ? bp - 1 : bp;
+				const bool next_raw = !last && (sty & STY_LAZY) && nbp < numbps - 4 && ntype < 2;
+				emit_marker(q, SYM_PASS_END | (term ? SYM_TERM : 0u) | (last ? SYM_LAST : 0u) | (next_raw ? SYM_NEXT_RAW : 0u), lane);
+			}
 			if (lane == 0 && (uint32_t) npass < B.max_passes) my_dists[npass] = rate_control ? cum : 0.0;
 			npass++;
 		}
@@ -349,7 +365,7 @@ __device__ __forceinline__ void mqt_byteout(MqT &q, uint8_t *out, uint32_t cap, 
 	else { q.last = (q.c >> 19) & 0xFF; q.c &= 0x7FFFFu; q.ct = 8; }
 }
 
-template<int LANES>
+template<int LANES, bool STY>
 __global__ void __launch_bounds__(MQ_WARPS * 32) t1_mq_kernel(const EncBlock *__restrict__ blocks, uint32_t nblocks,
 		const uint8_t *__restrict__ symbols, uint8_t *__restrict__ scratch, EncResult *__restrict__ results,
 		uint32_t *__restrict__ rates) {
@@ -410,45 +426,128 @@ __global__ void __launch_bounds__(MQ_WARPS * 32) t1_mq_kernel(const EncBlock *__
 		q.ct -= sh;
 	};
 
-	// one byte per symbol, 0x80 / 0x81 close a coding pass; eight symbols per load, the next eight already in flight.
-	// Groups without a marker (all but ~1 in 200) run fully unrolled.
 	const uint2 *sp = reinterpret_cast<const uint2*>(symbols + B.sym_off); // sym_off is 16-byte aligned
 	uint2 nxt = sp[0];
 	uint32_t word = 1, consumed = 0;
 	bool done = false;
-	while (!done) {
-		const uint2 cur = nxt;
-		nxt = sp[word++];
-		if (((cur.x | cur.y) & 0x80808080u) == 0) {
-			#pragma unroll
-			for (int j = 0; j < 8; ++j) code(((j < 4 ? cur.x : cur.y) >> (8 * (j & 3))) & 0xFFu);
-		} else {
+	if (!STY) {
+		// one byte per symbol, a marker closes every coding pass; eight symbols per load, the next eight already in
+		// flight.  Groups without a marker (all but ~1 in 200) run fully unrolled.
+		while (!done) {
+			const uint2 cur = nxt;
+			nxt = sp[word++];
+			if (((cur.x | cur.y) & 0x80808080u) == 0) {
+				#pragma unroll
+				for (int j = 0; j < 8; ++j) code(((j < 4 ? cur.x : cur.y) >> (8 * (j & 3))) & 0xFFu);
+			} else {
+				uint64_t grp = (uint64_t) cur.x | ((uint64_t) cur.y << 32);
+				#pragma unroll 1
+				for (uint32_t j = 0; j < 8 && !done; ++j, grp >>= 8) {
+					const uint32_t sym = (uint32_t) grp & 0xFFu;
+					if (!(sym & 0x80u)) { code(sym); continue; }
+					// end of a coding pass (t1.cpp:1255-1290)
+					uint32_t rate;
+					if (sym & SYM_LAST) { // FLUSH, mqc_enc.cpp:235-243, 274-287
+						const uint32_t t = q.c + (q.a >> 16);
+						q.c |= 0xFFFFu;
+						if (q.c >= t) q.c -= 0x8000u;
+						q.c <<= q.ct; mqt_byteout(q, out, cap, overflow);
+						q.c <<= q.ct; mqt_byteout(q, out, cap, overflow);
+						if (q.last != 0xFF) {
+							if ((uint32_t) q.pos < cap) out[q.pos] = (uint8_t) q.last; else overflow = 1;
+							q.pos++;
+						}
+						rate = (uint32_t) q.pos;
+						nsym = consumed + j - (uint32_t) npass;
+						done = true;
+					} else rate = (uint32_t) q.pos + (q.ct < 5 ? 6 : 5);
+					if ((uint32_t) npass < B.max_passes) my_rates[npass] = rate;
+					npass++;
+				}
+			}
+			consumed += 8;
+		}
+	} else {
+		// code-block style switches (t1.cpp:1223-1298): per-pass termination (TERMALL, LAZY), predictable termination
+		// (PTERM), context reset (RESET), raw passes (LAZY).  In raw mode q.pos is the next free byte and q.c / q.ct
+		// the partial byte (mqc_enc.cpp:291-377); in MQ mode q.pos is the index of the pending byte q.last.
+		const uint32_t sty = B.sty;
+		const bool pterm = (sty & STY_PTERM) != 0;
+		constexpr int RAW_CT_INIT = 0x7FFFFFFF;
+		bool raw = false;
+		auto byte_at = [&](int i) -> uint32_t { return (i >= 0 && (uint32_t) i < cap) ? out[i] : 0u; };
+		auto put = [&](uint32_t v) { if ((uint32_t) q.pos < cap) out[q.pos] = (uint8_t) v; else overflow = 1; q.pos++; };
+		auto raw_pending = [&]() { return q.ct < 7 || (q.ct == 7 && (pterm || byte_at(q.pos - 1) != 0xFFu)); };
+		while (!done) {
+			const uint2 cur = nxt;
+			nxt = sp[word++];
 			uint64_t grp = (uint64_t) cur.x | ((uint64_t) cur.y << 32);
 			#pragma unroll 1
 			for (uint32_t j = 0; j < 8 && !done; ++j, grp >>= 8) {
 				const uint32_t sym = (uint32_t) grp & 0xFFu;
-				if (!(sym & 0x80u)) { code(sym); continue; }
-				// end of a coding pass (t1.cpp:1255-1290)
-				uint32_t rate;
-				if (sym == SYM_FLUSH_END) { // FLUSH, mqc_enc.cpp:235-243, 274-287
-					const uint32_t t = q.c + (q.a >> 16);
-					q.c |= 0xFFFFu;
-					if (q.c >= t) q.c -= 0x8000u;
-					q.c <<= q.ct; mqt_byteout(q, out, cap, overflow);
-					q.c <<= q.ct; mqt_byteout(q, out, cap, overflow);
-					if (q.last != 0xFF) {
-						if ((uint32_t) q.pos < cap) out[q.pos] = (uint8_t) q.last; else overflow = 1;
-						q.pos++;
+				if (!(sym & 0x80u)) {
+					if (!raw) { code(sym); continue; }
+					if (q.ct == RAW_CT_INIT) q.ct = 8; // mqc_bypass_enc
+					q.ct--;
+					q.c += (sym & 1u) << q.ct;
+					if (q.ct == 0) {
+						put(q.c);
+						q.ct = q.c == 0xFFu ? 7 : 8; // the byte after 0xFF keeps its MSB clear
+						q.c = 0;
 					}
-					rate = (uint32_t) q.pos;
-					nsym = consumed + j - (uint32_t) npass;
-					done = true;
-				} else rate = (uint32_t) q.pos + (q.ct < 5 ? 6 : 5);
+					continue;
+				}
+				uint32_t rate;
+				if (sym & SYM_TERM) {
+					if (raw) { // mqc_bypass_flush_enc
+						if (raw_pending()) {
+							uint32_t bit = 0;
+							while (q.ct > 0) { q.ct--; q.c += bit << q.ct; bit ^= 1u; }
+							put(q.c);
+						} else if (q.ct == 7 && byte_at(q.pos - 1) == 0xFFu) q.pos--;
+						else if (q.ct == 8 && !pterm && byte_at(q.pos - 1) == 0x7Fu && byte_at(q.pos - 2) == 0xFFu) q.pos -= 2;
+					} else if (pterm) { // mqc_erterm_enc
+						int k = 11 - q.ct + 1;
+						while (k > 0) {
+							q.c <<= q.ct;
+							q.ct = 0;
+							mqt_byteout(q, out, cap, overflow);
+							k -= q.ct;
+						}
+						if (q.last != 0xFF) mqt_byteout(q, out, cap, overflow);
+					} else { // mqc_flush_enc
+						const uint32_t t = q.c + (q.a >> 16);
+						q.c |= 0xFFFFu;
+						if (q.c >= t) q.c -= 0x8000u;
+						q.c <<= q.ct; mqt_byteout(q, out, cap, overflow);
+						q.c <<= q.ct; mqt_byteout(q, out, cap, overflow);
+						if (q.last != 0xFF) put(q.last);
+					}
+					rate = (uint32_t) max(q.pos, 0);
+				} else if (raw) rate = (uint32_t) q.pos + (raw_pending() ? 2u : 1u);
+				else rate = (uint32_t) q.pos + (q.ct < 5 ? 6 : 5);
 				if ((uint32_t) npass < B.max_passes) my_rates[npass] = rate;
 				npass++;
+				if (sty & STY_RESET) {
+					#pragma unroll
+					for (int i = 0; i < NCTX; ++i) C[i] = tab[2 * (i == CTX_ZC0 ? 4 : i == CTX_AGG ? 3 : i == CTX_UNI ? 46 : 0)];
+				}
+				if (sym & SYM_LAST) {
+					nsym = consumed + j - (uint32_t) (npass - 1);
+					done = true;
+				} else if (sym & SYM_TERM) { // the next pass starts a new codeword segment
+					raw = (sym & SYM_NEXT_RAW) != 0;
+					if (raw) { q.c = 0; q.ct = RAW_CT_INIT; } // mqc_bypass_init_enc: q.pos is already the next free byte
+					else { // mqc_restart_init_enc: the last byte of the previous segment is pending again
+						q.a = 0x80000000u; q.c = 0; q.ct = 12;
+						q.pos--;
+						q.last = byte_at(q.pos);
+						if (q.last == 0xFFu) q.ct = 13;
+					}
+				}
 			}
+			consumed += 8;
 		}
-		consumed += 8;
 	}
 	// ---- rate fix-ups (t1.cpp:1300-1324): non-increasing from the end, no trailing 0xFF ------
 	const int np = min(npass, (int) B.max_passes);
@@ -499,7 +598,7 @@ __global__ void __launch_bounds__(256) t1_gather_kernel(const EncBlock *__restri
 
 static bool g_tables_ready = false;
 
-void launch_t1_encode(const EncBlock *blocks, uint32_t nblocks, int rate_control, uint8_t *symbols, uint8_t *scratch,
+void launch_t1_encode(const EncBlock *blocks, uint32_t nblocks, int rate_control, int styles, uint8_t *symbols, uint8_t *scratch,
 		EncResult *results, uint32_t *rates, double *dists, cudaStream_t s) {
 	if (!nblocks) return;
 	if (!g_tables_ready) { build_and_upload_t1_tables(); g_tables_ready = true; }
@@ -508,17 +607,19 @@ void launch_t1_encode(const EncBlock *blocks, uint32_t nblocks, int rate_control
 	int dev = 0, sms = 148;
 	cudaGetDevice(&dev);
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-	if (nblocks <= (uint32_t) sms * MQ_SPARSE_BLOCKS_PER_SM)
-		t1_mq_kernel<1><<<(nblocks + MQ_WARPS - 1) / MQ_WARPS, MQ_WARPS * 32, 0, s>>>(blocks, nblocks, symbols, scratch, results, rates);
+	if (styles)
+		t1_mq_kernel<1, true><<<(nblocks + MQ_WARPS - 1) / MQ_WARPS, MQ_WARPS * 32, 0, s>>>(blocks, nblocks, symbols, scratch, results, rates);
+	else if (nblocks <= (uint32_t) sms * MQ_SPARSE_BLOCKS_PER_SM)
+		t1_mq_kernel<1, false><<<(nblocks + MQ_WARPS - 1) / MQ_WARPS, MQ_WARPS * 32, 0, s>>>(blocks, nblocks, symbols, scratch, results, rates);
 	else
-		t1_mq_kernel<MQ_LANES><<<(nblocks + MQ_WARPS * MQ_LANES - 1) / (MQ_WARPS * MQ_LANES), MQ_WARPS * 32, 0, s>>>(blocks, nblocks, symbols, scratch, results, rates);
+		t1_mq_kernel<MQ_LANES, false><<<(nblocks + MQ_WARPS * MQ_LANES - 1) / (MQ_WARPS * MQ_LANES), MQ_WARPS * 32, 0, s>>>(blocks, nblocks, symbols, scratch, results, rates);
 }
 
 // bytes of symbol stream to reserve for a w x h block with at most `planes` coded bit-planes: every sample
 // yields at most one decision per plane plus one sign, run-length mode adds at most two per stripe column,
 // one marker per pass; rounded up so that streams stay 16-byte aligned and 16 bytes can be read past the end
 uint32_t t1_symbol_capacity(uint32_t w, uint32_t h, uint32_t planes) {
-	uint64_t n = (uint64_t) planes * (w * h + ((h + 3) / 4) * w * 2) + (uint64_t) w * h + 3 * planes + 8;
+	uint64_t n = (uint64_t) planes * (w * h + ((h + 3) / 4) * w * 2) + (uint64_t) w * h + 3 * planes + 4 * planes /* SEGSYM */ + 8;
 	return (uint32_t) ((n + 16 + 15) / 16 * 16);
 }
 

@@ -33,7 +33,7 @@ extern "C" {
 
 #define GB200_MAX_RES 33
 #define GB200_MAX_BANDS (3 * GB200_MAX_RES - 2)
-#define GB200_ABI_VERSION 1
+#define GB200_ABI_VERSION 2
 #if defined(__GNUC__)
 #define GB200_API __attribute__((visibility("default")))
 #else
@@ -65,7 +65,8 @@ typedef struct gb200_comp_params {
 	uint32_t prec;                      /* image component precision */
 	uint32_t sgnd;                      /* image component signedness */
 	int32_t dc_shift;                   /* tccp->m_dc_level_shift */
-	uint32_t cblk_sty;                  /* tccp->cblk_sty; only 0 is implemented */
+	uint32_t cblk_sty;                  /* tccp->cblk_sty: LAZY 0x01, RESET 0x02, TERMALL 0x04, VSC 0x08, PTERM 0x10, SEGSYM 0x20
+	                                     * (t1.cpp:1131-1151, 1223-1298); HT 0x40 is not implemented */
 	uint32_t roishift;                  /* tccp->roishift; only 0 is implemented */
 	float stepsize[GB200_MAX_BANDS];    /* band->stepsize (decoder side already carries the x0.5) */
 	uint32_t inv_step[GB200_MAX_BANDS]; /* band->inv_step, 13-bit fixed point */
@@ -183,6 +184,8 @@ typedef struct gb200_t1_block {
 	uint32_t inv_step;
 	float stepsize;       /* decoder: de-quantisation step (9/7) */
 	double rd_weight;
+	uint32_t cblk_sty;    /* code-block style switches, as gb200_comp_params::cblk_sty */
+	uint32_t reserved;
 } gb200_t1_block;
 GB200_API int gb200_t1_encode_blocks(gb200_ctx *ctx, const int32_t *plane, uint32_t width, uint32_t height, uint32_t nblocks,
 		const gb200_t1_block *blocks, int rate_control, uint32_t max_passes, gb200_cblk_enc *results,

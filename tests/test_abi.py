@@ -28,7 +28,7 @@ def test_every_declared_symbol_is_exported():
     out = subprocess.check_output(["nm", "-D", "--defined-only", gb.LIB_PATH], text=True)
     exported = set(re.findall(r" T (gb200_\w+)", out))
     assert exported == set(names)
-    assert L.gb200_abi_version() == 1
+    assert L.gb200_abi_version() == 2
 
 
 def test_struct_layouts_match_c(tmp_path):

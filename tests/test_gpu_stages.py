@@ -161,6 +161,38 @@ def test_t1_encode_blocks(ctx, rev, rd):
     assert total_dec > 100000
 
 
+STYLES = [1, 2, 4, 8, 16, 32, 1 | 4, 1 | 16, 4 | 16, 1 | 4 | 16, 2 | 8 | 32, 63, 1 | 2 | 8, 1 | 32, 4 | 8]
+
+
+@pytest.mark.parametrize("rd", [False, True])
+def test_t1_encode_blocks_with_style_switches(ctx, rd):
+    """LAZY / RESET / TERMALL / VSC / PTERM / SEGSYM and combinations: bytes, rates and distortions against the oracle"""
+    from _libs import oracle_t1_encode_sty
+    rng = np.random.default_rng(500 + rd)
+    blocks = _random_blocks(rng, 120)
+    plane, desc = _layout(blocks)
+    for i in range(len(blocks)):
+        desc[i]["orient"] = rng.integers(0, 4)
+        desc[i]["qmfbid"] = 1
+        desc[i]["inv_step"] = 8192
+        desc[i]["stepsize"] = 1.0
+        desc[i]["rd_weight"] = float(rng.choice([1.0, 0.0123, 3.7]))
+        desc[i]["cblk_sty"] = STYLES[i % len(STYLES)] if i % 7 else int(rng.integers(1, 64))
+    res, rates, dists, data = ctx.t1_encode_blocks(plane, desc, rate_control=rd, max_passes=100)
+    for i, b in enumerate(blocks):
+        sty = int(desc[i]["cblk_sty"])
+        q = (b.astype(np.int64) * 64).astype(np.int32)
+        ob, onb, orr, od, ot, ns = oracle_t1_encode_sty(q, int(desc[i]["orient"]), sty, rd, float(desc[i]["rd_weight"]))
+        r = res[i]
+        assert r["numbps"] == onb and r["numpasses"] == len(orr), (i, sty)
+        assert (rates[i, :len(orr)] == orr).all(), (i, sty, rates[i, :len(orr)], orr)
+        got = bytes(data[int(r["data_offset"]):int(r["data_offset"]) + int(r["data_len"])])
+        assert got == ob, (i, sty)
+        assert r["decisions"] == ns, (i, sty)
+        if rd:
+            assert (dists[i, :len(orr)] == od).all(), (i, sty)
+
+
 @pytest.mark.parametrize("rev", [1, 0])
 def test_t1_decode_blocks(ctx, rev):
     rng = np.random.default_rng(300 + rev)
