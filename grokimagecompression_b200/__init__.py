@@ -4,9 +4,9 @@ DWT, quantisation, EBCOT Tier-1) as hand-written sm_100a CUDA kernels behind a C
 The product is `libgrok_b200.so` (csrc/, include/grok_b200.h); this package is the thin host-side
 mirror used by the tests and bench.py.  There is no CPU fallback.
 """
-from .binding import (CBLK_DEC_DTYPE, CBLK_ENC_DTYPE, CBLK_INFO_DTYPE, T1_BLOCK_DTYPE, CompParams, Context,
+from .binding import (CBLK_DEC_DTYPE, CBLK_ENC_DTYPE, CBLK_INFO_DTYPE, CBLK_SEG_DTYPE, T1_BLOCK_DTYPE, CompParams, Context,
                       GrokB200Error, Plan, TileParams, lib, LIB_PATH, SYMBOLS)
 from . import params
 
 __all__ = ["Context", "Plan", "CompParams", "TileParams", "GrokB200Error", "lib", "params", "LIB_PATH", "SYMBOLS",
-           "CBLK_ENC_DTYPE", "CBLK_DEC_DTYPE", "CBLK_INFO_DTYPE", "T1_BLOCK_DTYPE"]
+           "CBLK_ENC_DTYPE", "CBLK_DEC_DTYPE", "CBLK_INFO_DTYPE", "CBLK_SEG_DTYPE", "T1_BLOCK_DTYPE"]

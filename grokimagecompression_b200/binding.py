@@ -47,6 +47,7 @@ CBLK_ENC_DTYPE = np.dtype([("numbps", np.uint32), ("numpasses", np.uint32), ("da
                            ("decisions", np.uint32), ("data_offset", np.uint64)])
 CBLK_DEC_DTYPE = np.dtype([("numbps", np.uint32), ("numpasses", np.uint32), ("data_len", np.uint32),
                            ("reserved", np.uint32), ("data_offset", np.uint64)])
+CBLK_SEG_DTYPE = np.dtype([("len", np.uint32), ("numpasses", np.uint32)])
 CBLK_INFO_DTYPE = np.dtype([(n, np.uint32) for n, _ in CblkInfo._fields_])
 T1_BLOCK_DTYPE = np.dtype([("x", np.uint32), ("y", np.uint32), ("w", np.uint32), ("h", np.uint32),
                            ("orient", np.uint32), ("qmfbid", np.uint32), ("inv_step", np.uint32),
@@ -62,7 +63,7 @@ SYMBOLS = [
     "gb200_decode_upload", "gb200_decode_run", "gb200_decode_download", "gb200_sync",
     "gb200_encode_stash", "gb200_encode_restore",
     "gb200_encode_run_stage", "gb200_decode_run_stage", "gb200_encode_get_coefficients",
-    "gb200_decode_set_coefficients",
+    "gb200_decode_set_coefficients", "gb200_decode_set_segments", "gb200_t1_decode_blocks_segs",
     "gb200_mct_encode_rev", "gb200_mct_decode_rev", "gb200_mct_encode_irrev", "gb200_mct_decode_irrev",
     "gb200_dc_shift_encode", "gb200_dc_shift_decode", "gb200_dwt_encode", "gb200_dwt_decode",
     "gb200_t1_encode_blocks", "gb200_t1_decode_blocks",
@@ -121,6 +122,8 @@ def lib():
     L.gb200_dwt_decode.argtypes = [vp, vp, u32, u32, u32, u32, u32, u32, C.c_int]
     L.gb200_t1_encode_blocks.argtypes = [vp, vp, u32, u32, u32, vp, C.c_int, u32, vp, vp, vp, vp, u64, C.POINTER(u64)]
     L.gb200_t1_decode_blocks.argtypes = [vp, vp, u32, u32, u32, vp, vp, vp, u64]
+    L.gb200_t1_decode_blocks_segs.argtypes = [vp, vp, u32, u32, u32, vp, vp, vp, vp, vp, u64]
+    L.gb200_decode_set_segments.argtypes = [vp, vp, vp]
     _lib = L
     return L
 
@@ -208,13 +211,21 @@ class Context:
                                             _ptr(data), cap, C.byref(dl)))
         return res, rates, dists, data[:dl.value]
 
-    def t1_decode_blocks(self, shape, blocks, inputs, data):
+    def t1_decode_blocks(self, shape, blocks, inputs, data, seg_start=None, segs=None):
+        """seg_start (len(blocks) + 1 prefix offsets) / segs (CBLK_SEG_DTYPE): codeword segments of TERMALL / LAZY blocks"""
         plane = np.zeros(shape, np.int32)
         blocks = np.ascontiguousarray(blocks, T1_BLOCK_DTYPE)
         inputs = np.ascontiguousarray(inputs, CBLK_DEC_DTYPE)
         data = np.ascontiguousarray(data, np.uint8)
-        check(lib().gb200_t1_decode_blocks(self._h, _ptr(plane), shape[1], shape[0], len(blocks), _ptr(blocks),
-                                            _ptr(inputs), _ptr(data) if data.size else None, data.size))
+        if seg_start is None:
+            check(lib().gb200_t1_decode_blocks(self._h, _ptr(plane), shape[1], shape[0], len(blocks), _ptr(blocks),
+                                                _ptr(inputs), _ptr(data) if data.size else None, data.size))
+        else:
+            seg_start = np.ascontiguousarray(seg_start, np.uint32)
+            segs = np.ascontiguousarray(segs, CBLK_SEG_DTYPE)
+            check(lib().gb200_t1_decode_blocks_segs(self._h, _ptr(plane), shape[1], shape[0], len(blocks), _ptr(blocks),
+                                                     _ptr(inputs), _ptr(seg_start), _ptr(segs) if segs.size else _ptr(np.zeros(1, CBLK_SEG_DTYPE)),
+                                                     _ptr(data) if data.size else None, data.size))
         return plane
 
 
@@ -336,6 +347,17 @@ class Plan:
         data = np.ascontiguousarray(data, np.uint8)
         self._dec_keep = (inputs, data)
         check(lib().gb200_decode_upload(self._h, _ptr(inputs), _ptr(data) if data.size else None, data.size))
+
+    def set_segments(self, seg_start=None, segs=None):
+        """codeword segments for the following decode calls (None = single-segment blocks)"""
+        if seg_start is None:
+            check(lib().gb200_decode_set_segments(self._h, None, None))
+            return
+        seg_start = np.ascontiguousarray(seg_start, np.uint32)
+        segs = np.ascontiguousarray(segs, CBLK_SEG_DTYPE)
+        if segs.size == 0:
+            segs = np.zeros(1, CBLK_SEG_DTYPE)
+        check(lib().gb200_decode_set_segments(self._h, _ptr(seg_start), _ptr(segs)))
 
     def decode_run(self):
         check(lib().gb200_decode_run(self._h))

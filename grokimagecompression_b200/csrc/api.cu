@@ -84,7 +84,8 @@ struct gb200_plan {
 	// Tier-1
 	std::vector<EncBlock> encblocks;
 	std::vector<DecBlock> decblocks;
-	DevBuf d_blocks, d_results, d_rates, d_dists, d_scratch, d_data, d_inputs, d_symbols;
+	DevBuf d_blocks, d_results, d_rates, d_dists, d_scratch, d_data, d_inputs, d_symbols, d_seg_start, d_segs;
+	bool have_segs = false;
 	uint64_t d_data_len = 0;
 	uint32_t max_bw = 1, max_bh = 1; // largest code block of the table
 	bool uniform = true; // every tile shares mct / qmfbid / shift / range parameters
@@ -223,7 +224,7 @@ void gb200_plan_destroy(gb200_plan *pl) {
 	for (auto &b : pl->stash) b.release();
 	for (int r = 0; r < 2; ++r) for (auto &l : pl->lvl[r]) { l.dev.release(); l.map.release(); }
 	pl->d_blocks.release(); pl->d_results.release(); pl->d_rates.release(); pl->d_dists.release();
-	pl->d_scratch.release(); pl->d_data.release(); pl->d_inputs.release(); pl->d_symbols.release();
+	pl->d_scratch.release(); pl->d_data.release(); pl->d_inputs.release(); pl->d_symbols.release(); pl->d_seg_start.release(); pl->d_segs.release();
 	delete pl;
 }
 
@@ -672,11 +673,30 @@ int gb200_decode_upload(gb200_plan *pl, const gb200_cblk_dec *blocks, const uint
 	return GB200_OK;
 }
 
+int gb200_decode_set_segments(gb200_plan *pl, const uint32_t *seg_start, const gb200_cblk_seg *segs) {
+	if (!pl || pl->encoder) FAIL(GB200_ERR_PARAM, "not a decoder plan");
+	CK(cudaSetDevice(pl->ctx->device));
+	static_assert(sizeof(gb200_cblk_seg) == sizeof(DecSeg), "ABI mismatch");
+	if (!seg_start || !segs) { pl->have_segs = false; return GB200_OK; }
+	const size_t nb = pl->blocks.size();
+	for (size_t i = 0; i < nb; ++i)
+		if (seg_start[i + 1] < seg_start[i]) FAIL(GB200_ERR_PARAM, "seg_start must be non-decreasing");
+	const size_t ns = seg_start[nb];
+	if (pl->d_seg_start.bytes < (nb + 1) * 4 && pl->d_seg_start.alloc((nb + 1) * 4)) FAIL(GB200_ERR_NOMEM, "cudaMalloc failed");
+	if (pl->d_segs.bytes < std::max<size_t>(ns, 1) * sizeof(DecSeg) && pl->d_segs.alloc(std::max<size_t>(ns, 1) * sizeof(DecSeg))) FAIL(GB200_ERR_NOMEM, "cudaMalloc failed");
+	CK(cudaMemcpyAsync(pl->d_seg_start.p, seg_start, (nb + 1) * 4, cudaMemcpyHostToDevice, pl->ctx->stream));
+	if (ns) CK(cudaMemcpyAsync(pl->d_segs.p, segs, ns * sizeof(DecSeg), cudaMemcpyHostToDevice, pl->ctx->stream));
+	CK(cudaStreamSynchronize(pl->ctx->stream)); /* the caller's arrays may go away */
+	pl->have_segs = true;
+	return GB200_OK;
+}
+
 static int run_t1_dec(gb200_plan *pl) {
 	const uint32_t nb = (uint32_t) pl->blocks.size();
 	if (!nb) return GB200_OK;
 	if (launch_t1_decode((const DecBlock*) pl->d_blocks.p, (const DecInput*) pl->d_inputs.p, nb, (const uint8_t*) pl->d_data.p,
-			pl->max_bw, pl->max_bh, pl->ctx->stream))
+			pl->max_bw, pl->max_bh, pl->styles ? 1 : 0, pl->have_segs ? (const uint32_t*) pl->d_seg_start.p : nullptr,
+			pl->have_segs ? (const DecSeg*) pl->d_segs.p : nullptr, pl->ctx->stream))
 		FAIL(GB200_ERR_UNSUPPORTED, "Tier-1 decode: code block state does not fit in shared memory");
 	return launch_check(pl->ctx, T1_DEC_LAUNCHES);
 }
@@ -965,12 +985,19 @@ int gb200_t1_encode_blocks(gb200_ctx *ctx, const int32_t *plane, uint32_t width,
 
 int gb200_t1_decode_blocks(gb200_ctx *ctx, int32_t *plane, uint32_t width, uint32_t height, uint32_t nblocks,
 		const gb200_t1_block *blocks, const gb200_cblk_dec *inputs, const uint8_t *data, uint64_t data_len) {
-	if (!ctx || !plane || !blocks || !inputs) FAIL(GB200_ERR_PARAM, "bad arguments");
+	return gb200_t1_decode_blocks_segs(ctx, plane, width, height, nblocks, blocks, inputs, nullptr, nullptr, data, data_len);
+}
+
+int gb200_t1_decode_blocks_segs(gb200_ctx *ctx, int32_t *plane, uint32_t width, uint32_t height, uint32_t nblocks,
+		const gb200_t1_block *blocks, const gb200_cblk_dec *inputs, const uint32_t *seg_start, const gb200_cblk_seg *segs,
+		const uint8_t *data, uint64_t data_len) {
+	if (!ctx || !plane || !blocks || !inputs || (seg_start && !segs)) FAIL(GB200_ERR_PARAM, "bad arguments");
 	CK(cudaSetDevice(ctx->device));
 	cudaStream_t s = ctx->stream;
 	std::vector<DecBlock> db(nblocks);
-	DevBuf d_plane, d_blocks, d_inputs, d_data;
-	auto freeall = [&]() { d_plane.release(); d_blocks.release(); d_inputs.release(); d_data.release(); };
+	DevBuf d_plane, d_blocks, d_inputs, d_data, d_seg_start, d_segs;
+	auto freeall = [&]() { d_plane.release(); d_blocks.release(); d_inputs.release(); d_data.release(); d_seg_start.release(); d_segs.release(); };
+	bool styles = false;
 	if (d_plane.alloc(std::max<size_t>((size_t) width * height * 4, 16))) FAIL(GB200_ERR_NOMEM, "cudaMalloc failed");
 	uint32_t maxw = 1, maxh = 1;
 	for (uint32_t i = 0; i < nblocks; ++i) {
@@ -983,6 +1010,9 @@ int gb200_t1_decode_blocks(gb200_ctx *ctx, int32_t *plane, uint32_t width, uint3
 		d.dst = (int32_t*) d_plane.p + (size_t) b.y * width + b.x;
 		d.stride = width; d.w = (uint16_t) b.w; d.h = (uint16_t) b.h; d.orient = (uint8_t) b.orient;
 		d.reversible = b.qmfbid == 1; d.stepsize = b.stepsize;
+		if (b.cblk_sty & ~(uint32_t) STY_ALL) { freeall(); FAIL(GB200_ERR_UNSUPPORTED, "HT code blocks are not implemented"); }
+		d.sty = (uint8_t) b.cblk_sty;
+		styles |= b.cblk_sty != 0;
 		maxw = std::max(maxw, b.w); maxh = std::max(maxh, b.h);
 	}
 	if (d_blocks.alloc(std::max<size_t>(nblocks, 1) * sizeof(DecBlock)) || d_inputs.alloc(std::max<size_t>(nblocks, 1) * sizeof(DecInput))
@@ -991,8 +1021,15 @@ int gb200_t1_decode_blocks(gb200_ctx *ctx, int32_t *plane, uint32_t width, uint3
 	cudaMemcpyAsync(d_blocks.p, db.data(), nblocks * sizeof(DecBlock), cudaMemcpyHostToDevice, s);
 	cudaMemcpyAsync(d_inputs.p, inputs, nblocks * sizeof(DecInput), cudaMemcpyHostToDevice, s);
 	if (data_len) cudaMemcpyAsync(d_data.p, data, data_len, cudaMemcpyHostToDevice, s);
+	if (seg_start) {
+		const size_t ns = seg_start[nblocks];
+		if (d_seg_start.alloc(((size_t) nblocks + 1) * 4) || d_segs.alloc(std::max<size_t>(ns, 1) * sizeof(DecSeg))) { freeall(); FAIL(GB200_ERR_NOMEM, "cudaMalloc failed"); }
+		cudaMemcpyAsync(d_seg_start.p, seg_start, ((size_t) nblocks + 1) * 4, cudaMemcpyHostToDevice, s);
+		if (ns) cudaMemcpyAsync(d_segs.p, segs, ns * sizeof(DecSeg), cudaMemcpyHostToDevice, s);
+	}
 	int rc = GB200_OK;
-	if (launch_t1_decode((const DecBlock*) d_blocks.p, (const DecInput*) d_inputs.p, nblocks, (const uint8_t*) d_data.p, maxw, maxh, s)) {
+	if (launch_t1_decode((const DecBlock*) d_blocks.p, (const DecInput*) d_inputs.p, nblocks, (const uint8_t*) d_data.p, maxw, maxh,
+			styles ? 1 : 0, seg_start ? (const uint32_t*) d_seg_start.p : nullptr, seg_start ? (const DecSeg*) d_segs.p : nullptr, s)) {
 		g_err = "Tier-1 decode: code block state does not fit in shared memory";
 		rc = GB200_ERR_UNSUPPORTED;
 	} else rc = launch_check(ctx, T1_DEC_LAUNCHES);

@@ -55,6 +55,10 @@ struct DecBlock {
 	uint32_t pad2;
 };
 
+struct DecSeg { // == gb200_cblk_seg: one codeword segment of a block (TERMALL / LAZY streams)
+	uint32_t len, numpasses;
+};
+
 struct DecInput { // == gb200_cblk_dec
 	uint32_t numbps, numpasses, data_len, reserved;
 	uint64_t data_offset;
@@ -90,7 +94,9 @@ void launch_t1_gather(const EncBlock *blocks, EncResult *results, uint32_t nbloc
 // readable for T1_DEC_DATA_SLACK bytes past the last segment.  Returns non-zero if a block cannot be placed.
 constexpr int T1_DEC_LAUNCHES = 3;
 constexpr size_t T1_DEC_DATA_SLACK = 64;
+// styles: some block has a style switch set; seg_start (nblocks + 1 prefix offsets) / segs: codeword segments, or NULL when
+// every block is a single segment
 int launch_t1_decode(const DecBlock *blocks, const DecInput *inputs, uint32_t nblocks, const uint8_t *data,
-		uint32_t max_w, uint32_t max_h, cudaStream_t s);
+		uint32_t max_w, uint32_t max_h, int styles, const uint32_t *seg_start, const DecSeg *segs, cudaStream_t s);
 
 } // namespace gb

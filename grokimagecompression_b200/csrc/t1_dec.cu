@@ -165,24 +165,46 @@ struct Blk {
 	int32_t *dst;
 	uint32_t stride;
 	int fw, nstripes;
+	// code-block style switches only (STY kernels)
+	bool vsc;             // stripe-causal contexts: a sample of row 0 is not shown to the stripe above (t1.cpp:177-182)
+	const uint8_t *rbuf;  // raw (bypass) segment reader, mqc_dec_inl.h:90-112
+	uint32_t rpos, rlen, rc;
+	int rct;
 };
+
+// one raw bit; bytes past the segment read as 0xFF, the byte after 0xFF carries 7 bits
+__device__ __forceinline__ uint32_t raw_bit(Blk &b) {
+	if (b.rct == 0) {
+		const uint32_t nb = b.rpos < b.rlen ? b.rbuf[b.rpos] : 0xFFu;
+		if (b.rc == 0xFFu) {
+			if (nb > 0x8Fu) { b.rc = 0xFFu; b.rct = 8; }
+			else { b.rc = nb; b.rpos++; b.rct = 7; }
+		} else { b.rc = nb; b.rpos++; b.rct = 8; }
+	}
+	b.rct--;
+	return (b.rc >> b.rct) & 1u;
+}
 
 constexpr uint32_t F_OWNSIG = 0x2490u; // significance of the own column, rows 0..3
 
 // sign of a sample that just turned significant (t1.cpp:115-140), mid-point store, neighbour updates (t1.cpp:168-195)
-template<int K>
+template<int K, bool STY = false, bool RAW = false>
 __device__ __forceinline__ void sign_and_mark(Blk &b, uint32_t &f, uint32_t *cw, int s, uint32_t off, int32_t oph) {
-	const uint32_t fW = cw[-1], fE = cw[1];
-	const uint32_t idx = ((f >> (3 * K)) & 0xAAu) | ((f >> (18 + K)) & 1u) | ((fW >> (17 + K)) & 4u) | ((fE >> (15 + K)) & 0x10u)
-			| ((f >> (14 + K)) & 0x40u);
-	const uint32_t v = b.sc[idx];
-	const uint32_t neg = mq_decode(b.q, b.C + (v & 31u), b.tab) ^ (v >> 5);
+	uint32_t neg;
+	if (RAW) neg = raw_bit(b); // raw passes carry the sign itself (t1.cpp:233-260)
+	else {
+		const uint32_t fW = cw[-1], fE = cw[1];
+		const uint32_t idx = ((f >> (3 * K)) & 0xAAu) | ((f >> (18 + K)) & 1u) | ((fW >> (17 + K)) & 4u) | ((fE >> (15 + K)) & 0x10u)
+				| ((f >> (14 + K)) & 0x40u);
+		const uint32_t v = b.sc[idx];
+		neg = mq_decode(b.q, b.C + (v & 31u), b.tab) ^ (v >> 5);
+	}
 	f |= fsig(K + 1, 1) | (neg << (19 + K));
 	b.dst[off + K * b.stride] = neg ? -oph : oph;
 	// the sample is the east neighbour of column x-1 and the west neighbour of column x+1
 	atomicOr(cw - 1, fsig(K + 1, 2));
 	atomicOr(cw + 1, fsig(K + 1, 0));
-	if (K == 0 && s > 0) { // row 4 of the stripe above
+	if (K == 0 && s > 0 && !(STY && b.vsc)) { // row 4 of the stripe above
 		uint32_t *up = cw - b.fw;
 		atomicOr(up - 1, fsig(5, 2));
 		atomicOr(up, fsig(5, 1) | (neg << 23));
@@ -197,21 +219,21 @@ __device__ __forceinline__ void sign_and_mark(Blk &b, uint32_t &f, uint32_t *cw,
 }
 
 // significance propagation, t1.cpp:381-441
-template<int K>
+template<int K, bool STY = false, bool RAW = false>
 __device__ __forceinline__ void sig_row(Blk &b, uint32_t &f, uint32_t *cw, int s, uint32_t off, int32_t oph) {
 	if ((f & (fsig(K + 1, 1) | (1u << (24 + K)))) == 0 && (f & (0x1EFu << (3 * K))) != 0) {
-		const uint32_t d = mq_decode(b.q, b.C + b.zc[(f >> (3 * K)) & 0x1FFu], b.tab);
+		const uint32_t d = RAW ? raw_bit(b) : mq_decode(b.q, b.C + b.zc[(f >> (3 * K)) & 0x1FFu], b.tab);
 		f |= 1u << (24 + K);
-		if (d) sign_and_mark<K>(b, f, cw, s, off, oph);
+		if (d) sign_and_mark<K, STY, RAW>(b, f, cw, s, off, oph);
 	}
 }
 
 // magnitude refinement: +-half a step towards the decoded bit, t1.cpp:476-496, 588-637
-template<int K>
+template<int K, bool RAW = false>
 __device__ __forceinline__ void ref_row(Blk &b, uint32_t &f, uint32_t off, int32_t half) {
 	if ((f & (fsig(K + 1, 1) | (1u << (24 + K)))) == fsig(K + 1, 1)) {
 		const uint32_t cx = (f & (1u << (28 + K))) ? CTX_MR0 + 2 : (f & (0x1EFu << (3 * K))) ? CTX_MR0 + 1 : CTX_MR0;
-		const uint32_t d = mq_decode(b.q, b.C + cx, b.tab);
+		const uint32_t d = RAW ? raw_bit(b) : mq_decode(b.q, b.C + cx, b.tab);
 		const uint32_t neg = (f >> (19 + K)) & 1u;
 		atomicAdd(b.dst + off + K * b.stride, (d ^ neg) ? half : -half);
 		f |= 1u << (28 + K);
@@ -219,18 +241,69 @@ __device__ __forceinline__ void ref_row(Blk &b, uint32_t &f, uint32_t off, int32
 }
 
 // cleanup, t1.cpp:784-870; start / implied: the row whose 1 the run-length code already delivered
-template<int K>
+template<int K, bool STY = false>
 __device__ __forceinline__ void cln_row(Blk &b, uint32_t &f, uint32_t *cw, int s, uint32_t off, int32_t oph, int start, bool implied) {
 	if (K >= start && (f & (fsig(K + 1, 1) | (1u << (24 + K)))) == 0) {
 		uint32_t d = 1;
 		if (!(implied && K == start)) d = mq_decode(b.q, b.C + b.zc[(f >> (3 * K)) & 0x1FFu], b.tab);
-		if (d) sign_and_mark<K>(b, f, cw, s, off, oph);
+		if (d) sign_and_mark<K, STY, false>(b, f, cw, s, off, oph);
 	}
 }
 
-template<int LANES>
+// one coding pass over the whole block
+template<bool STY, bool RAW>
+__device__ __forceinline__ void run_pass(Blk &b, uint32_t *F, int w, int fw, int type, int bp1, uint32_t last_pi) {
+	// values carry one extra low bit: the plane weight is 1 << bp1, the mid-point sits half a step above
+	const int32_t half = (1 << bp1) >> 1, oph = (1 << bp1) | half;
+	for (int s = 0; s < b.nstripes; ++s) {
+		uint32_t *cw = F + s * fw + 1;
+		uint32_t off = (uint32_t) (4 * s) * b.stride;
+		if (type == 0) {
+			for (int x = 0; x < w; ++x, ++cw, ++off) {
+				uint32_t f = *cw;
+				if (!(f & F_SIGMA_ALL) || (f & F_OWNSIG) == F_OWNSIG) continue; // nothing significant around / nothing left to find
+				sig_row<0, STY, RAW>(b, f, cw, s, off, oph);
+				sig_row<1, STY, RAW>(b, f, cw, s, off, oph);
+				sig_row<2, STY, RAW>(b, f, cw, s, off, oph);
+				sig_row<3, STY, RAW>(b, f, cw, s, off, oph);
+				*cw = f;
+			}
+		} else if (type == 1) {
+			for (int x = 0; x < w; ++x, ++cw, ++off) {
+				uint32_t f = *cw;
+				if (!(f & F_OWNSIG)) continue;
+				ref_row<0, RAW>(b, f, off, half);
+				ref_row<1, RAW>(b, f, off, half);
+				ref_row<2, RAW>(b, f, off, half);
+				ref_row<3, RAW>(b, f, off, half);
+				*cw = f;
+			}
+		} else if (!RAW) {
+			const uint32_t keep_pi = s == b.nstripes - 1 ? last_pi : 0u;
+			for (int x = 0; x < w; ++x, ++cw, ++off) {
+				uint32_t f = *cw;
+				int start = 0;
+				bool implied = false;
+				if ((f & (F_PI_ALL | F_SIGMA_ALL)) == 0) { // run-length mode, t1.cpp:749 (full stripes only: keep_pi)
+					if (!mq_decode(b.q, b.C + CTX_AGG, b.tab)) continue;
+					start = (int) mq_decode(b.q, b.C + CTX_UNI, b.tab) << 1;
+					start |= (int) mq_decode(b.q, b.C + CTX_UNI, b.tab);
+					implied = true;
+				}
+				cln_row<0, STY>(b, f, cw, s, off, oph, start, implied);
+				cln_row<1, STY>(b, f, cw, s, off, oph, start, implied);
+				cln_row<2, STY>(b, f, cw, s, off, oph, start, implied);
+				cln_row<3, STY>(b, f, cw, s, off, oph, start, implied);
+				*cw = (f & ~F_PI_ALL) | keep_pi;
+			}
+		}
+	}
+}
+
+template<int LANES, bool STY>
 __global__ void __launch_bounds__(DT_MAX_THREADS, 1) t1_decode_kernel(const DecBlock *__restrict__ blocks,
-		const DecInput *__restrict__ inputs, uint32_t nblocks, const uint8_t *__restrict__ data, int fw, int fwords, int nslots) {
+		const DecInput *__restrict__ inputs, uint32_t nblocks, const uint8_t *__restrict__ data, int fw, int fwords, int nslots,
+		const uint32_t *__restrict__ seg_start, const DecSeg *__restrict__ segs) {
 	extern __shared__ __align__(16) uint32_t sm[];
 	uint32_t *tab = sm;                                        // 94 (state, mps) rows
 	uint8_t *Lzc = reinterpret_cast<uint8_t*>(sm + 96);        // zero-coding context by the 9 neighbourhood bits of a word
@@ -283,58 +356,44 @@ __global__ void __launch_bounds__(DT_MAX_THREADS, 1) t1_decode_kernel(const DecB
 	b.sc = Lsc;
 	b.dst = B.dst;
 	b.stride = B.stride;
-	mq_init(b.q, data + I.data_offset, I.data_len);
-
 	// passes go cln(numbps), then sig / ref / cln per lower plane
-	const int npass = min((int) I.numpasses, 3 * numbps - 2);
 	int bp1 = numbps, type = 2;
-	for (int pass = 0; pass < npass; ++pass) {
-		// values carry one extra low bit: the plane weight is 1 << bp1, the mid-point sits half a step above
-		const int32_t half = (1 << bp1) >> 1, oph = (1 << bp1) | half;
-		for (int s = 0; s < b.nstripes; ++s) {
-			uint32_t *cw = F + s * fw + 1;
-			uint32_t off = (uint32_t) (4 * s) * B.stride;
-			if (type == 0) {
-				for (int x = 0; x < w; ++x, ++cw, ++off) {
-					uint32_t f = *cw;
-					if (!(f & F_SIGMA_ALL) || (f & F_OWNSIG) == F_OWNSIG) continue; // nothing significant around / nothing left to find
-					sig_row<0>(b, f, cw, s, off, oph);
-					sig_row<1>(b, f, cw, s, off, oph);
-					sig_row<2>(b, f, cw, s, off, oph);
-					sig_row<3>(b, f, cw, s, off, oph);
-					*cw = f;
-				}
-			} else if (type == 1) {
-				for (int x = 0; x < w; ++x, ++cw, ++off) {
-					uint32_t f = *cw;
-					if (!(f & F_OWNSIG)) continue;
-					ref_row<0>(b, f, off, half);
-					ref_row<1>(b, f, off, half);
-					ref_row<2>(b, f, off, half);
-					ref_row<3>(b, f, off, half);
-					*cw = f;
-				}
-			} else {
-				const uint32_t keep_pi = s == b.nstripes - 1 ? last_pi : 0u;
-				for (int x = 0; x < w; ++x, ++cw, ++off) {
-					uint32_t f = *cw;
-					int start = 0;
-					bool implied = false;
-					if ((f & (F_PI_ALL | F_SIGMA_ALL)) == 0) { // run-length mode, t1.cpp:749 (full stripes only: keep_pi)
-						if (!mq_decode(b.q, b.C + CTX_AGG, tab)) continue;
-						start = (int) mq_decode(b.q, b.C + CTX_UNI, tab) << 1;
-						start |= (int) mq_decode(b.q, b.C + CTX_UNI, tab);
-						implied = true;
+	if (!STY) {
+		mq_init(b.q, data + I.data_offset, I.data_len);
+		const int npass = min((int) I.numpasses, 3 * numbps - 2);
+		for (int pass = 0; pass < npass; ++pass) {
+			run_pass<false, false>(b, F, w, fw, type, bp1, last_pi);
+			if (++type == 3) { type = 0; bp1--; }
+		}
+	} else {
+		// codeword segments as Tier-2 delivers them (t1.cpp:1067-1114): every segment restarts the MQ decoder, or the raw
+		// reader for the bypassed passes of LAZY; RESET clears the contexts after every MQ pass; SEGSYM appends four
+		// UNIFORM decisions to every cleanup pass
+		const uint32_t sty = B.sty;
+		b.vsc = (sty & STY_VSC) != 0;
+		const uint32_t s0 = seg_start ? seg_start[bid] : 0u, nsegs = seg_start ? seg_start[bid + 1] - s0 : 1u;
+		uint32_t off = 0;
+		for (uint32_t sg = 0; sg < nsegs && bp1 >= 1; ++sg) {
+			const uint32_t len = seg_start ? segs[s0 + sg].len : I.data_len, np = seg_start ? segs[s0 + sg].numpasses : I.numpasses;
+			const bool raw = (sty & STY_LAZY) && bp1 <= numbps - 4 && type < 2;
+			const uint8_t *seg = data + I.data_offset + off;
+			if (raw) { b.rbuf = seg; b.rpos = 0; b.rlen = len; b.rc = 0; b.rct = 0; } // mqc_raw_init_dec
+			else mq_init(b.q, seg, len);
+			off += len;
+			for (uint32_t p = 0; p < np && bp1 >= 1; ++p) {
+				if (raw) run_pass<true, true>(b, F, w, fw, type, bp1, last_pi);
+				else {
+					run_pass<true, false>(b, F, w, fw, type, bp1, last_pi);
+					if (type == 2 && (sty & STY_SEGSYM)) // t1_dec_clnpass_check_segsym: read, a mismatch only warns
+						for (int i = 0; i < 4; ++i) mq_decode(b.q, b.C + CTX_UNI, b.tab);
+					if (sty & STY_RESET) {
+						#pragma unroll
+						for (int i = 0; i < NCTX; ++i) b.C[i] = tab[2 * (i == CTX_ZC0 ? 4 : i == CTX_AGG ? 3 : i == CTX_UNI ? 46 : 0)];
 					}
-					cln_row<0>(b, f, cw, s, off, oph, start, implied);
-					cln_row<1>(b, f, cw, s, off, oph, start, implied);
-					cln_row<2>(b, f, cw, s, off, oph, start, implied);
-					cln_row<3>(b, f, cw, s, off, oph, start, implied);
-					*cw = (f & ~F_PI_ALL) | keep_pi;
 				}
+				if (++type == 3) { type = 0; bp1--; }
 			}
 		}
-		if (++type == 3) { type = 0; bp1--; }
 	}
 }
 
@@ -365,7 +424,7 @@ __global__ void __launch_bounds__(256) t1_dec_finish_kernel(const DecBlock *__re
 static bool g_dec_tables_ready = false;
 
 int launch_t1_decode(const DecBlock *blocks, const DecInput *inputs, uint32_t nblocks, const uint8_t *data,
-		uint32_t max_w, uint32_t max_h, cudaStream_t s) {
+		uint32_t max_w, uint32_t max_h, int styles, const uint32_t *seg_start, const DecSeg *segs, cudaStream_t s) {
 	if (!nblocks) return 0;
 	if (!g_dec_tables_ready) { build_and_upload_t1_tables(); g_dec_tables_ready = true; }
 	int dev = 0, sms = 148, smem_max = 0;
@@ -393,11 +452,12 @@ int launch_t1_decode(const DecBlock *blocks, const DecInput *inputs, uint32_t nb
 	if (nslots < lanes) nslots = cap; // a partial warp: blocks too large for `lanes` of them
 	if (nslots < 1) return 1;
 	const size_t smem = (size_t) DT_FIXED_WORDS * 4 + (size_t) nslots * per_slot;
-	auto kernel = lanes == 1 ? t1_decode_kernel<1> : t1_decode_kernel<DT_LANES>;
+	auto kernel = (styles || seg_start) ? (lanes == 1 ? t1_decode_kernel<1, true> : t1_decode_kernel<DT_LANES, true>)
+			: (lanes == 1 ? t1_decode_kernel<1, false> : t1_decode_kernel<DT_LANES, false>);
 	if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) != cudaSuccess) return 1;
 	const int threads = (nslots + lanes - 1) / lanes * 32;
 	t1_dec_clear_kernel<<<(nblocks + 7) / 8, 256, 0, s>>>(blocks, nblocks);
-	kernel<<<(nblocks + nslots - 1) / nslots, threads, smem, s>>>(blocks, inputs, nblocks, data, fw, fwords, nslots);
+	kernel<<<(nblocks + nslots - 1) / nslots, threads, smem, s>>>(blocks, inputs, nblocks, data, fw, fwords, nslots, seg_start, segs);
 	t1_dec_finish_kernel<<<(nblocks + 7) / 8, 256, 0, s>>>(blocks, nblocks);
 	return 0;
 }

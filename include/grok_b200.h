@@ -110,6 +110,13 @@ typedef struct gb200_cblk_dec {
 	uint64_t data_offset; /* offset in the data buffer */
 } gb200_cblk_dec;
 
+/* One codeword segment of a code block (grk_tcd_seg: len, numpasses).  Blocks coded with TERMALL or LAZY arrive from
+ * Tier-2 as several segments (T2.cpp:835-851); their bytes are concatenated at gb200_cblk_dec::data_offset. */
+typedef struct gb200_cblk_seg {
+	uint32_t len;
+	uint32_t numpasses;
+} gb200_cblk_seg;
+
 /* ---- context ---------------------------------------------------------------------------------- */
 GB200_API int gb200_abi_version(void);
 GB200_API const char *gb200_last_error(void); /* thread-local, never NULL */
@@ -145,6 +152,10 @@ GB200_API int gb200_encode_run(gb200_plan *plan);      /* asynchronous on gb200_
 GB200_API int gb200_encode_download(gb200_plan *plan, gb200_cblk_enc *blocks, uint32_t *rates, double *dists, uint8_t *data,
 		uint64_t data_capacity, uint64_t *data_len);
 GB200_API int gb200_decode_upload(gb200_plan *plan, const gb200_cblk_dec *blocks, const uint8_t *data, uint64_t data_len);
+/* codeword segments for the next gb200_decode_upload / gb200_decode_tiles: block i owns segs[seg_start[i] .. seg_start[i+1])
+ * (seg_start has num_blocks + 1 entries); gb200_cblk_dec::numpasses / data_len stay the totals.  NULL, NULL = every
+ * block is one segment (the default). */
+GB200_API int gb200_decode_set_segments(gb200_plan *plan, const uint32_t *seg_start, const gb200_cblk_seg *segs);
 GB200_API int gb200_decode_run(gb200_plan *plan);      /* asynchronous on gb200_stream() */
 GB200_API int gb200_decode_download(gb200_plan *plan, int32_t *const *planes_out);
 GB200_API int gb200_sync(gb200_ctx *ctx);
@@ -193,6 +204,10 @@ GB200_API int gb200_t1_encode_blocks(gb200_ctx *ctx, const int32_t *plane, uint3
 /* T1Part1::decode + postDecode into a zeroed int32 plane */
 GB200_API int gb200_t1_decode_blocks(gb200_ctx *ctx, int32_t *plane, uint32_t width, uint32_t height, uint32_t nblocks,
 		const gb200_t1_block *blocks, const gb200_cblk_dec *inputs, const uint8_t *data, uint64_t data_len);
+/* the same with codeword segments (seg_start: nblocks + 1 prefix offsets into segs; NULL, NULL = single segments) */
+GB200_API int gb200_t1_decode_blocks_segs(gb200_ctx *ctx, int32_t *plane, uint32_t width, uint32_t height, uint32_t nblocks,
+		const gb200_t1_block *blocks, const gb200_cblk_dec *inputs, const uint32_t *seg_start, const gb200_cblk_seg *segs,
+		const uint8_t *data, uint64_t data_len);
 
 #ifdef __cplusplus
 }

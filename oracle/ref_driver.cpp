@@ -132,7 +132,7 @@ int ref_t1_encode_cblk(const int32_t *data, uint32_t w, uint32_t h, uint32_t ori
 		if (a > mx) mx = a;
 	}
 	/* reference allocates 2 zeroed pad bytes in front (TileProcessor.cpp:1997-2018) */
-	size_t cap = (size_t) w * h * 4 + 64;
+	size_t cap = (size_t) w * h * 4 + 1024; /* slack for the flush bytes of terminated passes on tiny blocks */
 	uint8_t *buf = (uint8_t*) grk_calloc(1, cap);
 	tcd_cblk_enc_t cblk;
 	memset(&cblk, 0, sizeof(cblk));

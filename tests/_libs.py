@@ -225,7 +225,7 @@ def oracle_t1_encode_sty(blk, orient, sty, do_rd=False, wbase=0.0):
     """as oracle_t1_encode with a code-block style byte -> (bytes, numbps, rates, dists, terms, nsym)"""
     L = oracle()
     h, w = blk.shape
-    buf = np.zeros(w * h * 4 + 64, np.uint8)
+    buf = np.zeros(w * h * 4 + 1024, np.uint8)  # terminated passes add flush bytes: tiny blocks outgrow 4wh
     rates = np.zeros(128, np.uint32)
     dists = np.zeros(128, np.float64)
     terms = np.zeros(128, np.uint8)
@@ -242,7 +242,7 @@ def ref_t1_encode_sty(blk, orient, sty, compno=0, level=0, qmfbid=1, stepsize=1.
     """-> (bytes, numbps, rates, dists, terms) from the unmodified reference"""
     L = ref()
     h, w = blk.shape
-    buf = np.zeros(w * h * 4 + 64, np.uint8)
+    buf = np.zeros(w * h * 4 + 1024, np.uint8)
     rates = np.zeros(128, np.uint32)
     lens = np.zeros(128, np.uint32)
     dists = np.zeros(128, np.float64)

@@ -194,6 +194,49 @@ def test_t1_encode_blocks_with_style_switches(ctx, rd):
 
 
 @pytest.mark.parametrize("rev", [1, 0])
+def test_t1_decode_blocks_with_style_switches(ctx, rev):
+    """segment-wise decode of LAZY / RESET / TERMALL / VSC / PTERM / SEGSYM streams (full and truncated at a pass
+    boundary) against the oracle"""
+    from _libs import oracle_t1_encode_sty, oracle_t1_decode_segs, segments_from_passes
+    rng = np.random.default_rng(700 + rev)
+    blocks = _random_blocks(rng, 120)
+    _, desc = _layout(blocks)
+    O = oracle()
+    inputs = np.zeros(len(blocks), gb.CBLK_DEC_DTYPE)
+    chunks, expect, seg_start, segs = [], [], [0], []
+    off = 0
+    for i, b in enumerate(blocks):
+        h, w = b.shape
+        orient = int(rng.integers(0, 4))
+        sty = STYLES[i % len(STYLES)] if i % 7 else int(rng.integers(1, 64))
+        desc[i]["orient"], desc[i]["qmfbid"], desc[i]["cblk_sty"] = orient, rev, sty
+        desc[i]["stepsize"] = 1.0 if rev else float(np.float32(rng.choice([0.5, 0.0371, 1.9])))
+        ob, onb, orr, _, ot, _ = oracle_t1_encode_sty((b.astype(np.int64) * 64).astype(np.int32), orient, sty)
+        npass = len(orr)
+        k = npass if (i % 3 == 0 or npass == 0) else int(rng.integers(1, npass + 1))
+        sl, sp = segments_from_passes(orr, ot, k) if k else (np.zeros(0, np.uint32), np.zeros(0, np.uint32))
+        ln = int(sl.sum())
+        inputs[i]["numbps"], inputs[i]["numpasses"], inputs[i]["data_len"], inputs[i]["data_offset"] = onb, k, ln, off
+        chunks.append(ob[:ln])
+        off += ln
+        for a, c in zip(sl, sp):
+            segs.append((int(a), int(c)))
+        seg_start.append(len(segs))
+        dec = oracle_t1_decode_segs(ob[:ln], sl, sp, onb, orient, sty, w, h) if k else np.zeros((h, w), np.int32)
+        out = np.zeros((h, w), np.int32)
+        O.gbo_dequantise_block(dec.ravel(), w, h, rev, float(desc[i]["stepsize"]), out.ctypes.data, w)
+        expect.append(out)
+    data = np.frombuffer(b"".join(chunks), np.uint8)
+    H = max(b.shape[0] for b in blocks)
+    W = sum(b.shape[1] for b in blocks)
+    plane = ctx.t1_decode_blocks((H, W), desc, inputs, data, np.array(seg_start, np.uint32), np.array(segs, gb.CBLK_SEG_DTYPE))
+    for i, e in enumerate(expect):
+        h, w = e.shape
+        x = int(desc[i]["x"])
+        assert (plane[:h, x:x + w] == e).all(), (i, int(desc[i]["cblk_sty"]))
+
+
+@pytest.mark.parametrize("rev", [1, 0])
 def test_t1_decode_blocks(ctx, rev):
     rng = np.random.default_rng(300 + rev)
     blocks = _random_blocks(rng, 96)
