@@ -59,6 +59,20 @@ struct TileResult {
 };
 std::map<grk::grk_tcd_tile*, TileResult> g_results;
 
+/* which coding passes end a codeword segment: t1_enc_is_term_pass, t1.cpp:1131-1151 (pass 0 is the cleanup pass of the
+ * top bit plane, then significance / refinement / cleanup per lower plane) */
+bool is_term_pass(uint32_t numbps, uint32_t cblksty, uint32_t passno) {
+	const int32_t bpno = (int32_t) numbps - 1 - (int32_t) ((passno + 2) / 3);
+	const uint32_t passtype = (passno + 2) % 3;
+	if (passtype == 2 && bpno == 0) return true;
+	if (cblksty & GRK_CBLKSTY_TERMALL) return true;
+	if (cblksty & GRK_CBLKSTY_LAZY) {
+		if (bpno == (int32_t) numbps - 4 && passtype == 2) return true;
+		if (bpno < (int32_t) numbps - 4 && passtype > 0) return true;
+	}
+	return false;
+}
+
 void fail(const char *what) {
 	fprintf(stderr, "grok_tcd_shim: %s: %s\n", what, gb200_last_error());
 	abort();
@@ -145,9 +159,9 @@ bool Tier1::encodeCodeblocks(grk_tcp *tcp, grk_tcd_tile *tile, const double *, u
 	const gb200_cblk_info *info = gb200_plan_blocks(R.plan);
 	size_t i = 0;
 	tile->distotile = 0;
-	(void) tcp;
 	for (uint32_t compno = 0; compno < tile->numcomps; ++compno) {
 		auto tilec = tile->comps + compno;
+		const uint32_t tilec_sty = tcp->tccps[compno].cblk_sty;
 		for (uint32_t resno = 0; resno < tilec->numresolutions; ++resno) {
 			auto res = tilec->resolutions + resno;
 			for (uint32_t bandno = 0; bandno < res->numbands; ++bandno) {
@@ -172,7 +186,7 @@ bool Tier1::encodeCodeblocks(grk_tcp *tcp, grk_tcd_tile *tile, const double *, u
 							pass->rate = R.rates[po + p];
 							pass->len = pass->rate - (p ? R.rates[po + p - 1] : 0);
 							pass->distortiondec = R.dists[po + p];
-							pass->term = (p + 1 == e.numpasses) ? 1 : 0; /* t1.cpp:1131-1135, cblk_sty == 0 */
+							pass->term = is_term_pass(e.numbps, tilec_sty, p) ? 1 : 0;
 						}
 						if (doRateControl && e.numpasses) tile->distotile += R.dists[po + e.numpasses - 1];
 					}
@@ -197,6 +211,8 @@ bool Tier1::decodeCodeblocks(grk_tcp *, uint16_t, uint16_t, std::vector<decodeBl
 	std::vector<gb200_t1_block> desc(n);
 	std::vector<gb200_cblk_dec> in(n);
 	std::vector<uint8_t> data;
+	std::vector<uint32_t> seg_start(n + 1, 0);
+	std::vector<gb200_cblk_seg> segs;
 	for (size_t i = 0; i < n; ++i) {
 		auto b = (*blocks)[i];
 		auto cblk = b->cblk;
@@ -204,16 +220,24 @@ bool Tier1::decodeCodeblocks(grk_tcp *, uint16_t, uint16_t, std::vector<decodeBl
 		memset(&d, 0, sizeof(d));
 		d.x = b->x; d.y = b->y; d.w = cblk->x1 - cblk->x0; d.h = cblk->y1 - cblk->y0;
 		d.orient = b->bandno; d.qmfbid = b->qmfbid; d.stepsize = b->stepsize;
+		d.cblk_sty = b->cblk_sty;
 		gb200_cblk_dec &c = in[i];
 		memset(&c, 0, sizeof(c));
-		if (b->cblk_sty != 0 || b->roishift != 0 || cblk->numSegments > 1) {
-			fprintf(stderr, "grok_tcd_shim: code-block style / ROI / multi-segment blocks are outside this build's scope\n");
+		if (b->roishift != 0 || (b->cblk_sty & GRK_CBLKSTY_HT)) {
+			fprintf(stderr, "grok_tcd_shim: ROI up-shift and HT blocks are outside this build's scope\n");
 			abort();
 		}
 		c.numbps = cblk->numbps - b->roishift;
 		c.data_offset = data.size();
 		uint32_t passes = 0;
-		for (uint32_t s = 0; s < cblk->numSegments; ++s) passes += cblk->segs[s].numpasses;
+		for (uint32_t s = 0; s < cblk->numSegments; ++s) { /* T1Part1.cpp:160-171 */
+			passes += cblk->segs[s].numpasses;
+			gb200_cblk_seg sg;
+			sg.len = cblk->segs[s].len;
+			sg.numpasses = cblk->segs[s].numpasses;
+			segs.push_back(sg);
+		}
+		seg_start[i + 1] = (uint32_t) segs.size();
 		c.numpasses = passes;
 		for (size_t k = 0; k < cblk->seg_buffers.size(); ++k) { /* T1Part1.cpp:153-158 */
 			grk_buf *seg = (grk_buf*) cblk->seg_buffers.get(k);
@@ -222,8 +246,10 @@ bool Tier1::decodeCodeblocks(grk_tcp *, uint16_t, uint16_t, std::vector<decodeBl
 		c.data_len = (uint32_t) (data.size() - c.data_offset);
 		delete b;
 	}
-	if (gb200_t1_decode_blocks(ctx(), plane, width, height, (uint32_t) n, desc.data(), in.data(), data.data(), data.size()) != GB200_OK)
-		fail("gb200_t1_decode_blocks");
+	if (segs.empty()) segs.resize(1);
+	if (gb200_t1_decode_blocks_segs(ctx(), plane, width, height, (uint32_t) n, desc.data(), in.data(), seg_start.data(), segs.data(),
+			data.data(), data.size()) != GB200_OK)
+		fail("gb200_t1_decode_blocks_segs");
 	return true;
 }
 

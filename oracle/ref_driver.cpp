@@ -265,6 +265,10 @@ void ref_band_stepsize(uint32_t expn, uint32_t mant, uint32_t resno, uint32_t ba
 
 static void quiet_cb(const char *, void *) {}
 
+/* code-block style byte (grk_compress -M) applied by the following ref_encode_image / ref_plugin_encode_file calls */
+static uint32_t g_cblk_sty = 0;
+void ref_set_cblk_sty(uint32_t sty) { g_cblk_sty = sty; }
+
 /* grk_compress-equivalent: planar int32 image -> raw J2K codestream.
  *   tile_w/tile_h 0 = single tile;  rates[numlayers] = compression ratios (-r); numlayers 0 = lossless
  *   cinema2k_fps 24/48 = -w profile.  Returns the codestream length, or -1. */
@@ -282,6 +286,7 @@ int64_t ref_encode_image(uint32_t numcomps, uint32_t w, uint32_t h, uint32_t pre
 	param.cblockh_init = cblkh;
 	param.irreversible = irreversible != 0;
 	param.rateControlAlgorithm = rc_algorithm;
+	param.cblk_sty = (uint8_t) g_cblk_sty;
 	if (tile_w && tile_h) {
 		param.tile_size_on = true;
 		param.cp_tdx = tile_w;

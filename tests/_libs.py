@@ -95,6 +95,7 @@ def ref():
                                      C.POINTER(C.c_uint32), u32p, u32p, f64p, C.POINTER(C.c_double)]
     L.ref_t1_decode_cblk.argtypes = [u8p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                      C.c_uint32, C.c_uint32, i32p]
+    L.ref_set_cblk_sty.argtypes = [C.c_uint32]
     L.ref_t1_want_terms.argtypes = [u8p]
     L.ref_t1_decode_cblk_segs.argtypes = [u8p, u32p, u32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                           C.c_uint32, i32p]
@@ -139,9 +140,10 @@ def ref_plugin_encode_file(infile, area, tile=(0, 0), numres=6, cblk=(64, 64), i
 
 
 def ref_encode_image(planes, prec, sgnd=0, tile=(0, 0), numres=6, cblk=(64, 64), irreversible=False, rates=(),
-                     cinema2k_fps=0, rc_algorithm=0):
-    """planes: list of int32 [h,w] -> J2K codestream bytes produced by the unmodified reference"""
+                     cinema2k_fps=0, rc_algorithm=0, cblk_sty=0):
+    """planes: list of int32 [h,w] -> J2K codestream bytes produced by the unmodified reference (cblk_sty = grk_compress -M)"""
     L = ref()
+    L.ref_set_cblk_sty(cblk_sty)
     h, w = planes[0].shape
     keep = [aligned(np.ascontiguousarray(p, np.int32)) for p in planes]
     pa = (C.c_void_p * len(keep))(*[k.ctypes.data for k in keep])

@@ -36,7 +36,15 @@ CASES = {
     # configs[4]-style decode sweep: tiled 5/3 and 9/7 streams at every reduction, and a layer-limited decode
     "sweep53": (1536, 1280, 3, 8, True, (512, 512), 6, (64, 64), (), "sweep"),
     "sweep97": (1536, 1280, 3, 8, False, (512, 512), 6, (64, 64), (10,), "sweep"),
+    # code-block style switches (grk_compress -M): LAZY 1, RESET 2, TERMALL 4, VSC 8, PTERM 16, SEGSYM 32
+    "lazy53": (300, 200, 3, 8, True, (128, 128), 5, (64, 64), (), 1),
+    "termall97": (256, 200, 3, 8, False, (128, 112), 6, (32, 32), (20, 8, 3), 0),
+    "resetvsc53": (211, 157, 1, 12, True, (0, 0), 4, (16, 32), (), 0),
+    "allmodes53": (256, 256, 3, 8, True, (0, 0), 6, (64, 64), (), 2),
+    "lazyterm97": (640, 480, 3, 8, False, (0, 0), 6, (64, 64), (30, 10, 4), 1),
+    "segsympterm16": (130, 90, 3, 16, True, (0, 0), 3, (64, 64), (), 0),
 }
+STYLES = {"lazy53": 1, "termall97": 4, "resetvsc53": 2 | 8, "allmodes53": 63, "lazyterm97": 1 | 4 | 16, "segsympterm16": 16 | 32}
 
 
 def main():
@@ -54,7 +62,7 @@ def main():
         kind = case[10] if len(case) > 10 else "smooth"
         img = synthetic_planes(w, h, nc, prec, seed=len(name) + w, kind=kind)
         # rate-control algorithm 1 so that a single lossless layer is formed from the synced pass data
-        cs = _libs.ref_encode_image(img, prec, tile=tile, numres=numres, cblk=cblk, irreversible=not rev, rates=rates, rc_algorithm=1)
+        cs = _libs.ref_encode_image(img, prec, tile=tile, numres=numres, cblk=cblk, irreversible=not rev, rates=rates, rc_algorithm=1, cblk_sty=STYLES.get(name, 0))
         res[name + "_cs"] = np.frombuffer(cs, np.uint8)
         res[name + "_dec"] = np.stack(_libs.ref_decode_image(cs, nc, w, h))
         if reduce == "sweep":
