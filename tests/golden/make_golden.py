@@ -12,7 +12,8 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
-from _libs import aligned, ref, ref_t1_encode, ref_t1_decode, ref_encode_image, ref_decode_image  # noqa: E402
+from _libs import (aligned, ref, ref_t1_encode, ref_t1_decode, ref_encode_image, ref_decode_image, ref_t1_encode_sty,  # noqa: E402
+                   ref_t1_decode_segs, segments_from_passes)
 from grokimagecompression_b200.synth import synthetic_planes  # noqa: E402
 
 
@@ -40,6 +41,35 @@ def t1_vectors():
             out[f"blk{i}_dec_half"] = ref_t1_decode(data[:int(rates[k - 1])], k, numbps, orient, w, h)
     out["count"] = np.array([len(shapes) * 3])
     np.savez_compressed(os.path.join(HERE, "t1_blocks.npz"), **out)
+
+
+def t1_style_vectors():
+    """code-block style switches: the reference's bytes, rates, termination flags and segment-wise decodes"""
+    rng = np.random.default_rng(20261019)
+    out = {}
+    styles = [1, 2, 4, 8, 16, 32, 1 | 4, 1 | 16, 1 | 4 | 16, 2 | 8 | 32, 63, 1 | 2 | 8, 4 | 16, 1 | 32]
+    shapes = [(64, 64), (32, 32), (17, 13), (64, 7), (33, 64)]
+    n = 0
+    for j, sty in enumerate(styles):
+        for (w, h) in (shapes[j % len(shapes)], shapes[(j + 2) % len(shapes)]):
+            amp = [25.0, 3000.0, 60000.0][n % 3]
+            orient = n % 4
+            q = (np.rint(rng.laplace(0, amp, (h, w))).astype(np.int64) * 64 + rng.integers(0, 64, (h, w))).astype(np.int32)
+            norms = np.array([1.732, 1.805, 1.573])
+            step, lvl, comp = 0.03125 * (1 + n % 3), n % 5, n % 3
+            data, numbps, rates, dists, terms = ref_t1_encode_sty(q, orient, sty, comp, lvl, 0, step, norms, True)
+            out[f"blk{n}_q"] = q
+            out[f"blk{n}_meta"] = np.array([orient, numbps, len(rates), sty], np.int64)
+            out[f"blk{n}_wbase"] = np.array([(norms[comp] * ref().ref_dwt_norm(lvl, orient, 0)) * step])
+            out[f"blk{n}_data"] = np.frombuffer(data, np.uint8)
+            out[f"blk{n}_rates"], out[f"blk{n}_dists"], out[f"blk{n}_terms"] = rates, dists, terms
+            if len(rates):
+                for tag, k in (("full", len(rates)), ("half", max(1, len(rates) // 2))):
+                    sl, sp = segments_from_passes(rates, terms, k)
+                    out[f"blk{n}_dec_{tag}"] = ref_t1_decode_segs(data[:int(sl.sum())], sl, sp, numbps, orient, sty, w, h)
+            n += 1
+    out["count"] = np.array([n])
+    np.savez_compressed(os.path.join(HERE, "t1_style_blocks.npz"), **out)
 
 
 def transform_vectors():
@@ -95,6 +125,7 @@ def codestream_vectors():
 
 if __name__ == "__main__":
     t1_vectors()
+    t1_style_vectors()
     transform_vectors()
     codestream_vectors()
     print("golden fixtures written to", HERE)

@@ -30,6 +30,28 @@ def test_t1_blocks_against_reference_vectors():
     assert coded >= 16
 
 
+def test_t1_style_blocks_against_reference_vectors():
+    """LAZY / RESET / TERMALL / VSC / PTERM / SEGSYM: the restatement against vectors the reference produced"""
+    from _libs import oracle_t1_encode_sty, oracle_t1_decode_segs, segments_from_passes
+    z = np.load(os.path.join(G, "t1_style_blocks.npz"))
+    n = int(z["count"][0])
+    assert n >= 24
+    for i in range(n):
+        q = z[f"blk{i}_q"]
+        orient, numbps, npass, sty = (int(v) for v in z[f"blk{i}_meta"])
+        data, nb, rates, dists, terms, _ = oracle_t1_encode_sty(q, orient, sty, True, float(z[f"blk{i}_wbase"][0]))
+        assert nb == numbps and len(rates) == npass, (i, sty)
+        assert (rates == z[f"blk{i}_rates"]).all() and (terms == z[f"blk{i}_terms"]).all(), (i, sty)
+        assert (dists == z[f"blk{i}_dists"]).all(), (i, sty)
+        assert data == z[f"blk{i}_data"].tobytes(), (i, sty)
+        if npass:
+            h, w = q.shape
+            for tag, k in (("full", npass), ("half", max(1, npass // 2))):
+                sl, sp = segments_from_passes(rates, terms, k)
+                got = oracle_t1_decode_segs(data[:int(sl.sum())], sl, sp, numbps, orient, sty, w, h)
+                assert (got == z[f"blk{i}_dec_{tag}"]).all(), (i, sty, tag)
+
+
 def test_transforms_against_reference_vectors():
     z = np.load(os.path.join(G, "transforms.npz"))
     O = oracle()
