@@ -51,7 +51,7 @@ CBLK_SEG_DTYPE = np.dtype([("len", np.uint32), ("numpasses", np.uint32)])
 CBLK_INFO_DTYPE = np.dtype([(n, np.uint32) for n, _ in CblkInfo._fields_])
 T1_BLOCK_DTYPE = np.dtype([("x", np.uint32), ("y", np.uint32), ("w", np.uint32), ("h", np.uint32),
                            ("orient", np.uint32), ("qmfbid", np.uint32), ("inv_step", np.uint32),
-                           ("stepsize", np.float32), ("rd_weight", np.float64), ("cblk_sty", np.uint32), ("reserved", np.uint32)],
+                           ("stepsize", np.float32), ("rd_weight", np.float64), ("cblk_sty", np.uint32), ("roishift", np.uint32)],
                           align=True)
 
 # every symbol include/grok_b200.h declares

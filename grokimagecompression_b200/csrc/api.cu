@@ -253,7 +253,7 @@ int gb200_plan_create(gb200_ctx *ctx, uint32_t ntiles, const gb200_tile_params *
 			if (p.numres < 1 || p.numres > GB200_MAX_RES || p.x1 < p.x0 || p.y1 < p.y0) return bail(GB200_ERR_PARAM, "bad component rectangle / numres");
 			if (p.cblk_sty & ~(uint32_t) STY_ALL) return bail(GB200_ERR_UNSUPPORTED, "HT code blocks (cblk_sty 0x40) are not implemented");
 			if (p.cblk_sty) pl->styles = true;
-			if (p.roishift != 0) return bail(GB200_ERR_UNSUPPORTED, "ROI shift is not implemented");
+			if (p.roishift > 30 - 1) return bail(GB200_ERR_UNSUPPORTED, "ROI shift of 30 or more bit planes (t1.cpp:1056)");
 			if (p.cblkw_expn > 6 || p.cblkh_expn > 6 || p.cblkw_expn < 2 || p.cblkh_expn < 2)
 				return bail(GB200_ERR_UNSUPPORTED, "code blocks larger than 64x64 are not implemented");
 			uint32_t nd = pl->encoder ? p.numres : (tp.numres_decode ? std::min(tp.numres_decode, p.numres) : p.numres);
@@ -442,6 +442,7 @@ int gb200_plan_create(gb200_ctx *ctx, uint32_t ntiles, const gb200_tile_params *
 					db.orient = (uint8_t) g.orient;
 					db.reversible = p.qmfbid == 1;
 					db.sty = (uint8_t) p.cblk_sty;
+					db.roishift = (uint8_t) p.roishift;
 					db.stepsize = p.stepsize[g.band_index];
 					pl->decblocks.push_back(db);
 				}
@@ -1004,7 +1005,7 @@ int gb200_t1_decode_blocks_segs(gb200_ctx *ctx, int32_t *plane, uint32_t width, 
 		const gb200_t1_block &b = blocks[i];
 		if (b.w > 64 || b.h > 64 || b.x + b.w > width || b.y + b.h > height || b.orient > 3) { freeall(); FAIL(GB200_ERR_PARAM, "bad block"); }
 		if (inputs[i].data_len && inputs[i].data_offset + inputs[i].data_len > data_len) { freeall(); FAIL(GB200_ERR_PARAM, "block bytes outside the data buffer"); }
-		if (inputs[i].numbps > 30) { freeall(); FAIL(GB200_ERR_UNSUPPORTED, "more than 30 bit planes (t1.cpp:1056)"); }
+		if (inputs[i].numbps + b.roishift > 30) { freeall(); FAIL(GB200_ERR_UNSUPPORTED, "more than 30 bit planes (t1.cpp:1056)"); }
 		DecBlock &d = db[i];
 		memset(&d, 0, sizeof(d));
 		d.dst = (int32_t*) d_plane.p + (size_t) b.y * width + b.x;
@@ -1013,6 +1014,8 @@ int gb200_t1_decode_blocks_segs(gb200_ctx *ctx, int32_t *plane, uint32_t width, 
 		if (b.cblk_sty & ~(uint32_t) STY_ALL) { freeall(); FAIL(GB200_ERR_UNSUPPORTED, "HT code blocks are not implemented"); }
 		d.sty = (uint8_t) b.cblk_sty;
 		styles |= b.cblk_sty != 0;
+		if (b.roishift > 29) { freeall(); FAIL(GB200_ERR_UNSUPPORTED, "ROI shift of 30 or more bit planes"); }
+		d.roishift = (uint8_t) b.roishift;
 		maxw = std::max(maxw, b.w); maxh = std::max(maxh, b.h);
 	}
 	if (d_blocks.alloc(std::max<size_t>(nblocks, 1) * sizeof(DecBlock)) || d_inputs.alloc(std::max<size_t>(nblocks, 1) * sizeof(DecInput))

@@ -50,7 +50,7 @@ struct DecBlock {
 	int32_t *dst;        // top-left of the block inside the coefficient plane
 	uint32_t stride;
 	uint16_t w, h;
-	uint8_t orient, reversible, sty, pad1;
+	uint8_t orient, reversible, sty, roishift /* ROI up-shift of the component (decoding starts roishift planes higher) */;
 	float stepsize;
 	uint32_t pad2;
 };

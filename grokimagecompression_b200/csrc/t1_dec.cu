@@ -336,8 +336,10 @@ __global__ void __launch_bounds__(DT_MAX_THREADS, 1) t1_decode_kernel(const DecB
 	const DecInput I = inputs[bid];
 	const int w = B.w, h = B.h;
 	const int numbps = (int) I.numbps;
-	// T1Part1.cpp:139, t1.cpp:1056: nothing to decode; the cleared block area stays zero
-	if (I.numpasses == 0 || I.data_len == 0 || numbps == 0 || numbps > 30 || w == 0 || h == 0) return;
+	// T1Part1.cpp:139, t1.cpp:1055-1060: nothing to decode; the cleared block area stays zero.  With an ROI up-shift the
+	// first coded plane lies roishift planes higher (bpno_plus_one = roishift + numbps)
+	const int top = numbps + (int) B.roishift;
+	if (I.numpasses == 0 || I.data_len == 0 || top == 0 || top > 30 || w == 0 || h == 0) return;
 
 	Blk b;
 	b.nstripes = (h + 3) >> 2;
@@ -357,10 +359,10 @@ __global__ void __launch_bounds__(DT_MAX_THREADS, 1) t1_decode_kernel(const DecB
 	b.dst = B.dst;
 	b.stride = B.stride;
 	// passes go cln(numbps), then sig / ref / cln per lower plane
-	int bp1 = numbps, type = 2;
+	int bp1 = top, type = 2;
 	if (!STY) {
 		mq_init(b.q, data + I.data_offset, I.data_len);
-		const int npass = min((int) I.numpasses, 3 * numbps - 2);
+		const int npass = min((int) I.numpasses, 3 * top - 2);
 		for (int pass = 0; pass < npass; ++pass) {
 			run_pass<false, false>(b, F, w, fw, type, bp1, last_pi);
 			if (++type == 3) { type = 0; bp1--; }
@@ -407,6 +409,7 @@ __global__ void __launch_bounds__(256) t1_dec_clear_kernel(const DecBlock *__res
 		for (int x = lane; x < B.w; x += 32) B.dst[(size_t) y * B.stride + x] = 0;
 }
 
+// T1Part1.cpp:230-252: samples at or above 2^roishift belong to the region of interest and are shifted back down;
 // T1Part1.cpp:300-327: reversible /2 (C division), irreversible float(value) * stepsize
 __global__ void __launch_bounds__(256) t1_dec_finish_kernel(const DecBlock *__restrict__ blocks, uint32_t nblocks) {
 	const uint32_t bid = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -416,7 +419,11 @@ __global__ void __launch_bounds__(256) t1_dec_finish_kernel(const DecBlock *__re
 	for (int y = 0; y < B.h; ++y)
 		for (int x = lane; x < B.w; x += 32) {
 			int32_t *p = B.dst + (size_t) y * B.stride + x;
-			const int32_t v = *p;
+			int32_t v = *p;
+			if (B.roishift) {
+				const int32_t mag = abs(v);
+				if (mag >= (1 << B.roishift)) v = v < 0 ? -(mag >> B.roishift) : (mag >> B.roishift);
+			}
 			*p = B.reversible ? v / 2 : __float_as_int(__fmul_rn((float) v, B.stepsize));
 		}
 }

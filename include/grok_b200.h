@@ -67,7 +67,8 @@ typedef struct gb200_comp_params {
 	int32_t dc_shift;                   /* tccp->m_dc_level_shift */
 	uint32_t cblk_sty;                  /* tccp->cblk_sty: LAZY 0x01, RESET 0x02, TERMALL 0x04, VSC 0x08, PTERM 0x10, SEGSYM 0x20
 	                                     * (t1.cpp:1131-1151, 1223-1298); HT 0x40 is not implemented */
-	uint32_t roishift;                  /* tccp->roishift; only 0 is implemented */
+	uint32_t roishift;                  /* tccp->roishift (max-shift ROI): the encoder only sees it through band_numbps, the decoder
+	                                     * starts roishift planes higher and shifts the ROI samples back (T1Part1.cpp:230-252) */
 	float stepsize[GB200_MAX_BANDS];    /* band->stepsize (decoder side already carries the x0.5) */
 	uint32_t inv_step[GB200_MAX_BANDS]; /* band->inv_step, 13-bit fixed point */
 	uint32_t band_numbps[GB200_MAX_BANDS]; /* band->numbps (upper bound of a block's bit planes) */
@@ -196,7 +197,7 @@ typedef struct gb200_t1_block {
 	float stepsize;       /* decoder: de-quantisation step (9/7) */
 	double rd_weight;
 	uint32_t cblk_sty;    /* code-block style switches, as gb200_comp_params::cblk_sty */
-	uint32_t reserved;
+	uint32_t roishift;    /* decoder: ROI up-shift of the component */
 } gb200_t1_block;
 GB200_API int gb200_t1_encode_blocks(gb200_ctx *ctx, const int32_t *plane, uint32_t width, uint32_t height, uint32_t nblocks,
 		const gb200_t1_block *blocks, int rate_control, uint32_t max_passes, gb200_cblk_enc *results,

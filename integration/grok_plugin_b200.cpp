@@ -283,7 +283,8 @@ extern "C" PLUGIN_API uint64_t grok_b200_plugin_stat(int i) { return i == 0 ? g_
 extern "C" PLUGIN_API int32_t plugin_encode(grk_cparameters *p, grk::PLUGIN_ENCODE_USER_CALLBACK callback) {
 	if (!g_ctx || !p || !callback) return -1;
 	/* what the single grk_plugin_tile of this ABI, or this build of the kernels, cannot express -> host CPU path */
-	if (p->isHT || p->cblk_sty != 0 || p->roi_compno >= 0 || p->decod_format != GRK_PXM_FMT) return 1;
+	/* (terminating styles would need pass->term, which encode_synch_with_plugin never sets: plugin_bridge.cpp:148-260) */
+	if (p->isHT || p->cblk_sty != 0 || p->decod_format != GRK_PXM_FMT) return 1;
 	grk_image *img = read_pnm(p);
 	if (!img) return 2;
 	struct ImgGuard { grk_image *i; ~ImgGuard() { grk_image_destroy(i); } } guard{img};

@@ -221,10 +221,11 @@ bool Tier1::decodeCodeblocks(grk_tcp *, uint16_t, uint16_t, std::vector<decodeBl
 		d.x = b->x; d.y = b->y; d.w = cblk->x1 - cblk->x0; d.h = cblk->y1 - cblk->y0;
 		d.orient = b->bandno; d.qmfbid = b->qmfbid; d.stepsize = b->stepsize;
 		d.cblk_sty = b->cblk_sty;
+		d.roishift = b->roishift;
 		gb200_cblk_dec &c = in[i];
 		memset(&c, 0, sizeof(c));
-		if (b->roishift != 0 || (b->cblk_sty & GRK_CBLKSTY_HT)) {
-			fprintf(stderr, "grok_tcd_shim: ROI up-shift and HT blocks are outside this build's scope\n");
+		if (b->cblk_sty & GRK_CBLKSTY_HT) {
+			fprintf(stderr, "grok_tcd_shim: HT blocks are outside this build's scope\n");
 			abort();
 		}
 		c.numbps = cblk->numbps - b->roishift;

@@ -1051,19 +1051,30 @@ GBO_API int gbo_t1_decode_block(const uint8_t *bytes, uint32_t len, int numpasse
  * bytes = the segments back to back; seg_len[i] / seg_passes[i] as Tier-2 delivers them (T2.cpp:835-851: one pass per
  * segment with TERMALL; 10, then 2, 1, 2, 1 ... with LAZY; otherwise a single segment).
  */
+GBO_API int gbo_t1_decode_block_roi(const uint8_t *bytes, const uint32_t *seg_len, const uint32_t *seg_passes, int nsegs,
+		int numbps, int roishift, int orient, int sty, int w, int h, int32_t *out);
+
 GBO_API int gbo_t1_decode_block_segs(const uint8_t *bytes, const uint32_t *seg_len, const uint32_t *seg_passes, int nsegs,
 		int numbps, int orient, int sty, int w, int h, int32_t *out) {
+	return gbo_t1_decode_block_roi(bytes, seg_len, seg_passes, nsegs, numbps, 0, orient, sty, w, h, out);
+}
+
+/* the same for a component with a max-shift region of interest: numbps = cblk->numbps - roishift as T1Part1::decode
+ * passes it (T1Part1.cpp:184-186); decoding starts at plane roishift + numbps (t1.cpp:1055) and samples at or above
+ * 2^roishift are shifted back down afterwards (T1Part1::post_decode, T1Part1.cpp:230-252) */
+GBO_API int gbo_t1_decode_block_roi(const uint8_t *bytes, const uint32_t *seg_len, const uint32_t *seg_passes, int nsegs,
+		int numbps, int roishift, int orient, int sty, int w, int h, int32_t *out) {
 	t1d d;
 	memset(&d, 0, sizeof(d));
 	memset(out, 0, sizeof(int32_t) * (size_t) w * h);
-	if (numbps >= 31)
+	if (numbps + roishift >= 31)
 		return 1;
 	if (t1s_alloc(&d.s, w, h, orient))
 		return -1;
 	d.s.vsc = (sty & STY_VSC) != 0;
 	d.data = out;
 	mq_reset_ctx(d.q.st, d.q.mps);
-	int bp1 = numbps, type = 2;
+	int bp1 = numbps + roishift, type = 2;
 	uint32_t off = 0;
 	for (int sg = 0; sg < nsegs; ++sg) {
 		d.raw = (bp1 <= numbps - 4) && type < 2 && (sty & STY_LAZY);
@@ -1085,6 +1096,13 @@ GBO_API int gbo_t1_decode_block_segs(const uint8_t *bytes, const uint32_t *seg_l
 			}
 			if ((sty & STY_RESET) && !d.raw) mq_reset_ctx(d.q.st, d.q.mps);
 			if (++type == 3) { type = 0; bp1--; }
+		}
+	}
+	if (roishift) {
+		const int32_t thresh = 1 << roishift;
+		for (int i = 0; i < w * h; ++i) {
+			int32_t mag = out[i] < 0 ? -out[i] : out[i];
+			if (mag >= thresh) out[i] = out[i] < 0 ? -(mag >> roishift) : (mag >> roishift);
 		}
 	}
 	t1s_free(&d.s);

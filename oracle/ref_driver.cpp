@@ -268,6 +268,10 @@ static void quiet_cb(const char *, void *) {}
 /* code-block style byte (grk_compress -M) applied by the following ref_encode_image / ref_plugin_encode_file calls */
 static uint32_t g_cblk_sty = 0;
 void ref_set_cblk_sty(uint32_t sty) { g_cblk_sty = sty; }
+/* max-shift region of interest (grk_compress -ROI c=compno,U=shift) for the following ref_encode_image calls; compno < 0 = none */
+static int32_t g_roi_compno = -1;
+static uint32_t g_roi_shift = 0;
+void ref_set_roi(int32_t compno, uint32_t shift) { g_roi_compno = compno; g_roi_shift = shift; }
 
 /* grk_compress-equivalent: planar int32 image -> raw J2K codestream.
  *   tile_w/tile_h 0 = single tile;  rates[numlayers] = compression ratios (-r); numlayers 0 = lossless
@@ -287,6 +291,8 @@ int64_t ref_encode_image(uint32_t numcomps, uint32_t w, uint32_t h, uint32_t pre
 	param.irreversible = irreversible != 0;
 	param.rateControlAlgorithm = rc_algorithm;
 	param.cblk_sty = (uint8_t) g_cblk_sty;
+	param.roi_compno = g_roi_compno;
+	param.roi_shift = g_roi_compno >= 0 ? g_roi_shift : 0;
 	if (tile_w && tile_h) {
 		param.tile_size_on = true;
 		param.cp_tdx = tile_w;

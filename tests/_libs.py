@@ -64,6 +64,7 @@ def oracle():
     L.gbo_t1_encode_block_sty.argtypes = [i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p,
                                           C.POINTER(C.c_uint32), u32p, f64p, u8p, C.POINTER(C.c_uint64)]
     L.gbo_t1_decode_block_segs.argtypes = [u8p, u32p, u32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i32p]
+    L.gbo_t1_decode_block_roi.argtypes = [u8p, u32p, u32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i32p]
     L.gbo_nmsedec_tables.argtypes = [i16p] * 4
     L.gbo_context_tables.argtypes = [u8p, u8p, u8p]
     L.gbo_enumerate_blocks.argtypes = [C.c_uint32] * 7 + [u32p, C.c_void_p]
@@ -96,6 +97,7 @@ def ref():
     L.ref_t1_decode_cblk.argtypes = [u8p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                      C.c_uint32, C.c_uint32, i32p]
     L.ref_set_cblk_sty.argtypes = [C.c_uint32]
+    L.ref_set_roi.argtypes = [C.c_int32, C.c_uint32]
     L.ref_t1_want_terms.argtypes = [u8p]
     L.ref_t1_decode_cblk_segs.argtypes = [u8p, u32p, u32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                           C.c_uint32, i32p]
@@ -140,10 +142,12 @@ def ref_plugin_encode_file(infile, area, tile=(0, 0), numres=6, cblk=(64, 64), i
 
 
 def ref_encode_image(planes, prec, sgnd=0, tile=(0, 0), numres=6, cblk=(64, 64), irreversible=False, rates=(),
-                     cinema2k_fps=0, rc_algorithm=0, cblk_sty=0):
-    """planes: list of int32 [h,w] -> J2K codestream bytes produced by the unmodified reference (cblk_sty = grk_compress -M)"""
+                     cinema2k_fps=0, rc_algorithm=0, cblk_sty=0, roi=(-1, 0)):
+    """planes: list of int32 [h,w] -> J2K codestream bytes produced by the unmodified reference (cblk_sty = grk_compress -M,
+    roi = (component, shift) = -ROI c=..,U=..)"""
     L = ref()
     L.ref_set_cblk_sty(cblk_sty)
+    L.ref_set_roi(roi[0], roi[1])
     h, w = planes[0].shape
     keep = [aligned(np.ascontiguousarray(p, np.int32)) for p in planes]
     pa = (C.c_void_p * len(keep))(*[k.ctypes.data for k in keep])
@@ -277,11 +281,11 @@ def segments_from_passes(rates, terms, npasses=None):
     return np.array(lens, np.uint32), np.array(cnts, np.uint32)
 
 
-def oracle_t1_decode_segs(data, seg_len, seg_passes, numbps, orient, sty, w, h):
+def oracle_t1_decode_segs(data, seg_len, seg_passes, numbps, orient, sty, w, h, roishift=0):
     out = np.zeros((h, w), np.int32)
     b = np.frombuffer(bytes(data) + b"\0\0", np.uint8).copy()
-    rc = oracle().gbo_t1_decode_block_segs(b, np.ascontiguousarray(seg_len, np.uint32), np.ascontiguousarray(seg_passes, np.uint32),
-                                           len(seg_len), numbps, orient, sty, w, h, out.ravel())
+    rc = oracle().gbo_t1_decode_block_roi(b, np.ascontiguousarray(seg_len, np.uint32), np.ascontiguousarray(seg_passes, np.uint32),
+                                          len(seg_len), numbps, roishift, orient, sty, w, h, out.ravel())
     assert rc == 0
     return out
 

@@ -43,7 +43,11 @@ CASES = {
     "allmodes53": (256, 256, 3, 8, True, (0, 0), 6, (64, 64), (), 2),
     "lazyterm97": (640, 480, 3, 8, False, (0, 0), 6, (64, 64), (30, 10, 4), 1),
     "segsympterm16": (130, 90, 3, 16, True, (0, 0), 3, (64, 64), (), 0),
+    # max-shift region of interest on one component (-ROI c=1,U=5 / c=0,U=3)
+    "roi53": (200, 150, 3, 8, True, (64, 64), 4, (32, 32), (), 1),
+    "roi97": (256, 192, 1, 8, False, (0, 0), 5, (64, 64), (20, 5), 0),
 }
+ROI = {"roi53": (1, 5), "roi97": (0, 3)}
 STYLES = {"lazy53": 1, "termall97": 4, "resetvsc53": 2 | 8, "allmodes53": 63, "lazyterm97": 1 | 4 | 16, "segsympterm16": 16 | 32}
 
 
@@ -62,7 +66,7 @@ def main():
         kind = case[10] if len(case) > 10 else "smooth"
         img = synthetic_planes(w, h, nc, prec, seed=len(name) + w, kind=kind)
         # rate-control algorithm 1 so that a single lossless layer is formed from the synced pass data
-        cs = _libs.ref_encode_image(img, prec, tile=tile, numres=numres, cblk=cblk, irreversible=not rev, rates=rates, rc_algorithm=1, cblk_sty=STYLES.get(name, 0))
+        cs = _libs.ref_encode_image(img, prec, tile=tile, numres=numres, cblk=cblk, irreversible=not rev, rates=rates, rc_algorithm=1, cblk_sty=STYLES.get(name, 0), roi=ROI.get(name, (-1, 0)))
         res[name + "_cs"] = np.frombuffer(cs, np.uint8)
         res[name + "_dec"] = np.stack(_libs.ref_decode_image(cs, nc, w, h))
         if reduce == "sweep":
