@@ -12,14 +12,19 @@
  *   grk::TileProcessor::mct_encode()                  TileProcessor.cpp:1473   (already done -> true)
  *   grk::TileProcessor::dwt_encode()                  TileProcessor.cpp:1520   (already done -> true)
  *   grk::Tier1::encodeCodeblocks(...)                 Tier1.cpp:24             (hands the device results to the host blocks)
- *   grk::Tier1::decodeCodeblocks(...)                 Tier1.cpp:177            gb200_t1_decode_blocks
- *   grk::Wavelet::decode(...)                         Wavelet.cpp:47           gb200_dwt_decode
- *   grk::mct::decode_rev / decode_irrev               mct.cpp:143, 352         gb200_mct_decode_*
- *   grk::TileProcessor::dc_level_shift_decode()       TileProcessor.cpp:1377   gb200_dc_shift_decode
+ *   grk::Tier1::decodeCodeblocks(...)                 Tier1.cpp:177            (collects the component's blocks and segments)
+ *   grk::Wavelet::decode(...)                         Wavelet.cpp:47           (notes the resolutions to reconstruct)
+ *   grk::TileProcessor::mct_decode()                  TileProcessor.cpp:1303   gb200_decode_tiles: the whole tile in one batch
+ *   grk::TileProcessor::dc_level_shift_decode()       TileProcessor.cpp:1377   (already done -> true)
+ *   grk::mct::decode_rev / decode_irrev               mct.cpp:143, 352         gb200_mct_decode_*   (window decode only)
  *
- * The encode side keeps a tile resident on the device from the level shift to the code-block bytes
- * (one H2D of the planes, one D2H of bytes + pass tables).  The decode side uses the stage-level entry
- * points on the host tile buffers, one call per reference stage.  GROK_B200_DEVICE selects the GPU.
+ * Both directions keep a tile resident on the device for the whole path: encode = one H2D of the planes, one D2H of
+ * bytes + pass tables; decode = one H2D of the tile's code-block bytes, one D2H of the finished planes.  The reference
+ * walks a tile component by component (TileProcessor.cpp:1141-1177); the shim defers the per-component calls and runs
+ * Tier-1, de-quantisation, inverse DWT, inverse MCT and level shift of ALL components of the tile in one batch when the
+ * host reaches mct_decode, so that the serial Tier-1 chains of every component overlap.  Plans (geometry, block tables,
+ * device buffers) are cached by tile geometry, so equal tiles cost no allocation.  Region (window) decodes keep the
+ * stage-level entry points, one call per reference stage.  GROK_B200_DEVICE selects the GPU.
  */
 #include "grok_includes.h"
 #include "Tier1.h"
@@ -35,7 +40,8 @@
 namespace {
 
 gb200_ctx *g_ctx = nullptr;
-std::mutex g_mu;
+std::mutex g_mu, g_mu2;
+void fail(const char *what);
 uint64_t g_calls[8] = {0};
 
 gb200_ctx *ctx() {
@@ -49,6 +55,57 @@ gb200_ctx *ctx() {
 	}
 	return g_ctx;
 }
+
+/* plans cached by the bytes of their parameters: equal tiles (every interior tile of an image) share one */
+struct CachedPlan {
+	std::vector<uint8_t> key;
+	gb200_plan *plan;
+	uint64_t stamp;
+};
+std::vector<CachedPlan> g_cache[2]; /* [0] decoder, [1] encoder */
+uint64_t g_stamp = 0;
+
+gb200_plan *cached_plan(const gb200_tile_params &tp, bool encoder) {
+	std::vector<uint8_t> key(sizeof(gb200_tile_params) + tp.numcomps * sizeof(gb200_comp_params));
+	gb200_tile_params head = tp;
+	head.comps = nullptr;
+	memcpy(key.data(), &head, sizeof(head));
+	memcpy(key.data() + sizeof(head), tp.comps, tp.numcomps * sizeof(gb200_comp_params));
+	std::lock_guard<std::mutex> lk(g_mu2);
+	auto &cache = g_cache[encoder ? 1 : 0];
+	for (auto &c : cache)
+		if (c.key == key) { c.stamp = ++g_stamp; return c.plan; }
+	if (cache.size() >= 12) { /* drop the least recently used */
+		size_t lru = 0;
+		for (size_t i = 1; i < cache.size(); ++i) if (cache[i].stamp < cache[lru].stamp) lru = i;
+		gb200_plan_destroy(cache[lru].plan);
+		cache.erase(cache.begin() + (long) lru);
+	}
+	gb200_plan *plan = nullptr;
+	if (gb200_plan_create(ctx(), 1, &tp, encoder ? 1 : 0, &plan) != GB200_OK) fail("gb200_plan_create");
+	cache.push_back({std::move(key), plan, ++g_stamp});
+	return plan;
+}
+
+/* what Tier1::decodeCodeblocks saw for one tile component, kept until the tile is complete */
+struct PendingBlock {
+	uint32_t resno, bandno, x0, y0; /* band coordinates of the block: the key into the plan's table */
+	uint32_t numbps, numpasses;
+	uint64_t data_offset, data_len;
+	uint32_t seg_first, seg_count;
+};
+struct PendingComp {
+	std::vector<PendingBlock> blocks;
+	std::vector<gb200_cblk_seg> segs;
+	std::vector<uint8_t> data;
+	uint32_t numres_decode = 0;
+	bool dwt_seen = false;
+	/* the band step sizes, taken while tilec->resolutions is alive: TileComponent::release_mem() frees it right after
+	 * Wavelet::decode (TileProcessor.cpp:1166) */
+	float stepsize[GB200_MAX_BANDS];
+};
+std::map<grk::TileComponent*, PendingComp> g_pending;
+std::map<grk::grk_tcd_tile*, bool> g_tile_done; /* tiles whose level shift already happened on the device */
 
 struct TileResult {
 	gb200_plan *plan = nullptr;
@@ -136,8 +193,7 @@ bool TileProcessor::dc_level_shift_encode() {
 	tp.rate_control = needs_rate_control();
 	tp.comps = cp.data();
 	TileResult &R = g_results[tile];
-	if (R.plan) { gb200_plan_destroy(R.plan); R.plan = nullptr; }
-	if (gb200_plan_create(ctx(), 1, &tp, 1, &R.plan) != GB200_OK) fail("gb200_plan_create");
+	R.plan = cached_plan(tp, true); /* owned by the cache */
 	R.blocks.resize(gb200_plan_num_blocks(R.plan));
 	R.rates.resize(gb200_plan_num_pass_slots(R.plan) + 1);
 	R.dists.resize(gb200_plan_num_pass_slots(R.plan) + 1);
@@ -194,16 +250,15 @@ bool Tier1::encodeCodeblocks(grk_tcp *tcp, grk_tcd_tile *tile, const double *, u
 			}
 		}
 	}
-	gb200_plan_destroy(R.plan);
 	g_results.erase(it);
 	return true;
 }
 
 /* ---- decode ------------------------------------------------------------------------------------ */
 
-bool Tier1::decodeCodeblocks(grk_tcp *, uint16_t, uint16_t, std::vector<decodeBlockInfo*> *blocks) {
-	g_calls[4]++;
-	if (!blocks || blocks->empty()) return true;
+/* region (window) decode: the reference works on a sparse array per component, so the stage-level entry points are used
+ * one reference stage at a time */
+static bool decode_blocks_now(std::vector<decodeBlockInfo*> *blocks) {
 	const size_t n = blocks->size();
 	auto tilec = (*blocks)[0]->tilec;
 	int32_t *plane = tilec->buf->get_ptr(0, 0, 0, 0);
@@ -224,14 +279,10 @@ bool Tier1::decodeCodeblocks(grk_tcp *, uint16_t, uint16_t, std::vector<decodeBl
 		d.roishift = b->roishift;
 		gb200_cblk_dec &c = in[i];
 		memset(&c, 0, sizeof(c));
-		if (b->cblk_sty & GRK_CBLKSTY_HT) {
-			fprintf(stderr, "grok_tcd_shim: HT blocks are outside this build's scope\n");
-			abort();
-		}
 		c.numbps = cblk->numbps - b->roishift;
 		c.data_offset = data.size();
 		uint32_t passes = 0;
-		for (uint32_t s = 0; s < cblk->numSegments; ++s) { /* T1Part1.cpp:160-171 */
+		for (uint32_t s = 0; s < cblk->numSegments; ++s) { /* T1Part1.cpp:173-182 */
 			passes += cblk->segs[s].numpasses;
 			gb200_cblk_seg sg;
 			sg.len = cblk->segs[s].len;
@@ -254,12 +305,174 @@ bool Tier1::decodeCodeblocks(grk_tcp *, uint16_t, uint16_t, std::vector<decodeBl
 	return true;
 }
 
+bool Tier1::decodeCodeblocks(grk_tcp *, uint16_t, uint16_t, std::vector<decodeBlockInfo*> *blocks) {
+	g_calls[4]++;
+	if (!blocks || blocks->empty()) return true;
+	auto tilec = (*blocks)[0]->tilec;
+	if ((*blocks)[0]->cblk_sty & GRK_CBLKSTY_HT) {
+		fprintf(stderr, "grok_tcd_shim: HT blocks are outside this build's scope\n");
+		abort();
+	}
+	if (!tilec->whole_tile_decoding) return decode_blocks_now(blocks);
+	/* whole-tile decode: only collect; the tile runs as one batch in TileProcessor::mct_decode */
+	std::lock_guard<std::mutex> lk(g_mu2);
+	PendingComp &P = g_pending[tilec];
+	P.blocks.clear(); P.segs.clear(); P.data.clear();
+	P.blocks.reserve(blocks->size());
+	for (auto b : *blocks) {
+		auto cblk = b->cblk;
+		PendingBlock pb;
+		pb.resno = b->resno; pb.bandno = b->bandno; pb.x0 = cblk->x0; pb.y0 = cblk->y0;
+		pb.numbps = cblk->numbps - b->roishift;
+		pb.seg_first = (uint32_t) P.segs.size();
+		pb.numpasses = 0;
+		for (uint32_t s = 0; s < cblk->numSegments; ++s) {
+			gb200_cblk_seg sg;
+			sg.len = cblk->segs[s].len;
+			sg.numpasses = cblk->segs[s].numpasses;
+			pb.numpasses += sg.numpasses;
+			P.segs.push_back(sg);
+		}
+		pb.seg_count = (uint32_t) P.segs.size() - pb.seg_first;
+		pb.data_offset = P.data.size();
+		for (size_t k = 0; k < cblk->seg_buffers.size(); ++k) {
+			grk_buf *seg = (grk_buf*) cblk->seg_buffers.get(k);
+			P.data.insert(P.data.end(), seg->buf, seg->buf + seg->len);
+		}
+		pb.data_len = P.data.size() - pb.data_offset;
+		P.blocks.push_back(pb);
+		delete b;
+	}
+	return true;
+}
+
 bool Wavelet::decode(TileProcessor *, TileComponent *tilec, uint32_t numres, uint8_t qmfbid) {
 	g_calls[5]++;
+	if (tilec->whole_tile_decoding) { /* deferred to mct_decode */
+		std::lock_guard<std::mutex> lk(g_mu2);
+		PendingComp &P = g_pending[tilec];
+		P.numres_decode = numres;
+		P.dwt_seen = true;
+		for (uint32_t r = 0; r < tilec->numresolutions; ++r) {
+			auto res = tilec->resolutions + r;
+			for (uint32_t b = 0; b < res->numbands; ++b) P.stepsize[r == 0 ? 0 : 3 * r - 2 + b] = res->bands[b].stepsize; /* carries the x0.5 */
+		}
+		return true;
+	}
 	auto full = tilec->resolutions + tilec->numresolutions - 1;
 	if (gb200_dwt_decode(ctx(), tilec->buf->get_ptr(0, 0, 0, 0), full->x0, full->y0, full->x1, full->y1, tilec->numresolutions,
 			numres, qmfbid) != GB200_OK)
 		fail("gb200_dwt_decode");
+	return true;
+}
+
+bool TileProcessor::mct_decode() {
+	g_calls[6]++;
+	if (!whole_tile_decoding) { /* region decode: the reference's own stage order, TileProcessor.cpp:1303-1375 */
+		if (!m_tcp->mct) return true;
+		if (m_tcp->mct == 2 || tile->numcomps < 3) {
+			fprintf(stderr, "grok_tcd_shim: array based MCT is outside this build's scope\n");
+			abort();
+		}
+		const uint64_t n = (uint64_t) tile->comps[0].buf->reduced_image_dim.area();
+		if (m_tcp->tccps->qmfbid == 1)
+			mct::decode_rev(tile->comps[0].buf->get_ptr(0, 0, 0, 0), tile->comps[1].buf->get_ptr(0, 0, 0, 0), tile->comps[2].buf->get_ptr(0, 0, 0, 0), n);
+		else
+			mct::decode_irrev((float*) tile->comps[0].buf->get_ptr(0, 0, 0, 0), (float*) tile->comps[1].buf->get_ptr(0, 0, 0, 0),
+					(float*) tile->comps[2].buf->get_ptr(0, 0, 0, 0), n);
+		return true;
+	}
+	const uint32_t nc = tile->numcomps;
+	/* ---- the whole tile in one batch: parameters as on the encode side, step sizes as the decoder derived them ---- */
+	std::vector<gb200_comp_params> cp(nc);
+	std::vector<PendingComp*> pend(nc, nullptr);
+	uint32_t numres_decode = 0;
+	{
+		std::lock_guard<std::mutex> lk(g_mu2);
+		for (uint32_t c = 0; c < nc; ++c) {
+			auto it = g_pending.find(tile->comps + c);
+			if (it != g_pending.end()) pend[c] = &it->second;
+		}
+	}
+	for (uint32_t c = 0; c < nc; ++c) {
+		auto tilec = tile->comps + c;
+		auto tccp = m_tcp->tccps + c;
+		gb200_comp_params &p = cp[c];
+		memset(&p, 0, sizeof(p));
+		/* on the decode side tilec->x0.. describe the highest DECODED resolution (TileComponent::finalizeCoordinates,
+		 * TileComponent.cpp:128-140); the plan wants the full-resolution rectangle */
+		p.x0 = (uint32_t) tilec->unreduced_tile_dim.x0; p.y0 = (uint32_t) tilec->unreduced_tile_dim.y0;
+		p.x1 = (uint32_t) tilec->unreduced_tile_dim.x1; p.y1 = (uint32_t) tilec->unreduced_tile_dim.y1;
+		p.numres = tilec->numresolutions;
+		p.cblkw_expn = tccp->cblkw; p.cblkh_expn = tccp->cblkh;
+		for (uint32_t r = 0; r < p.numres; ++r) { p.prcw_expn[r] = tccp->prcw[r]; p.prch_expn[r] = tccp->prch[r]; }
+		p.qmfbid = tccp->qmfbid;
+		p.prec = image->comps[c].prec; p.sgnd = image->comps[c].sgnd;
+		p.dc_shift = tccp->m_dc_level_shift;
+		p.cblk_sty = tccp->cblk_sty; p.roishift = tccp->roishift;
+		if (!pend[c] || !pend[c]->dwt_seen) { fprintf(stderr, "grok_tcd_shim: tile component reached mct_decode without Wavelet::decode\n"); abort(); }
+		for (uint32_t bi = 0; bi < 3 * p.numres - 2; ++bi) {
+			p.stepsize[bi] = pend[c]->stepsize[bi];
+			p.inv_step[bi] = 8192;
+			p.band_numbps[bi] = 16;
+			p.rd_weight[bi] = 1.0;
+		}
+		const uint32_t nd = pend[c]->numres_decode;
+		if (c == 0) numres_decode = nd;
+		else if (nd != numres_decode) { fprintf(stderr, "grok_tcd_shim: components decoded at different resolutions\n"); abort(); }
+	}
+	gb200_tile_params tp;
+	memset(&tp, 0, sizeof(tp));
+	tp.numcomps = nc;
+	tp.mct = m_tcp->mct;
+	tp.numres_decode = numres_decode;
+	tp.comps = cp.data();
+	if (tp.mct > 1) { fprintf(stderr, "grok_tcd_shim: array based MCT is outside this build's scope\n"); abort(); }
+	gb200_plan *plan = cached_plan(tp, false);
+	const size_t nb = gb200_plan_num_blocks(plan);
+	const gb200_cblk_info *info = gb200_plan_blocks(plan);
+	/* the host's blocks, found in the plan's table by (component, resolution, band, band coordinates) */
+	std::vector<gb200_cblk_dec> in(nb);
+	std::vector<uint32_t> seg_start(nb + 1, 0);
+	std::vector<gb200_cblk_seg> segs;
+	std::vector<uint8_t> data;
+	memset(in.data(), 0, nb * sizeof(gb200_cblk_dec));
+	{
+		std::map<uint64_t, const PendingBlock*> byKey;
+		size_t i = 0;
+		for (uint32_t c = 0; c < nc; ++c) {
+			byKey.clear();
+			if (pend[c])
+				for (auto &pb : pend[c]->blocks)
+					byKey[((uint64_t) pb.resno << 58) | ((uint64_t) pb.bandno << 56) | ((uint64_t) pb.x0 << 28) | pb.y0] = &pb;
+			const uint64_t base = data.size();
+			if (pend[c]) data.insert(data.end(), pend[c]->data.begin(), pend[c]->data.end());
+			for (; i < nb && info[i].compno == c; ++i) {
+				auto f = byKey.find(((uint64_t) info[i].resno << 58) | ((uint64_t) info[i].bandno << 56) | ((uint64_t) info[i].x0 << 28) | info[i].y0);
+				if (f != byKey.end()) {
+					const PendingBlock &pb = *f->second;
+					in[i].numbps = pb.numbps;
+					in[i].numpasses = pb.numpasses;
+					in[i].data_len = (uint32_t) pb.data_len;
+					in[i].data_offset = base + pb.data_offset;
+					for (uint32_t k = 0; k < pb.seg_count; ++k) segs.push_back(pend[c]->segs[pb.seg_first + k]);
+				}
+				seg_start[i + 1] = (uint32_t) segs.size();
+			}
+		}
+		for (; i < nb; ++i) seg_start[i + 1] = (uint32_t) segs.size();
+	}
+	if (segs.empty()) segs.resize(1);
+	std::vector<int32_t*> planes(nc);
+	for (uint32_t c = 0; c < nc; ++c) planes[c] = tile->comps[c].buf->get_ptr(0, 0, 0, 0);
+	if (gb200_decode_set_segments(plan, seg_start.data(), segs.data()) != GB200_OK) fail("gb200_decode_set_segments");
+	if (gb200_decode_tiles(plan, in.data(), data.empty() ? nullptr : data.data(), data.size(), planes.data()) != GB200_OK)
+		fail("gb200_decode_tiles");
+	{
+		std::lock_guard<std::mutex> lk(g_mu2);
+		for (uint32_t c = 0; c < nc; ++c) g_pending.erase(tile->comps + c);
+		g_tile_done[tile] = true;
+	}
 	return true;
 }
 
@@ -275,6 +488,11 @@ void mct::decode_irrev(float *c0, float *c1, float *c2, uint64_t n) {
 
 bool TileProcessor::dc_level_shift_decode() {
 	g_calls[7]++;
+	{
+		std::lock_guard<std::mutex> lk(g_mu2);
+		auto it = g_tile_done.find(tile);
+		if (it != g_tile_done.end()) { g_tile_done.erase(it); return true; } /* shifted and clamped on the device already */
+	}
 	for (uint32_t c = 0; c < tile->numcomps; ++c) {
 		auto tilec = tile->comps + c;
 		auto tccp = m_tcp->tccps + c;
