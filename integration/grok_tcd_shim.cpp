@@ -31,6 +31,7 @@
 #include "T1Interface.h"
 #include "dwt_utils.h"
 #include "../include/grok_b200.h"
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -40,9 +41,16 @@
 namespace {
 
 gb200_ctx *g_ctx = nullptr;
-std::mutex g_mu, g_mu2;
+std::mutex g_mu, g_mu2, g_dev_mu; /* g_dev_mu: one tile at a time on the device (cached plans are shared between equal tiles) */
 void fail(const char *what);
 uint64_t g_calls[8] = {0};
+double g_secs[8] = {0}; /* wall clock spent inside the bound stage calls, same indices as g_calls */
+struct Timer {
+	int i;
+	std::chrono::steady_clock::time_point t0;
+	explicit Timer(int idx) : i(idx), t0(std::chrono::steady_clock::now()) {}
+	~Timer() { g_secs[i] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+};
 
 gb200_ctx *ctx() {
 	std::lock_guard<std::mutex> lk(g_mu);
@@ -138,6 +146,8 @@ void fail(const char *what) {
 } // namespace
 
 extern "C" uint64_t grok_b200_shim_calls(int i) { return g_calls[i & 7]; }
+extern "C" double grok_b200_shim_seconds(int i) { return g_secs[i & 7]; }
+extern "C" void grok_b200_shim_reset_seconds(void) { for (auto &v : g_secs) v = 0; }
 
 namespace grk {
 
@@ -145,6 +155,7 @@ namespace grk {
 
 bool TileProcessor::dc_level_shift_encode() {
 	g_calls[0]++;
+	Timer timer(0);
 	const uint32_t nc = tile->numcomps;
 	std::vector<gb200_comp_params> cp(nc);
 	std::vector<const int32_t*> planes(nc);
@@ -192,6 +203,7 @@ bool TileProcessor::dc_level_shift_encode() {
 	tp.mct = m_tcp->mct;
 	tp.rate_control = needs_rate_control();
 	tp.comps = cp.data();
+	std::lock_guard<std::mutex> dev_lock(g_dev_mu);
 	TileResult &R = g_results[tile];
 	R.plan = cached_plan(tp, true); /* owned by the cache */
 	R.blocks.resize(gb200_plan_num_blocks(R.plan));
@@ -209,6 +221,7 @@ bool TileProcessor::dwt_encode() { g_calls[2]++; return true; }
 
 bool Tier1::encodeCodeblocks(grk_tcp *tcp, grk_tcd_tile *tile, const double *, uint32_t, bool doRateControl) {
 	g_calls[3]++;
+	Timer timer(3);
 	auto it = g_results.find(tile);
 	if (it == g_results.end()) { fprintf(stderr, "grok_tcd_shim: no device result for this tile\n"); abort(); }
 	TileResult &R = it->second;
@@ -307,6 +320,7 @@ static bool decode_blocks_now(std::vector<decodeBlockInfo*> *blocks) {
 
 bool Tier1::decodeCodeblocks(grk_tcp *, uint16_t, uint16_t, std::vector<decodeBlockInfo*> *blocks) {
 	g_calls[4]++;
+	Timer timer(4);
 	if (!blocks || blocks->empty()) return true;
 	auto tilec = (*blocks)[0]->tilec;
 	if ((*blocks)[0]->cblk_sty & GRK_CBLKSTY_HT) {
@@ -368,6 +382,7 @@ bool Wavelet::decode(TileProcessor *, TileComponent *tilec, uint32_t numres, uin
 
 bool TileProcessor::mct_decode() {
 	g_calls[6]++;
+	Timer timer(6);
 	if (!whole_tile_decoding) { /* region decode: the reference's own stage order, TileProcessor.cpp:1303-1375 */
 		if (!m_tcp->mct) return true;
 		if (m_tcp->mct == 2 || tile->numcomps < 3) {
@@ -428,6 +443,7 @@ bool TileProcessor::mct_decode() {
 	tp.numres_decode = numres_decode;
 	tp.comps = cp.data();
 	if (tp.mct > 1) { fprintf(stderr, "grok_tcd_shim: array based MCT is outside this build's scope\n"); abort(); }
+	std::lock_guard<std::mutex> dev_lock(g_dev_mu);
 	gb200_plan *plan = cached_plan(tp, false);
 	const size_t nb = gb200_plan_num_blocks(plan);
 	const gb200_cblk_info *info = gb200_plan_blocks(plan);
