@@ -76,15 +76,23 @@ struct MqT {
 	uint32_t endoff; // offset of the end of the segment relative to base8
 };
 
-// aligned word j of the segment; bytes at or beyond its end read as 0xFF
-__device__ __forceinline__ uint64_t mq_word(const MqT &q, uint32_t j) {
+// aligned word j of the segment; bytes at or beyond its end read as 0xFF.  Called once per 8 consumed bytes (every ~80
+// decisions) from 23 inlined decoders: kept out of line, with plain value arguments, so that it does not multiply the
+// kernel's code size (instruction fetch is a visible stall of this kernel)
+#ifdef DT_INLINE_REFILL
+__device__ __forceinline__
+#else
+__device__ __noinline__
+#endif
+uint64_t mq_word_at(const unsigned long long *base8, uint32_t j, uint32_t endoff) {
 	const uint32_t lo = 8u * j;
-	if (lo >= q.endoff) return ~0ull;
-	uint64_t w = __ldg(q.base8 + j);
-	const uint32_t valid = q.endoff - lo;
+	if (lo >= endoff) return ~0ull;
+	uint64_t w = __ldg(base8 + j);
+	const uint32_t valid = endoff - lo;
 	if (valid < 8u) w |= ~0ull << (8u * valid);
 	return w;
 }
+__device__ __forceinline__ uint64_t mq_word(const MqT &q, uint32_t j) { return mq_word_at(q.base8, j, q.endoff); }
 
 __device__ __forceinline__ void mq_advance(MqT &q) {
 	q.win >>= 8;
@@ -132,23 +140,27 @@ __device__ __forceinline__ void mq_init(MqT &q, const uint8_t *buf, uint32_t len
 __device__ __forceinline__ uint32_t mq_decode(MqT &q, uint32_t *crow, const uint32_t *tab) {
 	const uint32_t row = *crow;
 	const uint32_t qs = row & 0xFFFF0000u, mps = (row >> 15) & 1u;
-	q.a -= qs;
-	bool lps;
-	if (q.c < qs) { // (C >> 16) < Qe : the LPS sub-interval
-		lps = q.a >= qs; // conditional exchange
-		q.a = qs;
-	} else {
-		q.c -= qs;
-		if (q.a & 0x80000000u) return mps;
-		lps = q.a < qs;
+	const uint32_t a = q.a - qs, cs = q.c - qs;
+	const bool lpsint = q.c < qs; // (C >> 16) < Qe : the LPS sub-interval
+	if (!lpsint && (a & 0x80000000u)) { // MPS, no renormalisation: the one early exit
+		q.a = a;
+		q.c = cs;
+		return mps;
 	}
+	// the remaining three cases with selects instead of branches: LPS sub-interval (conditional exchange when A < Qe),
+	// or the MPS sub-interval with A below 0x8000 (exchange when A < Qe)
+	const bool lps = (a < qs) != lpsint;
+	q.c = lpsint ? q.c : cs;
+	q.a = lpsint ? qs : a;
 	*crow = tab[lps ? (row >> 8) & 0x7Fu : row & 0x7Fu];
 	int sh = __clz(q.a);
 	q.a <<= sh;
-	while (sh > q.ct) { // RENORMD with BYTEIN whenever the bit counter runs out
-		q.c <<= q.ct;
-		sh -= q.ct;
-		mq_bytein(q);
+	if (sh > q.ct) {
+		do { // RENORMD with BYTEIN whenever the bit counter runs out
+			q.c <<= q.ct;
+			sh -= q.ct;
+			mq_bytein(q);
+		} while (sh > q.ct);
 	}
 	q.c <<= sh;
 	q.ct -= sh;
