@@ -128,14 +128,23 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, ENC_MIN_CTAS) t1_model_kernel(
 	for (int i = lane; i < 66; i += 32) { W.sig[i] = 0; W.neg[i] = 0; W.vis[i] = 0; W.refd[i] = 0; W.bit[i] = 0; }
 	__syncwarp();
 	uint32_t mx = 0;
-	for (int y = 0; y < h; ++y) {
-		const int32_t *row = B.src + (size_t) y * B.stride;
-		int32_t v0 = lane < w ? quantise(row[lane], rev, B.inv_step) : 0;
-		int32_t v1 = lane + 32 < w ? quantise(row[lane + 32], rev, B.inv_step) : 0;
-		mx = max(mx, (uint32_t) abs(v0));
-		mx = max(mx, (uint32_t) abs(v1));
-		uint32_t n0 = __ballot_sync(0xffffffffu, v0 < 0), n1 = __ballot_sync(0xffffffffu, v1 < 0);
-		if (lane == 0) W.neg[y + 1] = (uint64_t) n0 | ((uint64_t) n1 << 32);
+	const bool in0 = lane < w, in1 = lane + 32 < w;
+	for (int yb = 0; yb < h; yb += 8) { // eight rows per trip: all sixteen loads of the warp in flight before the first ballot
+		int32_t r0[8], r1[8];
+		#pragma unroll
+		for (int j = 0; j < 8; ++j) {
+			const int32_t *row = B.src + (size_t) (yb + j) * B.stride;
+			r0[j] = (in0 && yb + j < h) ? row[lane] : 0;
+			r1[j] = (in1 && yb + j < h) ? row[lane + 32] : 0;
+		}
+		#pragma unroll
+		for (int j = 0; j < 8; ++j) {
+			const int32_t v0 = quantise(r0[j], rev, B.inv_step), v1 = quantise(r1[j], rev, B.inv_step);
+			mx = max(mx, (uint32_t) abs(v0));
+			mx = max(mx, (uint32_t) abs(v1));
+			const uint32_t n0 = __ballot_sync(0xffffffffu, v0 < 0), n1 = __ballot_sync(0xffffffffu, v1 < 0);
+			if (lane == j && yb + j < h) W.neg[yb + j + 1] = (uint64_t) n0 | ((uint64_t) n1 << 32);
+		}
 	}
 	#pragma unroll
 	for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -156,12 +165,20 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, ENC_MIN_CTAS) t1_model_kernel(
 
 	for (int bp = numbps - 1; bp >= 0; --bp) {
 		// ---- bit-plane masks for this plane -------------------------------------------------
-		for (int y = 0; y < h; ++y) {
-			const int32_t *row = B.src + (size_t) y * B.stride;
-			uint32_t m0 = lane < w ? (uint32_t) abs(quantise(row[lane], rev, B.inv_step)) : 0;
-			uint32_t m1 = lane + 32 < w ? (uint32_t) abs(quantise(row[lane + 32], rev, B.inv_step)) : 0;
-			uint32_t b0 = __ballot_sync(0xffffffffu, (m0 >> (bp + 6)) & 1), b1 = __ballot_sync(0xffffffffu, (m1 >> (bp + 6)) & 1);
-			if (lane == 0) W.bit[y + 1] = (uint64_t) b0 | ((uint64_t) b1 << 32);
+		for (int yb = 0; yb < h; yb += 8) {
+			int32_t r0[8], r1[8];
+			#pragma unroll
+			for (int j = 0; j < 8; ++j) {
+				const int32_t *row = B.src + (size_t) (yb + j) * B.stride;
+				r0[j] = (in0 && yb + j < h) ? row[lane] : 0;
+				r1[j] = (in1 && yb + j < h) ? row[lane + 32] : 0;
+			}
+			#pragma unroll
+			for (int j = 0; j < 8; ++j) {
+				const uint32_t m0 = (uint32_t) abs(quantise(r0[j], rev, B.inv_step)), m1 = (uint32_t) abs(quantise(r1[j], rev, B.inv_step));
+				const uint32_t b0 = __ballot_sync(0xffffffffu, (m0 >> (bp + 6)) & 1), b1 = __ballot_sync(0xffffffffu, (m1 >> (bp + 6)) & 1);
+				if (lane == j && yb + j < h) W.bit[yb + j + 1] = (uint64_t) b0 | ((uint64_t) b1 << 32);
+			}
 		}
 		__syncwarp();
 
@@ -406,15 +423,18 @@ __global__ void __launch_bounds__(MQ_WARPS * 32) t1_mq_kernel(const EncBlock *__
 		uint32_t *cr = C + (sym >> 1);
 		const uint32_t row = *cr;
 		const uint32_t qs = row & 0xFFFF0000u;
-		q.a -= qs;
-		if (((row >> 15) ^ sym) & 1u) { // CODELPS
-			if (q.a < qs) q.c += qs >> 16; else q.a = qs;
-			*cr = tabrow((row >> 8) & 0x7Fu);
-		} else {                        // CODEMPS
-			if (q.a & 0x80000000u) { q.c += qs >> 16; return; }
-			if (q.a < qs) q.a = qs; else q.c += qs >> 16;
-			*cr = tabrow(row & 0x7Fu);
+		const uint32_t a = q.a - qs;
+		const bool ismps = !(((row >> 15) ^ sym) & 1u);
+		if (ismps && (a & 0x80000000u)) { // CODEMPS without renormalisation: the one early exit
+			q.a = a;
+			q.c += qs >> 16;
+			return;
 		}
+		// CODEMPS: A < Qe ? A = Qe : C += Qe;  CODELPS: A < Qe ? C += Qe : A = Qe  -- one select pair
+		const bool takeq = ismps == (a < qs);
+		q.a = takeq ? qs : a;
+		q.c += takeq ? 0u : qs >> 16;
+		*cr = tabrow(ismps ? row & 0x7Fu : (row >> 8) & 0x7Fu);
 		int sh = __clz(q.a); // RENORME
 		q.a <<= sh;
 		while (sh >= q.ct) { // a byte is completed inside this shift
