@@ -16,15 +16,14 @@
  *   grk::Wavelet::decode(...)                         Wavelet.cpp:47           (notes the resolutions to reconstruct)
  *   grk::TileProcessor::mct_decode()                  TileProcessor.cpp:1303   gb200_decode_tiles: the whole tile in one batch
  *   grk::TileProcessor::dc_level_shift_decode()       TileProcessor.cpp:1377   (already done -> true)
- *   grk::mct::decode_rev / decode_irrev               mct.cpp:143, 352         gb200_mct_decode_*   (window decode only)
  *
  * Both directions keep a tile resident on the device for the whole path: encode = one H2D of the planes, one D2H of
  * bytes + pass tables; decode = one H2D of the tile's code-block bytes, one D2H of the finished planes.  The reference
  * walks a tile component by component (TileProcessor.cpp:1141-1177); the shim defers the per-component calls and runs
  * Tier-1, de-quantisation, inverse DWT, inverse MCT and level shift of ALL components of the tile in one batch when the
  * host reaches mct_decode, so that the serial Tier-1 chains of every component overlap.  Plans (geometry, block tables,
- * device buffers) are cached by tile geometry, so equal tiles cost no allocation.  Region (window) decodes keep the
- * stage-level entry points, one call per reference stage.  GROK_B200_DEVICE selects the GPU.
+ * device buffers) are cached by tile geometry, so equal tiles cost no allocation.  Region (window) decodes
+ * (grk_set_decode_area) reconstruct the whole tile on the device and cut the window out.  GROK_B200_DEVICE selects the GPU.
  */
 #include "grok_includes.h"
 #include "Tier1.h"
@@ -269,55 +268,6 @@ bool Tier1::encodeCodeblocks(grk_tcp *tcp, grk_tcd_tile *tile, const double *, u
 
 /* ---- decode ------------------------------------------------------------------------------------ */
 
-/* region (window) decode: the reference works on a sparse array per component, so the stage-level entry points are used
- * one reference stage at a time */
-static bool decode_blocks_now(std::vector<decodeBlockInfo*> *blocks) {
-	const size_t n = blocks->size();
-	auto tilec = (*blocks)[0]->tilec;
-	int32_t *plane = tilec->buf->get_ptr(0, 0, 0, 0);
-	const uint32_t width = tilec->width(), height = tilec->height();
-	std::vector<gb200_t1_block> desc(n);
-	std::vector<gb200_cblk_dec> in(n);
-	std::vector<uint8_t> data;
-	std::vector<uint32_t> seg_start(n + 1, 0);
-	std::vector<gb200_cblk_seg> segs;
-	for (size_t i = 0; i < n; ++i) {
-		auto b = (*blocks)[i];
-		auto cblk = b->cblk;
-		gb200_t1_block &d = desc[i];
-		memset(&d, 0, sizeof(d));
-		d.x = b->x; d.y = b->y; d.w = cblk->x1 - cblk->x0; d.h = cblk->y1 - cblk->y0;
-		d.orient = b->bandno; d.qmfbid = b->qmfbid; d.stepsize = b->stepsize;
-		d.cblk_sty = b->cblk_sty;
-		d.roishift = b->roishift;
-		gb200_cblk_dec &c = in[i];
-		memset(&c, 0, sizeof(c));
-		c.numbps = cblk->numbps - b->roishift;
-		c.data_offset = data.size();
-		uint32_t passes = 0;
-		for (uint32_t s = 0; s < cblk->numSegments; ++s) { /* T1Part1.cpp:173-182 */
-			passes += cblk->segs[s].numpasses;
-			gb200_cblk_seg sg;
-			sg.len = cblk->segs[s].len;
-			sg.numpasses = cblk->segs[s].numpasses;
-			segs.push_back(sg);
-		}
-		seg_start[i + 1] = (uint32_t) segs.size();
-		c.numpasses = passes;
-		for (size_t k = 0; k < cblk->seg_buffers.size(); ++k) { /* T1Part1.cpp:153-158 */
-			grk_buf *seg = (grk_buf*) cblk->seg_buffers.get(k);
-			data.insert(data.end(), seg->buf, seg->buf + seg->len);
-		}
-		c.data_len = (uint32_t) (data.size() - c.data_offset);
-		delete b;
-	}
-	if (segs.empty()) segs.resize(1);
-	if (gb200_t1_decode_blocks_segs(ctx(), plane, width, height, (uint32_t) n, desc.data(), in.data(), seg_start.data(), segs.data(),
-			data.data(), data.size()) != GB200_OK)
-		fail("gb200_t1_decode_blocks_segs");
-	return true;
-}
-
 bool Tier1::decodeCodeblocks(grk_tcp *, uint16_t, uint16_t, std::vector<decodeBlockInfo*> *blocks) {
 	g_calls[4]++;
 	Timer timer(4);
@@ -327,8 +277,7 @@ bool Tier1::decodeCodeblocks(grk_tcp *, uint16_t, uint16_t, std::vector<decodeBl
 		fprintf(stderr, "grok_tcd_shim: HT blocks are outside this build's scope\n");
 		abort();
 	}
-	if (!tilec->whole_tile_decoding) return decode_blocks_now(blocks);
-	/* whole-tile decode: only collect; the tile runs as one batch in TileProcessor::mct_decode */
+	/* only collect; the tile runs as one batch in TileProcessor::mct_decode */
 	std::lock_guard<std::mutex> lk(g_mu2);
 	PendingComp &P = g_pending[tilec];
 	P.blocks.clear(); P.segs.clear(); P.data.clear();
@@ -362,7 +311,7 @@ bool Tier1::decodeCodeblocks(grk_tcp *, uint16_t, uint16_t, std::vector<decodeBl
 
 bool Wavelet::decode(TileProcessor *, TileComponent *tilec, uint32_t numres, uint8_t qmfbid) {
 	g_calls[5]++;
-	if (tilec->whole_tile_decoding) { /* deferred to mct_decode */
+	{ /* deferred to mct_decode */
 		std::lock_guard<std::mutex> lk(g_mu2);
 		PendingComp &P = g_pending[tilec];
 		P.numres_decode = numres;
@@ -373,30 +322,11 @@ bool Wavelet::decode(TileProcessor *, TileComponent *tilec, uint32_t numres, uin
 		}
 		return true;
 	}
-	auto full = tilec->resolutions + tilec->numresolutions - 1;
-	if (gb200_dwt_decode(ctx(), tilec->buf->get_ptr(0, 0, 0, 0), full->x0, full->y0, full->x1, full->y1, tilec->numresolutions,
-			numres, qmfbid) != GB200_OK)
-		fail("gb200_dwt_decode");
-	return true;
 }
 
 bool TileProcessor::mct_decode() {
 	g_calls[6]++;
 	Timer timer(6);
-	if (!whole_tile_decoding) { /* region decode: the reference's own stage order, TileProcessor.cpp:1303-1375 */
-		if (!m_tcp->mct) return true;
-		if (m_tcp->mct == 2 || tile->numcomps < 3) {
-			fprintf(stderr, "grok_tcd_shim: array based MCT is outside this build's scope\n");
-			abort();
-		}
-		const uint64_t n = (uint64_t) tile->comps[0].buf->reduced_image_dim.area();
-		if (m_tcp->tccps->qmfbid == 1)
-			mct::decode_rev(tile->comps[0].buf->get_ptr(0, 0, 0, 0), tile->comps[1].buf->get_ptr(0, 0, 0, 0), tile->comps[2].buf->get_ptr(0, 0, 0, 0), n);
-		else
-			mct::decode_irrev((float*) tile->comps[0].buf->get_ptr(0, 0, 0, 0), (float*) tile->comps[1].buf->get_ptr(0, 0, 0, 0),
-					(float*) tile->comps[2].buf->get_ptr(0, 0, 0, 0), n);
-		return true;
-	}
 	const uint32_t nc = tile->numcomps;
 	/* ---- the whole tile in one batch: parameters as on the encode side, step sizes as the decoder derived them ---- */
 	std::vector<gb200_comp_params> cp(nc);
@@ -479,11 +409,32 @@ bool TileProcessor::mct_decode() {
 		for (; i < nb; ++i) seg_start[i + 1] = (uint32_t) segs.size();
 	}
 	if (segs.empty()) segs.resize(1);
+	/* a region (window) decode asks for a sub-rectangle of the tile (TileBuffer::reduced_image_dim inside reduced_tile_dim,
+	 * TileComponent.cpp:557-583): the device reconstructs the whole tile from the blocks the host selected and the
+	 * window is cut out afterwards; a whole-tile decode lands in the tile buffers directly */
 	std::vector<int32_t*> planes(nc);
-	for (uint32_t c = 0; c < nc; ++c) planes[c] = tile->comps[c].buf->get_ptr(0, 0, 0, 0);
+	std::vector<std::vector<int32_t>> whole(whole_tile_decoding ? 0 : nc);
+	for (uint32_t c = 0; c < nc; ++c) {
+		auto buf = tile->comps[c].buf;
+		if (whole_tile_decoding) planes[c] = buf->get_ptr(0, 0, 0, 0);
+		else {
+			whole[c].resize((size_t) buf->reduced_tile_dim.width() * buf->reduced_tile_dim.height());
+			planes[c] = whole[c].data();
+		}
+	}
 	if (gb200_decode_set_segments(plan, seg_start.data(), segs.data()) != GB200_OK) fail("gb200_decode_set_segments");
 	if (gb200_decode_tiles(plan, in.data(), data.empty() ? nullptr : data.data(), data.size(), planes.data()) != GB200_OK)
 		fail("gb200_decode_tiles");
+	if (!whole_tile_decoding)
+		for (uint32_t c = 0; c < nc; ++c) {
+			auto buf = tile->comps[c].buf;
+			const int64_t tw = buf->reduced_tile_dim.width(), ww = buf->reduced_image_dim.width(), wh = buf->reduced_image_dim.height();
+			const int64_t ox = buf->reduced_image_dim.x0 - buf->reduced_tile_dim.x0, oy = buf->reduced_image_dim.y0 - buf->reduced_tile_dim.y0;
+			if (!buf->data || ww <= 0 || wh <= 0) continue;
+			if (ox < 0 || oy < 0 || ox + ww > tw || oy + wh > buf->reduced_tile_dim.height()) { fprintf(stderr, "grok_tcd_shim: decode window outside the tile\n"); abort(); }
+			for (int64_t y = 0; y < wh; ++y)
+				memcpy(buf->data + y * ww, whole[c].data() + (oy + y) * tw + ox, (size_t) ww * sizeof(int32_t));
+		}
 	{
 		std::lock_guard<std::mutex> lk(g_mu2);
 		for (uint32_t c = 0; c < nc; ++c) g_pending.erase(tile->comps + c);
@@ -492,33 +443,12 @@ bool TileProcessor::mct_decode() {
 	return true;
 }
 
-void mct::decode_rev(int32_t *c0, int32_t *c1, int32_t *c2, uint64_t n) {
-	g_calls[6]++;
-	if (gb200_mct_decode_rev(ctx(), c0, c1, c2, n) != GB200_OK) fail("gb200_mct_decode_rev");
-}
-
-void mct::decode_irrev(float *c0, float *c1, float *c2, uint64_t n) {
-	g_calls[6]++;
-	if (gb200_mct_decode_irrev(ctx(), c0, c1, c2, n) != GB200_OK) fail("gb200_mct_decode_irrev");
-}
-
 bool TileProcessor::dc_level_shift_decode() {
 	g_calls[7]++;
-	{
-		std::lock_guard<std::mutex> lk(g_mu2);
-		auto it = g_tile_done.find(tile);
-		if (it != g_tile_done.end()) { g_tile_done.erase(it); return true; } /* shifted and clamped on the device already */
-	}
-	for (uint32_t c = 0; c < tile->numcomps; ++c) {
-		auto tilec = tile->comps + c;
-		auto tccp = m_tcp->tccps + c;
-		auto ic = image->comps + c;
-		const int32_t lo = ic->sgnd ? -(1 << (ic->prec - 1)) : 0;
-		const int32_t hi = ic->sgnd ? (1 << (ic->prec - 1)) - 1 : (int32_t) ((1u << ic->prec) - 1);
-		const uint64_t n = (uint64_t) tilec->buf->reduced_image_dim.width() * tilec->buf->reduced_image_dim.height();
-		if (gb200_dc_shift_decode(ctx(), tilec->buf->get_ptr(0, 0, 0, 0), n, tccp->m_dc_level_shift, tccp->qmfbid, lo, hi) != GB200_OK)
-			fail("gb200_dc_shift_decode");
-	}
+	std::lock_guard<std::mutex> lk(g_mu2);
+	auto it = g_tile_done.find(tile);
+	if (it == g_tile_done.end()) { fprintf(stderr, "grok_tcd_shim: level shift reached before the tile was decoded\n"); abort(); }
+	g_tile_done.erase(it); /* shifted and clamped on the device already */
 	return true;
 }
 

@@ -339,6 +339,10 @@ int64_t ref_encode_image(uint32_t numcomps, uint32_t w, uint32_t h, uint32_t pre
 	return len;
 }
 
+/* decode window (grk_decompress -d x0,y0,x1,y1) for the following ref_decode_image calls; all zero = whole image */
+static uint32_t g_da[4] = {0, 0, 0, 0};
+void ref_set_decode_area(uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1) { g_da[0] = x0; g_da[1] = y0; g_da[2] = x1; g_da[3] = y1; }
+
 /* grk_decompress-equivalent. planes_out[c] must hold the (reduced) component; returns 0 on success and
  * fills dims[0..1] = decoded width/height, dims[2] = numcomps. */
 int ref_decode_image(const uint8_t *buf, uint64_t len, uint32_t reduce, uint32_t layers, int32_t *const *planes_out,
@@ -355,6 +359,7 @@ int ref_decode_image(const uint8_t *buf, uint64_t len, uint32_t reduce, uint32_t
 	grk_image *image = nullptr;
 	int rc = 1;
 	if (codec && grk_setup_decoder(codec, &dp) && grk_read_header(codec, nullptr, &image)
+			&& ((g_da[2] == 0 && g_da[3] == 0) || grk_set_decode_area(codec, image, g_da[0], g_da[1], g_da[2], g_da[3]))
 			&& grk_decode(codec, nullptr, image) && grk_end_decompress(codec)) {
 		rc = 0;
 		dims[0] = image->comps[0].w; dims[1] = image->comps[0].h; dims[2] = image->numcomps;

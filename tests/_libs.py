@@ -98,6 +98,7 @@ def ref():
                                      C.c_uint32, C.c_uint32, i32p]
     L.ref_set_cblk_sty.argtypes = [C.c_uint32]
     L.ref_set_roi.argtypes = [C.c_int32, C.c_uint32]
+    L.ref_set_decode_area.argtypes = [C.c_uint32] * 4
     L.ref_t1_want_terms.argtypes = [u8p]
     L.ref_t1_decode_cblk_segs.argtypes = [u8p, u32p, u32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                           C.c_uint32, i32p]
@@ -160,11 +161,17 @@ def ref_encode_image(planes, prec, sgnd=0, tile=(0, 0), numres=6, cblk=(64, 64),
     return bytes(out[:n])
 
 
-def ref_decode_image(cs, numcomps, width, height, reduce=0, layers=0):
+def ref_decode_image(cs, numcomps, width, height, reduce=0, layers=0, window=None):
+    """window = (x0, y0, x1, y1) in full-resolution image coordinates: grk_decompress -d"""
     L = ref()
     buf = np.frombuffer(cs, np.uint8).copy()
     cd = lambda v: (v + (1 << reduce) - 1) >> reduce
-    planes = [np.zeros((cd(height), cd(width)), np.int32) for _ in range(numcomps)]
+    if window is None:
+        L.ref_set_decode_area(0, 0, 0, 0)
+        planes = [np.zeros((cd(height), cd(width)), np.int32) for _ in range(numcomps)]
+    else:
+        L.ref_set_decode_area(*window)
+        planes = [np.zeros((cd(window[3]) - cd(window[1]), cd(window[2]) - cd(window[0])), np.int32) for _ in range(numcomps)]
     pa = (C.c_void_p * numcomps)(*[p.ctypes.data for p in planes])
     dims = np.zeros(4, np.uint32)
     rc = L.ref_decode_image(buf, len(buf), reduce, layers, pa, planes[0].size, dims)

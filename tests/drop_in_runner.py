@@ -48,6 +48,9 @@ CASES = {
     "roi97": (256, 192, 1, 8, False, (0, 0), 5, (64, 64), (20, 5), 0),
 }
 ROI = {"roi53": (1, 5), "roi97": (0, 3)}
+# region (window) decodes, grk_decompress -d x0,y0,x1,y1 (full-resolution image coordinates), optionally reduced
+WINDOWS = {"rgb53_tiled": [((40, 30, 150, 120), 0), ((70, 10, 131, 75), 1)], "rgb97_layers": [((10, 20, 200, 180), 0), ((64, 64, 192, 160), 2)],
+           "sweep53": [((300, 200, 1100, 900), 0)], "lazy53": [((100, 50, 260, 190), 1)]}
 STYLES = {"lazy53": 1, "termall97": 4, "resetvsc53": 2 | 8, "allmodes53": 63, "lazyterm97": 1 | 4 | 16, "segsympterm16": 16 | 32}
 
 
@@ -76,6 +79,8 @@ def main():
                 res[name + "_dec_l1"] = np.stack(_libs.ref_decode_image(cs, nc, w, h, layers=1))
         elif reduce:
             res[name + "_dec_r"] = np.stack(_libs.ref_decode_image(cs, nc, w, h, reduce=reduce))
+        for k, (win, red) in enumerate(WINDOWS.get(name, [])):
+            res[name + f"_dec_w{k}"] = np.stack(_libs.ref_decode_image(cs, nc, w, h, reduce=red, window=win))
         res[name + "_img"] = np.stack(img)
     if shim is not None:
         shim.grok_b200_shim_calls.restype = C.c_uint64
