@@ -348,6 +348,7 @@ def main():
     t_e2e_single = (time.perf_counter() - t0) / args.steps
     barrier()
     t_e2e = t_e2e_single
+    t_dev_conc = None
     nthreads = max(1, args.e2e_threads)
     if nthreads > 1:
         workers = []
@@ -389,6 +390,33 @@ def main():
         torch.cuda.synchronize()
         t_e2e = (max(ends) - t0) / (args.steps * nthreads)  # mean wall time per frame with nthreads frames in flight
         barrier()
+
+        # the same concurrency with every frame resident in HBM (no host copies): what the device sustains when several
+        # frames are in flight on separate streams
+        for (c2, ep2, dp2, hp2, o2, hi2, ho2) in workers:
+            ep2.encode_upload(hp2); ep2.encode_stash(); dp2.decode_upload(hi2, o2[3][:enc_bytes]); c2.sync()
+        gate2 = threading.Barrier(nthreads + 1)
+
+        def run_dev(idx):
+            c, ep, dp = (ctx, eplan, dplan) if idx == 0 else workers[idx - 1][:3]
+            for it in range(args.warmup + args.steps):
+                if it == args.warmup:
+                    c.sync()
+                    gate2.wait()
+                ep.encode_restore(); ep.encode_run(); dp.decode_run()
+            c.sync()
+            ends[idx] = time.perf_counter()
+
+        ths = [threading.Thread(target=run_dev, args=(i,)) for i in range(nthreads)]
+        for t in ths:
+            t.start()
+        gate2.wait()
+        t0 = time.perf_counter()
+        for t in ths:
+            t.join()
+        torch.cuda.synchronize()
+        t_dev_conc = max_over_ranks((max(ends) - t0) / (args.steps * nthreads))
+        barrier()
     clk = clocks.stop()
     t_e2e = max_over_ranks(t_e2e)
     t_e2e_single = max_over_ranks(t_e2e_single)
@@ -422,6 +450,9 @@ def main():
         "e2e": {"value": round(e2e_value, 2), "unit": "Mpixel/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": round(t_e2e * 1e3, 3), "host_threads": nthreads,
                 "single_thread": {"value": round(world * 2 * pixels / t_e2e_single / 1e6, 2), "ms_per_step": round(t_e2e_single * 1e3, 3)}},
+        "device_concurrent": None if t_dev_conc is None else {
+            "value": round(world * 2 * pixels / t_dev_conc / 1e6, 2), "unit": "Mpixel/s", "streams": nthreads, "ms_per_step": round(t_dev_conc * 1e3, 3),
+            "note": "device-resident like `value`, but with one frame in flight per stream (wall clock incl. the restore copy of the input planes)"},
         "gpu_launches": int(launches),
         "clocks": clk,
         "roofline": {"kernel": "dwt_fwd_kernel (all levels of one image, %d launches)" % dwt_launches, "bound": "hbm",
