@@ -162,7 +162,7 @@ def cpu_reference_run(name, steps, warmup, budget_s=150.0, seed=1):
     t_enc, t_dec = sum(tes) / steps, sum(tds) / steps
     return dict(pixels=px, t_enc=t_enc, t_dec=t_dec, cores=cores,
                 sample=f"{w['width']}x{px // w['width']} crop ({crop}/{rows} tile rows) of {WORKLOAD_TEXT[name]}; "
-                       f"reference grk public API, memory streams, includes its host-side PCRD/T2/codestream (<5%)")
+                       f"reference grk public API, memory streams, includes its host-side PCRD/T2/codestream")
 
 
 def run_reference(args):
@@ -438,6 +438,23 @@ def main():
             traffic = json.load(open(tp)).get(args.workload)
         except Exception:
             traffic = None
+    # integer-issue view of the Tier-1 kernels: warp instructions per MQ decision from the ncu capture of this build
+    # (profiles/t1_issue.json) x decisions / the live event-timed duration, against one warp instruction per cycle per SM
+    # sub-partition at the SM clock sampled during the run
+    issue = None
+    ip = os.path.join(ROOT, "profiles", "t1_issue.json")
+    if os.path.exists(ip) and args.workload == "c2":
+        try:
+            ti = json.load(open(ip))
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            peak = sms * 4 * (clk.get("sm_mhz") or 1965.0) * 1e6  # warp instructions per second
+            issue = {"peak_warp_inst_per_s": peak, "source": ti.get("source"),
+                     "encode": {"warp_inst_per_decision": ti["model"] + ti["mq"],
+                                "issue_frac": round((ti["model"] + ti["mq"]) * decisions / (t_t1e * 1e-3) / peak, 4)},
+                     "decode": {"warp_inst_per_decision": ti["decode"],
+                                "issue_frac": round(ti["decode"] * decisions / (t_t1d * 1e-3) / peak, 4)}}
+        except Exception:
+            issue = None
     line = {
         "metric": "encode/decode Mpixel/s", "value": round(value, 2), "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -460,7 +477,7 @@ def main():
                      "peak_source": peak_src, "algorithmic_bytes": int(dwt_bytes), "ms": round(t_dwt, 4)},
         "t1": {"bound": "integer issue (serial MQ coder), no tensor work", "encode_ms": round(t_t1e, 4), "decode_ms": round(t_t1d, 4),
                "encode_mdecisions_s": round(decisions / (t_t1e * 1e-3) / 1e6, 1), "decode_mdecisions_s": round(decisions / (t_t1d * 1e-3) / 1e6, 1),
-               "share_of_encode": round(t_t1e / t_enc, 3), "share_of_decode": round(t_t1d / t_dec, 3)},
+               "share_of_encode": round(t_t1e / t_enc, 3), "share_of_decode": round(t_t1d / t_dec, 3), "issue": issue},
     }
     # the reversible 5/3 transform at configs[2] scale (8192x8192x3, 1024x1024 tiles): same kernel family, exact int32 lifting
     # with a fifth of the ALU work of the fixed-point 9/7, i.e. the case that is bound by HBM alone

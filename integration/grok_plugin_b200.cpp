@@ -35,7 +35,14 @@
 #include "dwt_utils.h"
 #include "plugin/plugin_interface.h"
 #include "../include/grok_b200.h"
+#include <atomic>
+#include <algorithm>
+#include <condition_variable>
 #include <cstdio>
+#include <deque>
+#include <dirent.h>
+#include <mutex>
+#include <thread>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -280,14 +287,27 @@ extern "C" PLUGIN_API bool plugin_init(grk_plugin_init_info info) {
 extern "C" PLUGIN_API uint64_t grok_b200_plugin_stat(int i) { return i == 0 ? g_encodes : i == 1 ? g_blocks : g_decodes; }
 
 /* ---- encode -------------------------------------------------------------------------------------------------- */
-extern "C" PLUGIN_API int32_t plugin_encode(grk_cparameters *p, grk::PLUGIN_ENCODE_USER_CALLBACK callback) {
-	if (!g_ctx || !p || !callback) return -1;
+namespace {
+
+/* one image after the device path: the image, the tree over the result buffers, and what the callback needs */
+struct EncodedFrame {
+	grk_image *img = nullptr;
+	Tree T;
+	std::string infile, outfile;
+	~EncodedFrame() { if (img) grk_image_destroy(img); }
+};
+
+/* read p->infile, run DC shift .. Tier-1 on the device, describe the result as a grk_plugin_tile.  0 = ok; 1 = a request
+ * this ABI / build cannot express (the host keeps its CPU path); >1 = failure */
+int encode_frame(const grk_cparameters *p, EncodedFrame &F) {
 	/* what the single grk_plugin_tile of this ABI, or this build of the kernels, cannot express -> host CPU path */
 	/* (terminating styles would need pass->term, which encode_synch_with_plugin never sets: plugin_bridge.cpp:148-260) */
 	if (p->isHT || p->cblk_sty != 0 || p->decod_format != GRK_PXM_FMT) return 1;
 	grk_image *img = read_pnm(p);
 	if (!img) return 2;
-	struct ImgGuard { grk_image *i; ~ImgGuard() { grk_image_destroy(i); } } guard{img};
+	F.img = img;
+	F.infile = p->infile;
+	F.outfile = p->outfile;
 	if (p->tile_size_on && (p->cp_tx0 + p->cp_tdx < img->x1 || p->cp_ty0 + p->cp_tdy < img->y1)) return 1; /* more than one tile */
 	const uint32_t nc = img->numcomps;
 	/* MCT decision of grk_compress.cpp:1996-1998 and j2k.cpp:1961-1970 */
@@ -309,7 +329,7 @@ extern "C" PLUGIN_API int32_t plugin_encode(grk_cparameters *p, grk::PLUGIN_ENCO
 	std::vector<gb200_cblk_enc> enc(nb);
 	std::vector<uint32_t> rates(gb200_plan_num_pass_slots(plan) + 1);
 	std::vector<double> dists(gb200_plan_num_pass_slots(plan) + 1);
-	Tree T;
+	Tree &T = F.T;
 	T.data.resize(gb200_plan_data_capacity(plan) + 16);
 	std::vector<const int32_t*> planes(nc);
 	for (uint32_t c = 0; c < nc; ++c) planes[c] = img->comps[c].data;
@@ -338,22 +358,150 @@ extern "C" PLUGIN_API int32_t plugin_encode(grk_cparameters *p, grk::PLUGIN_ENCO
 	}
 	g_encodes++;
 	g_blocks += nb;
+	return 0;
+}
 
+/* the host's turn: header + PCRD + Tier-2 + file write happen inside the callback, synchronously */
+int hand_over(EncodedFrame &F, grk_cparameters *p, grk::PLUGIN_ENCODE_USER_CALLBACK callback, bool relative) {
 	grk::plugin_encode_user_callback_info cbinfo;
 	memset(&cbinfo, 0, sizeof(cbinfo));
-	cbinfo.input_file_name = p->infile;
-	cbinfo.outputFileNameIsRelative = false;
-	cbinfo.output_file_name = p->outfile;
+	cbinfo.input_file_name = F.infile.c_str();
+	cbinfo.outputFileNameIsRelative = relative;
+	cbinfo.output_file_name = F.outfile.c_str();
 	cbinfo.encoder_parameters = p;
-	cbinfo.image = img;
-	cbinfo.tile = &T.tile;
+	cbinfo.image = F.img;
+	cbinfo.tile = &F.T.tile;
 	cbinfo.error_code = 0;
 	try {
-		callback(&cbinfo); /* synchronous: header + PCRD + Tier-2 + file write happen in here */
+		callback(&cbinfo);
 	} catch (...) {
 		return 6; /* nothing in libgrok catches what its callback throws */
 	}
 	return cbinfo.error_code;
+}
+
+} // namespace
+
+extern "C" PLUGIN_API int32_t plugin_encode(grk_cparameters *p, grk::PLUGIN_ENCODE_USER_CALLBACK callback) {
+	if (!g_ctx || !p || !callback) return -1;
+	EncodedFrame F;
+	const int rc = encode_frame(p, F);
+	if (rc) return rc;
+	return hand_over(F, p, callback, false);
+}
+
+/* ---- batch encode: the plugin owns the frame loop (plugin_interface.h:80-86, grk_compress.cpp:2222-2240) -----------------
+ * plugin_batch_encode returns at once; a producer thread runs every PNM file of input_dir through the device path, a
+ * consumer thread hands the finished frames to the host's callback in file-name order (the callback is the host's
+ * single-threaded PCRD / Tier-2 / file writer), so the device works on frame i+1 while the host finishes frame i.
+ * Frames the ABI cannot express are handed over with tile = NULL: the host's callback then encodes them itself. */
+namespace {
+
+struct Batch {
+	std::thread producer, consumer;
+	std::mutex mu;
+	std::condition_variable cv;
+	std::deque<std::unique_ptr<EncodedFrame>> ready;
+	std::vector<std::string> files;
+	grk_cparameters params;
+	grk::PLUGIN_ENCODE_USER_CALLBACK callback = nullptr;
+	bool produced_all = false;
+	std::atomic<bool> stop{false}, complete{true};
+};
+Batch *g_batch = nullptr;
+
+bool has_pnm_extension(const std::string &n) {
+	const size_t d = n.rfind('.');
+	if (d == std::string::npos) return false;
+	std::string e = n.substr(d + 1);
+	for (auto &c : e) c = (char) tolower(c);
+	return e == "pgm" || e == "ppm" || e == "pnm";
+}
+
+void batch_join(Batch *b) {
+	if (b->producer.joinable()) b->producer.join();
+	if (b->consumer.joinable()) b->consumer.join();
+}
+
+} // namespace
+
+extern "C" PLUGIN_API int32_t plugin_batch_encode(const char *input_dir, const char *output_dir, grk_cparameters *p,
+		grk::PLUGIN_ENCODE_USER_CALLBACK callback) {
+	(void) output_dir; /* the host's callback composes the output path from the relative name (grk_compress.cpp:1783-1797) */
+	if (!g_ctx || !input_dir || !p || !callback) return -1;
+	if (g_batch) {
+		if (!g_batch->complete) return -1; /* one batch at a time */
+		batch_join(g_batch);
+		delete g_batch;
+		g_batch = nullptr;
+	}
+	DIR *d = opendir(input_dir);
+	if (!d) return 2;
+	Batch *b = new Batch();
+	while (dirent *e = readdir(d))
+		if (has_pnm_extension(e->d_name)) b->files.push_back(std::string(input_dir) + "/" + e->d_name);
+	closedir(d);
+	std::sort(b->files.begin(), b->files.end());
+	b->params = *p;
+	b->callback = callback;
+	b->complete = false;
+	g_batch = b;
+	b->producer = std::thread([b]() {
+		for (const std::string &f : b->files) {
+			if (b->stop) break;
+			std::unique_ptr<EncodedFrame> F(new EncodedFrame());
+			grk_cparameters fp = b->params;
+			snprintf(fp.infile, sizeof(fp.infile), "%s", f.c_str());
+			const int rc = encode_frame(&fp, *F);
+			F->infile = f;
+			F->outfile = f; /* relative: the host keeps the base name */
+			if (rc) { F->T.tile.tileComponents = nullptr; F->T.tile.numComponents = 0; if (F->img) { grk_image_destroy(F->img); F->img = nullptr; } }
+			std::unique_lock<std::mutex> lk(b->mu);
+			b->cv.wait(lk, [b]() { return b->ready.size() < 2 || b->stop; }); /* at most two frames ahead of the host */
+			b->ready.push_back(std::move(F));
+			b->cv.notify_all();
+		}
+		std::lock_guard<std::mutex> lk(b->mu);
+		b->produced_all = true;
+		b->cv.notify_all();
+	});
+	b->consumer = std::thread([b]() {
+		for (;;) {
+			std::unique_ptr<EncodedFrame> F;
+			{
+				std::unique_lock<std::mutex> lk(b->mu);
+				b->cv.wait(lk, [b]() { return !b->ready.empty() || b->produced_all; });
+				if (b->ready.empty()) break;
+				F = std::move(b->ready.front());
+				b->ready.pop_front();
+				b->cv.notify_all();
+			}
+			grk_cparameters fp = b->params; /* the callback may settle tcp_mct etc. in its copy */
+			snprintf(fp.infile, sizeof(fp.infile), "%s", F->infile.c_str());
+			grk::plugin_encode_user_callback_info cbinfo;
+			memset(&cbinfo, 0, sizeof(cbinfo));
+			cbinfo.input_file_name = F->infile.c_str();
+			cbinfo.outputFileNameIsRelative = true;
+			cbinfo.output_file_name = F->outfile.c_str();
+			cbinfo.encoder_parameters = &fp;
+			cbinfo.image = F->img; /* NULL + tile NULL: the host loads and encodes the file itself */
+			cbinfo.tile = F->img ? &F->T.tile : nullptr;
+			try { b->callback(&cbinfo); } catch (...) {}
+		}
+		b->complete = true;
+	});
+	return 0;
+}
+
+extern "C" PLUGIN_API bool plugin_is_batch_complete(void) { return !g_batch || g_batch->complete; }
+
+extern "C" PLUGIN_API void plugin_stop_batch_encode(void) {
+	if (!g_batch) return;
+	g_batch->stop = true;
+	{ std::lock_guard<std::mutex> lk(g_batch->mu); g_batch->cv.notify_all(); }
+	batch_join(g_batch);
+	delete g_batch;
+	g_batch = nullptr;
 }
 
 /* ---- decode --------------------------------------------------------------------------------------------------
@@ -505,11 +653,8 @@ extern "C" PLUGIN_API int32_t plugin_decode(grk_decompress_parameters *dp, grk::
 	return clean(rc);
 }
 
-/* the batch entry points of the ABI are exported so that the host's dlsym succeeds; they report "not handled" and the
- * host keeps its own frame loop (grk_compress.cpp:2215-2219, grk_decompress.cpp) */
-extern "C" PLUGIN_API int32_t plugin_batch_encode(const char *, const char *, grk_cparameters *, grk::PLUGIN_ENCODE_USER_CALLBACK) { return -1; }
-extern "C" PLUGIN_API bool plugin_is_batch_complete(void) { return true; }
-extern "C" PLUGIN_API void plugin_stop_batch_encode(void) {}
+/* the batch DECODE entry points are exported so that the host's dlsym succeeds; they report "not handled" and the host keeps
+ * its own frame loop (grk_decompress.cpp) */
 extern "C" PLUGIN_API int32_t plugin_init_batch_decode(const char *, const char *, grk_decompress_parameters *, grk::PLUGIN_DECODE_USER_CALLBACK) { return -1; }
 extern "C" PLUGIN_API int32_t plugin_batch_decode(void) { return -1; }
 extern "C" PLUGIN_API void plugin_stop_batch_decode(void) {}

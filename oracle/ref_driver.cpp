@@ -28,6 +28,7 @@
 #include <cstdlib>
 #include <new>
 #include <vector>
+#include <unistd.h>
 
 using namespace grk;
 
@@ -531,6 +532,70 @@ int ref_plugin_decode(const char *plugin_dir, const uint8_t *buf, uint64_t len, 
 	grk_plugin_cleanup();
 	if (rc) return -2;
 	return g_dec_stored ? 0 : -3;
+}
+
+/* ---- the official plugin path, batch encode: grk_plugin_batch_encode over a directory, then polling
+ * grk_plugin_is_batch_complete, exactly like grk_compress -y <dir> (grk_compress.cpp:2222-2240).  The callback runs on the
+ * plugin's thread, once per frame in file-name order; codestreams are appended to `out`, their lengths to lens[].
+ * Returns the number of frames encoded through the plugin, or a negative status. */
+static uint8_t *g_b_out = nullptr;
+static uint64_t g_b_cap = 0, g_b_used = 0;
+static uint64_t *g_b_lens = nullptr;
+static uint32_t g_b_max = 0, g_b_count = 0, g_b_failed = 0;
+
+static bool plugin_batch_cb(grk_plugin_encode_user_callback_info *info) {
+	grk_cparameters *param = info->encoder_parameters;
+	grk_image *image = info->image;
+	if (!image || !info->tile || g_b_count >= g_b_max) { g_b_failed++; return false; }
+	if (param->tcp_mct == 255) param->tcp_mct = (image->numcomps >= 3) ? 1 : 0;
+	int64_t len = -1;
+	grk_stream *stream = grk_stream_create_mem_stream(g_b_out + g_b_used, g_b_cap - g_b_used, false, false);
+	grk_codec *codec = stream ? grk_create_compress(GRK_CODEC_J2K, stream) : nullptr;
+	if (codec && grk_setup_encoder(codec, param, image) && grk_start_compress(codec, image)
+			&& grk_encode_with_plugin(codec, info->tile) && grk_end_compress(codec))
+		len = (int64_t) grk_stream_get_write_mem_stream_length(stream);
+	if (stream) grk_stream_destroy(stream);
+	if (codec) grk_destroy_codec(codec);
+	if (len < 0) { g_b_failed++; return false; }
+	g_b_lens[g_b_count++] = (uint64_t) len;
+	g_b_used += (uint64_t) len;
+	return true;
+}
+
+int32_t ref_plugin_batch_encode(const char *plugin_dir, const char *in_dir, uint32_t numres, uint32_t cblkw, uint32_t cblkh,
+		int irreversible, uint32_t numlayers, const double *rates, uint32_t rc_algorithm, uint8_t *out, uint64_t cap,
+		uint64_t *lens, uint32_t max_frames) {
+	grk_set_info_handler(quiet_cb, nullptr);
+	grk_set_warning_handler(quiet_cb, nullptr);
+	grk_set_error_handler(quiet_cb, nullptr);
+	grk_plugin_load_info li;
+	li.plugin_path = plugin_dir;
+	if (!grk_plugin_load(li)) return -1;
+	grk_plugin_init_info ii;
+	ii.deviceId = 0;
+	ii.verbose = true;
+	if (!grk_plugin_init(ii)) { grk_plugin_cleanup(); return -1; }
+	grk_cparameters param;
+	grk_set_default_encoder_parameters(&param);
+	param.decod_format = GRK_PXM_FMT;
+	param.cod_format = GRK_J2K_FMT;
+	param.numresolution = numres;
+	param.cblockw_init = cblkw;
+	param.cblockh_init = cblkh;
+	param.irreversible = irreversible != 0;
+	param.rateControlAlgorithm = rc_algorithm;
+	param.tcp_numlayers = numlayers ? numlayers : 1;
+	for (uint32_t i = 0; i < numlayers; ++i) param.tcp_rates[i] = rates[i];
+	if (!numlayers) param.tcp_rates[0] = 0;
+	param.cp_disto_alloc = 1;
+	param.tcp_mct = 255;
+	g_b_out = out; g_b_cap = cap; g_b_used = 0; g_b_lens = lens; g_b_max = max_frames; g_b_count = 0; g_b_failed = 0;
+	int32_t rc = grk_plugin_batch_encode(in_dir, in_dir, &param, plugin_batch_cb);
+	if (rc) { grk_plugin_cleanup(); return -2; }
+	while (!grk_plugin_is_batch_complete()) usleep(1000);
+	grk_plugin_stop_batch_encode();
+	grk_plugin_cleanup();
+	return g_b_failed ? -3 : (int32_t) g_b_count;
 }
 
 } /* extern "C" */

@@ -113,6 +113,9 @@ def ref():
     L.ref_plugin_encode_file.argtypes = [C.c_char_p, C.c_char_p] + [C.c_uint32] * 5 + [C.c_int, C.c_uint32, C.c_void_p, C.c_uint32,
                                          u8p, C.c_uint64]
     L.ref_plugin_encode_file.restype = C.c_int64
+    L.ref_plugin_batch_encode.argtypes = [C.c_char_p, C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_void_p,
+                                          C.c_uint32, u8p, C.c_uint64, np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS"), C.c_uint32]
+    L.ref_plugin_batch_encode.restype = C.c_int32
     L.ref_plugin_decode.argtypes = [C.c_char_p, u8p, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p), C.c_uint64, u32p]
     L.ref_init(int(os.environ.get("GRK_REF_THREADS", "0")) or (os.cpu_count() or 1))
     _ref = L
@@ -178,6 +181,25 @@ def ref_decode_image(cs, numcomps, width, height, reduce=0, layers=0, window=Non
     assert rc == 0, f"reference decode failed rc={rc}"
     assert (dims[0], dims[1], dims[2]) == (planes[0].shape[1], planes[0].shape[0], numcomps), dims
     return planes
+
+
+def ref_plugin_batch_encode(in_dir, max_frames, frame_area, numres=6, cblk=(64, 64), irreversible=False, rates=(), rc_algorithm=1):
+    """`grk_compress -g oracle/_ref -y in_dir`: the plugin owns the frame loop.  Returns the list of codestreams in file-name
+    order, or the negative status of ref_plugin_batch_encode."""
+    L = ref()
+    cap = max_frames * (frame_area * 4 * 3 + (1 << 20))
+    out = np.zeros(cap, np.uint8)
+    lens = np.zeros(max_frames, np.uint64)
+    r = np.ascontiguousarray(rates, np.float64)
+    n = L.ref_plugin_batch_encode(os.path.join(ORACLE_DIR, "_ref").encode(), in_dir.encode(), numres, cblk[0], cblk[1], int(irreversible),
+                                  len(r), r.ctypes.data if len(r) else None, rc_algorithm, out, cap, lens, max_frames)
+    if n < 0:
+        return int(n)
+    res, off = [], 0
+    for k in range(n):
+        res.append(bytes(out[off:off + int(lens[k])]))
+        off += int(lens[k])
+    return res
 
 
 def ref_plugin_decode(cs, numcomps, width, height, reduce=0, layers=0):

@@ -83,3 +83,31 @@ def test_multi_tile_request_is_declined(tmp_path):
                           'cs = _libs.ref_plugin_encode_file(path, w * h * nc, tile=(64, 64), numres=numres')
     code = code.replace('assert not isinstance(cs, int), f"{name}: plugin path status {cs}"', 'assert cs == -2, cs; sys.exit(0)')
     subprocess.check_call([sys.executable, "-c", code, HERE, "plugin", str(tmp_path / "x.npz"), "gray53"], timeout=300)
+
+
+BATCH_RUNNER = r"""
+import os, sys
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.dirname(sys.argv[1]))
+import numpy as np, _libs
+from grokimagecompression_b200.synth import synthetic_planes
+d = sys.argv[2]
+w, h, nc, prec, n = 320, 240, 3, 12, 7
+frames = [synthetic_planes(w, h, nc, prec, seed=1000 + f) for f in range(n)]
+for f, img in enumerate(frames):
+    _libs.write_pnm(os.path.join(d, "frame%03d.ppm" % f), img, prec)
+open(os.path.join(d, "notes.txt"), "w").write("not an image")
+got = _libs.ref_plugin_batch_encode(d, n + 2, w * h * nc, numres=5, cblk=(32, 32), irreversible=True, rates=(12, 4))
+assert not isinstance(got, int), got
+assert len(got) == n, len(got)
+for f, img in enumerate(frames):
+    want = _libs.ref_encode_image(img, prec, numres=5, cblk=(32, 32), irreversible=True, rates=(12, 4), rc_algorithm=1)
+    assert got[f] == want, f
+print("batch ok", n)
+"""
+
+
+def test_plugin_batch_encode_owns_the_frame_loop(tmp_path):
+    """plugin_batch_encode / plugin_is_batch_complete / plugin_stop_batch_encode: every PNM frame of a directory goes through
+    the device while the host's callback finishes the previous one; each codestream equals the pure reference's"""
+    out = subprocess.check_output([sys.executable, "-c", BATCH_RUNNER, HERE, str(tmp_path)], timeout=600, text=True)
+    assert "batch ok 7" in out
