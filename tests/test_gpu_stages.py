@@ -213,6 +213,10 @@ def test_t1_decode_blocks_with_style_switches(ctx, rev):
         desc[i]["stepsize"] = 1.0 if rev else float(np.float32(rng.choice([0.5, 0.0371, 1.9])))
         ob, onb, orr, _, ot, _ = oracle_t1_encode_sty((b.astype(np.int64) * 64).astype(np.int32), orient, sty)
         npass = len(orr)
+        # every fifth block belongs to a component with a max-shift ROI: the stream is decoded roishift planes higher and
+        # samples at or above 2^roishift are shifted back (T1Part1.cpp:184-186, 230-252)
+        roishift = int(rng.integers(1, 8)) if (i % 5 == 4 and onb + 8 < 30) else 0
+        desc[i]["roishift"] = roishift
         k = npass if (i % 3 == 0 or npass == 0) else int(rng.integers(1, npass + 1))
         sl, sp = segments_from_passes(orr, ot, k) if k else (np.zeros(0, np.uint32), np.zeros(0, np.uint32))
         ln = int(sl.sum())
@@ -222,7 +226,7 @@ def test_t1_decode_blocks_with_style_switches(ctx, rev):
         for a, c in zip(sl, sp):
             segs.append((int(a), int(c)))
         seg_start.append(len(segs))
-        dec = oracle_t1_decode_segs(ob[:ln], sl, sp, onb, orient, sty, w, h) if k else np.zeros((h, w), np.int32)
+        dec = oracle_t1_decode_segs(ob[:ln], sl, sp, onb, orient, sty, w, h, roishift) if k else np.zeros((h, w), np.int32)
         out = np.zeros((h, w), np.int32)
         O.gbo_dequantise_block(dec.ravel(), w, h, rev, float(desc[i]["stepsize"]), out.ctypes.data, w)
         expect.append(out)
