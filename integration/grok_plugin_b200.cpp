@@ -493,7 +493,8 @@ extern "C" PLUGIN_API int32_t plugin_batch_encode(const char *input_dir, const c
 	return 0;
 }
 
-extern "C" PLUGIN_API bool plugin_is_batch_complete(void) { return !g_batch || g_batch->complete; }
+bool decode_batch_complete();
+extern "C" PLUGIN_API bool plugin_is_batch_complete(void) { return (!g_batch || g_batch->complete) && decode_batch_complete(); }
 
 extern "C" PLUGIN_API void plugin_stop_batch_encode(void) {
 	if (!g_batch) return;
@@ -577,12 +578,15 @@ int decode_init(grk_header_info *h, grk_image *img) {
 
 } // namespace
 
-extern "C" PLUGIN_API int32_t plugin_decode(grk_decompress_parameters *dp, grk::PLUGIN_DECODE_USER_CALLBACK callback) {
-	if (!g_ctx || !dp || !callback) return -1;
+namespace {
+
+/* one codestream through the staged protocol; infile / outfile as the callback shall see them */
+int32_t decode_one(grk_decompress_parameters *dp, const std::string &infile, const std::string &outfile, GRK_SUPPORTED_FILE_FMT fmt,
+		grk::PLUGIN_DECODE_USER_CALLBACK callback) {
 	DecodeJob J;
 	J.reduce = dp->core.cp_reduce;
 	g_job = &J;
-	grk::PluginDecodeCallbackInfo info(dp->infile, dp->outfile, dp, dp->decod_format, GRK_DECODE_HEADER);
+	grk::PluginDecodeCallbackInfo info(infile, outfile, dp, fmt, GRK_DECODE_HEADER);
 	info.init_decoders_func = decode_init;
 	auto clean = [&](int32_t rc) {
 		info.decode_flags = GRK_PLUGIN_DECODE_CLEAN;
@@ -653,11 +657,108 @@ extern "C" PLUGIN_API int32_t plugin_decode(grk_decompress_parameters *dp, grk::
 	return clean(rc);
 }
 
-/* the batch DECODE entry points are exported so that the host's dlsym succeeds; they report "not handled" and the host keeps
- * its own frame loop (grk_decompress.cpp) */
-extern "C" PLUGIN_API int32_t plugin_init_batch_decode(const char *, const char *, grk_decompress_parameters *, grk::PLUGIN_DECODE_USER_CALLBACK) { return -1; }
-extern "C" PLUGIN_API int32_t plugin_batch_decode(void) { return -1; }
-extern "C" PLUGIN_API void plugin_stop_batch_decode(void) {}
+} // namespace
+
+extern "C" PLUGIN_API int32_t plugin_decode(grk_decompress_parameters *dp, grk::PLUGIN_DECODE_USER_CALLBACK callback) {
+	if (!g_ctx || !dp || !callback) return -1;
+	return decode_one(dp, dp->infile, dp->outfile, dp->decod_format, callback);
+}
+
+/* ---- batch decode: plugin_init_batch_decode / plugin_batch_decode / plugin_stop_batch_decode (plugin_interface.h:124-130).
+ * The shipped CLI calls plugin_batch_decode only when the init call FAILED (`if (success) success = ...batch_decode()`,
+ * grk_decompress.cpp:1242-1247) and then polls plugin_is_batch_complete, so the work starts in the init call; a host that
+ * does call plugin_batch_decode afterwards finds the batch already running.  One thread walks the .j2k / .j2c / .jp2 files
+ * of input_dir in name order and runs each through the staged protocol; a stream the ABI cannot express is left to the
+ * host by passing GRK_DECODE_ALL (full CPU decode inside the callback, grk_decompress.cpp:1338-1342). */
+namespace {
+
+struct DecBatch {
+	std::thread worker;
+	std::vector<std::string> files;
+	std::string out_dir;
+	grk_decompress_parameters params;
+	grk::PLUGIN_DECODE_USER_CALLBACK callback = nullptr;
+	std::atomic<bool> stop{false}, complete{true};
+};
+DecBatch *g_dec_batch = nullptr;
+
+const char *out_extension(uint32_t cod_format) {
+	switch (cod_format) {
+	case GRK_PXM_FMT: return "ppm";
+	case GRK_PGX_FMT: return "pgx";
+	case GRK_BMP_FMT: return "bmp";
+	case GRK_TIF_FMT: return "tif";
+	case GRK_RAW_FMT: return "raw";
+	case GRK_RAWL_FMT: return "rawl";
+	case GRK_PNG_FMT: return "png";
+	case GRK_JPG_FMT: return "jpg";
+	default: return "out";
+	}
+}
+
+} // namespace
+
+extern "C" PLUGIN_API int32_t plugin_init_batch_decode(const char *input_dir, const char *output_dir, grk_decompress_parameters *dp,
+		grk::PLUGIN_DECODE_USER_CALLBACK callback) {
+	if (!g_ctx || !input_dir || !output_dir || !dp || !callback) return -1;
+	if (g_dec_batch) {
+		if (!g_dec_batch->complete) return -1;
+		if (g_dec_batch->worker.joinable()) g_dec_batch->worker.join();
+		delete g_dec_batch;
+		g_dec_batch = nullptr;
+	}
+	DIR *d = opendir(input_dir);
+	if (!d) return 2;
+	DecBatch *b = new DecBatch();
+	while (dirent *e = readdir(d)) {
+		std::string n = e->d_name;
+		const size_t dot = n.rfind('.');
+		if (dot == std::string::npos) continue;
+		std::string ext = n.substr(dot + 1);
+		for (auto &c : ext) c = (char) tolower(c);
+		if (ext == "j2k" || ext == "j2c" || ext == "jp2") b->files.push_back(n);
+	}
+	closedir(d);
+	std::sort(b->files.begin(), b->files.end());
+	b->out_dir = output_dir;
+	b->params = *dp;
+	b->callback = callback;
+	b->complete = false;
+	g_dec_batch = b;
+	const std::string in_dir = input_dir;
+	b->worker = std::thread([b, in_dir]() {
+		for (const std::string &n : b->files) {
+			if (b->stop) break;
+			const size_t dot = n.rfind('.');
+			std::string ext = n.substr(dot + 1);
+			for (auto &c : ext) c = (char) tolower(c);
+			const GRK_SUPPORTED_FILE_FMT fmt = ext == "jp2" ? GRK_JP2_FMT : GRK_J2K_FMT;
+			const std::string in = in_dir + "/" + n, out = b->out_dir + "/" + n.substr(0, dot) + "." + out_extension(b->params.cod_format);
+			grk_decompress_parameters fp = b->params;
+			fp.infile[0] = 0; fp.outfile[0] = 0; /* the callback takes the names from the info struct */
+			fp.decod_format = fmt;
+			const int32_t rc = decode_one(&fp, in, out, fmt, b->callback);
+			if (rc) { /* not ours: let the host decode this one on its own in a single callback */
+				grk::PluginDecodeCallbackInfo info(in, out, &fp, fmt, GRK_DECODE_ALL);
+				try { b->callback(&info); } catch (...) {}
+			}
+		}
+		b->complete = true;
+	});
+	return 0;
+}
+
+bool decode_batch_complete() { return !g_dec_batch || g_dec_batch->complete; }
+extern "C" PLUGIN_API int32_t plugin_batch_decode(void) { return g_dec_batch ? 0 : -1; }
+
+extern "C" PLUGIN_API void plugin_stop_batch_decode(void) {
+	if (!g_dec_batch) return;
+	g_dec_batch->stop = true;
+	if (g_dec_batch->worker.joinable()) g_dec_batch->worker.join();
+	delete g_dec_batch;
+	g_dec_batch = nullptr;
+}
+
 extern "C" PLUGIN_API uint32_t plugin_get_debug_state(void) { return GRK_PLUGIN_STATE_NO_DEBUG; }
 extern "C" PLUGIN_API void plugin_debug_mqc_next_cxd(grk::grk_plugin_debug_mqc *, uint32_t) {}
 extern "C" PLUGIN_API void plugin_debug_mqc_next_plane(grk::grk_plugin_debug_mqc *) {}

@@ -446,6 +446,9 @@ static int32_t *const *g_dec_out = nullptr;
 static uint64_t g_dec_cap = 0;
 static uint32_t *g_dec_dims = nullptr;
 static int g_dec_stored = 0;
+static bool g_dec_from_files = false; /* batch decode: input named by the plugin, planes of frame k appended at k * 3 * cap */
+static int32_t *g_dec_batch_out = nullptr;
+static uint32_t g_dec_batch_max = 0;
 
 static int32_t plugin_dec_cb(grk_plugin_decode_callback_info *info) {
 	int32_t rc = -1;
@@ -462,7 +465,8 @@ static int32_t plugin_dec_cb(grk_plugin_decode_callback_info *info) {
 	if (info->decode_flags & (GRK_DECODE_HEADER | GRK_DECODE_T1 | GRK_DECODE_T2)) { /* pre_decode */
 		bool failed = false;
 		if (!info->l_stream) {
-			info->l_stream = grk_stream_create_mem_stream(const_cast<uint8_t*>(g_dec_in), g_dec_in_len, false, true);
+			info->l_stream = g_dec_from_files ? grk_stream_create_mapped_file_read_stream(info->input_file_name)
+					: grk_stream_create_mem_stream(const_cast<uint8_t*>(g_dec_in), g_dec_in_len, false, true);
 			info->l_codec = info->l_stream ? grk_create_decompress(GRK_CODEC_J2K, info->l_stream) : nullptr;
 			if (!info->l_codec || !grk_setup_decoder(info->l_codec, &param->core)) failed = true;
 		}
@@ -494,13 +498,16 @@ static int32_t plugin_dec_cb(grk_plugin_decode_callback_info *info) {
 		rc = 1;
 		if (image) {
 			rc = 0;
-			g_dec_dims[0] = image->comps[0].w; g_dec_dims[1] = image->comps[0].h; g_dec_dims[2] = image->numcomps;
+			if (g_dec_from_files && ((uint32_t) g_dec_stored >= g_dec_batch_max || image->numcomps > 3)) return 2;
+			uint32_t *dims = g_dec_from_files ? g_dec_dims + 3 * g_dec_stored : g_dec_dims;
+			dims[0] = image->comps[0].w; dims[1] = image->comps[0].h; dims[2] = image->numcomps;
 			for (uint32_t c = 0; c < image->numcomps; ++c) {
 				uint64_t n = (uint64_t) image->comps[c].w * image->comps[c].h;
 				if (n > g_dec_cap || !image->comps[c].data) { rc = 2; break; }
-				memcpy(g_dec_out[c], image->comps[c].data, n * sizeof(int32_t));
+				int32_t *dst = g_dec_from_files ? g_dec_batch_out + ((uint64_t) g_dec_stored * 3 + c) * g_dec_cap : g_dec_out[c];
+				memcpy(dst, image->comps[c].data, n * sizeof(int32_t));
 			}
-			if (!rc) g_dec_stored = 1;
+			if (!rc) g_dec_stored = g_dec_from_files ? g_dec_stored + 1 : 1;
 		}
 	}
 	return rc;
@@ -527,11 +534,46 @@ int ref_plugin_decode(const char *plugin_dir, const uint8_t *buf, uint64_t len, 
 	param.cod_format = GRK_PXM_FMT;
 	strcpy(param.infile, "memory.j2k");
 	strcpy(param.outfile, "memory.ppm");
+	g_dec_from_files = false;
 	g_dec_in = buf; g_dec_in_len = len; g_dec_out = planes_out; g_dec_cap = plane_capacity; g_dec_dims = dims; g_dec_stored = 0;
 	int32_t rc = grk_plugin_decode(&param, plugin_dec_cb);
 	grk_plugin_cleanup();
 	if (rc) return -2;
 	return g_dec_stored ? 0 : -3;
+}
+
+/* ---- the official plugin path, batch decode: grk_plugin_init_batch_decode over a directory of codestreams, then
+ * grk_plugin_batch_decode and polling grk_plugin_is_batch_complete like grk_decompress -y <dir> (grk_decompress.cpp:1236-1262).
+ * The callback runs on the plugin's thread, file-name order; the planes of frame k land at out + (3k + c) * plane_capacity,
+ * its dimensions at dims[3k..3k+2].  Returns the number of frames stored, or a negative status. */
+int32_t ref_plugin_batch_decode(const char *plugin_dir, const char *in_dir, uint32_t reduce, int32_t *out, uint64_t plane_capacity,
+		uint32_t *dims, uint32_t max_frames) {
+	grk_set_info_handler(quiet_cb, nullptr);
+	grk_set_warning_handler(quiet_cb, nullptr);
+	grk_set_error_handler(quiet_cb, nullptr);
+	grk_plugin_load_info li;
+	li.plugin_path = plugin_dir;
+	if (!grk_plugin_load(li)) return -1;
+	grk_plugin_init_info ii;
+	ii.deviceId = 0;
+	ii.verbose = true;
+	if (!grk_plugin_init(ii)) { grk_plugin_cleanup(); return -1; }
+	grk_decompress_parameters param;
+	memset(&param, 0, sizeof(param));
+	grk_set_default_decoder_parameters(&param.core);
+	param.core.cp_reduce = reduce;
+	param.decod_format = GRK_J2K_FMT;
+	param.cod_format = GRK_PXM_FMT;
+	g_dec_from_files = true;
+	g_dec_batch_out = out; g_dec_cap = plane_capacity; g_dec_dims = dims; g_dec_batch_max = max_frames; g_dec_stored = 0;
+	int32_t rc = grk_plugin_init_batch_decode(in_dir, in_dir, &param, plugin_dec_cb);
+	if (rc) { g_dec_from_files = false; grk_plugin_cleanup(); return -2; }
+	grk_plugin_batch_decode(); /* (the CLI only gets here when the init call failed; the plugin tolerates both orders) */
+	while (!grk_plugin_is_batch_complete()) usleep(1000);
+	grk_plugin_stop_batch_decode();
+	grk_plugin_cleanup();
+	g_dec_from_files = false;
+	return g_dec_stored;
 }
 
 /* ---- the official plugin path, batch encode: grk_plugin_batch_encode over a directory, then polling

@@ -116,6 +116,9 @@ def ref():
     L.ref_plugin_batch_encode.argtypes = [C.c_char_p, C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_void_p,
                                           C.c_uint32, u8p, C.c_uint64, np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS"), C.c_uint32]
     L.ref_plugin_batch_encode.restype = C.c_int32
+    L.ref_plugin_batch_decode.argtypes = [C.c_char_p, C.c_char_p, C.c_uint32, np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS"), C.c_uint64,
+                                          np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS"), C.c_uint32]
+    L.ref_plugin_batch_decode.restype = C.c_int32
     L.ref_plugin_decode.argtypes = [C.c_char_p, u8p, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p), C.c_uint64, u32p]
     L.ref_init(int(os.environ.get("GRK_REF_THREADS", "0")) or (os.cpu_count() or 1))
     _ref = L
@@ -199,6 +202,22 @@ def ref_plugin_batch_encode(in_dir, max_frames, frame_area, numres=6, cblk=(64, 
     for k in range(n):
         res.append(bytes(out[off:off + int(lens[k])]))
         off += int(lens[k])
+    return res
+
+
+def ref_plugin_batch_decode(in_dir, max_frames, plane_area, reduce=0):
+    """`grk_decompress -g oracle/_ref -y in_dir`: the plugin walks the codestreams of the directory.  Returns a list of
+    (comps, h, w) int32 arrays in file-name order, or the negative status of ref_plugin_batch_decode."""
+    L = ref()
+    out = np.zeros(max_frames * 3 * plane_area, np.int32)
+    dims = np.zeros(max_frames * 3, np.uint32)
+    n = L.ref_plugin_batch_decode(os.path.join(ORACLE_DIR, "_ref").encode(), in_dir.encode(), reduce, out, plane_area, dims, max_frames)
+    if n < 0:
+        return int(n)
+    res = []
+    for k in range(n):
+        w, h, nc = (int(v) for v in dims[3 * k:3 * k + 3])
+        res.append(np.stack([out[(3 * k + c) * plane_area:(3 * k + c) * plane_area + w * h].reshape(h, w) for c in range(nc)]))
     return res
 
 

@@ -111,3 +111,36 @@ def test_plugin_batch_encode_owns_the_frame_loop(tmp_path):
     the device while the host's callback finishes the previous one; each codestream equals the pure reference's"""
     out = subprocess.check_output([sys.executable, "-c", BATCH_RUNNER, HERE, str(tmp_path)], timeout=600, text=True)
     assert "batch ok 7" in out
+
+
+BATCH_DEC_RUNNER = r"""
+import os, sys
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.dirname(sys.argv[1]))
+import numpy as np, _libs
+from grokimagecompression_b200.synth import synthetic_planes
+d = sys.argv[2]
+specs = [(320, 240, 3, 8, True, ()), (200, 150, 1, 12, False, (10,)), (256, 256, 3, 8, False, (20, 5)), (130, 90, 3, 16, True, ()),
+         (320, 240, 3, 8, True, ())]
+streams = []
+for f, (w, h, nc, prec, rev, rates) in enumerate(specs):
+    img = synthetic_planes(w, h, nc, prec, seed=2000 + f)
+    cs = _libs.ref_encode_image(img, prec, numres=5, cblk=(32, 32), irreversible=not rev, rates=rates, rc_algorithm=1)
+    open(os.path.join(d, "frame%03d.j2k" % f), "wb").write(cs)
+    streams.append(cs)
+open(os.path.join(d, "notes.txt"), "w").write("not a codestream")
+for reduce in (0, 1):
+    got = _libs.ref_plugin_batch_decode(d, len(specs) + 2, 320 * 256, reduce=reduce)
+    assert not isinstance(got, int), got
+    assert len(got) == len(specs), len(got)
+    for f, (w, h, nc, prec, rev, rates) in enumerate(specs):
+        want = np.stack(_libs.ref_decode_image(streams[f], nc, w, h, reduce=reduce))
+        assert got[f].shape == want.shape and (got[f] == want).all(), (f, reduce)
+print("batch decode ok", len(specs))
+"""
+
+
+def test_plugin_batch_decode_walks_the_directory(tmp_path):
+    """plugin_init_batch_decode / plugin_batch_decode / plugin_stop_batch_decode: every codestream of a directory (mixed
+    geometry, precision and wavelet) is decoded on the device and handed to the host's callback; pixels equal the pure reference's"""
+    out = subprocess.check_output([sys.executable, "-c", BATCH_DEC_RUNNER, HERE, str(tmp_path)], timeout=600, text=True)
+    assert "batch decode ok 5" in out
