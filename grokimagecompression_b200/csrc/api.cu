@@ -62,8 +62,10 @@ struct LevelLaunch {
 	std::vector<uint32_t> cta_plane; // CTA -> index into host
 	DevBuf dev, map;
 	uint32_t ctas = 0;
-	uint32_t ctas64 = 0;  // CTA count with 64-row tiles (decides tile_rows)
-	int tile_rows = 64;
+	uint32_t ctas64 = 0;  // CTA count with 64-row tiles (decides tile_rows of the shared-memory kernels)
+	uint32_t items[4] = {0, 0, 0, 0}; // work items of the streaming kernels with 128 / 64 / 32 / 16 rows each
+	int tile_rows = 64;   // > 0: shared-memory kernels; < 0: streaming kernels, -tile_rows rows per work item
+	int unroll = 2;
 };
 
 } // namespace
@@ -305,9 +307,15 @@ int gb200_plan_create(gb200_ctx *ctx, uint32_t ntiles, const gb200_tile_params *
 	}
 	// ---- DWT launch tables ------------------------------------------------------------------------
 	for (int r = 0; r < 2; ++r) pl->lvl[r].resize(pl->maxlevels);
-	// rows per CTA of each level launch: big levels use 64-row tiles; a level that would not even fill the
-	// machine once is cut finer, because then the latency of one CTA is what the launch costs
 	auto level_of = [&](const CompGeom &cg, uint32_t i) { return pl->encoder ? cg.top + i : cg.p.numres - 2 - i; };
+	// Which kernels: the streaming ones (dwt_stream.cuh) unless GB200_DWT_LEGACY=1 asks for the first generation
+	// (kept for A/B measurements).  GB200_DWT_ROWS / GB200_DWT_UNROLL / GB200_DWT_FILL override the tuning below.
+	auto env_int = [](const char *name, int dflt) { const char *e = getenv(name); return e && *e ? atoi(e) : dflt; };
+	const bool legacy = env_int("GB200_DWT_LEGACY", 0) != 0;
+	const int force_rows = env_int("GB200_DWT_ROWS", 0), unroll = env_int("GB200_DWT_UNROLL", 2), fill = env_int("GB200_DWT_FILL", 16);
+	static const uint32_t SROWS[4] = {128, 64, 32, 16};
+	uint32_t stw;
+	dwt_stream_shape(&stw);
 	for (auto &tg : pl->tiles)
 		for (uint32_t c = 0; c < tg.numcomps; ++c) {
 			const CompGeom &cg = tg.comps[c];
@@ -316,15 +324,32 @@ int gb200_plan_create(gb200_ctx *ctx, uint32_t ntiles, const gb200_tile_params *
 			for (uint32_t i = 0; i < cg.levels; ++i) {
 				const uint32_t lvl = level_of(cg, i);
 				const uint32_t rw = cdiv2n(cg.p.x1, lvl) - cdiv2n(cg.p.x0, lvl), rh = cdiv2n(cg.p.y1, lvl) - cdiv2n(cg.p.y0, lvl);
-				if (rw && rh) pl->lvl[cg.p.qmfbid == 1][i].ctas64 += ((rw + tw - 1) / tw) * ((rh + 63) / 64);
+				if (!rw || !rh) continue;
+				LevelLaunch &L = pl->lvl[cg.p.qmfbid == 1][i];
+				L.ctas64 += ((rw + tw - 1) / tw) * ((rh + 63) / 64);
+				const uint32_t cx = cdiv2n(cg.p.x0, lvl) & 1, cy = cdiv2n(cg.p.y0, lvl) & 1;
+				for (int k = 0; k < 4; ++k) L.items[k] += ((rw + cx + stw - 1) / stw) * ((rh + cy + SROWS[k] - 1) / SROWS[k]);
 			}
 		}
 	{
 		int sms = 148;
 		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
 		for (int r = 0; r < 2; ++r)
-			for (auto &L : pl->lvl[r])
-				L.tile_rows = L.ctas64 >= (uint32_t) sms * 6 ? 64 : (L.ctas64 >= (uint32_t) sms * 2 ? 32 : 16);
+			for (auto &L : pl->lvl[r]) {
+				L.unroll = unroll;
+				if (legacy) {
+					// big levels use 64-row tiles; a level that would not even fill the machine once is cut finer,
+					// because then the latency of one CTA is what the launch costs
+					L.tile_rows = L.ctas64 >= (uint32_t) sms * 6 ? 64 : (L.ctas64 >= (uint32_t) sms * 2 ? 32 : 16);
+				} else {
+					// the longest strips that still give every SM `fill` warps: long strips amortise the 2 * halo rows a
+					// warp reads before its first result, short ones keep a small level from running on a few SMs
+					int rows = 16;
+					for (int k = 0; k < 4; ++k) if (L.items[k] >= (uint32_t) (sms * fill)) { rows = (int) SROWS[k]; break; }
+					if (force_rows >= 2) rows = force_rows & ~1;
+					L.tile_rows = -rows;
+				}
+			}
 	}
 	pl->final_role.clear();
 	for (auto &tg : pl->tiles)
@@ -339,7 +364,7 @@ int gb200_plan_create(gb200_ctx *ctx, uint32_t ntiles, const gb200_tile_params *
 				// encoder: i-th launch transforms decomposition level cg.top + i (finest first)
 				// decoder: i-th launch reconstructs level (numres-2-i) (coarsest first)
 				const uint32_t lvl = level_of(cg, i);
-				const uint32_t THt = (uint32_t) pl->lvl[rev][i].tile_rows;
+				const int trows = pl->lvl[rev][i].tile_rows;
 				DwtPlane d;
 				memset(&d, 0, sizeof(d));
 				d.rw = cdiv2n(p.x1, lvl) - cdiv2n(p.x0, lvl);
@@ -362,8 +387,13 @@ int gb200_plan_create(gb200_ctx *ctx, uint32_t ntiles, const gb200_tile_params *
 					d.dst = plane_ptr(pl, dst_role, c, cg.plane_off);
 					role_final = dst_role;
 				}
-				d.tiles_x = (d.rw + TWt - 1) / TWt;
-				d.tiles_y = (d.rh + THt - 1) / THt;
+				if (trows > 0) {
+					d.tiles_x = (d.rw + TWt - 1) / TWt;
+					d.tiles_y = (d.rh + trows - 1) / trows;
+				} else { // streaming kernels: a strip starts cas columns / rows before the region (a low-pass line comes first)
+					d.tiles_x = (d.rw + d.cas_x + stw - 1) / stw;
+					d.tiles_y = (d.rh + d.cas_y + (uint32_t) -trows - 1) / (uint32_t) -trows;
+				}
 				if (d.rw == 0 || d.rh == 0) { d.tiles_x = d.tiles_y = 0; }
 				LevelLaunch &L = pl->lvl[rev][i];
 				d.first_cta = L.ctas;
@@ -562,8 +592,8 @@ static int run_dwt(gb200_plan *pl, bool fwd) {
 		for (int r = 0; r < 2; ++r) {
 			LevelLaunch &L = pl->lvl[r][i];
 			if (!L.ctas) continue;
-			if (fwd) launch_dwt_fwd((const DwtPlane*) L.dev.p, (const uint32_t*) L.map.p, L.ctas, r, L.tile_rows, ctx->stream);
-			else launch_dwt_inv((const DwtPlane*) L.dev.p, (const uint32_t*) L.map.p, L.ctas, r, L.tile_rows, ctx->stream);
+			if (fwd) launch_dwt_fwd((const DwtPlane*) L.dev.p, (const uint32_t*) L.map.p, L.ctas, r, L.tile_rows, L.unroll, ctx->stream);
+			else launch_dwt_inv((const DwtPlane*) L.dev.p, (const uint32_t*) L.map.p, L.ctas, r, L.tile_rows, L.unroll, ctx->stream);
 			n++;
 		}
 	return launch_check(ctx, n);

@@ -2,23 +2,9 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include "dwt_plane.h"
 
 namespace gb {
-
-// One tile-component plane of one decomposition level, as the DWT kernels see it.
-// (a-4..a-7 of SURVEY.md section 8: WaveletForward.h:40-161, dwt.cpp:724-858, 1544-1738)
-struct DwtPlane {
-	const int32_t *src;   // forward: samples of the level-l LL region; inverse: LL_{l+1} (low-low quadrant)
-	const int32_t *band;  // inverse only: buffer holding HL/LH/HH of this level in Mallat position
-	int32_t *dst;         // forward: Mallat layout of this level; inverse: reconstructed LL_l
-	uint32_t src_stride, band_stride, dst_stride;
-	uint32_t rw, rh;      // size of the level-l region
-	uint32_t sw, sh;      // low-pass counts (size of LL_{l+1})
-	uint32_t cas_x, cas_y; // parity of the region origin on the canvas (1: first sample is high-pass)
-	uint32_t tiles_x, tiles_y; // CTA tiling of this plane
-	uint32_t first_cta;   // prefix sum of CTAs over the planes of the launch
-	uint32_t pad;
-};
 
 // Encoder-side code block (a-8, a-9 of SURVEY.md section 8: T1Part1.cpp:58-133, t1.cpp:1182-1326)
 struct EncBlock {
@@ -76,12 +62,16 @@ void launch_mct_inv(int32_t *c0, int32_t *c1, int32_t *c2, uint64_t n, const int
 		const int32_t hi[3], int reversible, int do_shift_clamp, cudaStream_t s);
 
 // dwt.cu : one launch = one decomposition level of every plane in `planes` (device array).
-// tile_rows: 64, 32 or 16 valid rows per CTA (DwtPlane::tiles_y must have been computed with the same value)
+// tile_rows > 0: shared-memory kernels, 64, 32 or 16 valid rows per CTA, dwt_tile_shape() valid columns;
+// tile_rows < 0: streaming kernels (dwt_stream.cuh), one warp per work item of -tile_rows rows by dwt_stream_shape() columns,
+//                `unroll` row pairs prefetched (1, 2 or 4); total_ctas counts work items.
+// DwtPlane::tiles_x / tiles_y must have been computed for the same shape (streaming: over rw + cas_x / rh + cas_y).
 void launch_dwt_fwd(const DwtPlane *planes_dev, const uint32_t *cta_plane_dev, uint32_t total_ctas, int reversible, int tile_rows,
-		cudaStream_t s);
+		int unroll, cudaStream_t s);
 void launch_dwt_inv(const DwtPlane *planes_dev, const uint32_t *cta_plane_dev, uint32_t total_ctas, int reversible, int tile_rows,
-		cudaStream_t s);
+		int unroll, cudaStream_t s);
 void dwt_tile_shape(int reversible, uint32_t *tw); // valid columns per CTA
+void dwt_stream_shape(uint32_t *tw);               // valid columns per work item of the streaming kernels
 
 // t1_enc.cu / t1_dec.cu
 uint32_t t1_symbol_capacity(uint32_t w, uint32_t h, uint32_t planes);

@@ -24,6 +24,7 @@
 // results (the (c+c)*x special case of dwt.cpp:1463-1469 rounds like (x+x)*c).  Lines of length 1
 // are the exception and are handled explicitly (dwt53.cpp:160, dwt.cpp:344-349, 1482-1490).
 #include "common.cuh"
+#include "dwt_stream.cuh"
 
 namespace gb {
 
@@ -293,17 +294,42 @@ static void launch_inv_t(const DwtPlane *p, const uint32_t *m, uint32_t n, int t
 	else dwt_inv_kernel<REV, 16><<<n, NCOL, 0, s>>>(p, m);
 }
 
+// tile_rows > 0: shared-memory kernels above (first generation), 64 / 32 / 16 valid rows per CTA
+// tile_rows < 0: streaming kernels of dwt_stream.cuh, -tile_rows rows per work item (one warp each); `total_ctas` counts work items
+template<bool REV>
+static void launch_fwd_s(const DwtPlane *p, const uint32_t *m, uint32_t n, int rows, int unroll, cudaStream_t s) {
+	const uint32_t grid = (n + DWS_WARPS - 1) / DWS_WARPS;
+	if (unroll == 1) dwt_fwd_stream_kernel<REV, 1><<<grid, DWS_WARPS * 32, 0, s>>>(p, m, n, rows);
+	else if (unroll == 4) dwt_fwd_stream_kernel<REV, 4><<<grid, DWS_WARPS * 32, 0, s>>>(p, m, n, rows);
+	else dwt_fwd_stream_kernel<REV, 2><<<grid, DWS_WARPS * 32, 0, s>>>(p, m, n, rows);
+}
+template<bool REV>
+static void launch_inv_s(const DwtPlane *p, const uint32_t *m, uint32_t n, int rows, int unroll, cudaStream_t s) {
+	const uint32_t grid = (n + DWS_WARPS - 1) / DWS_WARPS;
+	if (unroll == 1) dwt_inv_stream_kernel<REV, 1><<<grid, DWS_WARPS * 32, 0, s>>>(p, m, n, rows);
+	else if (unroll == 4) dwt_inv_stream_kernel<REV, 4><<<grid, DWS_WARPS * 32, 0, s>>>(p, m, n, rows);
+	else dwt_inv_stream_kernel<REV, 2><<<grid, DWS_WARPS * 32, 0, s>>>(p, m, n, rows);
+}
+
+void dwt_stream_shape(uint32_t *tw) { *tw = DWS_TW; }
+
 void launch_dwt_fwd(const DwtPlane *planes_dev, const uint32_t *cta_plane_dev, uint32_t total_ctas, int reversible, int tile_rows,
-		cudaStream_t s) {
+		int unroll, cudaStream_t s) {
 	if (!total_ctas) return;
-	if (reversible) launch_fwd_t<true>(planes_dev, cta_plane_dev, total_ctas, tile_rows, s);
+	if (tile_rows < 0) {
+		if (reversible) launch_fwd_s<true>(planes_dev, cta_plane_dev, total_ctas, -tile_rows, unroll, s);
+		else launch_fwd_s<false>(planes_dev, cta_plane_dev, total_ctas, -tile_rows, unroll, s);
+	} else if (reversible) launch_fwd_t<true>(planes_dev, cta_plane_dev, total_ctas, tile_rows, s);
 	else launch_fwd_t<false>(planes_dev, cta_plane_dev, total_ctas, tile_rows, s);
 }
 
 void launch_dwt_inv(const DwtPlane *planes_dev, const uint32_t *cta_plane_dev, uint32_t total_ctas, int reversible, int tile_rows,
-		cudaStream_t s) {
+		int unroll, cudaStream_t s) {
 	if (!total_ctas) return;
-	if (reversible) launch_inv_t<true>(planes_dev, cta_plane_dev, total_ctas, tile_rows, s);
+	if (tile_rows < 0) {
+		if (reversible) launch_inv_s<true>(planes_dev, cta_plane_dev, total_ctas, -tile_rows, unroll, s);
+		else launch_inv_s<false>(planes_dev, cta_plane_dev, total_ctas, -tile_rows, unroll, s);
+	} else if (reversible) launch_inv_t<true>(planes_dev, cta_plane_dev, total_ctas, tile_rows, s);
 	else launch_inv_t<false>(planes_dev, cta_plane_dev, total_ctas, tile_rows, s);
 }
 
