@@ -65,7 +65,7 @@ struct LevelLaunch {
 	uint32_t ctas64 = 0;  // CTA count with 64-row tiles (decides tile_rows of the shared-memory kernels)
 	uint32_t items[4] = {0, 0, 0, 0}; // work items of the streaming kernels with 128 / 64 / 32 / 16 rows each
 	int tile_rows = 64;   // > 0: shared-memory kernels; < 0: streaming kernels, -tile_rows rows per work item
-	int unroll = 2;
+	int unroll = 2, halo_lanes = 1;
 };
 
 } // namespace
@@ -313,9 +313,10 @@ int gb200_plan_create(gb200_ctx *ctx, uint32_t ntiles, const gb200_tile_params *
 	auto env_int = [](const char *name, int dflt) { const char *e = getenv(name); return e && *e ? atoi(e) : dflt; };
 	const bool legacy = env_int("GB200_DWT_LEGACY", 0) != 0;
 	const int force_rows = env_int("GB200_DWT_ROWS", 0), unroll = env_int("GB200_DWT_UNROLL", 2), fill = env_int("GB200_DWT_FILL", 16);
+	const int halo_lanes = env_int("GB200_DWT_HL", 1) == 2 ? 2 : 1;
 	static const uint32_t SROWS[4] = {128, 64, 32, 16};
 	uint32_t stw;
-	dwt_stream_shape(&stw);
+	dwt_stream_shape(halo_lanes, &stw);
 	for (auto &tg : pl->tiles)
 		for (uint32_t c = 0; c < tg.numcomps; ++c) {
 			const CompGeom &cg = tg.comps[c];
@@ -337,6 +338,7 @@ int gb200_plan_create(gb200_ctx *ctx, uint32_t ntiles, const gb200_tile_params *
 		for (int r = 0; r < 2; ++r)
 			for (auto &L : pl->lvl[r]) {
 				L.unroll = unroll;
+				L.halo_lanes = halo_lanes;
 				if (legacy) {
 					// big levels use 64-row tiles; a level that would not even fill the machine once is cut finer,
 					// because then the latency of one CTA is what the launch costs
@@ -588,12 +590,14 @@ static int run_dc_mct_fwd(gb200_plan *pl) {
 static int run_dwt(gb200_plan *pl, bool fwd) {
 	gb200_ctx *ctx = pl->ctx;
 	int n = 0;
+	const char *only_env = getenv("GB200_DWT_ONLY"); // measurement knob (tools/dwt_bench.py): run a single level launch
+	const int only = only_env && *only_env ? atoi(only_env) : -1;
 	for (uint32_t i = 0; i < pl->maxlevels; ++i)
 		for (int r = 0; r < 2; ++r) {
 			LevelLaunch &L = pl->lvl[r][i];
-			if (!L.ctas) continue;
-			if (fwd) launch_dwt_fwd((const DwtPlane*) L.dev.p, (const uint32_t*) L.map.p, L.ctas, r, L.tile_rows, L.unroll, ctx->stream);
-			else launch_dwt_inv((const DwtPlane*) L.dev.p, (const uint32_t*) L.map.p, L.ctas, r, L.tile_rows, L.unroll, ctx->stream);
+			if (!L.ctas || (only >= 0 && (int) i != only)) continue;
+			if (fwd) launch_dwt_fwd((const DwtPlane*) L.dev.p, (const uint32_t*) L.map.p, L.ctas, r, L.tile_rows, L.unroll, L.halo_lanes, ctx->stream);
+			else launch_dwt_inv((const DwtPlane*) L.dev.p, (const uint32_t*) L.map.p, L.ctas, r, L.tile_rows, L.unroll, L.halo_lanes, ctx->stream);
 			n++;
 		}
 	return launch_check(ctx, n);

@@ -64,14 +64,14 @@ void launch_mct_inv(int32_t *c0, int32_t *c1, int32_t *c2, uint64_t n, const int
 // dwt.cu : one launch = one decomposition level of every plane in `planes` (device array).
 // tile_rows > 0: shared-memory kernels, 64, 32 or 16 valid rows per CTA, dwt_tile_shape() valid columns;
 // tile_rows < 0: streaming kernels (dwt_stream.cuh), one warp per work item of -tile_rows rows by dwt_stream_shape() columns,
-//                `unroll` row pairs prefetched (1, 2 or 4); total_ctas counts work items.
+//                `unroll` row pairs prefetched (1, 2 or 4), `halo_lanes` 1 or 2; total_ctas counts work items.
 // DwtPlane::tiles_x / tiles_y must have been computed for the same shape (streaming: over rw + cas_x / rh + cas_y).
 void launch_dwt_fwd(const DwtPlane *planes_dev, const uint32_t *cta_plane_dev, uint32_t total_ctas, int reversible, int tile_rows,
-		int unroll, cudaStream_t s);
+		int unroll, int halo_lanes, cudaStream_t s);
 void launch_dwt_inv(const DwtPlane *planes_dev, const uint32_t *cta_plane_dev, uint32_t total_ctas, int reversible, int tile_rows,
-		int unroll, cudaStream_t s);
+		int unroll, int halo_lanes, cudaStream_t s);
 void dwt_tile_shape(int reversible, uint32_t *tw); // valid columns per CTA
-void dwt_stream_shape(uint32_t *tw);               // valid columns per work item of the streaming kernels
+void dwt_stream_shape(int halo_lanes, uint32_t *tw); // valid columns per work item of the streaming kernels (halo_lanes 1 or 2)
 
 // t1_enc.cu / t1_dec.cu
 uint32_t t1_symbol_capacity(uint32_t w, uint32_t h, uint32_t planes);

@@ -296,39 +296,54 @@ static void launch_inv_t(const DwtPlane *p, const uint32_t *m, uint32_t n, int t
 
 // tile_rows > 0: shared-memory kernels above (first generation), 64 / 32 / 16 valid rows per CTA
 // tile_rows < 0: streaming kernels of dwt_stream.cuh, -tile_rows rows per work item (one warp each); `total_ctas` counts work items
-template<bool REV>
-static void launch_fwd_s(const DwtPlane *p, const uint32_t *m, uint32_t n, int rows, int unroll, cudaStream_t s) {
-	const uint32_t grid = (n + DWS_WARPS - 1) / DWS_WARPS;
-	if (unroll == 1) dwt_fwd_stream_kernel<REV, 1><<<grid, DWS_WARPS * 32, 0, s>>>(p, m, n, rows);
-	else if (unroll == 4) dwt_fwd_stream_kernel<REV, 4><<<grid, DWS_WARPS * 32, 0, s>>>(p, m, n, rows);
-	else dwt_fwd_stream_kernel<REV, 2><<<grid, DWS_WARPS * 32, 0, s>>>(p, m, n, rows);
-}
-template<bool REV>
-static void launch_inv_s(const DwtPlane *p, const uint32_t *m, uint32_t n, int rows, int unroll, cudaStream_t s) {
-	const uint32_t grid = (n + DWS_WARPS - 1) / DWS_WARPS;
-	if (unroll == 1) dwt_inv_stream_kernel<REV, 1><<<grid, DWS_WARPS * 32, 0, s>>>(p, m, n, rows);
-	else if (unroll == 4) dwt_inv_stream_kernel<REV, 4><<<grid, DWS_WARPS * 32, 0, s>>>(p, m, n, rows);
-	else dwt_inv_stream_kernel<REV, 2><<<grid, DWS_WARPS * 32, 0, s>>>(p, m, n, rows);
+// the prefetch queues want the shared-memory end of the L1 / shared split
+template<typename K>
+static void prefer_shared(K kernel) { cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); }
+static void stream_kernels_setup() {
+	static bool done = false; // per process; the attribute is per function and device-independent in the runtime API
+	if (done) return;
+	done = true;
+	prefer_shared(dwt_fwd_stream_kernel<true, 8>); prefer_shared(dwt_fwd_stream_kernel<true, 16>); prefer_shared(dwt_fwd_stream_kernel<true, 24>);
+	prefer_shared(dwt_fwd_stream_kernel<false, 8>); prefer_shared(dwt_fwd_stream_kernel<false, 16>); prefer_shared(dwt_fwd_stream_kernel<false, 24>);
+	prefer_shared(dwt_inv_stream_kernel<true, 8>); prefer_shared(dwt_inv_stream_kernel<true, 16>); prefer_shared(dwt_inv_stream_kernel<true, 24>);
+	prefer_shared(dwt_inv_stream_kernel<false, 8>); prefer_shared(dwt_inv_stream_kernel<false, 16>); prefer_shared(dwt_inv_stream_kernel<false, 24>);
 }
 
-void dwt_stream_shape(uint32_t *tw) { *tw = DWS_TW; }
+template<bool REV>
+static void launch_fwd_s(const DwtPlane *p, const uint32_t *m, uint32_t n, int rows, int unroll, int hl, cudaStream_t s) {
+	const uint32_t grid = (n + DWS_WARPS - 1) / DWS_WARPS;
+	if (unroll == 1) dwt_fwd_stream_kernel<REV, 8><<<grid, DWS_WARPS * 32, 0, s>>>(p, m, n, rows, hl);
+	else if (unroll == 4) dwt_fwd_stream_kernel<REV, 24><<<grid, DWS_WARPS * 32, 0, s>>>(p, m, n, rows, hl);
+	else dwt_fwd_stream_kernel<REV, 16><<<grid, DWS_WARPS * 32, 0, s>>>(p, m, n, rows, hl);
+}
+template<bool REV>
+static void launch_inv_s(const DwtPlane *p, const uint32_t *m, uint32_t n, int rows, int unroll, int hl, cudaStream_t s) {
+	const uint32_t grid = (n + DWS_WARPS - 1) / DWS_WARPS;
+	if (unroll == 1) dwt_inv_stream_kernel<REV, 8><<<grid, DWS_WARPS * 32, 0, s>>>(p, m, n, rows, hl);
+	else if (unroll == 4) dwt_inv_stream_kernel<REV, 24><<<grid, DWS_WARPS * 32, 0, s>>>(p, m, n, rows, hl);
+	else dwt_inv_stream_kernel<REV, 16><<<grid, DWS_WARPS * 32, 0, s>>>(p, m, n, rows, hl);
+}
+
+void dwt_stream_shape(int halo_lanes, uint32_t *tw) { *tw = dws_tw(halo_lanes); }
 
 void launch_dwt_fwd(const DwtPlane *planes_dev, const uint32_t *cta_plane_dev, uint32_t total_ctas, int reversible, int tile_rows,
-		int unroll, cudaStream_t s) {
+		int unroll, int halo_lanes, cudaStream_t s) {
 	if (!total_ctas) return;
 	if (tile_rows < 0) {
-		if (reversible) launch_fwd_s<true>(planes_dev, cta_plane_dev, total_ctas, -tile_rows, unroll, s);
-		else launch_fwd_s<false>(planes_dev, cta_plane_dev, total_ctas, -tile_rows, unroll, s);
+		stream_kernels_setup();
+		if (reversible) launch_fwd_s<true>(planes_dev, cta_plane_dev, total_ctas, -tile_rows, unroll, halo_lanes, s);
+		else launch_fwd_s<false>(planes_dev, cta_plane_dev, total_ctas, -tile_rows, unroll, halo_lanes, s);
 	} else if (reversible) launch_fwd_t<true>(planes_dev, cta_plane_dev, total_ctas, tile_rows, s);
 	else launch_fwd_t<false>(planes_dev, cta_plane_dev, total_ctas, tile_rows, s);
 }
 
 void launch_dwt_inv(const DwtPlane *planes_dev, const uint32_t *cta_plane_dev, uint32_t total_ctas, int reversible, int tile_rows,
-		int unroll, cudaStream_t s) {
+		int unroll, int halo_lanes, cudaStream_t s) {
 	if (!total_ctas) return;
 	if (tile_rows < 0) {
-		if (reversible) launch_inv_s<true>(planes_dev, cta_plane_dev, total_ctas, -tile_rows, unroll, s);
-		else launch_inv_s<false>(planes_dev, cta_plane_dev, total_ctas, -tile_rows, unroll, s);
+		stream_kernels_setup();
+		if (reversible) launch_inv_s<true>(planes_dev, cta_plane_dev, total_ctas, -tile_rows, unroll, halo_lanes, s);
+		else launch_inv_s<false>(planes_dev, cta_plane_dev, total_ctas, -tile_rows, unroll, halo_lanes, s);
 	} else if (reversible) launch_inv_t<true>(planes_dev, cta_plane_dev, total_ctas, tile_rows, s);
 	else launch_inv_t<false>(planes_dev, cta_plane_dev, total_ctas, tile_rows, s);
 }

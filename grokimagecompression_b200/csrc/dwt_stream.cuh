@@ -26,6 +26,7 @@
 // This header is also compiled for the CPU by tests/dwt_emu (GB_EMU: one OS thread per lane), which checks
 // the kernels against the oracle without a GPU.
 #pragma once
+#include <type_traits>
 #ifndef GB_EMU
 #include "common.cuh"
 #else
@@ -34,8 +35,16 @@
 
 namespace gb {
 
-constexpr int DWS_TW = 120;      // valid columns per work item (lanes 1..30)
-constexpr int DWS_WARPS = 4;     // work items per CTA
+// halo lanes each side: 1 (120 valid columns per work item) or 2 (112 valid columns: every sub-band row segment a warp
+// stores then starts on a 32-byte sector when the band does)
+__host__ __device__ constexpr int dws_tw(int hl) { return 128 - 8 * hl; }
+#ifndef DWS_WARPS_PER_CTA
+#define DWS_WARPS_PER_CTA 4
+#endif
+#ifndef DWS_MINB
+#define DWS_MINB 1   // __launch_bounds__ minimum CTAs per SM (register cap), a tuning knob
+#endif
+constexpr int DWS_WARPS = DWS_WARPS_PER_CTA; // work items per CTA
 
 __device__ __forceinline__ int dws_reflect(int i, int len) {
 	if ((unsigned) i < (unsigned) len) return i;
@@ -66,6 +75,28 @@ __device__ __forceinline__ int32_t dws_ld1(const int32_t *p) { return __ldg(p); 
 __device__ __forceinline__ void dws_st4(int32_t *p, int32_t a, int32_t b, int32_t c, int32_t d) { DWS_ALIGNED(p, 16); __stcg(reinterpret_cast<int4*>(p), make_int4(a, b, c, d)); }
 __device__ __forceinline__ void dws_st2(int32_t *p, int32_t a, int32_t b) { DWS_ALIGNED(p, 8); __stcg(reinterpret_cast<int2*>(p), make_int2(a, b)); }
 __device__ __forceinline__ void dws_st1(int32_t *p, int32_t a) { __stcg(p, a); }
+
+// asynchronous global -> shared copies (LDGSTS): the prefetch queue of a warp.  A lane only ever reads back the 16 bytes it
+// copied itself, so cp.async.wait_group is all the synchronisation the queue needs.
+#ifdef GB_EMU
+__device__ __forceinline__ void dws_cp16(void *sm, const void *g) { DWS_ALIGNED(g, 16); memcpy(sm, g, 16); }
+__device__ __forceinline__ void dws_cp8(void *sm, const void *g) { DWS_ALIGNED(g, 8); memcpy(sm, g, 8); }
+__device__ __forceinline__ void dws_cp4(void *sm, const void *g) { memcpy(sm, g, 4); }
+__device__ __forceinline__ void dws_commit() {}
+template<int N> __device__ __forceinline__ void dws_wait() {}
+#else
+__device__ __forceinline__ void dws_cp16(void *sm, const void *g) {
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t) __cvta_generic_to_shared(sm)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void dws_cp8(void *sm, const void *g) {
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((uint32_t) __cvta_generic_to_shared(sm)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void dws_cp4(void *sm, const void *g) {
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((uint32_t) __cvta_generic_to_shared(sm)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void dws_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template<int N> __device__ __forceinline__ void dws_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+#endif
 
 __device__ __forceinline__ int32_t dws_down(int32_t v) { return __shfl_down_sync(0xffffffffu, v, 1); }
 __device__ __forceinline__ int32_t dws_up(int32_t v) { return __shfl_up_sync(0xffffffffu, v, 1); }
@@ -196,68 +227,119 @@ struct DwsItem {
 };
 
 __device__ __forceinline__ bool dws_item(const DwtPlane *__restrict__ planes, const uint32_t *__restrict__ item_plane, uint32_t nitems,
-		int R, DwtPlane &P, DwsItem &it) {
+		int R, int hl, DwtPlane &P, DwsItem &it) {
 	it.lane = threadIdx.x & 31;
 	uint32_t item = blockIdx.x * DWS_WARPS + (threadIdx.x >> 5);
 	if (item >= nitems) return false;
 	P = planes[__ldg(item_plane + item)];
 	item -= P.first_cta;
-	it.X0 = (int) (item % P.tiles_x) * DWS_TW;
+	it.X0 = (int) (item % P.tiles_x) * dws_tw(hl);
 	it.Y0 = (int) (item / P.tiles_x) * R;
-	it.c = it.X0 - 4 - (int) P.cas_x + 4 * it.lane;
+	it.c = it.X0 - 4 * hl - (int) P.cas_x + 4 * it.lane;
 	return true;
 }
 
 // =========================================================================================================
 // forward
 // =========================================================================================================
-template<bool REV, int U>
-__global__ void __launch_bounds__(DWS_WARPS * 32) dwt_fwd_stream_kernel(const DwtPlane *__restrict__ planes,
-		const uint32_t *__restrict__ item_plane, uint32_t nitems, int R) {
-	DwtPlane P;
-	DwsItem it;
-	if (!dws_item(planes, item_plane, nitems, R, P, it)) return;
+// two rows in lock step: twice the independent work between two shuffles
+template<bool REV>
+__device__ __forceinline__ void dws_hfwd2(Quad &p, Quad &q) {
+	if (REV) {
+		int32_t pe2 = dws_down(p.e0), qe2 = dws_down(q.e0);
+		p.o0 -= (p.e0 + p.e1) >> 1; q.o0 -= (q.e0 + q.e1) >> 1;
+		p.o1 -= (p.e1 + pe2) >> 1; q.o1 -= (q.e1 + qe2) >> 1;
+		int32_t pom = dws_up(p.o1), qom = dws_up(q.o1);
+		p.e0 += (pom + p.o0 + 2) >> 2; q.e0 += (qom + q.o0 + 2) >> 2;
+		p.e1 += (p.o0 + p.o1 + 2) >> 2; q.e1 += (q.o0 + q.o1 + 2) >> 2;
+	} else {
+		int32_t pe2 = dws_down(p.e0), qe2 = dws_down(q.e0);
+		p.o0 -= dws_fix13(p.e0 + p.e1, 12994); q.o0 -= dws_fix13(q.e0 + q.e1, 12994);
+		p.o1 -= dws_fix13(p.e1 + pe2, 12994); q.o1 -= dws_fix13(q.e1 + qe2, 12994);
+		int32_t pom = dws_up(p.o1), qom = dws_up(q.o1);
+		p.e0 -= dws_fix13(pom + p.o0, 434); q.e0 -= dws_fix13(qom + q.o0, 434);
+		p.e1 -= dws_fix13(p.o0 + p.o1, 434); q.e1 -= dws_fix13(q.o0 + q.o1, 434);
+		pe2 = dws_down(p.e0); qe2 = dws_down(q.e0);
+		p.o0 += dws_fix13(p.e0 + p.e1, 7233); q.o0 += dws_fix13(q.e0 + q.e1, 7233);
+		p.o1 += dws_fix13(p.e1 + pe2, 7233); q.o1 += dws_fix13(q.e1 + qe2, 7233);
+		pom = dws_up(p.o1); qom = dws_up(q.o1);
+		p.e0 += dws_fix13(pom + p.o0, 3633); q.e0 += dws_fix13(qom + q.o0, 3633);
+		p.e1 += dws_fix13(p.o0 + p.o1, 3633); q.e1 += dws_fix13(q.o0 + q.o1, 3633);
+		p.e0 = dws_fix13(p.e0, 6659); p.e1 = dws_fix13(p.e1, 6659); q.e0 = dws_fix13(q.e0, 6659); q.e1 = dws_fix13(q.e1, 6659);
+		p.o0 = dws_fix13(p.o0, 5039); p.o1 = dws_fix13(p.o1, 5039); q.o0 = dws_fix13(q.o0, 5039); q.o1 = dws_fix13(q.o1, 5039);
+	}
+}
+
+__device__ __forceinline__ const int32_t *dws_at(const int32_t *p, uint32_t row, uint32_t stride_bytes) {
+	return reinterpret_cast<const int32_t*>(reinterpret_cast<const char*>(p) + (size_t) row * stride_bytes); // one IMAD.WIDE.U32
+}
+__device__ __forceinline__ int32_t *dws_at(int32_t *p, uint32_t row, uint32_t stride_bytes) {
+	return reinterpret_cast<int32_t*>(reinterpret_cast<char*>(p) + (size_t) row * stride_bytes);
+}
+
+// One strip.  EDGE = false: every lane loads 16 aligned bytes of the region and every valid lane stores full aligned
+// pairs (strips in the interior of a plane whose rows are 16-byte aligned): no predicates, no fallbacks in the loop.
+// EDGE = true: the strip touches the left or right border of the region (or the plane is not aligned): every lane
+// gathers its four (reflected) columns with 4-byte copies and stores element by element under predicates.
+// ring: this warp's prefetch queue, D rows of 32 x 16 bytes in shared memory, filled by asynchronous copies D / 2 trips
+// ahead of their use.
+template<bool REV, int D, bool EDGE>
+__device__ __forceinline__ void dws_fwd_strip(const DwtPlane &P, const DwsItem &it, int R, int hl, int4 *ring) {
 	const int rw = (int) P.rw, rh = (int) P.rh, casx = (int) P.cas_x, casy = (int) P.cas_y;
 	const int c = it.c;
-	const size_t sstr = P.src_stride, dstr = P.dst_stride;
+	const uint32_t sstr4 = P.src_stride * 4u, dstr4 = P.dst_stride * 4u;
 
-	// source columns (reflected) and the 16-byte fast path
-	const int g0 = dws_reflect(c, rw), g1 = dws_reflect(c + 1, rw), g2 = dws_reflect(c + 2, rw), g3 = dws_reflect(c + 3, rw);
-	const bool vld = c >= 0 && c + 3 < rw && (c & 3) == 0 && (P.src_stride & 3) == 0 && (((size_t) P.src) & 15) == 0;
-	auto load_row = [&](int y) -> Quad {
-		const int32_t *p = P.src + (size_t) dws_reflect(y, rh) * sstr;
-		Quad q;
-		if (vld) {
-			const int4 v = dws_ld4(p + c);
-			q.e0 = v.x; q.o0 = v.y; q.e1 = v.z; q.o1 = v.w;
-		} else {
-			q.e0 = dws_ld1(p + g0); q.o0 = dws_ld1(p + g1); q.e1 = dws_ld1(p + g2); q.o1 = dws_ld1(p + g3);
+	const int32_t *s0 = P.src + (EDGE ? dws_reflect(c, rw) : c);
+	const int32_t *s1 = P.src + dws_reflect(c + 1, rw), *s2 = P.src + dws_reflect(c + 2, rw), *s3 = P.src + dws_reflect(c + 3, rw);
+	int4 *const slot0 = ring + it.lane;
+	auto issue_row = [&](int y, int slot) {
+		const uint32_t gy = (uint32_t) dws_reflect(y, rh);
+		int4 *sm = slot0 + 32 * slot;
+		if (!EDGE) dws_cp16(sm, dws_at(s0, gy, sstr4));
+		else {
+			int32_t *e = reinterpret_cast<int32_t*>(sm);
+			dws_cp4(e, dws_at(s0, gy, sstr4)); dws_cp4(e + 1, dws_at(s1, gy, sstr4));
+			dws_cp4(e + 2, dws_at(s2, gy, sstr4)); dws_cp4(e + 3, dws_at(s3, gy, sstr4));
 		}
+	};
+	auto read_row = [&](int slot) -> Quad {
+		const int4 v = slot0[32 * slot];
+		Quad q;
+		q.e0 = v.x; q.o0 = v.y; q.e1 = v.z; q.o1 = v.w;
 		return q;
 	};
 
-	// destination columns: element at region column cc goes to index cc >> 1 of its sub-band
-	const bool lv = it.lane >= 1 && it.lane <= 30;
+	// destination columns: the element at region column cc goes to index cc >> 1 of its sub-band
+	const bool lv = it.lane >= hl && it.lane <= 31 - hl;
 	const bool okE0 = lv && (unsigned) c < (unsigned) rw, okO0 = lv && (unsigned) (c + 1) < (unsigned) rw;
 	const bool okE1 = lv && (unsigned) (c + 2) < (unsigned) rw, okO1 = lv && (unsigned) (c + 3) < (unsigned) rw;
-	const int iL = c >> 1, iH = (int) P.sw + ((c + 1) >> 1); // second element of each kind: + 1
-	const bool al = (P.dst_stride & 1) == 0 && (((size_t) P.dst) & 7) == 0;
-	const bool vL = okE0 && okE1 && al && (iL & 1) == 0, vH = okO0 && okO1 && al && (iH & 1) == 0;
-
-	auto emit = [&](Quad q, int y, bool high_row) {
-		if (rw > 1) dws_hfwd<REV>(q);
+	int32_t *const dL = P.dst + (c >> 1), *const dH = P.dst + ((int) P.sw + ((c + 1) >> 1)); // second element of each kind: + 1
+	auto store_row = [&](const Quad &q, uint32_t row) {
+		int32_t *oL = dws_at(dL, row, dstr4), *oH = dws_at(dH, row, dstr4);
+		if (!EDGE) {
+			if (lv) { dws_st2(oL, q.e0, q.e1); dws_st2(oH, q.o0, q.o1); }
+		} else {
+			if (okE0) dws_st1(oL, q.e0);
+			if (okE1) dws_st1(oL + 1, q.e1);
+			if (okO0) dws_st1(oH, q.o0);
+			if (okO1) dws_st1(oH + 1, q.o1);
+		}
+	};
+	const bool hlift = !EDGE || rw > 1;
+	auto emit1 = [&](Quad q, int y, bool high_row) {
+		if (hlift) dws_hfwd<REV>(q);
 		else if (REV && casx) { q.e0 *= 2; q.o0 *= 2; q.e1 *= 2; q.o1 *= 2; } // dwt53.cpp:160
-		int32_t *o = P.dst + (size_t) ((y >> 1) + (high_row ? (int) P.sh : 0)) * dstr;
-		if (vL) dws_st2(o + iL, q.e0, q.e1);
-		else { if (okE0) dws_st1(o + iL, q.e0); if (okE1) dws_st1(o + iL + 1, q.e1); }
-		if (vH) dws_st2(o + iH, q.o0, q.o1);
-		else { if (okO0) dws_st1(o + iH, q.o0); if (okO1) dws_st1(o + iH + 1, q.o1); }
+		store_row(q, (uint32_t) ((y >> 1) + (high_row ? (int) P.sh : 0)));
 	};
 
 	if (rh == 1) { // a single row is not lifted vertically; with an odd origin it is a high-pass row (x2 for 5/3)
-		Quad q = load_row(0);
+		if (it.Y0 != 0) return;
+		issue_row(0, 0);
+		dws_commit();
+		dws_wait<0>();
+		Quad q = read_row(0);
 		if (REV && casy) { q.e0 *= 2; q.o0 *= 2; q.e1 *= 2; q.o1 *= 2; }
-		emit(q, 0, casy != 0);
+		emit1(q, 0, casy != 0);
 		return;
 	}
 
@@ -269,96 +351,149 @@ __global__ void __launch_bounds__(DWS_WARPS * 32) dwt_fwd_stream_kernel(const Dw
 
 	VFwd<REV> v0, v1, v2, v3;
 	v0.init(); v1.init(); v2.init(); v3.init();
-	Quad nxt[2 * U];
+	constexpr int G = D / 2; // trips in flight: one copy group per trip (two rows)
 	#pragma unroll
-	for (int u = 0; u < 2 * U; ++u) nxt[u] = load_row(ys + u);
-	for (int j0 = 0; j0 < niter; j0 += U) {
-		Quad cur[2 * U];
-		#pragma unroll
-		for (int u = 0; u < 2 * U; ++u) cur[u] = nxt[u];
-		if (j0 + U < niter) {
-			#pragma unroll
-			for (int u = 0; u < 2 * U; ++u) nxt[u] = load_row(ys + 2 * (j0 + U) + u);
-		}
-		#pragma unroll
-		for (int u = 0; u < U; ++u) {
-			const int j = j0 + u;
-			if (j < niter) {
-				const Quad a = cur[2 * u], b = cur[2 * u + 1];
-				Quad lo, hi;
-				v0.feed(a.e0, b.e0, lo.e0, hi.e0);
-				v1.feed(a.o0, b.o0, lo.o0, hi.o0);
-				v2.feed(a.e1, b.e1, lo.e1, hi.e1);
-				v3.feed(a.o1, b.o1, lo.o1, hi.o1);
-				const int yl = ys + 2 * (j - LAG);
-				if (j >= 2 * LAG) {
-					if (yl >= yv0 && yl < yv1) emit(lo, yl, false);
-					if (yl + 1 >= yv0 && yl + 1 < yv1) emit(hi, yl + 1, true);
-				}
-			}
+	for (int g = 0; g < G; ++g) {
+		if (g < niter) { issue_row(ys + 2 * g, 2 * g); issue_row(ys + 2 * g + 1, 2 * g + 1); }
+		dws_commit();
+	}
+	int slot = 0;
+	#pragma unroll 2
+	for (int j = 0; j < niter; ++j) {
+		dws_wait<G - 1>();
+		const Quad a = read_row(slot), b = read_row(slot + 1);
+		if (j + G < niter) { issue_row(ys + 2 * (j + G), slot); issue_row(ys + 2 * (j + G) + 1, slot + 1); }
+		dws_commit();
+		slot = slot + 2 == D ? 0 : slot + 2;
+		Quad lo, hi;
+		v0.feed(a.e0, b.e0, lo.e0, hi.e0);
+		v1.feed(a.o0, b.o0, lo.o0, hi.o0);
+		v2.feed(a.e1, b.e1, lo.e1, hi.e1);
+		v3.feed(a.o1, b.o1, lo.o1, hi.o1);
+		// rows before the first owned one come out of the warm-up trips and fail the range test, as do rows past the last
+		const int yl = ys + 2 * (j - LAG);
+		const bool vl = yl >= yv0 && yl < yv1, vh = yl + 1 >= yv0 && yl + 1 < yv1;
+		if (vl && vh && hlift) {
+			dws_hfwd2<REV>(lo, hi);
+			store_row(lo, (uint32_t) (yl >> 1));
+			store_row(hi, (uint32_t) (((yl + 1) >> 1) + (int) P.sh));
+		} else {
+			if (vl) emit1(lo, yl, false);
+			if (vh) emit1(hi, yl + 1, true);
 		}
 	}
+}
+
+template<bool REV, int D>
+__global__ void __launch_bounds__(DWS_WARPS * 32, DWS_MINB) dwt_fwd_stream_kernel(const DwtPlane *__restrict__ planes,
+		const uint32_t *__restrict__ item_plane, uint32_t nitems, int R, int hl) {
+	__shared__ int4 ring[DWS_WARPS][D][32];
+	DwtPlane P;
+	DwsItem it;
+	if (!dws_item(planes, item_plane, nitems, R, hl, P, it)) return;
+	const int c = it.c, rw = (int) P.rw;
+	const bool lv = it.lane >= hl && it.lane <= 31 - hl;
+	const bool vld = c >= 0 && c + 3 < rw && (c & 3) == 0 && (P.src_stride & 3) == 0 && (((size_t) P.src) & 15) == 0;
+	const bool vst = (P.dst_stride & 1) == 0 && (((size_t) P.dst) & 7) == 0 && ((c >> 1) & 1) == 0 && ((P.sw + ((c + 1) >> 1)) & 1) == 0;
+	int4 *const my_ring = &ring[threadIdx.x >> 5][0][0];
+	if (__all_sync(0xffffffffu, vld && (vst || !lv))) dws_fwd_strip<REV, D, false>(P, it, R, hl, my_ring);
+	else dws_fwd_strip<REV, D, true>(P, it, R, hl, my_ring);
 }
 
 // =========================================================================================================
 // inverse
 // =========================================================================================================
-template<bool REV, int U>
-__global__ void __launch_bounds__(DWS_WARPS * 32) dwt_inv_stream_kernel(const DwtPlane *__restrict__ planes,
-		const uint32_t *__restrict__ item_plane, uint32_t nitems, int R) {
-	DwtPlane P;
-	DwsItem it;
-	if (!dws_item(planes, item_plane, nitems, R, P, it)) return;
+template<bool REV>
+__device__ __forceinline__ void dws_hinv2(Quad &p, Quad &q) {
+	if (REV) {
+		int32_t pom = dws_up(p.o1), qom = dws_up(q.o1);
+		p.e0 -= (pom + p.o0 + 2) >> 2; q.e0 -= (qom + q.o0 + 2) >> 2;
+		p.e1 -= (p.o0 + p.o1 + 2) >> 2; q.e1 -= (q.o0 + q.o1 + 2) >> 2;
+		int32_t pe2 = dws_down(p.e0), qe2 = dws_down(q.e0);
+		p.o0 += (p.e0 + p.e1) >> 1; q.o0 += (q.e0 + q.e1) >> 1;
+		p.o1 += (p.e1 + pe2) >> 1; q.o1 += (q.e1 + qe2) >> 1;
+	} else {
+		float pe0 = __fmul_rn(dws_f(p.e0), DWS_KL), pe1 = __fmul_rn(dws_f(p.e1), DWS_KL), qe0 = __fmul_rn(dws_f(q.e0), DWS_KL), qe1 = __fmul_rn(dws_f(q.e1), DWS_KL);
+		float po0 = __fmul_rn(dws_f(p.o0), DWS_KH), po1 = __fmul_rn(dws_f(p.o1), DWS_KH), qo0 = __fmul_rn(dws_f(q.o0), DWS_KH), qo1 = __fmul_rn(dws_f(q.o1), DWS_KH);
+		float pom = dws_f(dws_up(dws_i(po1))), qom = dws_f(dws_up(dws_i(qo1)));
+		pe0 = dws_step(pe0, pom, po0, DWS_C1); qe0 = dws_step(qe0, qom, qo0, DWS_C1);
+		pe1 = dws_step(pe1, po0, po1, DWS_C1); qe1 = dws_step(qe1, qo0, qo1, DWS_C1);
+		float pe2 = dws_f(dws_down(dws_i(pe0))), qe2 = dws_f(dws_down(dws_i(qe0)));
+		po0 = dws_step(po0, pe0, pe1, DWS_C2); qo0 = dws_step(qo0, qe0, qe1, DWS_C2);
+		po1 = dws_step(po1, pe1, pe2, DWS_C2); qo1 = dws_step(qo1, qe1, qe2, DWS_C2);
+		pom = dws_f(dws_up(dws_i(po1))); qom = dws_f(dws_up(dws_i(qo1)));
+		pe0 = dws_step(pe0, pom, po0, DWS_C3); qe0 = dws_step(qe0, qom, qo0, DWS_C3);
+		pe1 = dws_step(pe1, po0, po1, DWS_C3); qe1 = dws_step(qe1, qo0, qo1, DWS_C3);
+		pe2 = dws_f(dws_down(dws_i(pe0))); qe2 = dws_f(dws_down(dws_i(qe0)));
+		po0 = dws_step(po0, pe0, pe1, DWS_C4); qo0 = dws_step(qo0, qe0, qe1, DWS_C4);
+		po1 = dws_step(po1, pe1, pe2, DWS_C4); qo1 = dws_step(qo1, qe1, qe2, DWS_C4);
+		p.e0 = dws_i(pe0); p.o0 = dws_i(po0); p.e1 = dws_i(pe1); p.o1 = dws_i(po1);
+		q.e0 = dws_i(qe0); q.o0 = dws_i(qo0); q.e1 = dws_i(qe1); q.o1 = dws_i(qo1);
+	}
+}
+
+// EDGE as in the forward kernel: false = every lane loads aligned pairs of all four sub-bands and every valid lane stores
+// 16 aligned bytes; true = 4-byte gathers through reflected indices, element-wise predicated stores.  Queue slot of a lane:
+// (low, low, high, high) = the two 8-byte pairs as they lie in the sub-bands.
+template<bool REV, int D, bool EDGE>
+__device__ __forceinline__ void dws_inv_strip(const DwtPlane &P, const DwsItem &it, int R, int hl, int4 *ring) {
 	const int rw = (int) P.rw, rh = (int) P.rh, casx = (int) P.cas_x, casy = (int) P.cas_y;
 	const int c = it.c;
-	const size_t sstr = P.src_stride, bstr = P.band_stride, dstr = P.dst_stride;
+	const uint32_t sstr4 = P.src_stride * 4u, bstr4 = P.band_stride * 4u, dstr4 = P.dst_stride * 4u;
 
 	// coefficient columns: the sample at region column g is index g >> 1 of the low-pass (LL / LH) or high-pass (HL / HH) band
-	const int k0 = dws_reflect(c, rw) >> 1, k1 = (int) P.sw + (dws_reflect(c + 1, rw) >> 1);
+	const int k0 = (EDGE ? dws_reflect(c, rw) : c) >> 1, k1 = (int) P.sw + ((EDGE ? dws_reflect(c + 1, rw) : c + 1) >> 1);
 	const int k2 = dws_reflect(c + 2, rw) >> 1, k3 = (int) P.sw + (dws_reflect(c + 3, rw) >> 1);
-	const bool inside = c >= 0 && c + 3 < rw;
-	const bool vsrc = inside && (k0 & 1) == 0 && (P.src_stride & 1) == 0 && (((size_t) P.src) & 7) == 0;
-	const bool bal = (P.band_stride & 1) == 0 && (((size_t) P.band) & 7) == 0;
-	const bool vbl = inside && (k0 & 1) == 0 && bal, vbh = inside && (k1 & 1) == 0 && bal;
-	auto load_row = [&](int y) -> Quad {
-		const int gy = dws_reflect(y, rh);
-		const int k = gy >> 1;
-		const bool high = ((gy + casy) & 1) != 0;
-		Quad q;
-		if (!high) { // LL from the previous level's output, HL from the coefficient plane
-			const int32_t *pl = P.src + (size_t) k * sstr, *ph = P.band + (size_t) k * bstr;
-			if (vsrc) { const int2 v = dws_ld2(pl + k0); q.e0 = v.x; q.e1 = v.y; }
-			else { q.e0 = dws_ld1(pl + k0); q.e1 = dws_ld1(pl + k2); }
-			if (vbh) { const int2 v = dws_ld2(ph + k1); q.o0 = v.x; q.o1 = v.y; }
-			else { q.o0 = dws_ld1(ph + k1); q.o1 = dws_ld1(ph + k3); }
-		} else { // LH and HH
-			const int32_t *pb = P.band + (size_t) ((int) P.sh + k) * bstr;
-			if (vbl) { const int2 v = dws_ld2(pb + k0); q.e0 = v.x; q.e1 = v.y; }
-			else { q.e0 = dws_ld1(pb + k0); q.e1 = dws_ld1(pb + k2); }
-			if (vbh) { const int2 v = dws_ld2(pb + k1); q.o0 = v.x; q.o1 = v.y; }
-			else { q.o0 = dws_ld1(pb + k1); q.o1 = dws_ld1(pb + k3); }
+	const int32_t *const pLL = P.src + k0, *const pLL2 = P.src + k2;   // vertical low-pass rows: LL (previous level's output) | HL
+	const int32_t *const pLH = P.band + k0, *const pLH2 = P.band + k2; // vertical high-pass rows: LH | HH
+	const int32_t *const pH = P.band + k1, *const pH2 = P.band + k3;   // HL and HH columns
+	int4 *const slot0 = ring + it.lane;
+	auto issue_row = [&](int y, bool high, int slot) {
+		const uint32_t k = (uint32_t) (dws_reflect(y, rh) >> 1) + (high ? P.sh : 0u);
+		const int32_t *pl = high ? pLH : pLL, *pl2 = high ? pLH2 : pLL2;
+		const uint32_t lstr4 = high ? bstr4 : sstr4;
+		int32_t *e = reinterpret_cast<int32_t*>(slot0 + 32 * slot);
+		if (!EDGE) { dws_cp8(e, dws_at(pl, k, lstr4)); dws_cp8(e + 2, dws_at(pH, k, bstr4)); }
+		else {
+			dws_cp4(e, dws_at(pl, k, lstr4)); dws_cp4(e + 1, dws_at(pl2, k, lstr4));
+			dws_cp4(e + 2, dws_at(pH, k, bstr4)); dws_cp4(e + 3, dws_at(pH2, k, bstr4));
 		}
+	};
+	auto read_row = [&](int slot) -> Quad {
+		const int4 v = slot0[32 * slot];
+		Quad q;
+		q.e0 = v.x; q.e1 = v.y; q.o0 = v.z; q.o1 = v.w;
 		return q;
 	};
-	// horizontal synthesis of a loaded row (at consumption time, so that the prefetch does not wait for its loads)
-	auto hsyn = [&](Quad &q) {
-		if (rw > 1) dws_hinv<REV>(q);
+	const bool hlift = !EDGE || rw > 1;
+	auto hsyn1 = [&](Quad &q) {
+		if (hlift) dws_hinv<REV>(q);
 		else if (REV && casx) { q.e0 /= 2; q.o0 /= 2; q.e1 /= 2; q.o1 /= 2; } // dwt.cpp:344-349 (C division)
 	};
 
-	const bool lv = it.lane >= 1 && it.lane <= 30;
+	const bool lv = it.lane >= hl && it.lane <= 31 - hl;
 	const bool ok0 = lv && (unsigned) c < (unsigned) rw, ok1 = lv && (unsigned) (c + 1) < (unsigned) rw;
 	const bool ok2 = lv && (unsigned) (c + 2) < (unsigned) rw, ok3 = lv && (unsigned) (c + 3) < (unsigned) rw;
-	const bool vst = ok0 && ok3 && (c & 3) == 0 && (P.dst_stride & 3) == 0 && (((size_t) P.dst) & 15) == 0;
+	int32_t *const d0 = P.dst + c;
 	auto store_row = [&](const Quad &q, int y) {
-		int32_t *o = P.dst + (size_t) y * dstr + c;
-		if (vst) dws_st4(o, q.e0, q.o0, q.e1, q.o1);
-		else { if (ok0) dws_st1(o, q.e0); if (ok1) dws_st1(o + 1, q.o0); if (ok2) dws_st1(o + 2, q.e1); if (ok3) dws_st1(o + 3, q.o1); }
+		int32_t *o = dws_at(d0, (uint32_t) y, dstr4);
+		if (!EDGE) {
+			if (lv) dws_st4(o, q.e0, q.o0, q.e1, q.o1);
+		} else {
+			if (ok0) dws_st1(o, q.e0);
+			if (ok1) dws_st1(o + 1, q.o0);
+			if (ok2) dws_st1(o + 2, q.e1);
+			if (ok3) dws_st1(o + 3, q.o1);
+		}
 	};
 
-	if (rh == 1) {
-		Quad q = load_row(0);
-		hsyn(q);
+	if (rh == 1) { // a single row: low-pass (LL | HL) with an even origin, high-pass with an odd one; no vertical step
+		if (it.Y0 != 0) return;
+		issue_row(0, casy != 0, 0);
+		dws_commit();
+		dws_wait<0>();
+		Quad q = read_row(0);
+		hsyn1(q);
 		if (REV && casy) { q.e0 /= 2; q.o0 /= 2; q.e1 /= 2; q.o1 /= 2; }
 		store_row(q, 0);
 		return;
@@ -372,36 +507,48 @@ __global__ void __launch_bounds__(DWS_WARPS * 32) dwt_inv_stream_kernel(const Dw
 
 	VInv<REV> v0, v1, v2, v3;
 	v0.init(); v1.init(); v2.init(); v3.init();
-	Quad nxt[2 * U];
+	// rows ys + 2 j are vertical low-pass rows, ys + 2 j + 1 high-pass ones (reflection keeps the parity)
+	constexpr int G = D / 2;
 	#pragma unroll
-	for (int u = 0; u < 2 * U; ++u) nxt[u] = load_row(ys + u);
-	for (int j0 = 0; j0 < niter; j0 += U) {
-		Quad cur[2 * U];
-		#pragma unroll
-		for (int u = 0; u < 2 * U; ++u) cur[u] = nxt[u];
-		if (j0 + U < niter) {
-			#pragma unroll
-			for (int u = 0; u < 2 * U; ++u) nxt[u] = load_row(ys + 2 * (j0 + U) + u);
-		}
-		#pragma unroll
-		for (int u = 0; u < U; ++u) {
-			const int j = j0 + u;
-			if (j < niter) {
-				Quad a = cur[2 * u], b = cur[2 * u + 1];
-				hsyn(a); hsyn(b);
-				Quad r0, r1;
-				v0.feed(a.e0, b.e0, r0.e0, r1.e0);
-				v1.feed(a.o0, b.o0, r0.o0, r1.o0);
-				v2.feed(a.e1, b.e1, r0.e1, r1.e1);
-				v3.feed(a.o1, b.o1, r0.o1, r1.o1);
-				const int yl = ys + 2 * (j - LAG);
-				if (j >= 2 * LAG) {
-					if (yl >= yv0 && yl < yv1) store_row(r0, yl);
-					if (yl + 1 >= yv0 && yl + 1 < yv1) store_row(r1, yl + 1);
-				}
-			}
-		}
+	for (int g = 0; g < G; ++g) {
+		if (g < niter) { issue_row(ys + 2 * g, false, 2 * g); issue_row(ys + 2 * g + 1, true, 2 * g + 1); }
+		dws_commit();
 	}
+	int slot = 0;
+	#pragma unroll 2
+	for (int j = 0; j < niter; ++j) {
+		dws_wait<G - 1>();
+		Quad a = read_row(slot), b = read_row(slot + 1);
+		if (j + G < niter) { issue_row(ys + 2 * (j + G), false, slot); issue_row(ys + 2 * (j + G) + 1, true, slot + 1); }
+		dws_commit();
+		slot = slot + 2 == D ? 0 : slot + 2;
+		if (hlift) dws_hinv2<REV>(a, b);
+		else { hsyn1(a); hsyn1(b); }
+		Quad r0, r1;
+		v0.feed(a.e0, b.e0, r0.e0, r1.e0);
+		v1.feed(a.o0, b.o0, r0.o0, r1.o0);
+		v2.feed(a.e1, b.e1, r0.e1, r1.e1);
+		v3.feed(a.o1, b.o1, r0.o1, r1.o1);
+		const int yl = ys + 2 * (j - LAG);
+		if (yl >= yv0 && yl < yv1) store_row(r0, yl);
+		if (yl + 1 >= yv0 && yl + 1 < yv1) store_row(r1, yl + 1);
+	}
+}
+
+template<bool REV, int D>
+__global__ void __launch_bounds__(DWS_WARPS * 32, DWS_MINB) dwt_inv_stream_kernel(const DwtPlane *__restrict__ planes,
+		const uint32_t *__restrict__ item_plane, uint32_t nitems, int R, int hl) {
+	__shared__ int4 ring[DWS_WARPS][D][32];
+	DwtPlane P;
+	DwsItem it;
+	if (!dws_item(planes, item_plane, nitems, R, hl, P, it)) return;
+	const int c = it.c, rw = (int) P.rw;
+	const bool inside = c >= 0 && c + 3 < rw && (c & 3) == 0; // then the low-pass index c / 2 is even
+	const bool vld = inside && (P.sw & 1) == 0 && ((P.src_stride | P.band_stride) & 1) == 0 && ((((size_t) P.src) | ((size_t) P.band)) & 7) == 0;
+	const bool vst = (P.dst_stride & 3) == 0 && (((size_t) P.dst) & 15) == 0;
+	int4 *const my_ring = &ring[threadIdx.x >> 5][0][0];
+	if (__all_sync(0xffffffffu, vld && vst)) dws_inv_strip<REV, D, false>(P, it, R, hl, my_ring);
+	else dws_inv_strip<REV, D, true>(P, it, R, hl, my_ring);
 }
 
 } // namespace gb

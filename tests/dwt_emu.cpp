@@ -18,9 +18,11 @@
 
 // ---- the handful of CUDA names the kernels use -----------------------------------------------------------
 #define __device__
+#define __host__
 #define __global__
 #define __forceinline__ inline
-#define __launch_bounds__(x)
+#define __launch_bounds__(...)
+#define __shared__ static
 struct int2 { int x, y; };
 struct int4 { int x, y, z, w; };
 static inline int2 make_int2(int a, int b) { return {a, b}; }
@@ -41,6 +43,14 @@ static inline int __shfl_up_sync(unsigned, int v, int d) {
 	emu_buf[emu_lane] = v;
 	emu_bar.arrive_and_wait();
 	int r = emu_lane - d >= 0 ? emu_buf[emu_lane - d] : v;
+	emu_bar.arrive_and_wait();
+	return r;
+}
+static inline int __all_sync(unsigned, int pred) {
+	emu_buf[emu_lane] = pred;
+	emu_bar.arrive_and_wait();
+	int r = 1;
+	for (int i = 0; i < 32; ++i) r &= emu_buf[i] != 0;
 	emu_bar.arrive_and_wait();
 	return r;
 }
@@ -66,7 +76,7 @@ extern "C" int gbo_dwt_inv(int32_t *buf, uint32_t x0, uint32_t y0, uint32_t x1, 
 using gb::DwtPlane;
 
 template<typename K>
-static void launch(K kernel, const DwtPlane *planes, const uint32_t *map, uint32_t nitems, int R) {
+static void launch(K kernel, const DwtPlane *planes, const uint32_t *map, uint32_t nitems, int R, int hl) {
 	const unsigned grid = (nitems + gb::DWS_WARPS - 1) / gb::DWS_WARPS;
 	std::vector<std::thread> th;
 	for (int lane = 0; lane < 32; ++lane)
@@ -76,7 +86,7 @@ static void launch(K kernel, const DwtPlane *planes, const uint32_t *map, uint32
 				for (unsigned w = 0; w < (unsigned) gb::DWS_WARPS; ++w) {
 					blockIdx.x = b;
 					threadIdx.x = w * 32 + lane;
-					kernel(planes, map, nitems, R);
+					kernel(planes, map, nitems, R, hl);
 				}
 		});
 	for (auto &t : th) t.join();
@@ -85,19 +95,21 @@ static void launch(K kernel, const DwtPlane *planes, const uint32_t *map, uint32
 static uint32_t cdiv2n(uint32_t a, uint32_t n) { return (uint32_t) (((uint64_t) a + (1ull << n) - 1) >> n); }
 
 // the plan's table for one level of one plane (csrc/api.cu)
+static int g_hl = 1;
 static void one_level(DwtPlane d, bool fwd, int rev, int R) {
-	d.tiles_x = (d.rw + d.cas_x + gb::DWS_TW - 1) / gb::DWS_TW;
+	const int hl = g_hl;
+	d.tiles_x = (d.rw + d.cas_x + gb::dws_tw(hl) - 1) / gb::dws_tw(hl);
 	d.tiles_y = (d.rh + d.cas_y + R - 1) / R;
 	d.first_cta = 0;
 	if (!d.rw || !d.rh) return;
 	const uint32_t n = d.tiles_x * d.tiles_y;
 	std::vector<uint32_t> map(n, 0);
 	if (fwd) {
-		if (rev) launch(gb::dwt_fwd_stream_kernel<true, 2>, &d, map.data(), n, R);
-		else launch(gb::dwt_fwd_stream_kernel<false, 2>, &d, map.data(), n, R);
+		if (rev) launch(gb::dwt_fwd_stream_kernel<true, 8>, &d, map.data(), n, R, hl);
+		else launch(gb::dwt_fwd_stream_kernel<false, 16>, &d, map.data(), n, R, hl);
 	} else {
-		if (rev) launch(gb::dwt_inv_stream_kernel<true, 2>, &d, map.data(), n, R);
-		else launch(gb::dwt_inv_stream_kernel<false, 2>, &d, map.data(), n, R);
+		if (rev) launch(gb::dwt_inv_stream_kernel<true, 16>, &d, map.data(), n, R, hl);
+		else launch(gb::dwt_inv_stream_kernel<false, 8>, &d, map.data(), n, R, hl);
 	}
 }
 
@@ -187,6 +199,7 @@ int main(int argc, char **argv) {
 	for (int rev = 1; rev >= 0; --rev)
 		for (const Geom &g : geoms)
 			for (int R : {16, 64}) {
+				g_hl = R == 16 ? 1 : 2;
 				fails += check_fwd(g, rev, R, rng); ++cases;
 				std::vector<uint32_t> nds = {g.nr, std::max(1u, g.nr - 1), g.nr > 3 ? g.nr - 3 : 1u, 1u};
 				std::sort(nds.begin(), nds.end());

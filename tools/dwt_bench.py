@@ -23,6 +23,7 @@ from grokimagecompression_b200 import params as P
 def main():
     name = sys.argv[1] if len(sys.argv) > 1 else "c2"
     steps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+    warm = int(os.environ.get("DWT_BENCH_WARMUP", "3"))
     variants = sys.argv[3:]
     w = bench.WORKLOADS[name]
     frames = w.get("frames", 1)
@@ -43,7 +44,7 @@ def main():
     print(f"workload {name}: {nbytes / 1e6:.1f} MB algorithmic per direction, {launches} level launches, peak {peak} GB/s")
     out = []
     for v in variants:
-        for k in ("GB200_DWT_LEGACY", "GB200_DWT_ROWS", "GB200_DWT_UNROLL", "GB200_DWT_FILL"):
+        for k in ("GB200_DWT_LEGACY", "GB200_DWT_ROWS", "GB200_DWT_UNROLL", "GB200_DWT_FILL", "GB200_DWT_HL", "GB200_DWT_ONLY"):
             os.environ.pop(k, None)
         if v == "legacy":
             os.environ["GB200_DWT_LEGACY"] = "1"
@@ -56,14 +57,14 @@ def main():
             plan = gb.Plan(ctx, tiles, encoder=enc)
             run = (lambda: plan.encode_run_stage(1)) if enc else (lambda: plan.decode_run_stage(1))
             evs = []
-            for i in range(3 + steps):
+            for i in range(warm + steps):
                 with torch.cuda.stream(stream):
                     flush.zero_()
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record(stream); run(); b.record(stream)
                 evs.append((a, b))
             ctx.sync(); torch.cuda.synchronize()
-            ts = sorted(a.elapsed_time(b) for a, b in evs[3:])
+            ts = sorted(a.elapsed_time(b) for a, b in evs[warm:])
             ms = sum(ts) / len(ts)
             res["fwd" if enc else "inv"] = {"ms": round(ms, 4), "min_ms": round(ts[0], 4), "gbs": round(nbytes / ms / 1e6, 1), "frac": round(nbytes / ms / 1e6 / peak, 3)}
             plan.close()
