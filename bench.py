@@ -293,7 +293,7 @@ def main():
     ctx.sync()
 
     def timed_device(nsteps, record):
-        t_enc = t_dec = t_dwt = t_t1e = t_t1d = 0.0
+        t_enc = t_dec = t_dwt = t_t1e = t_t1d = t_idwt = 0.0
         evs = []
         for _ in range(nsteps):
             eplan.encode_restore()
@@ -315,18 +315,19 @@ def main():
             for e in evs:
                 t_enc += e[0].elapsed_time(e[3]); t_dec += e[4].elapsed_time(e[7])
                 t_dwt += e[1].elapsed_time(e[2]); t_t1e += e[2].elapsed_time(e[3]); t_t1d += e[4].elapsed_time(e[5])
-        return t_enc, t_dec, t_dwt, t_t1e, t_t1d
+                t_idwt += e[5].elapsed_time(e[6])
+        return t_enc, t_dec, t_dwt, t_t1e, t_t1d, t_idwt
 
     timed_device(args.warmup, False)
     barrier()
     clocks = ClockSampler(local_rank)
     clocks.start()
     l0 = ctx.launch_count()
-    t_enc, t_dec, t_dwt, t_t1e, t_t1d = timed_device(args.steps, True)
+    t_enc, t_dec, t_dwt, t_t1e, t_t1d, t_idwt = timed_device(args.steps, True)
     launches = ctx.launch_count() - l0
     barrier()
     t_enc, t_dec = max_over_ranks(t_enc / args.steps), max_over_ranks(t_dec / args.steps)  # ms per step
-    t_dwt, t_t1e, t_t1d = t_dwt / args.steps, t_t1e / args.steps, t_t1d / args.steps
+    t_dwt, t_t1e, t_t1d, t_idwt = t_dwt / args.steps, t_t1e / args.steps, t_t1d / args.steps, t_idwt / args.steps
 
     # ---- end to end through the C ABI with host buffers (e2e) ---------------------------------------
     # Every step copies that step's input planes H2D, runs the path and reads the code-block bytes + pass tables back, then
@@ -472,9 +473,12 @@ def main():
             "note": "device-resident like `value`, but with one frame in flight per stream (wall clock incl. the restore copy of the input planes)"},
         "gpu_launches": int(launches),
         "clocks": clk,
-        "roofline": {"kernel": "dwt_fwd_kernel (all levels of one image, %d launches)" % dwt_launches, "bound": "hbm",
-                     "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
+        "roofline": {"kernel": "dwt_fwd_stream_kernel<%s> (all levels of one image, %d launches)" % ("5/3" if w["reversible"] else "9/7", dwt_launches),
+                     "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
                      "peak_source": peak_src, "algorithmic_bytes": int(dwt_bytes), "ms": round(t_dwt, 4)},
+        "roofline_inverse": {"kernel": "dwt_inv_stream_kernel<%s> (all levels of one image, %d launches)" % ("5/3" if w["reversible"] else "9/7", dwt_launches),
+                             "bound": "hbm", "achieved": round(dwt_bytes / (t_idwt * 1e-3) / 1e9, 1), "peak": peak, "unit": "GB/s",
+                             "frac": round(dwt_bytes / (t_idwt * 1e-3) / 1e9 / peak, 4), "algorithmic_bytes": int(dwt_bytes), "ms": round(t_idwt, 4)},
         "t1": {"bound": "integer issue (serial MQ coder), no tensor work", "encode_ms": round(t_t1e, 4), "decode_ms": round(t_t1d, 4),
                "encode_mdecisions_s": round(decisions / (t_t1e * 1e-3) / 1e6, 1), "decode_mdecisions_s": round(decisions / (t_t1d * 1e-3) / 1e6, 1),
                "share_of_encode": round(t_t1e / t_enc, 3), "share_of_decode": round(t_t1d / t_dec, 3), "issue": issue},
@@ -485,21 +489,27 @@ def main():
         try:
             eplan.close(); dplan.close()
             from grokimagecompression_b200 import params as P2
-            t53 = P2.image_tiles(8192, 8192, 3, 16, True, (1024, 1024), 6)
-            p53 = gb.Plan(ctx, t53, encoder=True)
-            b53, _ = dwt_algorithmic_bytes(t53)
-            evs = []
-            for i in range(args.warmup + args.steps):
-                flush_l2()
-                a, b_ = ev(), ev()
-                a.record(stream); p53.encode_run_stage(1); b_.record(stream)
-                evs.append((a, b_))
-            ctx.sync(); torch.cuda.synchronize()
-            ms53 = sum(a.elapsed_time(b_) for a, b_ in evs[args.warmup:]) / args.steps
-            line["roofline_5_3"] = {"kernel": "dwt_fwd_kernel<5/3> (5 levels, 8192x8192x3 int32, 1024x1024 tiles)", "bound": "hbm",
-                                    "achieved": round(b53 / (ms53 * 1e-3) / 1e9, 1), "peak": peak, "unit": "GB/s",
-                                    "frac": round(b53 / (ms53 * 1e-3) / 1e9 / peak, 4), "algorithmic_bytes": int(b53), "ms": round(ms53, 4)}
-            p53.close()
+            b53 = None
+            for enc in (True, False):
+                t53 = P2.image_tiles(8192, 8192, 3, 16, True, (1024, 1024), 6, encoder=enc)
+                p53 = gb.Plan(ctx, t53, encoder=enc)
+                if b53 is None:
+                    b53, _ = dwt_algorithmic_bytes(t53)
+                evs = []
+                for i in range(args.warmup + args.steps):
+                    flush_l2()
+                    a, b_ = ev(), ev()
+                    a.record(stream)
+                    p53.encode_run_stage(1) if enc else p53.decode_run_stage(1)
+                    b_.record(stream)
+                    evs.append((a, b_))
+                ctx.sync(); torch.cuda.synchronize()
+                ms53 = sum(a.elapsed_time(b_) for a, b_ in evs[args.warmup:]) / args.steps
+                line["roofline_5_3" if enc else "roofline_5_3_inverse"] = {
+                    "kernel": "dwt_%s_stream_kernel<5/3> (5 levels, 8192x8192x3 int32, 1024x1024 tiles)" % ("fwd" if enc else "inv"), "bound": "hbm",
+                    "achieved": round(b53 / (ms53 * 1e-3) / 1e9, 1), "peak": peak, "unit": "GB/s",
+                    "frac": round(b53 / (ms53 * 1e-3) / 1e9 / peak, 4), "algorithmic_bytes": int(b53), "ms": round(ms53, 4)}
+                p53.close()
         except Exception as exc:  # never let the auxiliary measurement break the bench line
             line["roofline_5_3"] = {"error": str(exc)[:200]}
     if not args.no_cpu_baseline and world == 1:

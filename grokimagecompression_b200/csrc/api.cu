@@ -11,6 +11,7 @@
 #include <new>
 #include <string>
 #include <vector>
+#include <cmath>
 
 using namespace gb;
 
@@ -63,7 +64,7 @@ struct LevelLaunch {
 	DevBuf dev, map;
 	uint32_t ctas = 0;
 	uint32_t ctas64 = 0;  // CTA count with 64-row tiles (decides tile_rows of the shared-memory kernels)
-	uint32_t items[4] = {0, 0, 0, 0}; // work items of the streaming kernels with 128 / 64 / 32 / 16 rows each
+	std::vector<std::pair<uint32_t, uint32_t>> strips; // streaming kernels: (strips across, rows incl. the parity offset) of every plane
 	int tile_rows = 64;   // > 0: shared-memory kernels; < 0: streaming kernels, -tile_rows rows per work item
 	int unroll = 2, halo_lanes = 1;
 };
@@ -312,9 +313,8 @@ int gb200_plan_create(gb200_ctx *ctx, uint32_t ntiles, const gb200_tile_params *
 	// (kept for A/B measurements).  GB200_DWT_ROWS / GB200_DWT_UNROLL / GB200_DWT_FILL override the tuning below.
 	auto env_int = [](const char *name, int dflt) { const char *e = getenv(name); return e && *e ? atoi(e) : dflt; };
 	const bool legacy = env_int("GB200_DWT_LEGACY", 0) != 0;
-	const int force_rows = env_int("GB200_DWT_ROWS", 0), unroll = env_int("GB200_DWT_UNROLL", 2), fill = env_int("GB200_DWT_FILL", 16);
+	const int force_rows = env_int("GB200_DWT_ROWS", 0), unroll = env_int("GB200_DWT_UNROLL", 1), fill = env_int("GB200_DWT_FILL", 4);
 	const int halo_lanes = env_int("GB200_DWT_HL", 1) == 2 ? 2 : 1;
-	static const uint32_t SROWS[4] = {128, 64, 32, 16};
 	uint32_t stw;
 	dwt_stream_shape(halo_lanes, &stw);
 	for (auto &tg : pl->tiles)
@@ -329,7 +329,7 @@ int gb200_plan_create(gb200_ctx *ctx, uint32_t ntiles, const gb200_tile_params *
 				LevelLaunch &L = pl->lvl[cg.p.qmfbid == 1][i];
 				L.ctas64 += ((rw + tw - 1) / tw) * ((rh + 63) / 64);
 				const uint32_t cx = cdiv2n(cg.p.x0, lvl) & 1, cy = cdiv2n(cg.p.y0, lvl) & 1;
-				for (int k = 0; k < 4; ++k) L.items[k] += ((rw + cx + stw - 1) / stw) * ((rh + cy + SROWS[k] - 1) / SROWS[k]);
+				L.strips.emplace_back((rw + cx + stw - 1) / stw, rh + cy);
 			}
 		}
 	{
@@ -344,12 +344,31 @@ int gb200_plan_create(gb200_ctx *ctx, uint32_t ntiles, const gb200_tile_params *
 					// because then the latency of one CTA is what the launch costs
 					L.tile_rows = L.ctas64 >= (uint32_t) sms * 6 ? 64 : (L.ctas64 >= (uint32_t) sms * 2 ? 32 : 16);
 				} else {
-					// the longest strips that still give every SM `fill` warps: long strips amortise the 2 * halo rows a
-					// warp reads before its first result, short ones keep a small level from running on a few SMs
+					// Rows per work item.  A launch runs in waves of `slots` resident warps, and a partly filled last wave
+					// costs as much as a full one, so the row count is chosen by a small model: waves x trips per item
+					// (rows / 2 + the warm-up trips every item spends before its first result + a fixed start-up term).
+					// Few items: the shortest strips win (latency of one warp); one wave or a few: the count that just
+					// fits; many waves: long strips (least warm-up work).
+					const int slots = sms * dwt_stream_warps_per_sm(r, pl->encoder ? 1 : 0, unroll);
+					const int warm = (r ? 2 : 4) + fill; // trips: 2 * LAG + start-up (tables, first rows), `fill` is the knob
 					int rows = 16;
-					for (int k = 0; k < 4; ++k) if (L.items[k] >= (uint32_t) (sms * fill)) { rows = (int) SROWS[k]; break; }
+					double best = 1e300;
+					for (int cand = 8; cand <= 128; cand += cand < 32 ? 2 : 4) {
+						uint64_t items = 0;
+						for (auto &sp : L.strips) items += (uint64_t) sp.first * ((sp.second + cand - 1) / cand);
+						const double w = (double) items / slots;
+						const double waves = w <= 4.0 ? std::ceil(w) : w + 0.5;
+						const double cost = waves * (cand / 2 + warm);
+						if (cost < best * 0.999) { best = cost; rows = cand; }
+					}
 					if (force_rows >= 2) rows = force_rows & ~1;
 					L.tile_rows = -rows;
+					if (env_int("GB200_DWT_VERBOSE", 0) && !L.strips.empty()) {
+						uint64_t items = 0;
+						for (auto &sp : L.strips) items += (uint64_t) sp.first * ((sp.second + rows - 1) / rows);
+						fprintf(stderr, "[gb200] dwt %s %s level launch %d: %zu planes, %d rows per item, %llu items, %d slots\n", pl->encoder ? "fwd" : "inv",
+								r ? "5/3" : "9/7", (int) (&L - &pl->lvl[r][0]), L.strips.size(), rows, (unsigned long long) items, slots);
+					}
 				}
 			}
 	}

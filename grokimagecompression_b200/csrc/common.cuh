@@ -71,6 +71,7 @@ void launch_dwt_fwd(const DwtPlane *planes_dev, const uint32_t *cta_plane_dev, u
 void launch_dwt_inv(const DwtPlane *planes_dev, const uint32_t *cta_plane_dev, uint32_t total_ctas, int reversible, int tile_rows,
 		int unroll, int halo_lanes, cudaStream_t s);
 void dwt_tile_shape(int reversible, uint32_t *tw); // valid columns per CTA
+int dwt_stream_warps_per_sm(int reversible, int forward, int unroll); // work items resident per SM (occupancy of that kernel)
 void dwt_stream_shape(int halo_lanes, uint32_t *tw); // valid columns per work item of the streaming kernels (halo_lanes 1 or 2)
 
 // t1_enc.cu / t1_dec.cu

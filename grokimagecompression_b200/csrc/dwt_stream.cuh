@@ -221,6 +221,18 @@ template<> struct VInv<false> {
 	}
 };
 
+// Programmatic dependent launch: the level launches of a transform form a chain; every kernel lets its successor start
+// at once (launch_dependents first thing), and the successor reads its tables, which no kernel writes, before it waits
+// for the predecessor's results (griddepcontrol.wait = the whole predecessor grid has finished and its writes are visible).
+// So launch latency and the start-up table reads of level l + 1 overlap the tail of level l.
+#ifdef GB_EMU
+__device__ __forceinline__ void dws_launch_dependents() {}
+__device__ __forceinline__ void dws_grid_wait() {}
+#else
+__device__ __forceinline__ void dws_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void dws_grid_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+
 // decode the work item of this warp; returns false if the warp has nothing to do
 struct DwsItem {
 	int lane, X0, Y0, c; // c: region column of the lane's first element (a low-pass column)
@@ -228,6 +240,7 @@ struct DwsItem {
 
 __device__ __forceinline__ bool dws_item(const DwtPlane *__restrict__ planes, const uint32_t *__restrict__ item_plane, uint32_t nitems,
 		int R, int hl, DwtPlane &P, DwsItem &it) {
+	dws_launch_dependents();
 	it.lane = threadIdx.x & 31;
 	uint32_t item = blockIdx.x * DWS_WARPS + (threadIdx.x >> 5);
 	if (item >= nitems) return false;
@@ -236,6 +249,7 @@ __device__ __forceinline__ bool dws_item(const DwtPlane *__restrict__ planes, co
 	it.X0 = (int) (item % P.tiles_x) * dws_tw(hl);
 	it.Y0 = (int) (item / P.tiles_x) * R;
 	it.c = it.X0 - 4 * hl - (int) P.cas_x + 4 * it.lane;
+	dws_grid_wait(); // from here on the planes are read
 	return true;
 }
 
@@ -281,9 +295,12 @@ __device__ __forceinline__ int32_t *dws_at(int32_t *p, uint32_t row, uint32_t st
 // pairs (strips in the interior of a plane whose rows are 16-byte aligned): no predicates, no fallbacks in the loop.
 // EDGE = true: the strip touches the left or right border of the region (or the plane is not aligned): every lane
 // gathers its four (reflected) columns with 4-byte copies and stores element by element under predicates.
-// ring: this warp's prefetch queue, D rows of 32 x 16 bytes in shared memory, filled by asynchronous copies D / 2 trips
-// ahead of their use.
-template<bool REV, int D, bool EDGE>
+// Rows are fetched G trips (2 G rows) ahead of their use, into one of two prefetch queues:
+// RING = true : this warp's ring of 2 G rows of 32 x 16 bytes in shared memory, filled by asynchronous copies (no
+//               registers held while the rows are in flight: the choice for the arithmetic-heavy 9/7 kernels);
+// RING = false: 2 G row registers per lane, filled by ordinary loads (nothing between DRAM and the registers: the
+//               choice for the 5/3 kernels, which are bound by memory alone).
+template<bool REV, int G, bool EDGE, bool RING>
 __device__ __forceinline__ void dws_fwd_strip(const DwtPlane &P, const DwsItem &it, int R, int hl, int4 *ring) {
 	const int rw = (int) P.rw, rh = (int) P.rh, casx = (int) P.cas_x, casy = (int) P.cas_y;
 	const int c = it.c;
@@ -292,17 +309,30 @@ __device__ __forceinline__ void dws_fwd_strip(const DwtPlane &P, const DwsItem &
 	const int32_t *s0 = P.src + (EDGE ? dws_reflect(c, rw) : c);
 	const int32_t *s1 = P.src + dws_reflect(c + 1, rw), *s2 = P.src + dws_reflect(c + 2, rw), *s3 = P.src + dws_reflect(c + 3, rw);
 	int4 *const slot0 = ring + it.lane;
+	Quad regs[RING ? 1 : 2 * G]; // RING = false: the queue (slots are compile-time constants once the trip loop is unrolled)
 	auto issue_row = [&](int y, int slot) {
 		const uint32_t gy = (uint32_t) dws_reflect(y, rh);
-		int4 *sm = slot0 + 32 * slot;
-		if (!EDGE) dws_cp16(sm, dws_at(s0, gy, sstr4));
-		else {
-			int32_t *e = reinterpret_cast<int32_t*>(sm);
-			dws_cp4(e, dws_at(s0, gy, sstr4)); dws_cp4(e + 1, dws_at(s1, gy, sstr4));
-			dws_cp4(e + 2, dws_at(s2, gy, sstr4)); dws_cp4(e + 3, dws_at(s3, gy, sstr4));
+		if (RING) {
+			int4 *sm = slot0 + 32 * slot;
+			if (!EDGE) dws_cp16(sm, dws_at(s0, gy, sstr4));
+			else {
+				int32_t *e = reinterpret_cast<int32_t*>(sm);
+				dws_cp4(e, dws_at(s0, gy, sstr4)); dws_cp4(e + 1, dws_at(s1, gy, sstr4));
+				dws_cp4(e + 2, dws_at(s2, gy, sstr4)); dws_cp4(e + 3, dws_at(s3, gy, sstr4));
+			}
+		} else {
+			Quad &q = regs[RING ? 0 : slot];
+			if (!EDGE) {
+				const int4 v = dws_ld4(dws_at(s0, gy, sstr4));
+				q.e0 = v.x; q.o0 = v.y; q.e1 = v.z; q.o1 = v.w;
+			} else {
+				q.e0 = dws_ld1(dws_at(s0, gy, sstr4)); q.o0 = dws_ld1(dws_at(s1, gy, sstr4));
+				q.e1 = dws_ld1(dws_at(s2, gy, sstr4)); q.o1 = dws_ld1(dws_at(s3, gy, sstr4));
+			}
 		}
 	};
 	auto read_row = [&](int slot) -> Quad {
+		if (!RING) return regs[RING ? 0 : slot];
 		const int4 v = slot0[32 * slot];
 		Quad q;
 		q.e0 = v.x; q.o0 = v.y; q.e1 = v.z; q.o1 = v.w;
@@ -335,8 +365,7 @@ __device__ __forceinline__ void dws_fwd_strip(const DwtPlane &P, const DwsItem &
 	if (rh == 1) { // a single row is not lifted vertically; with an odd origin it is a high-pass row (x2 for 5/3)
 		if (it.Y0 != 0) return;
 		issue_row(0, 0);
-		dws_commit();
-		dws_wait<0>();
+		if (RING) { dws_commit(); dws_wait<0>(); }
 		Quad q = read_row(0);
 		if (REV && casy) { q.e0 *= 2; q.o0 *= 2; q.e1 *= 2; q.o1 *= 2; }
 		emit1(q, 0, casy != 0);
@@ -351,43 +380,44 @@ __device__ __forceinline__ void dws_fwd_strip(const DwtPlane &P, const DwsItem &
 
 	VFwd<REV> v0, v1, v2, v3;
 	v0.init(); v1.init(); v2.init(); v3.init();
-	constexpr int G = D / 2; // trips in flight: one copy group per trip (two rows)
 	#pragma unroll
-	for (int g = 0; g < G; ++g) {
+	for (int g = 0; g < G; ++g) { // one copy group per trip (two rows), G trips in flight
 		if (g < niter) { issue_row(ys + 2 * g, 2 * g); issue_row(ys + 2 * g + 1, 2 * g + 1); }
-		dws_commit();
+		if (RING) dws_commit();
 	}
-	int slot = 0;
-	#pragma unroll 2
-	for (int j = 0; j < niter; ++j) {
-		dws_wait<G - 1>();
-		const Quad a = read_row(slot), b = read_row(slot + 1);
-		if (j + G < niter) { issue_row(ys + 2 * (j + G), slot); issue_row(ys + 2 * (j + G) + 1, slot + 1); }
-		dws_commit();
-		slot = slot + 2 == D ? 0 : slot + 2;
-		Quad lo, hi;
-		v0.feed(a.e0, b.e0, lo.e0, hi.e0);
-		v1.feed(a.o0, b.o0, lo.o0, hi.o0);
-		v2.feed(a.e1, b.e1, lo.e1, hi.e1);
-		v3.feed(a.o1, b.o1, lo.o1, hi.o1);
-		// rows before the first owned one come out of the warm-up trips and fail the range test, as do rows past the last
-		const int yl = ys + 2 * (j - LAG);
-		const bool vl = yl >= yv0 && yl < yv1, vh = yl + 1 >= yv0 && yl + 1 < yv1;
-		if (vl && vh && hlift) {
-			dws_hfwd2<REV>(lo, hi);
-			store_row(lo, (uint32_t) (yl >> 1));
-			store_row(hi, (uint32_t) (((yl + 1) >> 1) + (int) P.sh));
-		} else {
-			if (vl) emit1(lo, yl, false);
-			if (vh) emit1(hi, yl + 1, true);
+	for (int j0 = 0; j0 < niter; j0 += G) {
+		#pragma unroll
+		for (int u = 0; u < G; ++u) {
+			const int j = j0 + u;
+			if (j >= niter) break;
+			if (RING) dws_wait<G - 1>();
+			const Quad a = read_row(2 * u), b = read_row(2 * u + 1);
+			if (j + G < niter) { issue_row(ys + 2 * (j + G), 2 * u); issue_row(ys + 2 * (j + G) + 1, 2 * u + 1); }
+			if (RING) dws_commit();
+			Quad lo, hi;
+			v0.feed(a.e0, b.e0, lo.e0, hi.e0);
+			v1.feed(a.o0, b.o0, lo.o0, hi.o0);
+			v2.feed(a.e1, b.e1, lo.e1, hi.e1);
+			v3.feed(a.o1, b.o1, lo.o1, hi.o1);
+			// rows before the first owned one come out of the warm-up trips and fail the range test, as do rows past the last
+			const int yl = ys + 2 * (j - LAG);
+			const bool vl = yl >= yv0 && yl < yv1, vh = yl + 1 >= yv0 && yl + 1 < yv1;
+			if (vl && vh && hlift) {
+				dws_hfwd2<REV>(lo, hi);
+				store_row(lo, (uint32_t) (yl >> 1));
+				store_row(hi, (uint32_t) (((yl + 1) >> 1) + (int) P.sh));
+			} else {
+				if (vl) emit1(lo, yl, false);
+				if (vh) emit1(hi, yl + 1, true);
+			}
 		}
 	}
 }
 
-template<bool REV, int D>
+template<bool REV, int G, bool RING>
 __global__ void __launch_bounds__(DWS_WARPS * 32, DWS_MINB) dwt_fwd_stream_kernel(const DwtPlane *__restrict__ planes,
 		const uint32_t *__restrict__ item_plane, uint32_t nitems, int R, int hl) {
-	__shared__ int4 ring[DWS_WARPS][D][32];
+	__shared__ int4 ring[RING ? DWS_WARPS : 1][RING ? 2 * G : 1][RING ? 32 : 1];
 	DwtPlane P;
 	DwsItem it;
 	if (!dws_item(planes, item_plane, nitems, R, hl, P, it)) return;
@@ -395,9 +425,9 @@ __global__ void __launch_bounds__(DWS_WARPS * 32, DWS_MINB) dwt_fwd_stream_kerne
 	const bool lv = it.lane >= hl && it.lane <= 31 - hl;
 	const bool vld = c >= 0 && c + 3 < rw && (c & 3) == 0 && (P.src_stride & 3) == 0 && (((size_t) P.src) & 15) == 0;
 	const bool vst = (P.dst_stride & 1) == 0 && (((size_t) P.dst) & 7) == 0 && ((c >> 1) & 1) == 0 && ((P.sw + ((c + 1) >> 1)) & 1) == 0;
-	int4 *const my_ring = &ring[threadIdx.x >> 5][0][0];
-	if (__all_sync(0xffffffffu, vld && (vst || !lv))) dws_fwd_strip<REV, D, false>(P, it, R, hl, my_ring);
-	else dws_fwd_strip<REV, D, true>(P, it, R, hl, my_ring);
+	int4 *const my_ring = &ring[RING ? threadIdx.x >> 5 : 0][0][0];
+	if (__all_sync(0xffffffffu, vld && (vst || !lv))) dws_fwd_strip<REV, G, false, RING>(P, it, R, hl, my_ring);
+	else dws_fwd_strip<REV, G, true, RING>(P, it, R, hl, my_ring);
 }
 
 // =========================================================================================================
@@ -435,7 +465,7 @@ __device__ __forceinline__ void dws_hinv2(Quad &p, Quad &q) {
 // EDGE as in the forward kernel: false = every lane loads aligned pairs of all four sub-bands and every valid lane stores
 // 16 aligned bytes; true = 4-byte gathers through reflected indices, element-wise predicated stores.  Queue slot of a lane:
 // (low, low, high, high) = the two 8-byte pairs as they lie in the sub-bands.
-template<bool REV, int D, bool EDGE>
+template<bool REV, int G, bool EDGE, bool RING>
 __device__ __forceinline__ void dws_inv_strip(const DwtPlane &P, const DwsItem &it, int R, int hl, int4 *ring) {
 	const int rw = (int) P.rw, rh = (int) P.rh, casx = (int) P.cas_x, casy = (int) P.cas_y;
 	const int c = it.c;
@@ -448,18 +478,31 @@ __device__ __forceinline__ void dws_inv_strip(const DwtPlane &P, const DwsItem &
 	const int32_t *const pLH = P.band + k0, *const pLH2 = P.band + k2; // vertical high-pass rows: LH | HH
 	const int32_t *const pH = P.band + k1, *const pH2 = P.band + k3;   // HL and HH columns
 	int4 *const slot0 = ring + it.lane;
+	Quad regs[RING ? 1 : 2 * G];
 	auto issue_row = [&](int y, bool high, int slot) {
 		const uint32_t k = (uint32_t) (dws_reflect(y, rh) >> 1) + (high ? P.sh : 0u);
 		const int32_t *pl = high ? pLH : pLL, *pl2 = high ? pLH2 : pLL2;
 		const uint32_t lstr4 = high ? bstr4 : sstr4;
-		int32_t *e = reinterpret_cast<int32_t*>(slot0 + 32 * slot);
-		if (!EDGE) { dws_cp8(e, dws_at(pl, k, lstr4)); dws_cp8(e + 2, dws_at(pH, k, bstr4)); }
-		else {
-			dws_cp4(e, dws_at(pl, k, lstr4)); dws_cp4(e + 1, dws_at(pl2, k, lstr4));
-			dws_cp4(e + 2, dws_at(pH, k, bstr4)); dws_cp4(e + 3, dws_at(pH2, k, bstr4));
+		if (RING) {
+			int32_t *e = reinterpret_cast<int32_t*>(slot0 + 32 * slot);
+			if (!EDGE) { dws_cp8(e, dws_at(pl, k, lstr4)); dws_cp8(e + 2, dws_at(pH, k, bstr4)); }
+			else {
+				dws_cp4(e, dws_at(pl, k, lstr4)); dws_cp4(e + 1, dws_at(pl2, k, lstr4));
+				dws_cp4(e + 2, dws_at(pH, k, bstr4)); dws_cp4(e + 3, dws_at(pH2, k, bstr4));
+			}
+		} else {
+			Quad &q = regs[RING ? 0 : slot];
+			if (!EDGE) {
+				const int2 v = dws_ld2(dws_at(pl, k, lstr4)), w = dws_ld2(dws_at(pH, k, bstr4));
+				q.e0 = v.x; q.e1 = v.y; q.o0 = w.x; q.o1 = w.y;
+			} else {
+				q.e0 = dws_ld1(dws_at(pl, k, lstr4)); q.e1 = dws_ld1(dws_at(pl2, k, lstr4));
+				q.o0 = dws_ld1(dws_at(pH, k, bstr4)); q.o1 = dws_ld1(dws_at(pH2, k, bstr4));
+			}
 		}
 	};
 	auto read_row = [&](int slot) -> Quad {
+		if (!RING) return regs[RING ? 0 : slot];
 		const int4 v = slot0[32 * slot];
 		Quad q;
 		q.e0 = v.x; q.e1 = v.y; q.o0 = v.z; q.o1 = v.w;
@@ -490,8 +533,7 @@ __device__ __forceinline__ void dws_inv_strip(const DwtPlane &P, const DwsItem &
 	if (rh == 1) { // a single row: low-pass (LL | HL) with an even origin, high-pass with an odd one; no vertical step
 		if (it.Y0 != 0) return;
 		issue_row(0, casy != 0, 0);
-		dws_commit();
-		dws_wait<0>();
+		if (RING) { dws_commit(); dws_wait<0>(); }
 		Quad q = read_row(0);
 		hsyn1(q);
 		if (REV && casy) { q.e0 /= 2; q.o0 /= 2; q.e1 /= 2; q.o1 /= 2; }
@@ -508,37 +550,38 @@ __device__ __forceinline__ void dws_inv_strip(const DwtPlane &P, const DwsItem &
 	VInv<REV> v0, v1, v2, v3;
 	v0.init(); v1.init(); v2.init(); v3.init();
 	// rows ys + 2 j are vertical low-pass rows, ys + 2 j + 1 high-pass ones (reflection keeps the parity)
-	constexpr int G = D / 2;
 	#pragma unroll
 	for (int g = 0; g < G; ++g) {
 		if (g < niter) { issue_row(ys + 2 * g, false, 2 * g); issue_row(ys + 2 * g + 1, true, 2 * g + 1); }
-		dws_commit();
+		if (RING) dws_commit();
 	}
-	int slot = 0;
-	#pragma unroll 2
-	for (int j = 0; j < niter; ++j) {
-		dws_wait<G - 1>();
-		Quad a = read_row(slot), b = read_row(slot + 1);
-		if (j + G < niter) { issue_row(ys + 2 * (j + G), false, slot); issue_row(ys + 2 * (j + G) + 1, true, slot + 1); }
-		dws_commit();
-		slot = slot + 2 == D ? 0 : slot + 2;
-		if (hlift) dws_hinv2<REV>(a, b);
-		else { hsyn1(a); hsyn1(b); }
-		Quad r0, r1;
-		v0.feed(a.e0, b.e0, r0.e0, r1.e0);
-		v1.feed(a.o0, b.o0, r0.o0, r1.o0);
-		v2.feed(a.e1, b.e1, r0.e1, r1.e1);
-		v3.feed(a.o1, b.o1, r0.o1, r1.o1);
-		const int yl = ys + 2 * (j - LAG);
-		if (yl >= yv0 && yl < yv1) store_row(r0, yl);
-		if (yl + 1 >= yv0 && yl + 1 < yv1) store_row(r1, yl + 1);
+	for (int j0 = 0; j0 < niter; j0 += G) {
+		#pragma unroll
+		for (int u = 0; u < G; ++u) {
+			const int j = j0 + u;
+			if (j >= niter) break;
+			if (RING) dws_wait<G - 1>();
+			Quad a = read_row(2 * u), b = read_row(2 * u + 1);
+			if (j + G < niter) { issue_row(ys + 2 * (j + G), false, 2 * u); issue_row(ys + 2 * (j + G) + 1, true, 2 * u + 1); }
+			if (RING) dws_commit();
+			if (hlift) dws_hinv2<REV>(a, b);
+			else { hsyn1(a); hsyn1(b); }
+			Quad r0, r1;
+			v0.feed(a.e0, b.e0, r0.e0, r1.e0);
+			v1.feed(a.o0, b.o0, r0.o0, r1.o0);
+			v2.feed(a.e1, b.e1, r0.e1, r1.e1);
+			v3.feed(a.o1, b.o1, r0.o1, r1.o1);
+			const int yl = ys + 2 * (j - LAG);
+			if (yl >= yv0 && yl < yv1) store_row(r0, yl);
+			if (yl + 1 >= yv0 && yl + 1 < yv1) store_row(r1, yl + 1);
+		}
 	}
 }
 
-template<bool REV, int D>
+template<bool REV, int G, bool RING>
 __global__ void __launch_bounds__(DWS_WARPS * 32, DWS_MINB) dwt_inv_stream_kernel(const DwtPlane *__restrict__ planes,
 		const uint32_t *__restrict__ item_plane, uint32_t nitems, int R, int hl) {
-	__shared__ int4 ring[DWS_WARPS][D][32];
+	__shared__ int4 ring[RING ? DWS_WARPS : 1][RING ? 2 * G : 1][RING ? 32 : 1];
 	DwtPlane P;
 	DwsItem it;
 	if (!dws_item(planes, item_plane, nitems, R, hl, P, it)) return;
@@ -546,9 +589,9 @@ __global__ void __launch_bounds__(DWS_WARPS * 32, DWS_MINB) dwt_inv_stream_kerne
 	const bool inside = c >= 0 && c + 3 < rw && (c & 3) == 0; // then the low-pass index c / 2 is even
 	const bool vld = inside && (P.sw & 1) == 0 && ((P.src_stride | P.band_stride) & 1) == 0 && ((((size_t) P.src) | ((size_t) P.band)) & 7) == 0;
 	const bool vst = (P.dst_stride & 3) == 0 && (((size_t) P.dst) & 15) == 0;
-	int4 *const my_ring = &ring[threadIdx.x >> 5][0][0];
-	if (__all_sync(0xffffffffu, vld && vst)) dws_inv_strip<REV, D, false>(P, it, R, hl, my_ring);
-	else dws_inv_strip<REV, D, true>(P, it, R, hl, my_ring);
+	int4 *const my_ring = &ring[RING ? threadIdx.x >> 5 : 0][0][0];
+	if (__all_sync(0xffffffffu, vld && vst)) dws_inv_strip<REV, G, false, RING>(P, it, R, hl, my_ring);
+	else dws_inv_strip<REV, G, true, RING>(P, it, R, hl, my_ring);
 }
 
 } // namespace gb

@@ -95,7 +95,7 @@ static void launch(K kernel, const DwtPlane *planes, const uint32_t *map, uint32
 static uint32_t cdiv2n(uint32_t a, uint32_t n) { return (uint32_t) (((uint64_t) a + (1ull << n) - 1) >> n); }
 
 // the plan's table for one level of one plane (csrc/api.cu)
-static int g_hl = 1;
+static int g_hl = 1, g_ring = 1;
 static void one_level(DwtPlane d, bool fwd, int rev, int R) {
 	const int hl = g_hl;
 	d.tiles_x = (d.rw + d.cas_x + gb::dws_tw(hl) - 1) / gb::dws_tw(hl);
@@ -105,11 +105,11 @@ static void one_level(DwtPlane d, bool fwd, int rev, int R) {
 	const uint32_t n = d.tiles_x * d.tiles_y;
 	std::vector<uint32_t> map(n, 0);
 	if (fwd) {
-		if (rev) launch(gb::dwt_fwd_stream_kernel<true, 8>, &d, map.data(), n, R, hl);
-		else launch(gb::dwt_fwd_stream_kernel<false, 16>, &d, map.data(), n, R, hl);
+		if (rev) { if (g_ring) launch(gb::dwt_fwd_stream_kernel<true, 4, true>, &d, map.data(), n, R, hl); else launch(gb::dwt_fwd_stream_kernel<true, 2, false>, &d, map.data(), n, R, hl); }
+		else { if (g_ring) launch(gb::dwt_fwd_stream_kernel<false, 8, true>, &d, map.data(), n, R, hl); else launch(gb::dwt_fwd_stream_kernel<false, 3, false>, &d, map.data(), n, R, hl); }
 	} else {
-		if (rev) launch(gb::dwt_inv_stream_kernel<true, 16>, &d, map.data(), n, R, hl);
-		else launch(gb::dwt_inv_stream_kernel<false, 8>, &d, map.data(), n, R, hl);
+		if (rev) { if (g_ring) launch(gb::dwt_inv_stream_kernel<true, 8, true>, &d, map.data(), n, R, hl); else launch(gb::dwt_inv_stream_kernel<true, 4, false>, &d, map.data(), n, R, hl); }
+		else { if (g_ring) launch(gb::dwt_inv_stream_kernel<false, 4, true>, &d, map.data(), n, R, hl); else launch(gb::dwt_inv_stream_kernel<false, 2, false>, &d, map.data(), n, R, hl); }
 	}
 }
 
@@ -198,8 +198,9 @@ int main(int argc, char **argv) {
 	int fails = 0, cases = 0;
 	for (int rev = 1; rev >= 0; --rev)
 		for (const Geom &g : geoms)
-			for (int R : {16, 64}) {
+			for (int R : {10, 16, 64}) {
 				g_hl = R == 16 ? 1 : 2;
+				g_ring = R != 16;
 				fails += check_fwd(g, rev, R, rng); ++cases;
 				std::vector<uint32_t> nds = {g.nr, std::max(1u, g.nr - 1), g.nr > 3 ? g.nr - 3 : 1u, 1u};
 				std::sort(nds.begin(), nds.end());

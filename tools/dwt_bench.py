@@ -44,7 +44,7 @@ def main():
     print(f"workload {name}: {nbytes / 1e6:.1f} MB algorithmic per direction, {launches} level launches, peak {peak} GB/s")
     out = []
     for v in variants:
-        for k in ("GB200_DWT_LEGACY", "GB200_DWT_ROWS", "GB200_DWT_UNROLL", "GB200_DWT_FILL", "GB200_DWT_HL", "GB200_DWT_ONLY"):
+        for k in ("GB200_DWT_LEGACY", "GB200_DWT_ROWS", "GB200_DWT_UNROLL", "GB200_DWT_FILL", "GB200_DWT_HL", "GB200_DWT_ONLY", "GB200_DWT_RING"):
             os.environ.pop(k, None)
         if v == "legacy":
             os.environ["GB200_DWT_LEGACY"] = "1"

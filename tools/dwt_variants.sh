@@ -1,6 +1,7 @@
-for v in "" _m4 _m5 _m6 _m8 _w1m16; do
-  export GB200_LIB=$PWD/grokimagecompression_b200/libgrok_b200$v.so
-  echo "== variant '$v'"
-  python tools/dwt_bench.py c2 10 rows=0,unroll=2 rows=0,unroll=1 rows=32,unroll=1 2>&1 | grep variant | cut -c1-260
-  python tools/dwt_bench.py c3 5 rows=0,unroll=2 rows=0,unroll=1 2>&1 | grep variant | cut -c1-260
+# usage: tools/dwt_variants.sh "<suffixes>" <workload> <steps> <variant args...>   (A/B of library builds made by tools/build_variant.sh)
+sfx=$1; shift
+for v in $sfx; do
+  if [ "$v" == "base" ]; then export GB200_LIB=$PWD/grokimagecompression_b200/libgrok_b200.so; else export GB200_LIB=$PWD/grokimagecompression_b200/libgrok_b200_$v.so; fi
+  echo "== build '$v'"
+  python tools/dwt_bench.py "$@" 2>&1 | grep variant | cut -c1-230
 done
