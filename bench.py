@@ -448,12 +448,12 @@ def main():
         try:
             ti = json.load(open(ip))
             sms = torch.cuda.get_device_properties(dev).multi_processor_count
-            peak = sms * 4 * (clk.get("sm_mhz") or 1965.0) * 1e6  # warp instructions per second
-            issue = {"peak_warp_inst_per_s": peak, "source": ti.get("source"),
+            issue_peak = sms * 4 * (clk.get("sm_mhz") or 1965.0) * 1e6  # warp instructions per second
+            issue = {"peak_warp_inst_per_s": issue_peak, "source": ti.get("source"),
                      "encode": {"warp_inst_per_decision": ti["model"] + ti["mq"],
-                                "issue_frac": round((ti["model"] + ti["mq"]) * decisions / (t_t1e * 1e-3) / peak, 4)},
+                                "issue_frac": round((ti["model"] + ti["mq"]) * decisions / (t_t1e * 1e-3) / issue_peak, 4)},
                      "decode": {"warp_inst_per_decision": ti["decode"],
-                                "issue_frac": round(ti["decode"] * decisions / (t_t1d * 1e-3) / peak, 4)}}
+                                "issue_frac": round(ti["decode"] * decisions / (t_t1d * 1e-3) / issue_peak, 4)}}
         except Exception:
             issue = None
     line = {

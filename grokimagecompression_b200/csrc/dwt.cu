@@ -6,10 +6,15 @@
 // inverse 5/3  dwt.cpp:724-858, 256-363, 661-718             (int32, exact)
 // inverse 9/7  dwt.cpp:1544-1738, 1413-1537, constants 172-178 (fp32, multiply-then-add, no FMA)
 //
-// HBM-bound by design: one read and one write of the level's region (8 B/sample algorithmic), and
-// few enough instructions per sample that issue does not get in the way.  A CTA of 128 threads owns
-// a tile of the interleaved (spatial) domain, 128 columns wide INCLUDING the halo of 2 (5/3) or
-// 4 (9/7) samples each side, 64 rows high plus halo.  Lifting runs in REGISTERS, fully unrolled:
+// Two generations live here.  The product path is the STREAMING kernels of dwt_stream.cuh (one warp per strip, vertical
+// lifting recurrences in registers, horizontal lifting across lanes, no shared memory, no barrier); this file holds
+// their launch code.  The FIRST generation below (a CTA stages a 128-column tile in shared memory, thread = column,
+// then thread = half a row) is kept behind GB200_DWT_LEGACY=1 as the A/B baseline of tools/dwt_bench.py:
+// B200, configs[1] planes 9/7: 0.135 -> 0.116 ms forward, 0.367 -> 0.094 ms inverse; configs[2] planes 5/3: 0.467 -> 0.42 ms
+// forward (78 % of the measured HBM copy peak), 1.90 -> 0.40 ms inverse (82 %).
+//
+// First generation: a CTA of 128 threads owns a tile of the interleaved (spatial) domain, 128 columns wide INCLUDING
+// the halo of 2 (5/3) or 4 (9/7) samples each side, 64 rows high plus halo.  Lifting runs in REGISTERS, fully unrolled:
 //   forward: thread = column; it loads its 64+2H samples straight from global memory (every load of
 //            the warp is one coalesced row segment, all loads in flight at once), lifts vertically,
 //            parks the 64 valid rows in shared memory; then thread = half a row lifts horizontally

@@ -1,4 +1,4 @@
-// K2 / K3, second generation: streaming wavelet kernels, one WARP per work item, no shared memory.
+// K2 / K3, second generation: streaming wavelet kernels, one WARP per work item, no barrier.
 //
 // forward 5/3  WaveletForward.h:40-161 + dwt53.cpp:150-169   (int32, exact)
 // forward 9/7  WaveletForward.h:40-161 + dwt97.cpp:90-123    (int32 13-bit fixed point, exact)
@@ -6,24 +6,26 @@
 // inverse 9/7  dwt.cpp:1544-1738, 1413-1537, constants 172-178 (fp32, multiply-then-add, no FMA)
 //
 // A work item is a strip of the level's region: 128 columns (4 per lane; the outer lanes are the halo,
-// 120 valid columns) by R rows.  The warp walks down the strip two rows per trip:
+// 120 valid columns) by R rows (R chosen per launch by the plan, csrc/api.cu).  The warp walks down the strip two rows
+// per trip:
 //   forward: every lane loads its four columns of a low-pass and a high-pass row (one 16-byte load each,
 //            the warp reads 512 contiguous bytes per row), advances the vertical lifting recurrences that it
 //            keeps in registers (5 values per column for 9/7, 3 for 5/3), and for the two rows that
 //            become final runs the horizontal lifting ACROSS LANES: a lane holds (low, high, low, high), the
-//            neighbour's value arrives by one shuffle per lifting step.  The four sub-band rows leave as
-//            8-byte stores, 240 contiguous bytes per warp and sub-band.
+//            neighbour's value arrives by one shuffle per lifting step, two rows per shuffle round.  The four
+//            sub-band rows leave as 8-byte stores, 240 contiguous bytes per warp and sub-band.
 //   inverse: the mirror image: sub-band rows in (8-byte loads), horizontal synthesis across lanes, vertical
 //            synthesis recurrences in registers, 16-byte stores of finished rows.
 // The vertical recurrences are the same arithmetic as lifting a window with a halo of 4 (9/7) / 2 (5/3)
 // rows: a result row depends on source rows at distance <= halo, so a warp starts 2*LAG trips early and the
 // first rows it emits are already exact.  Borders use whole-sample symmetric reflection of the source
 // index, which reproduces the reference's clamped-neighbour code (see the note in dwt.cu); lines of length
-// 1 are not lifted (dwt53.cpp:160, dwt.cpp:344-349, 1482-1490).  Rows are prefetched U trips ahead in
-// registers; with no barrier and no shared memory every warp of the SM overlaps its loads with the others'
-// arithmetic.
+// 1 are not lifted (dwt53.cpp:160, dwt.cpp:344-349, 1482-1490).  Rows are fetched G trips ahead, into registers
+// (default) or into a per-warp ring in shared memory filled by cp.async; with no barrier every warp of the SM
+// overlaps its loads with the others' arithmetic.  The level launches of a transform are chained by programmatic
+// dependent launch, so the start-up of level l + 1 overlaps the tail of level l.
 //
-// This header is also compiled for the CPU by tests/dwt_emu (GB_EMU: one OS thread per lane), which checks
+// This header is also compiled for the CPU by tests/dwt_emu.cpp (GB_EMU: one OS thread per lane), which checks
 // the kernels against the oracle without a GPU.
 #pragma once
 #include <type_traits>

@@ -41,6 +41,7 @@
 #include <cstdio>
 #include <deque>
 #include <dirent.h>
+#include <dlfcn.h>
 #include <mutex>
 #include <thread>
 #include <cstdlib>
@@ -267,6 +268,12 @@ extern "C" PLUGIN_API grk::minpf_exit_func minpf_post_load_plugin(const char *, 
 	rp.createFunc = plugin_create;
 	rp.destroyFunc = plugin_destroy;
 	if (!services || services->registerObject("GrokB200", &rp) < 0) return nullptr;
+	/* Pin this library (and libgrok_b200.so with the CUDA runtime linked into it) for the life of the process: the host
+	 * dlclose()s the plugin in grk_plugin_cleanup (minpf_plugin_manager.cpp), and a CUDA runtime that is unloaded and loaded
+	 * again while worker threads of the first instance have used it does not survive that (seen as a SIGSEGV in the batch
+	 * decode worker of a second load / cleanup cycle).  RTLD_NODELETE makes the later dlclose a reference drop only. */
+	Dl_info self;
+	if (dladdr((void*) &grok_b200_plugin_exit, &self) && self.dli_fname) dlopen(self.dli_fname, RTLD_NOW | RTLD_NODELETE);
 	return grok_b200_plugin_exit;
 }
 

@@ -29,6 +29,8 @@
 #include <new>
 #include <vector>
 #include <unistd.h>
+#include <execinfo.h>
+#include <signal.h>
 
 using namespace grk;
 
@@ -551,12 +553,22 @@ int32_t ref_plugin_batch_decode(const char *plugin_dir, const char *in_dir, uint
 	grk_set_info_handler(quiet_cb, nullptr);
 	grk_set_warning_handler(quiet_cb, nullptr);
 	grk_set_error_handler(quiet_cb, nullptr);
+	const bool trace = getenv("GRK_REF_TRACE") != nullptr;
+	if (trace) signal(SIGSEGV, [](int) { /* test aid: where did it crash (resolve with addr2line on the same .so files) */
+		void *frames[48];
+		const int n = backtrace(frames, 48);
+		backtrace_symbols_fd(frames, n, 2);
+		_exit(139);
+	});
+#define REF_TRACE(msg) do { if (trace) { fprintf(stderr, "[ref_driver] batch decode: %s\n", msg); fflush(stderr); } } while (0)
 	grk_plugin_load_info li;
 	li.plugin_path = plugin_dir;
+	REF_TRACE("load");
 	if (!grk_plugin_load(li)) return -1;
 	grk_plugin_init_info ii;
 	ii.deviceId = 0;
 	ii.verbose = true;
+	REF_TRACE("init");
 	if (!grk_plugin_init(ii)) { grk_plugin_cleanup(); return -1; }
 	grk_decompress_parameters param;
 	memset(&param, 0, sizeof(param));
@@ -566,12 +578,19 @@ int32_t ref_plugin_batch_decode(const char *plugin_dir, const char *in_dir, uint
 	param.cod_format = GRK_PXM_FMT;
 	g_dec_from_files = true;
 	g_dec_batch_out = out; g_dec_cap = plane_capacity; g_dec_dims = dims; g_dec_batch_max = max_frames; g_dec_stored = 0;
+	REF_TRACE("init_batch_decode");
 	int32_t rc = grk_plugin_init_batch_decode(in_dir, in_dir, &param, plugin_dec_cb);
 	if (rc) { g_dec_from_files = false; grk_plugin_cleanup(); return -2; }
+	REF_TRACE("batch_decode");
 	grk_plugin_batch_decode(); /* (the CLI only gets here when the init call failed; the plugin tolerates both orders) */
+	REF_TRACE("poll");
 	while (!grk_plugin_is_batch_complete()) usleep(1000);
+	REF_TRACE("stop");
 	grk_plugin_stop_batch_decode();
+	REF_TRACE("cleanup");
 	grk_plugin_cleanup();
+	REF_TRACE("done");
+#undef REF_TRACE
 	g_dec_from_files = false;
 	return g_dec_stored;
 }

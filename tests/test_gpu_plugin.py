@@ -118,6 +118,7 @@ import os, sys
 sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.dirname(sys.argv[1]))
 import numpy as np, _libs
 from grokimagecompression_b200.synth import synthetic_planes
+os.environ["GRK_REF_TRACE"] = "1"  # step markers on stderr (shown by pytest only when the runner fails)
 d = sys.argv[2]
 specs = [(320, 240, 3, 8, True, ()), (200, 150, 1, 12, False, (10,)), (256, 256, 3, 8, False, (20, 5)), (130, 90, 3, 16, True, ()),
          (320, 240, 3, 8, True, ())]
@@ -142,5 +143,5 @@ print("batch decode ok", len(specs))
 def test_plugin_batch_decode_walks_the_directory(tmp_path):
     """plugin_init_batch_decode / plugin_batch_decode / plugin_stop_batch_decode: every codestream of a directory (mixed
     geometry, precision and wavelet) is decoded on the device and handed to the host's callback; pixels equal the pure reference's"""
-    out = subprocess.check_output([sys.executable, "-c", BATCH_DEC_RUNNER, HERE, str(tmp_path)], timeout=600, text=True)
+    out = subprocess.check_output([sys.executable, "-X", "faulthandler", "-c", BATCH_DEC_RUNNER, HERE, str(tmp_path)], timeout=600, text=True)
     assert "batch decode ok 5" in out
