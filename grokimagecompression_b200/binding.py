@@ -60,7 +60,7 @@ SYMBOLS = [
     "gb200_plan_create", "gb200_plan_destroy", "gb200_plan_num_blocks", "gb200_plan_num_pass_slots",
     "gb200_plan_num_samples", "gb200_plan_blocks", "gb200_plan_data_capacity",
     "gb200_encode_tiles", "gb200_decode_tiles", "gb200_encode_upload", "gb200_encode_run", "gb200_encode_download",
-    "gb200_decode_upload", "gb200_decode_run", "gb200_decode_download", "gb200_sync",
+    "gb200_decode_upload", "gb200_decode_run", "gb200_decode_download", "gb200_sync", "gb200_encode_slopes",
     "gb200_encode_stash", "gb200_encode_restore",
     "gb200_encode_run_stage", "gb200_decode_run_stage", "gb200_encode_get_coefficients",
     "gb200_decode_set_coefficients", "gb200_decode_set_segments", "gb200_t1_decode_blocks_segs",
@@ -105,6 +105,7 @@ def lib():
     L.gb200_encode_upload.argtypes = [vp, C.POINTER(vp)]
     L.gb200_encode_run.argtypes = [vp]
     L.gb200_encode_download.argtypes = [vp, vp, vp, vp, vp, u64, C.POINTER(u64)]
+    L.gb200_encode_slopes.argtypes = [vp, vp]
     L.gb200_decode_upload.argtypes = [vp, vp, vp, u64]
     L.gb200_decode_run.argtypes = [vp]
     L.gb200_decode_download.argtypes = [vp, C.POINTER(vp)]
@@ -318,6 +319,13 @@ class Plan:
         dl = C.c_uint64()
         check(lib().gb200_encode_download(self._h, _ptr(res), _ptr(rates), _ptr(dists), _ptr(data), data.size, C.byref(dl)))
         return res, rates, dists, data[:dl.value]
+
+    def encode_slopes(self):
+        """feasible truncation points of the last encode run: uint16 ln(slope) in 8.8 fixed point per pass slot, 0 = none
+        (RateControl::convexHull on the device)"""
+        out = np.zeros(max(self.num_pass_slots, 1), np.uint16)
+        check(lib().gb200_encode_slopes(self._h, _ptr(out)))
+        return out[:self.num_pass_slots]
 
     def coefficients(self, tileno, compno):
         idx = self._plane_index(tileno, compno)

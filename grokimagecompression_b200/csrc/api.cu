@@ -88,6 +88,7 @@ struct gb200_plan {
 	std::vector<EncBlock> encblocks;
 	std::vector<DecBlock> decblocks;
 	DevBuf d_blocks, d_results, d_rates, d_dists, d_scratch, d_data, d_inputs, d_symbols, d_seg_start, d_segs;
+	DevBuf d_slopes, d_slope_cache; // allocated by the first gb200_encode_slopes
 	bool have_segs = false;
 	uint64_t d_data_len = 0;
 	uint32_t max_bw = 1, max_bh = 1; // largest code block of the table
@@ -227,6 +228,7 @@ void gb200_plan_destroy(gb200_plan *pl) {
 	for (auto &b : pl->stash) b.release();
 	for (int r = 0; r < 2; ++r) for (auto &l : pl->lvl[r]) { l.dev.release(); l.map.release(); }
 	pl->d_blocks.release(); pl->d_results.release(); pl->d_rates.release(); pl->d_dists.release();
+	pl->d_slopes.release(); pl->d_slope_cache.release();
 	pl->d_scratch.release(); pl->d_data.release(); pl->d_inputs.release(); pl->d_symbols.release(); pl->d_seg_start.release(); pl->d_segs.release();
 	delete pl;
 }
@@ -674,6 +676,24 @@ int gb200_encode_download(gb200_plan *pl, gb200_cblk_enc *blocks, uint32_t *rate
 		CK(cudaMemcpyAsync(data, pl->d_data.p, total, cudaMemcpyDeviceToHost, s));
 		CK(cudaStreamSynchronize(s));
 	}
+	return GB200_OK;
+}
+
+// PCRD preparation: RateControl::convexHull for every block of the last encode run, on the device
+int gb200_encode_slopes(gb200_plan *pl, uint16_t *slopes) {
+	if (!pl || !pl->encoder || !slopes) FAIL(GB200_ERR_PARAM, "gb200_encode_slopes: bad arguments");
+	CK(cudaSetDevice(pl->ctx->device));
+	cudaStream_t s = pl->ctx->stream;
+	const uint64_t slots = std::max<uint64_t>(pl->pass_slots, 1);
+	if (!pl->d_slopes.p && (pl->d_slopes.alloc(slots * sizeof(uint16_t)) || pl->d_slope_cache.alloc(slots * sizeof(double))))
+		FAIL(GB200_ERR_NOMEM, "cudaMalloc failed for the slope tables");
+	CK(cudaMemsetAsync(pl->d_slopes.p, 0, slots * sizeof(uint16_t), s));
+	launch_rd_slopes((const EncBlock*) pl->d_blocks.p, (const EncResult*) pl->d_results.p, (uint32_t) pl->blocks.size(),
+			(const uint32_t*) pl->d_rates.p, (const double*) pl->d_dists.p, (uint16_t*) pl->d_slopes.p, (double*) pl->d_slope_cache.p, s);
+	int rc = launch_check(pl->ctx, 1);
+	if (rc) return rc;
+	if (pl->pass_slots) CK(cudaMemcpyAsync(slopes, pl->d_slopes.p, pl->pass_slots * sizeof(uint16_t), cudaMemcpyDeviceToHost, s));
+	CK(cudaStreamSynchronize(s));
 	return GB200_OK;
 }
 

@@ -81,6 +81,9 @@ void launch_t1_encode(const EncBlock *blocks, uint32_t nblocks, int rate_control
 		EncResult *results, uint32_t *rates, double *dists, cudaStream_t s);
 void launch_t1_gather(const EncBlock *blocks, EncResult *results, uint32_t nblocks, const uint8_t *scratch,
 		uint8_t *data, cudaStream_t s);
+// rd.cu : feasible truncation points and 8.8 log slopes of every block (RateControl.cpp:31-168); cache: one double per pass slot
+void launch_rd_slopes(const EncBlock *blocks, const EncResult *results, uint32_t nblocks, const uint32_t *rates, const double *dists,
+		uint16_t *slopes, double *cache, cudaStream_t s);
 // three launches (clear, decode, de-quantise); max_w / max_h: largest block of the table; `data` must stay
 // readable for T1_DEC_DATA_SLACK bytes past the last segment.  Returns non-zero if a block cannot be placed.
 constexpr int T1_DEC_LAUNCHES = 3;

@@ -152,6 +152,12 @@ GB200_API int gb200_encode_upload(gb200_plan *plan, const int32_t *const *planes
 GB200_API int gb200_encode_run(gb200_plan *plan);      /* asynchronous on gb200_stream() */
 GB200_API int gb200_encode_download(gb200_plan *plan, gb200_cblk_enc *blocks, uint32_t *rates, double *dists, uint8_t *data,
 		uint64_t data_capacity, uint64_t *data_len);
+/* PCRD preparation on the device, replaces the per-block RateControl::convexHull calls of the rate allocator
+ * (t2/RateControl.cpp:31-118, called from TileProcessor.cpp:409): for every code block of the last encode run, which
+ * passes are feasible truncation points and their distortion-rate slopes as ln(slope) in 8.8 fixed point (slopeToLog,
+ * RateControl.cpp:159-168); 0 = not a truncation point.  slopes has gb200_plan_num_pass_slots() entries, pass p of block i at
+ * gb200_cblk_info::pass_offset + p (= grk_tcd_pass::slope).  Needs rates and distortions, i.e. a plan with rate control on. */
+GB200_API int gb200_encode_slopes(gb200_plan *plan, uint16_t *slopes);
 GB200_API int gb200_decode_upload(gb200_plan *plan, const gb200_cblk_dec *blocks, const uint8_t *data, uint64_t data_len);
 /* codeword segments for the next gb200_decode_upload / gb200_decode_tiles: block i owns segs[seg_start[i] .. seg_start[i+1])
  * (seg_start has num_blocks + 1 entries); gb200_cblk_dec::numpasses / data_len stay the totals.  NULL, NULL = every

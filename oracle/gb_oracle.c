@@ -1180,3 +1180,45 @@ GBO_API int gbo_enumerate_blocks(uint32_t tx0, uint32_t ty0, uint32_t tx1, uint3
 	}
 	return n;
 }
+
+/* ---- PCRD preparation: feasible truncation points of one code block -----------------------------------
+ * RateControl.cpp:31-118 (convexHull) and :159-168 (slopeToLog).  Walks the passes of a block; a pass is a
+ * feasible truncation point if the distortion-rate slope towards every earlier feasible point is positive,
+ * finite and strictly decreasing; its slope is stored as ln(slope) in 8.8 fixed point (0 = not feasible).
+ * len[p]: bytes the pass adds; dist[p]: CUMULATIVE distortion decrease up to and including pass p. */
+static uint16_t slope_to_log(double slope) {
+	const double cutoff = pow(2, 64), scale = 256 / log(2), shift = 1 << 16;
+	double v;
+	if (slope > cutoff) slope = cutoff;
+	v = log(slope) * scale - log(cutoff) * scale + shift;
+	if (v < 1) v = 1;
+	if (v > 0xFFFF) v = 0xFFFF;
+	return (uint16_t) v;
+}
+
+GBO_API void gbo_rd_convex_hull(const uint32_t *len, const double *dist, uint32_t numpasses, uint16_t *slope) {
+	double *cache = (double*) malloc(sizeof(double) * (numpasses ? numpasses : 1));
+	uint32_t p;
+	for (p = 0; p < numpasses; ++p) {
+		double dd = 0, dr = 0;
+		int q = (int) p; /* the intermediate point, walking down from p */
+		slope[p] = 0;
+		for (;;) {
+			dr += len[q];
+			dd += q == 0 ? dist[q] : dist[q] - dist[q - 1];
+			if (dd <= 0) { slope[p] = 0; break; } /* Corollary 8.3: every intermediate slope must be positive */
+			--q;
+			if (q == -1) { cache[p] = dd / dr; slope[p] = slope_to_log(cache[p]); break; }
+			if (slope[q] == 0) continue; /* rejected earlier */
+			if (dr == 0) slope[q] = 0; /* the slope must be finite */
+			else if (cache[q] * dr <= dd) slope[q] = 0; /* ... and strictly decreasing */
+			else {
+				cache[p] = dd / dr;
+				slope[p] = slope_to_log(cache[p]);
+				if (slope[p] >= slope[q]) slope[q] = 0; /* the coarser log domain may break monotonicity: drop the earlier point */
+				break;
+			}
+		}
+	}
+	free(cache);
+}

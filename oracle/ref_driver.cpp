@@ -24,6 +24,7 @@
 #include "dwt53.h"
 #include "dwt97.h"
 #include "HTParams.h"
+#include "RateControl.h"
 #include <cstring>
 #include <cstdlib>
 #include <new>
@@ -270,6 +271,14 @@ static void quiet_cb(const char *, void *) {}
 
 /* code-block style byte (grk_compress -M) applied by the following ref_encode_image / ref_plugin_encode_file calls */
 static uint32_t g_cblk_sty = 0;
+/* RateControl::convexHull (t2/RateControl.cpp:31) on one block's pass table: len / cumulative distortion in, log slopes out */
+void ref_rd_convex_hull(const uint32_t *len, const double *dist, uint32_t numpasses, uint16_t *slope) {
+	std::vector<grk_tcd_pass> passes(numpasses ? numpasses : 1);
+	for (uint32_t p = 0; p < numpasses; ++p) { passes[p].len = len[p]; passes[p].distortiondec = dist[p]; }
+	RateControl::convexHull(passes.data(), numpasses);
+	for (uint32_t p = 0; p < numpasses; ++p) slope[p] = passes[p].slope;
+}
+
 void ref_set_cblk_sty(uint32_t sty) { g_cblk_sty = sty; }
 /* max-shift region of interest (grk_compress -ROI c=compno,U=shift) for the following ref_encode_image calls; compno < 0 = none */
 static int32_t g_roi_compno = -1;

@@ -18,6 +18,7 @@ u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
 u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
 f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
 i16p = np.ctypeslib.ndpointer(np.int16, flags="C_CONTIGUOUS")
+u16p = np.ctypeslib.ndpointer(np.uint16, flags="C_CONTIGUOUS")
 
 _oracle = None
 _ref = None
@@ -61,6 +62,8 @@ def oracle():
     L.gbo_t1_encode_block.argtypes = [i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p,
                                       C.POINTER(C.c_uint32), u32p, f64p, C.POINTER(C.c_uint64)]
     L.gbo_t1_decode_block.argtypes = [u8p, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i32p]
+    L.gbo_rd_convex_hull.argtypes = [u32p, f64p, C.c_uint32, u16p]
+    L.gbo_rd_convex_hull.restype = None
     L.gbo_t1_encode_block_sty.argtypes = [i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p,
                                           C.POINTER(C.c_uint32), u32p, f64p, u8p, C.POINTER(C.c_uint64)]
     L.gbo_t1_decode_block_segs.argtypes = [u8p, u32p, u32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i32p]
@@ -94,6 +97,8 @@ def ref():
     L.ref_t1_encode_cblk.argtypes = [i32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                      C.c_double, C.c_uint32, C.c_void_p, C.c_uint32, C.c_int, u8p,
                                      C.POINTER(C.c_uint32), u32p, u32p, f64p, C.POINTER(C.c_double)]
+    L.ref_rd_convex_hull.argtypes = [u32p, f64p, C.c_uint32, u16p]
+    L.ref_rd_convex_hull.restype = None
     L.ref_t1_decode_cblk.argtypes = [u8p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                      C.c_uint32, C.c_uint32, i32p]
     L.ref_set_cblk_sty.argtypes = [C.c_uint32]
@@ -360,4 +365,22 @@ def ref_t1_decode(data, numpasses, numbps, orient, w, h):
     b = np.frombuffer(bytes(data) + b"\0\0", np.uint8).copy()
     rc = ref().ref_t1_decode_cblk(b, len(data), numpasses, numbps, orient, 0, 0, w, h, out.ravel())
     assert rc == 0
+    return out
+
+
+def random_pass_tables(rng, count):
+    """pass tables the way Tier-1 leaves them: byte counts with zeros, cumulative distortions that mostly decay, with flat
+    stretches, equal slopes and the occasional negative step (the cases the feasibility tests branch on)"""
+    out = []
+    for it in range(count):
+        n = int(rng.integers(1, 92))
+        lens = rng.integers(0, 400, n).astype(np.uint32)
+        lens[rng.random(n) < 0.15] = 0
+        step = rng.random(n) * (2.0 ** rng.integers(-8, 40)) * np.exp(-np.arange(n) * rng.random() * 0.3)
+        step[rng.random(n) < 0.1] = 0.0
+        if it % 5 == 0:
+            step[rng.random(n) < 0.1] *= -1.0
+        if it % 7 == 0:  # proportional rate and distortion: equal slopes
+            step = lens.astype(np.float64) * 3.0
+        out.append((lens, np.cumsum(step)))
     return out

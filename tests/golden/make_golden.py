@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 from _libs import (aligned, ref, ref_t1_encode, ref_t1_decode, ref_encode_image, ref_decode_image, ref_t1_encode_sty,  # noqa: E402
-                   ref_t1_decode_segs, segments_from_passes)
+                   ref_t1_decode_segs, segments_from_passes, random_pass_tables)
 from grokimagecompression_b200.synth import synthetic_planes  # noqa: E402
 
 
@@ -123,7 +123,27 @@ def codestream_vectors():
     np.savez_compressed(os.path.join(HERE, "codestreams.npz"), **out)
 
 
+def rd_vectors():
+    """RateControl::convexHull on pass tables: random ones (zero-length passes, flat and negative distortion steps, equal slopes)
+    and the real tables of the reference's Tier-1 on synthetic blocks"""
+    rng = np.random.default_rng(4242)
+    R = ref()
+    tables = random_pass_tables(rng, 120)
+    z = np.load(os.path.join(HERE, "t1_blocks.npz"))
+    for i in range(int(z["count"][0])):
+        rates = z[f"blk{i}_rates"].astype(np.int64)
+        if len(rates):
+            tables.append((np.diff(np.concatenate([[0], rates])).astype(np.uint32), z[f"blk{i}_dists"].astype(np.float64)))
+    out = {"count": np.array([len(tables)])}
+    for i, (lens, dist) in enumerate(tables):
+        slopes = np.zeros(len(lens), np.uint16)
+        R.ref_rd_convex_hull(np.ascontiguousarray(lens), np.ascontiguousarray(dist), len(lens), slopes)
+        out[f"t{i}_len"], out[f"t{i}_dist"], out[f"t{i}_slope"] = lens, dist, slopes
+    np.savez_compressed(os.path.join(HERE, "rd_slopes.npz"), **out)
+
+
 if __name__ == "__main__":
+    rd_vectors()
     t1_vectors()
     t1_style_vectors()
     transform_vectors()

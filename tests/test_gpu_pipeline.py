@@ -86,6 +86,37 @@ def test_encode_decode_vs_oracle(ctx, case):
                 assert (a == b).all()
 
 
+@pytest.mark.parametrize("case", [c for c in CASES if not c[4]] + [(512, 384, 3, 8, False, (256, 256), 6, (6, 6))])
+def test_rd_slopes_vs_oracle(ctx, case):
+    """PCRD preparation on the device (gb200_encode_slopes = RateControl::convexHull, t2/RateControl.cpp:31-168): feasible
+    truncation points and 8.8 log slopes of every block equal the oracle's on the encoder's own pass tables"""
+    from _libs import oracle
+    width, height, nc, prec, rev, tile, numres, cblk = case
+    img = synthetic_planes(width, height, nc, prec, seed=3 * width + height, kind="smooth")
+    tiles = P.image_tiles(width, height, nc, prec, rev, tile, numres, rate_control=True, cblk_expn=cblk)
+    planes = P.split_planes(img, width, height, tile)
+    plan = gb.Plan(ctx, tiles, encoder=True)
+    res, rates, dists, data = plan.encode(planes)
+    slopes = plan.encode_slopes()
+    assert len(slopes) == plan.num_pass_slots
+    O = oracle()
+    passes = feasible = 0
+    for i in range(plan.num_blocks):
+        n, po = int(res[i]["numpasses"]), int(plan.blocks[i]["pass_offset"])
+        if not n:
+            continue
+        r = rates[po:po + n].astype(np.int64)
+        lens = np.diff(np.concatenate([[0], r])).astype(np.uint32)
+        want = np.zeros(n, np.uint16)
+        O.gbo_rd_convex_hull(lens, np.ascontiguousarray(dists[po:po + n]), n, want)
+        assert (slopes[po:po + n] == want).all(), (i, slopes[po:po + n], want)
+        passes += n
+        feasible += int((want != 0).sum())
+    assert passes > 500 and feasible > 100
+    # a second call gives the same table (the slope cache is rebuilt, not accumulated)
+    assert (plan.encode_slopes() == slopes).all()
+
+
 def test_truncated_layers_decode(ctx):
     """decode a prefix of the passes of every block, as a lower quality layer would deliver them"""
     width, height = 192, 160

@@ -102,3 +102,18 @@ def test_degenerate_and_empty_blocks():
     data, nb, rates, dists, nsym = oracle_t1_encode(q, 3)
     assert nb == 3 and len(rates) == 7
     assert oracle_t1_decode(data, 7, 3, 3, 1, 1)[0, 0] == -(5 * 2 + 1)
+
+
+def test_rd_convex_hull_against_reference_vectors():
+    """feasible truncation points and 8.8 log slopes (RateControl.cpp:31-168) of 120 random and the real Tier-1 pass tables"""
+    z = np.load(os.path.join(G, "rd_slopes.npz"))
+    O = oracle()
+    n = int(z["count"][0])
+    feasible = 0
+    for i in range(n):
+        lens, dist = np.ascontiguousarray(z[f"t{i}_len"]), np.ascontiguousarray(z[f"t{i}_dist"])
+        got = np.zeros(len(lens), np.uint16)
+        O.gbo_rd_convex_hull(lens, dist, len(lens), got)
+        assert (got == z[f"t{i}_slope"]).all(), i
+        feasible += int((got != 0).sum())
+    assert n >= 130 and feasible > 500

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from _libs import (aligned, have_ref, oracle, oracle_t1_decode, oracle_t1_encode, ref, ref_t1_decode, ref_t1_encode,
-                   ref_encode_image, ref_decode_image)
+                   ref_encode_image, ref_decode_image, random_pass_tables)
 
 pytestmark = pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
 
@@ -133,3 +133,15 @@ def test_whole_codec_golden_is_current():
     assert cs == z["gray53_cs"].tobytes()
     assert (np.stack(ref_decode_image(cs, 1, 160, 112)) == z["gray53_dec"]).all()
     assert (z["gray53_dec"][0] == img[0]).all()
+
+
+def test_rd_convex_hull_matches_the_reference():
+    """RateControl::convexHull (t2/RateControl.cpp:31-118) incl. the 8.8 log-slope conversion (:159-168)"""
+    rng = np.random.default_rng(77)
+    O, R = oracle(), ref()
+    for lens, dist in random_pass_tables(rng, 600):
+        a = np.zeros(len(lens), np.uint16)
+        b = np.zeros(len(lens), np.uint16)
+        O.gbo_rd_convex_hull(lens, dist, len(lens), a)
+        R.ref_rd_convex_hull(lens, dist, len(lens), b)
+        assert (a == b).all(), (lens, dist, a, b)
