@@ -29,11 +29,14 @@
 #include "Tier1.h"
 #include "T1Interface.h"
 #include "dwt_utils.h"
+#include "RateControl.h"
 #include "../include/grok_b200.h"
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
+#include <dlfcn.h>
 #include <map>
+#include <unordered_set>
 #include <mutex>
 #include <vector>
 
@@ -43,6 +46,7 @@ gb200_ctx *g_ctx = nullptr;
 std::mutex g_mu, g_mu2, g_dev_mu; /* g_dev_mu: one tile at a time on the device (cached plans are shared between equal tiles) */
 void fail(const char *what);
 uint64_t g_calls[8] = {0};
+uint64_t g_hulls = 0;
 double g_secs[8] = {0}; /* wall clock spent inside the bound stage calls, same indices as g_calls */
 struct Timer {
 	int i;
@@ -119,9 +123,16 @@ struct TileResult {
 	std::vector<gb200_cblk_enc> blocks;
 	std::vector<uint32_t> rates;
 	std::vector<double> dists;
+	std::vector<uint16_t> slopes; /* feasible truncation points from the device (empty: the host computes them) */
 	std::vector<uint8_t> data;
 };
 std::map<grk::grk_tcd_tile*, TileResult> g_results;
+
+/* pass tables whose slopes came from the device (gb200_encode_slopes): RateControl::convexHull below skips those.
+ * GROK_B200_HOST_HULL=1 leaves the convex hull to the host (A/B). */
+std::mutex g_hull_mu;
+std::unordered_set<const grk::grk_tcd_pass*> g_hulled;
+bool device_hull() { static const bool on = !getenv("GROK_B200_HOST_HULL"); return on; }
 
 /* which coding passes end a codeword segment: t1_enc_is_term_pass, t1.cpp:1131-1151 (pass 0 is the cleanup pass of the
  * top bit plane, then significance / refinement / cleanup per lower plane) */
@@ -145,6 +156,7 @@ void fail(const char *what) {
 } // namespace
 
 extern "C" uint64_t grok_b200_shim_calls(int i) { return g_calls[i & 7]; }
+extern "C" uint64_t grok_b200_shim_hulls() { return g_hulls; } /* convexHull calls answered with the device's slopes */
 extern "C" double grok_b200_shim_seconds(int i) { return g_secs[i & 7]; }
 extern "C" void grok_b200_shim_reset_seconds(void) { for (auto &v : g_secs) v = 0; }
 
@@ -212,6 +224,11 @@ bool TileProcessor::dc_level_shift_encode() {
 	uint64_t len = 0;
 	if (gb200_encode_tiles(R.plan, planes.data(), R.blocks.data(), R.rates.data(), R.dists.data(), R.data.data(), R.data.size(), &len) != GB200_OK)
 		fail("gb200_encode_tiles");
+	R.slopes.clear();
+	if (tp.rate_control && device_hull()) { /* PCRD preparation while the pass tables are still on the device */
+		R.slopes.resize(gb200_plan_num_pass_slots(R.plan) + 1);
+		if (gb200_encode_slopes(R.plan, R.slopes.data()) != GB200_OK) fail("gb200_encode_slopes");
+	}
 	return true;
 }
 
@@ -255,6 +272,12 @@ bool Tier1::encodeCodeblocks(grk_tcp *tcp, grk_tcd_tile *tile, const double *, u
 							pass->len = pass->rate - (p ? R.rates[po + p - 1] : 0);
 							pass->distortiondec = R.dists[po + p];
 							pass->term = is_term_pass(e.numbps, tilec_sty, p) ? 1 : 0;
+							if (!R.slopes.empty()) pass->slope = R.slopes[po + p];
+						}
+						if (!R.slopes.empty() && e.numpasses) {
+							std::lock_guard<std::mutex> lk(g_hull_mu);
+							if (g_hulled.size() > (1u << 20)) g_hulled.clear(); /* tables the host never asked about (rate control off later) */
+							g_hulled.insert(cblk->passes);
 						}
 						if (doRateControl && e.numpasses) tile->distotile += R.dists[po + e.numpasses - 1];
 					}
@@ -264,6 +287,20 @@ bool Tier1::encodeCodeblocks(grk_tcp *tcp, grk_tcd_tile *tile, const double *, u
 	}
 	g_results.erase(it);
 	return true;
+}
+
+/* RateControl::convexHull(passes, n), t2/RateControl.cpp:31, called per block by the rate allocator (TileProcessor.cpp:409):
+ * the slopes of a table filled above are already in place; anything else goes to the host's own code. */
+void RateControl::convexHull(grk_tcd_pass *pass, uint32_t numPasses) {
+	{
+		std::lock_guard<std::mutex> lk(g_hull_mu);
+		auto it = g_hulled.find(pass);
+		if (it != g_hulled.end()) { g_hulled.erase(it); g_hulls++; return; }
+	}
+	using Fn = void (*)(grk_tcd_pass*, uint32_t);
+	static Fn real = (Fn) dlsym(RTLD_NEXT, "_ZN3grk11RateControl10convexHullEPNS_12grk_tcd_passEj");
+	if (!real) { fprintf(stderr, "grok_tcd_shim: the host's RateControl::convexHull is not visible\n"); abort(); }
+	real(pass, numPasses);
 }
 
 /* ---- decode ------------------------------------------------------------------------------------ */

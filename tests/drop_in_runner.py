@@ -85,6 +85,8 @@ def main():
     if shim is not None:
         shim.grok_b200_shim_calls.restype = C.c_uint64
         res["calls"] = np.array([shim.grok_b200_shim_calls(i) for i in range(8)], np.uint64)
+        shim.grok_b200_shim_hulls.restype = C.c_uint64
+        res["hulls"] = np.array([shim.grok_b200_shim_hulls()], np.uint64)
     np.savez_compressed(out, **res)
 
 

@@ -32,6 +32,10 @@ def test_codestreams_and_pixels_identical(tmp_path, cases):
     shim = _run("shim", str(tmp_path / "shim.npz"), cases)
     calls = shim["calls"]
     assert calls[0] > 0 and calls[3] > 0 and calls[4] > 0 and calls[5] > 0, calls  # the seam really was taken
+    # ... including the rate allocator's per-block RateControl::convexHull, answered with the slopes computed on the device
+    # (a single lossless layer needs no slopes: the host does not ask, TileProcessor.cpp:407)
+    if any("97" in n or n in ("c2_crop", "c4_frame") for n in cases):
+        assert int(shim["hulls"][0]) > 0
     for name in cases:
         lossless = name in ("gray53", "rgb53_tiled", "rgb16_53", "c1_full", "random53", "constant53", "ragged53", "tiny", "onepixel", "sweep53",
                             "lazy53", "resetvsc53", "allmodes53", "segsympterm16")  # (with -ROI the reference itself is not lossless: its encoder
