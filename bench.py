@@ -427,6 +427,7 @@ def main():
     if rank != 0:
         return
     ms_step = t_enc + t_dec
+    rc_on = len(w["rates"]) > 0
     value = world * 2 * pixels / (ms_step * 1e-3) / 1e6
     e2e_value = world * 2 * pixels / t_e2e / 1e6
     peak, peak_src = peaks()
@@ -483,6 +484,19 @@ def main():
                "encode_mdecisions_s": round(decisions / (t_t1e * 1e-3) / 1e6, 1), "decode_mdecisions_s": round(decisions / (t_t1d * 1e-3) / 1e6, 1),
                "share_of_encode": round(t_t1e / t_enc, 3), "share_of_decode": round(t_t1d / t_dec, 3), "issue": issue},
     }
+    # PCRD preparation on the device (gb200_encode_slopes: convex hull + log slopes of every block, kernel + D2H of the table),
+    # not part of the step: the reference does this inside its host-side rate allocator
+    if rc_on and world == 1:
+        try:
+            eplan.encode_restore(); eplan.encode_run(); ctx.sync()
+            eplan.encode_slopes()
+            t0 = time.perf_counter()
+            for _ in range(5):
+                sl = eplan.encode_slopes()
+            line["rd_slopes"] = {"ms_per_image_incl_d2h": round((time.perf_counter() - t0) / 5 * 1e3, 4), "passes": int(eplan.num_pass_slots),
+                                 "feasible_points": int((sl != 0).sum())}
+        except Exception as exc:
+            line["rd_slopes"] = {"error": str(exc)[:200]}
     # the reversible 5/3 transform at configs[2] scale (8192x8192x3, 1024x1024 tiles): same kernel family, exact int32 lifting
     # with a fifth of the ALU work of the fixed-point 9/7, i.e. the case that is bound by HBM alone
     if world == 1 and args.workload == "c2":
