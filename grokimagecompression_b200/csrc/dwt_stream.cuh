@@ -167,29 +167,30 @@ __device__ __forceinline__ void dws_hinv(Quad &q) {
 // forward: feed (a, b) = next low-pass and high-pass source rows; returns the low / high result rows that
 // became final: stream index j - LAG when fed pair j.
 template<bool REV> struct VFwd;
+// (pa, pb): the row pair of the previous trip, a: this trip's low-pass row (its high-pass row is used one trip later)
 template<> struct VFwd<true> {
 	static constexpr int LAG = 1;
-	int32_t pa, pb, pd;
-	__device__ __forceinline__ void init() { pa = pb = pd = 0; }
-	__device__ __forceinline__ void feed(int32_t a, int32_t b, int32_t &lo, int32_t &hi) {
+	int32_t pd;
+	__device__ __forceinline__ void init() { pd = 0; }
+	__device__ __forceinline__ void feed(int32_t pa, int32_t pb, int32_t a, int32_t &lo, int32_t &hi) {
 		const int32_t dn = pb - ((pa + a) >> 1);
 		lo = pa + ((pd + dn + 2) >> 2);
 		hi = dn;
-		pa = a; pb = b; pd = dn;
+		pd = dn;
 	}
 };
 template<> struct VFwd<false> {
 	static constexpr int LAG = 2;
-	int32_t pa, pb, pd1, ps1, pd2;
-	__device__ __forceinline__ void init() { pa = pb = pd1 = ps1 = pd2 = 0; }
-	__device__ __forceinline__ void feed(int32_t a, int32_t b, int32_t &lo, int32_t &hi) {
+	int32_t pd1, ps1, pd2;
+	__device__ __forceinline__ void init() { pd1 = ps1 = pd2 = 0; }
+	__device__ __forceinline__ void feed(int32_t pa, int32_t pb, int32_t a, int32_t &lo, int32_t &hi) {
 		const int32_t d1n = pb - dws_fix13(pa + a, 12994);
 		const int32_t s1n = pa - dws_fix13(pd1 + d1n, 434);
 		const int32_t d2n = pd1 + dws_fix13(ps1 + s1n, 7233);
 		const int32_t s2n = ps1 + dws_fix13(pd2 + d2n, 3633);
 		lo = dws_fix13(s2n, 6659);
 		hi = dws_fix13(d2n, 5039);
-		pa = a; pb = b; pd1 = d1n; ps1 = s1n; pd2 = d2n;
+		pd1 = d1n; ps1 = s1n; pd2 = d2n;
 	}
 };
 
@@ -311,7 +312,11 @@ __device__ __forceinline__ void dws_fwd_strip(const DwtPlane &P, const DwsItem &
 	const int32_t *s0 = P.src + (EDGE ? dws_reflect(c, rw) : c);
 	const int32_t *s1 = P.src + dws_reflect(c + 1, rw), *s2 = P.src + dws_reflect(c + 2, rw), *s3 = P.src + dws_reflect(c + 3, rw);
 	int4 *const slot0 = ring + it.lane;
-	Quad regs[RING ? 1 : 2 * G]; // RING = false: the queue (slots are compile-time constants once the trip loop is unrolled)
+	// RING = false: the queue.  It has one row pair more than the G that are in flight: the vertical pass needs the previous
+	// trip's rows once more, so they stay where they were loaded and their slot is refilled one trip later (no copies; the slot
+	// numbers are compile-time constants once the trip loop is unrolled).
+	constexpr int K = RING ? G : G + 1; // row pairs in the queue; trip t lives in pair t % K
+	Quad regs[RING ? 1 : 2 * K];
 	auto issue_row = [&](int y, int slot) {
 		const uint32_t gy = (uint32_t) dws_reflect(y, rh);
 		if (RING) {
@@ -387,20 +392,25 @@ __device__ __forceinline__ void dws_fwd_strip(const DwtPlane &P, const DwsItem &
 		if (g < niter) { issue_row(ys + 2 * g, 2 * g); issue_row(ys + 2 * g + 1, 2 * g + 1); }
 		if (RING) dws_commit();
 	}
-	for (int j0 = 0; j0 < niter; j0 += G) {
+	Quad pa = {0, 0, 0, 0}, pb = {0, 0, 0, 0}; // RING: the previous trip's rows (copies)
+	if (!RING) { regs[RING ? 0 : 2 * (K - 1)] = pa; regs[RING ? 0 : 2 * (K - 1) + 1] = pb; } // "trip -1": part of the warm-up
+	for (int j0 = 0; j0 < niter; j0 += K) {
 		#pragma unroll
-		for (int u = 0; u < G; ++u) {
+		for (int u = 0; u < K; ++u) {
 			const int j = j0 + u;
 			if (j >= niter) break;
+			const int prev = (u + K - 1) % K; // pair of trip j - 1
 			if (RING) dws_wait<G - 1>();
 			const Quad a = read_row(2 * u), b = read_row(2 * u + 1);
-			if (j + G < niter) { issue_row(ys + 2 * (j + G), 2 * u); issue_row(ys + 2 * (j + G) + 1, 2 * u + 1); }
-			if (RING) dws_commit();
+			const Quad qa = RING ? pa : read_row(2 * prev), qb = RING ? pb : read_row(2 * prev + 1);
 			Quad lo, hi;
-			v0.feed(a.e0, b.e0, lo.e0, hi.e0);
-			v1.feed(a.o0, b.o0, lo.o0, hi.o0);
-			v2.feed(a.e1, b.e1, lo.e1, hi.e1);
-			v3.feed(a.o1, b.o1, lo.o1, hi.o1);
+			v0.feed(qa.e0, qb.e0, a.e0, lo.e0, hi.e0);
+			v1.feed(qa.o0, qb.o0, a.o0, lo.o0, hi.o0);
+			v2.feed(qa.e1, qb.e1, a.e1, lo.e1, hi.e1);
+			v3.feed(qa.o1, qb.o1, a.o1, lo.o1, hi.o1);
+			// refill: RING overwrites the pair just read (it was copied out), the register queue the pair of trip j - 1
+			if (j + G < niter) { issue_row(ys + 2 * (j + G), RING ? 2 * u : 2 * prev); issue_row(ys + 2 * (j + G) + 1, RING ? 2 * u + 1 : 2 * prev + 1); }
+			if (RING) { dws_commit(); pa = a; pb = b; }
 			// rows before the first owned one come out of the warm-up trips and fail the range test, as do rows past the last
 			const int yl = ys + 2 * (j - LAG);
 			const bool vl = yl >= yv0 && yl < yv1, vh = yl + 1 >= yv0 && yl + 1 < yv1;
