@@ -10,7 +10,8 @@
 // per trip:
 //   forward: every lane loads its four columns of a low-pass and a high-pass row (one 16-byte load each,
 //            the warp reads 512 contiguous bytes per row), advances the vertical lifting recurrences that it
-//            keeps in registers (5 values per column for 9/7, 3 for 5/3), and for the two rows that
+//            keeps in registers (3 values per column for 9/7, 1 for 5/3, plus the previous row pair, which simply stays in
+//            the prefetch queue), and for the two rows that
 //            become final runs the horizontal lifting ACROSS LANES: a lane holds (low, high, low, high), the
 //            neighbour's value arrives by one shuffle per lifting step, two rows per shuffle round.  The four
 //            sub-band rows leave as 8-byte stores, 240 contiguous bytes per warp and sub-band.
@@ -28,7 +29,6 @@
 // This header is also compiled for the CPU by tests/dwt_emu.cpp (GB_EMU: one OS thread per lane), which checks
 // the kernels against the oracle without a GPU.
 #pragma once
-#include <type_traits>
 #ifndef GB_EMU
 #include "common.cuh"
 #else
