@@ -574,10 +574,15 @@ __device__ __forceinline__ void dws_inv_strip(const DwtPlane &P, const DwsItem &
 			if (j >= niter) break;
 			if (RING) dws_wait<G - 1>();
 			Quad a = read_row(2 * u), b = read_row(2 * u + 1);
-			if (j + G < niter) { issue_row(ys + 2 * (j + G), false, 2 * u); issue_row(ys + 2 * (j + G) + 1, true, 2 * u + 1); }
-			if (RING) dws_commit();
+			if (RING) { // the ring slot was copied out by the read: refill it at once
+				if (j + G < niter) { issue_row(ys + 2 * (j + G), false, 2 * u); issue_row(ys + 2 * (j + G) + 1, true, 2 * u + 1); }
+				dws_commit();
+			}
 			if (hlift) dws_hinv2<REV>(a, b);
 			else { hsyn1(a); hsyn1(b); }
+			// register queue: the raw rows are dead once the horizontal synthesis has consumed them; reloading their registers
+			// only now saves the copies a refill before that would force
+			if (!RING && j + G < niter) { issue_row(ys + 2 * (j + G), false, 2 * u); issue_row(ys + 2 * (j + G) + 1, true, 2 * u + 1); }
 			Quad r0, r1;
 			v0.feed(a.e0, b.e0, r0.e0, r1.e0);
 			v1.feed(a.o0, b.o0, r0.o0, r1.o0);
