@@ -188,6 +188,25 @@ static int check_inv(const Geom &g, uint32_t nd, int rev, int R, std::mt19937 &r
 
 int main(int argc, char **argv) {
 	const bool quick = argc > 1 && !strcmp(argv[1], "quick");
+	if (argc > 1 && !strcmp(argv[1], "fuzz")) { // dwt_emu fuzz <cases> <seed>: random origins, sizes, levels, rows per item, queues
+		const int n = argc > 2 ? atoi(argv[2]) : 100;
+		std::mt19937 rng(argc > 3 ? atoi(argv[3]) : 1);
+		auto U = [&](int lo, int hi) { return (uint32_t) std::uniform_int_distribution<int>(lo, hi)(rng); };
+		int fails = 0;
+		for (int i = 0; i < n; ++i) {
+			Geom g;
+			g.x0 = U(0, 1) ? U(0, 9) : 0; g.y0 = U(0, 1) ? U(0, 9) : 0;
+			g.x1 = g.x0 + (U(0, 3) ? U(1, 300) : U(1, 9)); g.y1 = g.y0 + (U(0, 3) ? U(1, 150) : U(1, 9));
+			if (U(0, 4) == 0) g.x1 = g.x0 + 4 * U(30, 130); // aligned widths reach the interior (vector) strips
+			g.nr = U(1, 6);
+			const int rev = (int) U(0, 1), R = (int) (2 * U(4, 40));
+			g_hl = (int) U(1, 2); g_ring = (int) U(0, 1);
+			fails += check_fwd(g, rev, R, rng);
+			fails += check_inv(g, U(1, g.nr), rev, R, rng);
+		}
+		printf("fuzz: %d cases, %d failed\n", 2 * n, fails);
+		return fails ? 1 : 0;
+	}
 	// the geometries of tests/test_gpu_stages.py plus a few that cross strip / chunk borders
 	std::vector<Geom> geoms = {{0, 0, 64, 64, 6}, {0, 0, 37, 53, 4}, {3, 5, 40, 41, 6}, {1, 1, 2, 2, 3}, {7, 0, 8, 33, 5}, {0, 0, 1, 1, 2},
 		{5, 3, 300, 211, 6}, {1, 0, 3, 1, 3}, {0, 0, 129, 65, 3}, {63, 63, 64 + 130, 64 + 67, 4}, {0, 0, 5, 1, 4}, {0, 0, 1, 7, 4},

