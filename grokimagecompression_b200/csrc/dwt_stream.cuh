@@ -299,10 +299,10 @@ __device__ __forceinline__ int32_t *dws_at(int32_t *p, uint32_t row, uint32_t st
 // EDGE = true: the strip touches the left or right border of the region (or the plane is not aligned): every lane
 // gathers its four (reflected) columns with 4-byte copies and stores element by element under predicates.
 // Rows are fetched G trips (2 G rows) ahead of their use, into one of two prefetch queues:
+// RING = false: row registers of the lane, filled by ordinary loads (nothing between DRAM and the registers); the default
+//               for all four kernels: measured faster than the ring on every workload (profiles/README.md);
 // RING = true : this warp's ring of 2 G rows of 32 x 16 bytes in shared memory, filled by asynchronous copies (no
-//               registers held while the rows are in flight: the choice for the arithmetic-heavy 9/7 kernels);
-// RING = false: 2 G row registers per lane, filled by ordinary loads (nothing between DRAM and the registers: the
-//               choice for the 5/3 kernels, which are bound by memory alone).
+//               registers held while the rows are in flight; GB200_DWT_RING=1).
 template<bool REV, int G, bool EDGE, bool RING>
 __device__ __forceinline__ void dws_fwd_strip(const DwtPlane &P, const DwsItem &it, int R, int hl, int4 *ring) {
 	const int rw = (int) P.rw, rh = (int) P.rh, casx = (int) P.cas_x, casy = (int) P.cas_y;
