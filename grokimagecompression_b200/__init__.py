@@ -5,8 +5,8 @@ The product is `libgrok_b200.so` (csrc/, include/grok_b200.h); this package is t
 mirror used by the tests and bench.py.  There is no CPU fallback.
 """
 from .binding import (CBLK_DEC_DTYPE, CBLK_ENC_DTYPE, CBLK_INFO_DTYPE, CBLK_SEG_DTYPE, T1_BLOCK_DTYPE, CompParams, Context,
-                      GrokB200Error, Plan, TileParams, lib, LIB_PATH, SYMBOLS)
+                      GrokB200Error, Plan, TileParams, lib, LIB_PATH, SYMBOLS, ABI_VERSION)
 from . import params
 
-__all__ = ["Context", "Plan", "CompParams", "TileParams", "GrokB200Error", "lib", "params", "LIB_PATH", "SYMBOLS",
+__all__ = ["Context", "Plan", "CompParams", "TileParams", "GrokB200Error", "lib", "params", "LIB_PATH", "SYMBOLS", "ABI_VERSION",
            "CBLK_ENC_DTYPE", "CBLK_DEC_DTYPE", "CBLK_INFO_DTYPE", "CBLK_SEG_DTYPE", "T1_BLOCK_DTYPE"]

@@ -9,6 +9,7 @@ import os
 import numpy as np
 
 MAX_RES = 33
+ABI_VERSION = 3  # GB200_ABI_VERSION of include/grok_b200.h
 MAX_BANDS = 3 * MAX_RES - 2
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -58,7 +59,9 @@ T1_BLOCK_DTYPE = np.dtype([("x", np.uint32), ("y", np.uint32), ("w", np.uint32),
 SYMBOLS = [
     "gb200_abi_version", "gb200_last_error", "gb200_create", "gb200_destroy", "gb200_launch_count", "gb200_stream",
     "gb200_plan_create", "gb200_plan_destroy", "gb200_plan_num_blocks", "gb200_plan_num_pass_slots",
-    "gb200_plan_num_samples", "gb200_plan_blocks", "gb200_plan_data_capacity",
+    "gb200_plan_num_samples", "gb200_plan_blocks", "gb200_plan_data_capacity", "gb200_precinct_grid", "gb200_enumerate_blocks",
+    "gb200_plan_set_sample_bytes", "gb200_encode_tiles_packed", "gb200_decode_tiles_packed", "gb200_encode_upload_packed",
+    "gb200_decode_download_packed",
     "gb200_encode_tiles", "gb200_decode_tiles", "gb200_encode_upload", "gb200_encode_run", "gb200_encode_download",
     "gb200_decode_upload", "gb200_decode_run", "gb200_decode_download", "gb200_sync", "gb200_encode_slopes",
     "gb200_encode_stash", "gb200_encode_restore",
@@ -100,6 +103,14 @@ def lib():
         getattr(L, n).restype = u64
     L.gb200_plan_blocks.argtypes = [vp]
     L.gb200_plan_blocks.restype = C.POINTER(CblkInfo)
+    L.gb200_enumerate_blocks.argtypes = [C.POINTER(CompParams), u32, vp, u64]
+    L.gb200_enumerate_blocks.restype = u64
+    L.gb200_precinct_grid.argtypes = [C.POINTER(CompParams), u32, C.POINTER(u32), C.POINTER(u32)]
+    L.gb200_plan_set_sample_bytes.argtypes = [vp, u32]
+    L.gb200_encode_tiles_packed.argtypes = [vp, C.POINTER(vp), vp, vp, vp, vp, u64, C.POINTER(u64)]
+    L.gb200_decode_tiles_packed.argtypes = [vp, vp, vp, u64, C.POINTER(vp)]
+    L.gb200_encode_upload_packed.argtypes = [vp, C.POINTER(vp)]
+    L.gb200_decode_download_packed.argtypes = [vp, C.POINTER(vp)]
     L.gb200_encode_tiles.argtypes = [vp, C.POINTER(vp), vp, vp, vp, vp, u64, C.POINTER(u64)]
     L.gb200_decode_tiles.argtypes = [vp, vp, vp, u64, C.POINTER(vp)]
     L.gb200_encode_upload.argtypes = [vp, C.POINTER(vp)]
@@ -233,9 +244,12 @@ class Context:
 class Plan:
     """Geometry + block table + device buffers of a batch of tiles (gb200_plan)."""
 
-    def __init__(self, ctx, tiles, encoder=True):
-        """tiles: list of dicts {numcomps, mct, rate_control, numres_decode, comps: [CompParams]}"""
+    def __init__(self, ctx, tiles, encoder=True, sample_bytes=4):
+        """tiles: list of dicts {numcomps, mct, rate_control, numres_decode, comps: [CompParams]};
+        sample_bytes 1 / 2: the host planes are packed uint8 / uint16 (int8 / int16 for signed components)"""
         self.ctx = ctx
+        self.sample_bytes = int(sample_bytes)
+        self.comp_signed = [bool(cp.sgnd) for t in tiles for cp in t["comps"]]
         self.encoder = bool(encoder)
         self._keep = []
         arr = (TileParams * len(tiles))()
@@ -256,6 +270,8 @@ class Plan:
         self._h = C.c_void_p()
         check(lib().gb200_plan_create(ctx.handle, len(tiles), arr, int(self.encoder), C.byref(self._h)))
         L = lib()
+        if self.sample_bytes != 4:
+            check(L.gb200_plan_set_sample_bytes(self._h, self.sample_bytes))
         self.num_blocks = int(L.gb200_plan_num_blocks(self._h))
         self.num_pass_slots = int(L.gb200_plan_num_pass_slots(self._h))
         self.num_samples = int(L.gb200_plan_num_samples(self._h))
@@ -295,12 +311,29 @@ class Plan:
         """planes: list of int32 arrays (tile-major, component-minor). -> (blocks, rates, dists, data)"""
         res, rates, dists, data = outputs if outputs is not None else self.alloc_encode_outputs()
         dl = C.c_uint64()
-        pa = self._ptr_array(planes)
-        check(lib().gb200_encode_tiles(self._h, pa, _ptr(res), _ptr(rates), _ptr(dists), _ptr(data), data.size, C.byref(dl)))
+        pa = self._ptr_array(self._check_planes(planes))
+        f = lib().gb200_encode_tiles if self.sample_bytes == 4 else lib().gb200_encode_tiles_packed
+        check(f(self._h, pa, _ptr(res), _ptr(rates), _ptr(dists), _ptr(data), data.size, C.byref(dl)))
         return res, rates, dists, data[:dl.value]
 
+    def sample_dtype(self, i=0):
+        """numpy dtype of host plane i (tile-major, component-minor)"""
+        if self.sample_bytes == 4:
+            return np.dtype(np.int32)
+        return np.dtype({(1, False): np.uint8, (1, True): np.int8, (2, False): np.uint16, (2, True): np.int16}[(self.sample_bytes, self.comp_signed[i])])
+
+    def _check_planes(self, planes):
+        for i, a in enumerate(planes):
+            if isinstance(a, np.ndarray):
+                assert a.dtype == self.sample_dtype(i) and a.flags["C_CONTIGUOUS"], (i, a.dtype, self.sample_dtype(i))
+        return planes
+
+    def _alloc_planes(self):
+        return [np.zeros(s, self.sample_dtype(i)) for i, s in enumerate(self.comp_shapes)]
+
     def encode_upload(self, planes):
-        check(lib().gb200_encode_upload(self._h, self._ptr_array(planes)))
+        f = lib().gb200_encode_upload if self.sample_bytes == 4 else lib().gb200_encode_upload_packed
+        check(f(self._h, self._ptr_array(self._check_planes(planes))))
 
     def encode_stash(self):
         check(lib().gb200_encode_stash(self._h))
@@ -345,9 +378,9 @@ class Plan:
     def decode(self, inputs, data, out=None):
         inputs = np.ascontiguousarray(inputs, CBLK_DEC_DTYPE)
         data = np.ascontiguousarray(data, np.uint8)
-        planes = out if out is not None else [np.zeros(s, np.int32) for s in self.comp_shapes]
-        check(lib().gb200_decode_tiles(self._h, _ptr(inputs), _ptr(data) if data.size else None, data.size,
-                                        self._ptr_array(planes)))
+        planes = self._check_planes(out) if out is not None else self._alloc_planes()
+        f = lib().gb200_decode_tiles if self.sample_bytes == 4 else lib().gb200_decode_tiles_packed
+        check(f(self._h, _ptr(inputs), _ptr(data) if data.size else None, data.size, self._ptr_array(planes)))
         return planes
 
     def decode_upload(self, inputs, data):
@@ -374,8 +407,9 @@ class Plan:
         check(lib().gb200_decode_run_stage(self._h, stage))
 
     def decode_download(self, out=None):
-        planes = out if out is not None else [np.zeros(s, np.int32) for s in self.comp_shapes]
-        check(lib().gb200_decode_download(self._h, self._ptr_array(planes)))
+        planes = self._check_planes(out) if out is not None else self._alloc_planes()
+        f = lib().gb200_decode_download if self.sample_bytes == 4 else lib().gb200_decode_download_packed
+        check(f(self._h, self._ptr_array(planes)))
         return planes
 
     def set_coefficients(self, tileno, compno, arr):

@@ -63,9 +63,8 @@ struct LevelLaunch {
 	std::vector<uint32_t> cta_plane; // CTA -> index into host
 	DevBuf dev, map;
 	uint32_t ctas = 0;
-	uint32_t ctas64 = 0;  // CTA count with 64-row tiles (decides tile_rows of the shared-memory kernels)
-	std::vector<std::pair<uint32_t, uint32_t>> strips; // streaming kernels: (strips across, rows incl. the parity offset) of every plane
-	int tile_rows = 64;   // > 0: shared-memory kernels; < 0: streaming kernels, -tile_rows rows per work item
+	std::vector<std::pair<uint32_t, uint32_t>> strips; // (strips across, rows incl. the parity offset) of every plane
+	int rows = 16;        // rows per work item (one warp each)
 	int unroll = 2, halo_lanes = 1;
 };
 
@@ -98,6 +97,12 @@ struct gb200_plan {
 	// where each tile-component's final decoded plane lives (0 A, 1 B, 2 C)
 	std::vector<int> final_role;
 	std::vector<DevBuf> stash;
+	// narrow-sample boundary: bytes per sample of the host planes (4 = int32, the reference's tile-buffer contract; 1 / 2 =
+	// packed image samples, widened / narrowed inside the level-shift + MCT pass)
+	uint32_t sample_bytes = 4;
+	DevBuf d_total;            // byte count of the compacted code-block data, written by the offsets kernel
+	uint64_t *h_total = nullptr; // pinned host copy of it
+	cudaEvent_t ev_total = nullptr;
 };
 
 extern "C" {
@@ -230,6 +235,9 @@ void gb200_plan_destroy(gb200_plan *pl) {
 	pl->d_blocks.release(); pl->d_results.release(); pl->d_rates.release(); pl->d_dists.release();
 	pl->d_slopes.release(); pl->d_slope_cache.release();
 	pl->d_scratch.release(); pl->d_data.release(); pl->d_inputs.release(); pl->d_symbols.release(); pl->d_seg_start.release(); pl->d_segs.release();
+	pl->d_total.release();
+	if (pl->h_total) cudaFreeHost(pl->h_total);
+	if (pl->ev_total) cudaEventDestroy(pl->ev_total);
 	delete pl;
 }
 
@@ -311,10 +319,8 @@ int gb200_plan_create(gb200_ctx *ctx, uint32_t ntiles, const gb200_tile_params *
 	// ---- DWT launch tables ------------------------------------------------------------------------
 	for (int r = 0; r < 2; ++r) pl->lvl[r].resize(pl->maxlevels);
 	auto level_of = [&](const CompGeom &cg, uint32_t i) { return pl->encoder ? cg.top + i : cg.p.numres - 2 - i; };
-	// Which kernels: the streaming ones (dwt_stream.cuh) unless GB200_DWT_LEGACY=1 asks for the first generation
-	// (kept for A/B measurements).  GB200_DWT_ROWS / GB200_DWT_UNROLL / GB200_DWT_FILL override the tuning below.
+	// GB200_DWT_ROWS / GB200_DWT_UNROLL / GB200_DWT_FILL override the tuning below (measurement knobs).
 	auto env_int = [](const char *name, int dflt) { const char *e = getenv(name); return e && *e ? atoi(e) : dflt; };
-	const bool legacy = env_int("GB200_DWT_LEGACY", 0) != 0;
 	const int force_rows = env_int("GB200_DWT_ROWS", 0), unroll = env_int("GB200_DWT_UNROLL", 1), fill = env_int("GB200_DWT_FILL", 4);
 	const int halo_lanes = env_int("GB200_DWT_HL", 1) == 2 ? 2 : 1;
 	uint32_t stw;
@@ -322,14 +328,11 @@ int gb200_plan_create(gb200_ctx *ctx, uint32_t ntiles, const gb200_tile_params *
 	for (auto &tg : pl->tiles)
 		for (uint32_t c = 0; c < tg.numcomps; ++c) {
 			const CompGeom &cg = tg.comps[c];
-			uint32_t tw;
-			dwt_tile_shape(cg.p.qmfbid == 1, &tw);
 			for (uint32_t i = 0; i < cg.levels; ++i) {
 				const uint32_t lvl = level_of(cg, i);
 				const uint32_t rw = cdiv2n(cg.p.x1, lvl) - cdiv2n(cg.p.x0, lvl), rh = cdiv2n(cg.p.y1, lvl) - cdiv2n(cg.p.y0, lvl);
 				if (!rw || !rh) continue;
 				LevelLaunch &L = pl->lvl[cg.p.qmfbid == 1][i];
-				L.ctas64 += ((rw + tw - 1) / tw) * ((rh + 63) / 64);
 				const uint32_t cx = cdiv2n(cg.p.x0, lvl) & 1, cy = cdiv2n(cg.p.y0, lvl) & 1;
 				L.strips.emplace_back((rw + cx + stw - 1) / stw, rh + cy);
 			}
@@ -341,11 +344,7 @@ int gb200_plan_create(gb200_ctx *ctx, uint32_t ntiles, const gb200_tile_params *
 			for (auto &L : pl->lvl[r]) {
 				L.unroll = unroll;
 				L.halo_lanes = halo_lanes;
-				if (legacy) {
-					// big levels use 64-row tiles; a level that would not even fill the machine once is cut finer,
-					// because then the latency of one CTA is what the launch costs
-					L.tile_rows = L.ctas64 >= (uint32_t) sms * 6 ? 64 : (L.ctas64 >= (uint32_t) sms * 2 ? 32 : 16);
-				} else {
+				{
 					// Rows per work item.  A launch runs in waves of `slots` resident warps, and a partly filled last wave
 					// costs as much as a full one, so the row count is chosen by a small model: waves x trips per item
 					// (rows / 2 + the warm-up trips every item spends before its first result + a fixed start-up term).
@@ -364,7 +363,7 @@ int gb200_plan_create(gb200_ctx *ctx, uint32_t ntiles, const gb200_tile_params *
 						if (cost < best * 0.999) { best = cost; rows = cand; }
 					}
 					if (force_rows >= 2) rows = force_rows & ~1;
-					L.tile_rows = -rows;
+					L.rows = rows;
 					if (env_int("GB200_DWT_VERBOSE", 0) && !L.strips.empty()) {
 						uint64_t items = 0;
 						for (auto &sp : L.strips) items += (uint64_t) sp.first * ((sp.second + rows - 1) / rows);
@@ -380,14 +379,12 @@ int gb200_plan_create(gb200_ctx *ctx, uint32_t ntiles, const gb200_tile_params *
 			CompGeom &cg = tg.comps[c];
 			const gb200_comp_params &p = cg.p;
 			const int rev = p.qmfbid == 1;
-			uint32_t TWt;
-			dwt_tile_shape(rev, &TWt);
 			int role_final = 0;
 			for (uint32_t i = 0; i < cg.levels; ++i) {
 				// encoder: i-th launch transforms decomposition level cg.top + i (finest first)
 				// decoder: i-th launch reconstructs level (numres-2-i) (coarsest first)
 				const uint32_t lvl = level_of(cg, i);
-				const int trows = pl->lvl[rev][i].tile_rows;
+				const uint32_t trows = (uint32_t) pl->lvl[rev][i].rows;
 				DwtPlane d;
 				memset(&d, 0, sizeof(d));
 				d.rw = cdiv2n(p.x1, lvl) - cdiv2n(p.x0, lvl);
@@ -410,13 +407,9 @@ int gb200_plan_create(gb200_ctx *ctx, uint32_t ntiles, const gb200_tile_params *
 					d.dst = plane_ptr(pl, dst_role, c, cg.plane_off);
 					role_final = dst_role;
 				}
-				if (trows > 0) {
-					d.tiles_x = (d.rw + TWt - 1) / TWt;
-					d.tiles_y = (d.rh + trows - 1) / trows;
-				} else { // streaming kernels: a strip starts cas columns / rows before the region (a low-pass line comes first)
-					d.tiles_x = (d.rw + d.cas_x + stw - 1) / stw;
-					d.tiles_y = (d.rh + d.cas_y + (uint32_t) -trows - 1) / (uint32_t) -trows;
-				}
+				// a strip starts cas columns / rows before the region (a low-pass line comes first)
+				d.tiles_x = (d.rw + d.cas_x + stw - 1) / stw;
+				d.tiles_y = (d.rh + d.cas_y + trows - 1) / trows;
 				if (d.rw == 0 || d.rh == 0) { d.tiles_x = d.tiles_y = 0; }
 				LevelLaunch &L = pl->lvl[rev][i];
 				d.first_cta = L.ctas;
@@ -515,6 +508,10 @@ int gb200_plan_create(gb200_ctx *ctx, uint32_t ntiles, const gb200_tile_params *
 			return bail(GB200_ERR_CUDA, "upload of the block table failed");
 		cudaMemsetAsync(pl->d_scratch.p, 0, pl->d_scratch.bytes, ctx->stream);
 		pl->h_results.resize(nb);
+		if (pl->d_total.alloc(sizeof(uint64_t)) || cudaHostAlloc((void**) &pl->h_total, sizeof(uint64_t), cudaHostAllocDefault) != cudaSuccess
+				|| cudaEventCreateWithFlags(&pl->ev_total, cudaEventDisableTiming) != cudaSuccess)
+			return bail(GB200_ERR_NOMEM, "allocation of the byte counter failed");
+		cudaMemsetAsync(pl->d_total.p, 0, sizeof(uint64_t), ctx->stream);
 	} else {
 		if (pl->d_blocks.alloc(std::max<size_t>(nb, 1) * sizeof(DecBlock)) || pl->d_inputs.alloc(std::max<size_t>(nb, 1) * sizeof(DecInput)))
 			return bail(GB200_ERR_NOMEM, "cudaMalloc failed for the Tier-1 buffers");
@@ -526,6 +523,35 @@ int gb200_plan_create(gb200_ctx *ctx, uint32_t ntiles, const gb200_tile_params *
 	return GB200_OK;
 }
 
+uint64_t gb200_enumerate_blocks(const gb200_comp_params *p, uint32_t numres_limit, gb200_cblk_info *out, uint64_t cap) {
+	if (!p || p->numres < 1 || p->numres > GB200_MAX_RES) return 0;
+	std::vector<BlockGeom> geo;
+	enumerate_blocks(*p, numres_limit ? std::min(numres_limit, p->numres) : p->numres, geo);
+	uint64_t slots = 0;
+	for (size_t i = 0; i < geo.size(); ++i) {
+		const BlockGeom &g = geo[i];
+		const uint32_t mp = std::max<uint32_t>(1, 3 * std::max<uint32_t>(p->band_numbps[g.band_index], 1) - 2);
+		if (out && i < cap) {
+			gb200_cblk_info &bi = out[i];
+			bi.tileno = 0; bi.compno = 0; bi.resno = g.resno; bi.bandno = g.orient; bi.precno = g.precno; bi.cblkno = g.cblkno;
+			bi.x0 = g.x0; bi.y0 = g.y0; bi.x1 = g.x1; bi.y1 = g.y1;
+			bi.band_index = g.band_index; bi.pass_offset = (uint32_t) slots; bi.max_passes = mp;
+		}
+		slots += mp;
+	}
+	return geo.size();
+}
+
+int gb200_precinct_grid(const gb200_comp_params *p, uint32_t resno, uint32_t *pw, uint32_t *ph) {
+	if (!p || !pw || !ph || p->numres < 1 || p->numres > GB200_MAX_RES || resno >= p->numres) FAIL(GB200_ERR_PARAM, "gb200_precinct_grid: bad arguments");
+	const uint32_t lvl = p->numres - 1 - resno;
+	const uint32_t rx0 = cdiv2n(p->x0, lvl), ry0 = cdiv2n(p->y0, lvl), rx1 = cdiv2n(p->x1, lvl), ry1 = cdiv2n(p->y1, lvl);
+	const uint32_t pdx = p->prcw_expn[resno], pdy = p->prch_expn[resno];
+	*pw = rx0 == rx1 ? 0 : ((cdiv2n(rx1, pdx) << pdx) - ((rx0 >> pdx) << pdx)) >> pdx;
+	*ph = ry0 == ry1 ? 0 : ((cdiv2n(ry1, pdy) << pdy) - ((ry0 >> pdy) << pdy)) >> pdy;
+	return GB200_OK;
+}
+
 uint64_t gb200_plan_num_blocks(const gb200_plan *pl) { return pl ? pl->blocks.size() : 0; }
 uint64_t gb200_plan_num_pass_slots(const gb200_plan *pl) { return pl ? pl->pass_slots : 0; }
 uint64_t gb200_plan_num_samples(const gb200_plan *pl) { return pl ? pl->samples : 0; }
@@ -534,7 +560,28 @@ uint64_t gb200_plan_data_capacity(const gb200_plan *pl) { return pl ? pl->data_c
 
 // ---- encode ---------------------------------------------------------------------------------------
 
-int gb200_encode_upload(gb200_plan *pl, const int32_t *const *planes) {
+int gb200_plan_set_sample_bytes(gb200_plan *pl, uint32_t sample_bytes) {
+	if (!pl) FAIL(GB200_ERR_PARAM, "plan is NULL");
+	if (sample_bytes != 1 && sample_bytes != 2 && sample_bytes != 4) FAIL(GB200_ERR_PARAM, "sample_bytes must be 1, 2 or 4");
+	if (sample_bytes < 4)
+		for (auto &tg : pl->tiles) {
+			for (auto &cg : tg.comps)
+				if (cg.p.prec > 8 * sample_bytes) FAIL(GB200_ERR_PARAM, "component precision does not fit the packed sample type");
+			if (tg.mct && (tg.comps[0].p.sgnd != tg.comps[1].p.sgnd || tg.comps[0].p.sgnd != tg.comps[2].p.sgnd))
+				FAIL(GB200_ERR_UNSUPPORTED, "packed samples: the three MCT components must share their signedness");
+		}
+	pl->sample_bytes = sample_bytes;
+	return GB200_OK;
+}
+
+// packed planes wait in the B buffers (the partner of the first wavelet level's ping-pong, free until then); the widening
+// level-shift + MCT pass moves them into the A buffers
+static uint8_t *packed_ptr(gb200_plan *pl, int role, uint32_t compno, uint64_t elem_off) {
+	DevBuf &b = role == 0 ? pl->bufA[compno] : pl->bufB[compno];
+	return reinterpret_cast<uint8_t*>(b.p) + elem_off * pl->sample_bytes;
+}
+
+int gb200_encode_upload_packed(gb200_plan *pl, const void *const *planes) {
 	if (!pl || !pl->encoder || !planes) FAIL(GB200_ERR_PARAM, "gb200_encode_upload: bad arguments");
 	CK(cudaSetDevice(pl->ctx->device));
 	size_t i = 0;
@@ -542,19 +589,26 @@ int gb200_encode_upload(gb200_plan *pl, const int32_t *const *planes) {
 		for (uint32_t c = 0; c < tg.numcomps; ++c, ++i) {
 			const CompGeom &cg = tg.comps[c];
 			if (!planes[i]) FAIL(GB200_ERR_PARAM, "NULL plane pointer");
-			size_t bytes = (size_t) cg.w * cg.h * sizeof(int32_t);
-			if (bytes) CK(cudaMemcpyAsync(plane_ptr(pl, 0, c, cg.plane_off), planes[i], bytes, cudaMemcpyHostToDevice, pl->ctx->stream));
+			size_t bytes = (size_t) cg.w * cg.h * pl->sample_bytes;
+			void *dst = pl->sample_bytes == 4 ? (void*) plane_ptr(pl, 0, c, cg.plane_off) : (void*) packed_ptr(pl, 1, c, cg.plane_off);
+			if (bytes) CK(cudaMemcpyAsync(dst, planes[i], bytes, cudaMemcpyHostToDevice, pl->ctx->stream));
 		}
 	return GB200_OK;
+}
+
+int gb200_encode_upload(gb200_plan *pl, const int32_t *const *planes) {
+	if (pl && pl->sample_bytes != 4) FAIL(GB200_ERR_PARAM, "this plan takes packed samples: use gb200_encode_upload_packed");
+	return gb200_encode_upload_packed(pl, reinterpret_cast<const void *const *>(planes));
 }
 
 int gb200_encode_stash(gb200_plan *pl) {
 	if (!pl || !pl->encoder) FAIL(GB200_ERR_PARAM, "not an encoder plan");
 	CK(cudaSetDevice(pl->ctx->device));
 	pl->stash.resize(pl->maxcomps);
-	for (uint32_t c = 0; c < pl->maxcomps; ++c) {
-		if (pl->stash[c].bytes != pl->bufA[c].bytes && pl->stash[c].alloc(pl->bufA[c].bytes)) FAIL(GB200_ERR_NOMEM, "cudaMalloc failed");
-		CK(cudaMemcpyAsync(pl->stash[c].p, pl->bufA[c].p, pl->bufA[c].bytes, cudaMemcpyDeviceToDevice, pl->ctx->stream));
+	for (uint32_t c = 0; c < pl->maxcomps; ++c) { // int32 input lives in A, packed input in the front of B
+		const size_t bytes = pl->sample_bytes == 4 ? pl->bufA[c].bytes : pl->bufA[c].bytes / 4 * pl->sample_bytes;
+		if (pl->stash[c].bytes != bytes && pl->stash[c].alloc(bytes)) FAIL(GB200_ERR_NOMEM, "cudaMalloc failed");
+		CK(cudaMemcpyAsync(pl->stash[c].p, pl->sample_bytes == 4 ? pl->bufA[c].p : pl->bufB[c].p, bytes, cudaMemcpyDeviceToDevice, pl->ctx->stream));
 	}
 	return GB200_OK;
 }
@@ -563,11 +617,41 @@ int gb200_encode_restore(gb200_plan *pl) {
 	if (!pl || !pl->encoder || pl->stash.size() != pl->maxcomps) FAIL(GB200_ERR_PARAM, "nothing stashed");
 	CK(cudaSetDevice(pl->ctx->device));
 	for (uint32_t c = 0; c < pl->maxcomps; ++c)
-		CK(cudaMemcpyAsync(pl->bufA[c].p, pl->stash[c].p, pl->bufA[c].bytes, cudaMemcpyDeviceToDevice, pl->ctx->stream));
+		CK(cudaMemcpyAsync(pl->sample_bytes == 4 ? pl->bufA[c].p : pl->bufB[c].p, pl->stash[c].p, pl->stash[c].bytes, cudaMemcpyDeviceToDevice, pl->ctx->stream));
 	return GB200_OK;
 }
 
+// packed input: every component takes the widening pass, also a reversible one without level shift
+static int run_dc_mct_fwd_packed(gb200_plan *pl) {
+	gb200_ctx *ctx = pl->ctx;
+	cudaStream_t s = ctx->stream;
+	const uint32_t sb = pl->sample_bytes;
+	int n = 0;
+	auto one = [&](const TileGeom &tg, bool whole) {
+		uint32_t first = 0;
+		const auto &p = tg.comps;
+		auto off = [&](uint32_t c) { return whole ? (uint64_t) 0 : p[c].plane_off; };
+		auto cnt = [&](uint32_t c) { return whole ? pl->comp_elems[c] : (uint64_t) p[c].w * p[c].h; };
+		if (tg.mct) {
+			launch_mct_fwd_packed(packed_ptr(pl, 1, 0, off(0)), packed_ptr(pl, 1, 1, off(1)), packed_ptr(pl, 1, 2, off(2)),
+					plane_ptr(pl, 0, 0, off(0)), plane_ptr(pl, 0, 1, off(1)), plane_ptr(pl, 0, 2, off(2)), cnt(0),
+					p[0].p.dc_shift, p[1].p.dc_shift, p[2].p.dc_shift, p[0].p.qmfbid == 1, sb, (int) p[0].p.sgnd, s);
+			n++;
+			first = 3;
+		}
+		for (uint32_t c = first; c < tg.numcomps; ++c) {
+			launch_dcshift_fwd_packed(packed_ptr(pl, 1, c, off(c)), plane_ptr(pl, 0, c, off(c)), cnt(c), p[c].p.dc_shift, p[c].p.qmfbid == 1, sb,
+					(int) p[c].p.sgnd, s);
+			n++;
+		}
+	};
+	if (pl->uniform) one(pl->tiles[0], true);
+	else for (auto &tg : pl->tiles) one(tg, false);
+	return launch_check(ctx, n);
+}
+
 static int run_dc_mct_fwd(gb200_plan *pl) {
+	if (pl->sample_bytes != 4) return run_dc_mct_fwd_packed(pl);
 	gb200_ctx *ctx = pl->ctx;
 	cudaStream_t s = ctx->stream;
 	int n = 0;
@@ -617,8 +701,8 @@ static int run_dwt(gb200_plan *pl, bool fwd) {
 		for (int r = 0; r < 2; ++r) {
 			LevelLaunch &L = pl->lvl[r][i];
 			if (!L.ctas || (only >= 0 && (int) i != only)) continue;
-			if (fwd) launch_dwt_fwd((const DwtPlane*) L.dev.p, (const uint32_t*) L.map.p, L.ctas, r, L.tile_rows, L.unroll, L.halo_lanes, ctx->stream);
-			else launch_dwt_inv((const DwtPlane*) L.dev.p, (const uint32_t*) L.map.p, L.ctas, r, L.tile_rows, L.unroll, L.halo_lanes, ctx->stream);
+			if (fwd) launch_dwt_fwd((const DwtPlane*) L.dev.p, (const uint32_t*) L.map.p, L.ctas, r, L.rows, L.unroll, L.halo_lanes, ctx->stream);
+			else launch_dwt_inv((const DwtPlane*) L.dev.p, (const uint32_t*) L.map.p, L.ctas, r, L.rows, L.unroll, L.halo_lanes, ctx->stream);
 			n++;
 		}
 	return launch_check(ctx, n);
@@ -633,7 +717,7 @@ static int run_t1_enc(gb200_plan *pl) {
 	launch_t1_encode((const EncBlock*) pl->d_blocks.p, nb, rc, pl->styles ? 1 : 0, (uint8_t*) pl->d_symbols.p, (uint8_t*) pl->d_scratch.p,
 			(EncResult*) pl->d_results.p, (uint32_t*) pl->d_rates.p, (double*) pl->d_dists.p, ctx->stream);
 	launch_t1_gather((const EncBlock*) pl->d_blocks.p, (EncResult*) pl->d_results.p, nb, (const uint8_t*) pl->d_scratch.p,
-			(uint8_t*) pl->d_data.p, ctx->stream);
+			(uint8_t*) pl->d_data.p, (uint64_t*) pl->d_total.p, ctx->stream);
 	return launch_check(ctx, 4);
 }
 
@@ -658,24 +742,28 @@ int gb200_encode_download(gb200_plan *pl, gb200_cblk_enc *blocks, uint32_t *rate
 	cudaStream_t s = pl->ctx->stream;
 	const size_t nb = pl->blocks.size();
 	static_assert(sizeof(gb200_cblk_enc) == sizeof(EncResult), "ABI mismatch");
+	// One pass over PCIe: the byte count of the compacted data comes back first (8 bytes behind the kernels), and while
+	// the block results and pass tables are still in flight the data copy is queued right behind them.
+	uint64_t total = 0;
 	if (nb) {
+		CK(cudaMemcpyAsync(pl->h_total, pl->d_total.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+		CK(cudaEventRecord(pl->ev_total, s));
 		CK(cudaMemcpyAsync(blocks, pl->d_results.p, nb * sizeof(EncResult), cudaMemcpyDeviceToHost, s));
 		CK(cudaMemcpyAsync(rates, pl->d_rates.p, pl->pass_slots * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-		CK(cudaMemcpyAsync(dists, pl->d_dists.p, pl->pass_slots * sizeof(double), cudaMemcpyDeviceToHost, s));
+		bool rc = false;
+		for (auto &tg : pl->tiles) rc |= tg.rate_control != 0;
+		if (rc) CK(cudaMemcpyAsync(dists, pl->d_dists.p, pl->pass_slots * sizeof(double), cudaMemcpyDeviceToHost, s));
+		else memset(dists, 0, pl->pass_slots * sizeof(double)); // no distortions are computed without rate control
+		CK(cudaEventSynchronize(pl->ev_total));
+		total = *pl->h_total;
+		if (total <= data_capacity && total && data) CK(cudaMemcpyAsync(data, pl->d_data.p, total, cudaMemcpyDeviceToHost, s));
 	}
 	CK(cudaStreamSynchronize(s));
 	CK(cudaGetLastError());
-	uint64_t total = 0;
-	for (size_t i = 0; i < nb; ++i) {
+	for (size_t i = 0; i < nb; ++i)
 		if (blocks[i].numpasses == 0xFFFFFFFFu) FAIL(GB200_ERR_CAPACITY, "a code block overflowed its byte or pass budget");
-		total = std::max<uint64_t>(total, blocks[i].data_offset + blocks[i].data_len);
-	}
 	*data_len = total;
 	if (total > data_capacity || (total && !data)) FAIL(GB200_ERR_CAPACITY, "data buffer too small for the compressed code blocks");
-	if (total) {
-		CK(cudaMemcpyAsync(data, pl->d_data.p, total, cudaMemcpyDeviceToHost, s));
-		CK(cudaStreamSynchronize(s));
-	}
 	return GB200_OK;
 }
 
@@ -700,6 +788,15 @@ int gb200_encode_slopes(gb200_plan *pl, uint16_t *slopes) {
 int gb200_encode_tiles(gb200_plan *pl, const int32_t *const *planes, gb200_cblk_enc *blocks, uint32_t *rates, double *dists,
 		uint8_t *data, uint64_t data_capacity, uint64_t *data_len) {
 	int rc = gb200_encode_upload(pl, planes);
+	if (rc) return rc;
+	rc = gb200_encode_run(pl);
+	if (rc) return rc;
+	return gb200_encode_download(pl, blocks, rates, dists, data, data_capacity, data_len);
+}
+
+int gb200_encode_tiles_packed(gb200_plan *pl, const void *const *planes, gb200_cblk_enc *blocks, uint32_t *rates, double *dists,
+		uint8_t *data, uint64_t data_capacity, uint64_t *data_len) {
+	int rc = gb200_encode_upload_packed(pl, planes);
 	if (rc) return rc;
 	rc = gb200_encode_run(pl);
 	if (rc) return rc;
@@ -735,9 +832,13 @@ int gb200_decode_upload(gb200_plan *pl, const gb200_cblk_dec *blocks, const uint
 	cudaStream_t s = pl->ctx->stream;
 	const size_t nb = pl->blocks.size();
 	static_assert(sizeof(gb200_cblk_dec) == sizeof(DecInput), "ABI mismatch");
-	for (size_t i = 0; i < nb; ++i)
+	for (size_t i = 0; i < nb; ++i) {
 		if (blocks[i].data_len && blocks[i].data_offset + blocks[i].data_len > data_len)
 			FAIL(GB200_ERR_PARAM, "code block bytes lie outside the data buffer");
+		// the reference fails the decode of such a block (t1.cpp:1055-1058); never leave it silently zero
+		if (blocks[i].data_len && blocks[i].numbps + pl->decblocks[i].roishift > 30)
+			FAIL(GB200_ERR_UNSUPPORTED, "a code block has more than 30 bit planes (t1.cpp:1056)");
+	}
 	if (pl->d_data.bytes < data_len + T1_DEC_DATA_SLACK) {
 		if (pl->d_data.alloc(align_up(data_len + T1_DEC_DATA_SLACK, 256))) FAIL(GB200_ERR_NOMEM, "cudaMalloc failed for the compressed data");
 	}
@@ -775,15 +876,56 @@ static int run_t1_dec(gb200_plan *pl) {
 	return launch_check(pl->ctx, T1_DEC_LAUNCHES);
 }
 
+static void sample_range(const gb200_comp_params &p, int32_t &lo, int32_t &hi) {
+	if (p.sgnd) { lo = -(1 << (p.prec - 1)); hi = (1 << (p.prec - 1)) - 1; }
+	else { lo = 0; hi = (int32_t) ((1u << p.prec) - 1); }
+}
+
+// packed output: the finished planes are narrowed into the A buffers (the coefficient planes, consumed by then)
+static int run_mct_dc_inv_packed(gb200_plan *pl) {
+	gb200_ctx *ctx = pl->ctx;
+	cudaStream_t s = ctx->stream;
+	const uint32_t sb = pl->sample_bytes;
+	int n = 0;
+	bool same_role = true;
+	for (int r : pl->final_role) if (r != pl->final_role[0]) same_role = false;
+	size_t tc = 0;
+	auto one = [&](const TileGeom &tg, bool whole) {
+		uint32_t first = 0;
+		const auto &p = tg.comps;
+		auto off = [&](uint32_t c) { return whole ? (uint64_t) 0 : p[c].plane_off; };
+		auto cnt = [&](uint32_t c) { return whole ? pl->comp_elems[c] : (uint64_t) p[c].w * p[c].h; };
+		auto role = [&](uint32_t c) { return pl->final_role[whole ? 0 : tc + c]; };
+		if (tg.mct) {
+			int32_t sh[3], lo[3], hi[3];
+			for (int c = 0; c < 3; ++c) { sh[c] = p[c].p.dc_shift; sample_range(p[c].p, lo[c], hi[c]); }
+			launch_mct_inv_packed(plane_ptr(pl, role(0), 0, off(0)), plane_ptr(pl, role(1), 1, off(1)), plane_ptr(pl, role(2), 2, off(2)),
+					packed_ptr(pl, 0, 0, off(0)), packed_ptr(pl, 0, 1, off(1)), packed_ptr(pl, 0, 2, off(2)), cnt(0), sh, lo, hi,
+					p[0].p.qmfbid == 1, sb, (int) p[0].p.sgnd, s);
+			n++;
+			first = 3;
+		}
+		for (uint32_t c = first; c < tg.numcomps; ++c) {
+			int32_t lo, hi;
+			sample_range(p[c].p, lo, hi);
+			launch_dcshift_inv_packed(plane_ptr(pl, role(c), c, off(c)), packed_ptr(pl, 0, c, off(c)), cnt(c), p[c].p.dc_shift, p[c].p.qmfbid == 1,
+					lo, hi, sb, (int) p[c].p.sgnd, s);
+			n++;
+		}
+		tc += tg.numcomps;
+	};
+	if (pl->uniform && same_role) one(pl->tiles[0], true);
+	else for (auto &tg : pl->tiles) one(tg, false);
+	return launch_check(ctx, n);
+}
+
 static int run_mct_dc_inv(gb200_plan *pl) {
+	if (pl->sample_bytes != 4) return run_mct_dc_inv_packed(pl);
 	gb200_ctx *ctx = pl->ctx;
 	cudaStream_t s = ctx->stream;
 	int n = 0;
 	size_t tc = 0;
-	auto range = [](const gb200_comp_params &p, int32_t &lo, int32_t &hi) {
-		if (p.sgnd) { lo = -(1 << (p.prec - 1)); hi = (1 << (p.prec - 1)) - 1; }
-		else { lo = 0; hi = (int32_t) ((1u << p.prec) - 1); }
-	};
+	auto range = [](const gb200_comp_params &p, int32_t &lo, int32_t &hi) { sample_range(p, lo, hi); };
 	const TileGeom &t0 = pl->tiles[0];
 	bool same_role = true;
 	for (int r : pl->final_role) if (r != pl->final_role[0]) same_role = false;
@@ -845,7 +987,7 @@ int gb200_decode_run(gb200_plan *pl) {
 	return GB200_OK;
 }
 
-int gb200_decode_download(gb200_plan *pl, int32_t *const *planes_out) {
+int gb200_decode_download_packed(gb200_plan *pl, void *const *planes_out) {
 	if (!pl || pl->encoder || !planes_out) FAIL(GB200_ERR_PARAM, "gb200_decode_download: bad arguments");
 	CK(cudaSetDevice(pl->ctx->device));
 	cudaStream_t s = pl->ctx->stream;
@@ -853,12 +995,18 @@ int gb200_decode_download(gb200_plan *pl, int32_t *const *planes_out) {
 	for (auto &tg : pl->tiles)
 		for (uint32_t c = 0; c < tg.numcomps; ++c, ++i) {
 			const CompGeom &cg = tg.comps[c];
-			size_t bytes = (size_t) cg.w * cg.h * sizeof(int32_t);
-			if (bytes) CK(cudaMemcpyAsync(planes_out[i], plane_ptr(pl, pl->final_role[i], c, cg.plane_off), bytes, cudaMemcpyDeviceToHost, s));
+			size_t bytes = (size_t) cg.w * cg.h * pl->sample_bytes;
+			const void *src = pl->sample_bytes == 4 ? (const void*) plane_ptr(pl, pl->final_role[i], c, cg.plane_off) : (const void*) packed_ptr(pl, 0, c, cg.plane_off);
+			if (bytes) CK(cudaMemcpyAsync(planes_out[i], src, bytes, cudaMemcpyDeviceToHost, s));
 		}
 	CK(cudaStreamSynchronize(s));
 	CK(cudaGetLastError());
 	return GB200_OK;
+}
+
+int gb200_decode_download(gb200_plan *pl, int32_t *const *planes_out) {
+	if (pl && pl->sample_bytes != 4) FAIL(GB200_ERR_PARAM, "this plan returns packed samples: use gb200_decode_download_packed");
+	return gb200_decode_download_packed(pl, reinterpret_cast<void *const *>(planes_out));
 }
 
 int gb200_decode_tiles(gb200_plan *pl, const gb200_cblk_dec *blocks, const uint8_t *data, uint64_t data_len, int32_t *const *planes_out) {
@@ -867,6 +1015,14 @@ int gb200_decode_tiles(gb200_plan *pl, const gb200_cblk_dec *blocks, const uint8
 	rc = gb200_decode_run(pl);
 	if (rc) return rc;
 	return gb200_decode_download(pl, planes_out);
+}
+
+int gb200_decode_tiles_packed(gb200_plan *pl, const gb200_cblk_dec *blocks, const uint8_t *data, uint64_t data_len, void *const *planes_out) {
+	int rc = gb200_decode_upload(pl, blocks, data, data_len);
+	if (rc) return rc;
+	rc = gb200_decode_run(pl);
+	if (rc) return rc;
+	return gb200_decode_download_packed(pl, planes_out);
 }
 
 int gb200_decode_set_coefficients(gb200_plan *pl, uint32_t tileno, uint32_t compno, const int32_t *in) {
@@ -1031,7 +1187,7 @@ int gb200_t1_encode_blocks(gb200_ctx *ctx, const int32_t *plane, uint32_t width,
 	cudaMemsetAsync(d_dists.p, 0, d_dists.bytes, s);
 	launch_t1_encode((const EncBlock*) d_blocks.p, nblocks, rate_control, styles ? 1 : 0, (uint8_t*) d_symbols.p, (uint8_t*) d_scratch.p,
 			(EncResult*) d_results.p, (uint32_t*) d_rates.p, (double*) d_dists.p, s);
-	launch_t1_gather((const EncBlock*) d_blocks.p, (EncResult*) d_results.p, nblocks, (const uint8_t*) d_scratch.p, (uint8_t*) d_data.p, s);
+	launch_t1_gather((const EncBlock*) d_blocks.p, (EncResult*) d_results.p, nblocks, (const uint8_t*) d_scratch.p, (uint8_t*) d_data.p, nullptr, s);
 	int rc = launch_check(ctx, 4);
 	if (!rc && nblocks) {
 		cudaMemcpyAsync(results, d_results.p, nblocks * sizeof(EncResult), cudaMemcpyDeviceToHost, s);

@@ -61,16 +61,24 @@ void launch_dcshift_inv(int32_t *x, uint64_t n, int32_t shift, int reversible, i
 void launch_mct_inv(int32_t *c0, int32_t *c1, int32_t *c2, uint64_t n, const int32_t shift[3], const int32_t lo[3],
 		const int32_t hi[3], int reversible, int do_shift_clamp, cudaStream_t s);
 
-// dwt.cu : one launch = one decomposition level of every plane in `planes` (device array).
-// tile_rows > 0: shared-memory kernels, 64, 32 or 16 valid rows per CTA, dwt_tile_shape() valid columns;
-// tile_rows < 0: streaming kernels (dwt_stream.cuh), one warp per work item of -tile_rows rows by dwt_stream_shape() columns,
-//                `unroll` row pairs prefetched (1, 2 or 4), `halo_lanes` 1 or 2; total_ctas counts work items.
-// DwtPlane::tiles_x / tiles_y must have been computed for the same shape (streaming: over rw + cas_x / rh + cas_y).
-void launch_dwt_fwd(const DwtPlane *planes_dev, const uint32_t *cta_plane_dev, uint32_t total_ctas, int reversible, int tile_rows,
+// narrow-sample boundary: packed 8 / 16-bit samples (sample_bytes 1 or 2, sgnd: int8 / int16) widened on load, narrowed on store
+void launch_mct_fwd_packed(const void *s0, const void *s1, const void *s2, int32_t *c0, int32_t *c1, int32_t *c2, uint64_t n,
+		int32_t sh0, int32_t sh1, int32_t sh2, int reversible, uint32_t sample_bytes, int sgnd, cudaStream_t s);
+void launch_mct_inv_packed(const int32_t *c0, const int32_t *c1, const int32_t *c2, void *d0, void *d1, void *d2, uint64_t n,
+		const int32_t shift[3], const int32_t lo[3], const int32_t hi[3], int reversible, uint32_t sample_bytes, int sgnd, cudaStream_t s);
+void launch_dcshift_fwd_packed(const void *src, int32_t *dst, uint64_t n, int32_t shift, int reversible, uint32_t sample_bytes, int sgnd,
+		cudaStream_t s);
+void launch_dcshift_inv_packed(const int32_t *src, void *dst, uint64_t n, int32_t shift, int reversible, int32_t lo, int32_t hi,
+		uint32_t sample_bytes, int sgnd, cudaStream_t s);
+
+// dwt.cu : one launch = one decomposition level of every plane in `planes` (device array).  Streaming kernels
+// (dwt_stream.cuh): one warp per work item of `rows` rows by dwt_stream_shape() columns, `unroll` row pairs prefetched
+// (1, 2 or 4), `halo_lanes` 1 or 2; total_items counts work items.  DwtPlane::tiles_x / tiles_y must have been computed for
+// the same shape (over rw + cas_x / rh + cas_y).
+void launch_dwt_fwd(const DwtPlane *planes_dev, const uint32_t *item_plane_dev, uint32_t total_items, int reversible, int rows,
 		int unroll, int halo_lanes, cudaStream_t s);
-void launch_dwt_inv(const DwtPlane *planes_dev, const uint32_t *cta_plane_dev, uint32_t total_ctas, int reversible, int tile_rows,
+void launch_dwt_inv(const DwtPlane *planes_dev, const uint32_t *item_plane_dev, uint32_t total_items, int reversible, int rows,
 		int unroll, int halo_lanes, cudaStream_t s);
-void dwt_tile_shape(int reversible, uint32_t *tw); // valid columns per CTA
 int dwt_stream_warps_per_sm(int reversible, int forward, int unroll); // work items resident per SM (occupancy of that kernel)
 void dwt_stream_shape(int halo_lanes, uint32_t *tw); // valid columns per work item of the streaming kernels (halo_lanes 1 or 2)
 
@@ -79,8 +87,9 @@ uint32_t t1_symbol_capacity(uint32_t w, uint32_t h, uint32_t planes);
 // styles: non-zero when any block of the table has a code-block style switch set (selects the general MQ kernel)
 void launch_t1_encode(const EncBlock *blocks, uint32_t nblocks, int rate_control, int styles, uint8_t *symbols, uint8_t *scratch,
 		EncResult *results, uint32_t *rates, double *dists, cudaStream_t s);
+// total (may be NULL): receives the byte count of the compacted data
 void launch_t1_gather(const EncBlock *blocks, EncResult *results, uint32_t nblocks, const uint8_t *scratch,
-		uint8_t *data, cudaStream_t s);
+		uint8_t *data, uint64_t *total, cudaStream_t s);
 // rd.cu : feasible truncation points and 8.8 log slopes of every block (RateControl.cpp:31-168); cache: one double per pass slot
 void launch_rd_slopes(const EncBlock *blocks, const EncResult *results, uint32_t nblocks, const uint32_t *rates, const double *dists,
 		uint16_t *slopes, double *cache, cudaStream_t s);

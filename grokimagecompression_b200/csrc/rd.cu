@@ -27,7 +27,9 @@ __global__ void __launch_bounds__(128) rd_slopes_kernel(const EncBlock *__restri
 		double *__restrict__ cache, SlopeConsts k) {
 	const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
 	if (b >= nblocks) return;
-	const uint32_t off = blocks[b].pass_offset, n = results[b].numpasses;
+	// an overflowed block carries numpasses = 0xFFFFFFFF (t1_enc.cu): nothing to do, and never walk past the block's slots
+	const uint32_t off = blocks[b].pass_offset, np = results[b].numpasses;
+	const uint32_t n = np == 0xFFFFFFFFu ? 0u : min(np, blocks[b].max_passes);
 	const uint32_t *rate = rates + off;  // cumulative bytes; the pass length is the difference (t1.cpp:1303-1324)
 	const double *dist = dists + off;    // cumulative distortion decrease
 	uint16_t *slope = slopes + off;

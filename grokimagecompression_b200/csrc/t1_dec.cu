@@ -388,7 +388,10 @@ __global__ void __launch_bounds__(DT_MAX_THREADS, 1) t1_decode_kernel(const DecB
 		const uint32_t s0 = seg_start ? seg_start[bid] : 0u, nsegs = seg_start ? seg_start[bid + 1] - s0 : 1u;
 		uint32_t off = 0;
 		for (uint32_t sg = 0; sg < nsegs && bp1 >= 1; ++sg) {
-			const uint32_t len = seg_start ? segs[s0 + sg].len : I.data_len, np = seg_start ? segs[s0 + sg].numpasses : I.numpasses;
+			// a segment never reaches past the block's bytes (corrupt packet headers: sum of the lengths > data_len); what is
+			// missing reads as the 0xFF fill of an exhausted segment
+			const uint32_t left = off < I.data_len ? I.data_len - off : 0u;
+			const uint32_t len = min(seg_start ? segs[s0 + sg].len : I.data_len, left), np = seg_start ? segs[s0 + sg].numpasses : I.numpasses;
 			const bool raw = (sty & STY_LAZY) && bp1 <= numbps - 4 && type < 2;
 			const uint8_t *seg = data + I.data_offset + off;
 			if (raw) { b.rbuf = seg; b.rpos = 0; b.rlen = len; b.rc = 0; b.rct = 0; } // mqc_raw_init_dec
@@ -440,12 +443,10 @@ __global__ void __launch_bounds__(256) t1_dec_finish_kernel(const DecBlock *__re
 		}
 }
 
-static bool g_dec_tables_ready = false;
-
 int launch_t1_decode(const DecBlock *blocks, const DecInput *inputs, uint32_t nblocks, const uint8_t *data,
 		uint32_t max_w, uint32_t max_h, int styles, const uint32_t *seg_start, const DecSeg *segs, cudaStream_t s) {
 	if (!nblocks) return 0;
-	if (!g_dec_tables_ready) { build_and_upload_t1_tables(); g_dec_tables_ready = true; }
+	ensure_t1_tables();
 	int dev = 0, sms = 148, smem_max = 0;
 	cudaGetDevice(&dev);
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

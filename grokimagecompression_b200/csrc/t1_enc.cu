@@ -588,7 +588,7 @@ __global__ void __launch_bounds__(MQ_WARPS * 32) t1_mq_kernel(const EncBlock *__
 }
 
 // ---- compaction: exclusive prefix sum of the block lengths, then one warp copies each block ----
-__global__ void __launch_bounds__(1024) t1_offsets_kernel(EncResult *results, uint32_t nblocks) {
+__global__ void __launch_bounds__(1024) t1_offsets_kernel(EncResult *results, uint32_t nblocks, uint64_t *total) {
 	__shared__ uint64_t part[1024];
 	const uint32_t per = (nblocks + 1023) / 1024;
 	const uint32_t b0 = threadIdx.x * per, b1 = min(nblocks, b0 + per);
@@ -603,6 +603,7 @@ __global__ void __launch_bounds__(1024) t1_offsets_kernel(EncResult *results, ui
 	__syncthreads();
 	uint64_t off = part[threadIdx.x];
 	for (uint32_t i = b0; i < b1; ++i) { results[i].data_offset = off; off += results[i].data_len; }
+	if (total && threadIdx.x == 1023) *total = off; // the last thread ends at the sum of all lengths
 }
 
 __global__ void __launch_bounds__(256) t1_gather_kernel(const EncBlock *__restrict__ blocks, const EncResult *__restrict__ results,
@@ -616,12 +617,10 @@ __global__ void __launch_bounds__(256) t1_gather_kernel(const EncBlock *__restri
 	for (uint32_t i = lane; i < n; i += 32) dst[i] = src[i];
 }
 
-static bool g_tables_ready = false;
-
 void launch_t1_encode(const EncBlock *blocks, uint32_t nblocks, int rate_control, int styles, uint8_t *symbols, uint8_t *scratch,
 		EncResult *results, uint32_t *rates, double *dists, cudaStream_t s) {
 	if (!nblocks) return;
-	if (!g_tables_ready) { build_and_upload_t1_tables(); g_tables_ready = true; }
+	ensure_t1_tables();
 	t1_model_kernel<<<(nblocks + ENC_WARPS - 1) / ENC_WARPS, ENC_WARPS * 32, 0, s>>>(blocks, nblocks, rate_control, symbols, results, dists);
 	// few blocks per SM: the launch is bound by the latency of one coder's chain, give every coder its own warp
 	int dev = 0, sms = 148;
@@ -644,9 +643,9 @@ uint32_t t1_symbol_capacity(uint32_t w, uint32_t h, uint32_t planes) {
 }
 
 void launch_t1_gather(const EncBlock *blocks, EncResult *results, uint32_t nblocks, const uint8_t *scratch, uint8_t *data,
-		cudaStream_t s) {
+		uint64_t *total, cudaStream_t s) {
 	if (!nblocks) return;
-	t1_offsets_kernel<<<1, 1024, 0, s>>>(results, nblocks);
+	t1_offsets_kernel<<<1, 1024, 0, s>>>(results, nblocks, total);
 	t1_gather_kernel<<<(nblocks + 7) / 8, 256, 0, s>>>(blocks, results, nblocks, scratch, data);
 }
 

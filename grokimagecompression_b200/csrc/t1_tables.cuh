@@ -6,6 +6,7 @@
 #include <cstdint>
 #include <cmath>
 #include <cuda_runtime.h>
+#include <mutex>
 
 namespace gb {
 
@@ -85,6 +86,20 @@ static inline void build_and_upload_t1_tables() {
 		nm[3][i] = fix(u * u);
 	}
 	cudaMemcpyToSymbol(c_nmsedec, nm, sizeof(nm));
+}
+
+// __constant__ memory is per device and a process may hold contexts on several (gb200_create(device)): the tables of this
+// translation unit are uploaded once per device, under a lock (contexts are driven from several host threads)
+static inline void ensure_t1_tables() {
+	static std::mutex mu;
+	static uint64_t ready[4] = {0, 0, 0, 0}; // bit per device ordinal
+	int dev = 0;
+	cudaGetDevice(&dev);
+	std::lock_guard<std::mutex> lk(mu);
+	if (dev >= 0 && dev < 256 && (ready[dev >> 6] >> (dev & 63) & 1)) return;
+	build_and_upload_t1_tables();
+	cudaDeviceSynchronize(); // cudaMemcpyToSymbol from pageable memory has completed on return; be explicit
+	if (dev >= 0 && dev < 256) ready[dev >> 6] |= 1ull << (dev & 63);
 }
 
 } // namespace gb

@@ -33,7 +33,7 @@ extern "C" {
 
 #define GB200_MAX_RES 33
 #define GB200_MAX_BANDS (3 * GB200_MAX_RES - 2)
-#define GB200_ABI_VERSION 2
+#define GB200_ABI_VERSION 3
 #if defined(__GNUC__)
 #define GB200_API __attribute__((visibility("default")))
 #else
@@ -137,6 +137,15 @@ GB200_API uint64_t gb200_plan_num_pass_slots(const gb200_plan *plan);
 GB200_API uint64_t gb200_plan_num_samples(const gb200_plan *plan); /* sum of tile-component areas */
 GB200_API const gb200_cblk_info *gb200_plan_blocks(const gb200_plan *plan);
 GB200_API uint64_t gb200_plan_data_capacity(const gb200_plan *plan); /* worst-case encoder output bytes */
+/* the code blocks of one tile-component in the host's traversal order (resno, band, precinct, block), the geometry
+ * gb200_plan_create builds its block table from (TileComponent.cpp:193-489): pure host code, needs no device.  Fills
+ * out[0 .. min(count, cap)) (tileno, compno = 0; pass_offset counted from 0) and returns the count; numres_limit = the
+ * resolutions to enumerate (0 = all). */
+GB200_API uint64_t gb200_enumerate_blocks(const gb200_comp_params *comp, uint32_t numres_limit, gb200_cblk_info *out, uint64_t cap);
+/* precinct grid of one resolution of a tile-component (grk_tcd_resolution::pw, ph: TileComponent.cpp:303-328), the
+ * number of precincts every band of that resolution has in the host's tree, empty ones included.  Pure geometry: needs
+ * no device. */
+GB200_API int gb200_precinct_grid(const gb200_comp_params *comp, uint32_t resno, uint32_t *pw, uint32_t *ph);
 
 /* ---- whole path, host buffers (the call the host TCD makes per tile batch) ------------------- */
 /* planes[t * numcomps + c]: int32 samples of tile t / component c, row stride = x1 - x0
@@ -146,6 +155,20 @@ GB200_API int gb200_encode_tiles(gb200_plan *plan, const int32_t *const *planes,
 /* planes_out[t * numcomps + c]: decoded int32 samples, row stride = width of the decoded resolution */
 GB200_API int gb200_decode_tiles(gb200_plan *plan, const gb200_cblk_dec *blocks, const uint8_t *data, uint64_t data_len,
 		int32_t *const *planes_out);
+
+/* ---- narrow-sample boundary --------------------------------------------------------------------
+ * The reference expands every image sample to int32 on the host before its tile coder sees it and narrows the decoded
+ * tile back afterwards (TileProcessor.cpp:1201-1258 copy-in, 1691-1921 copy-out); over PCIe that is 4 bytes per 8-bit
+ * sample in each direction.  A plan set to 1 or 2 bytes per sample takes / returns the packed samples themselves
+ * (uint8 / uint16, int8 / int16 for signed components; row stride = width) and widens / clamps + narrows them inside the
+ * level-shift + MCT pass on the device.  Every component's precision must fit the type.  4 (the default) = int32 planes. */
+GB200_API int gb200_plan_set_sample_bytes(gb200_plan *plan, uint32_t sample_bytes);
+GB200_API int gb200_encode_tiles_packed(gb200_plan *plan, const void *const *planes, gb200_cblk_enc *blocks, uint32_t *rates,
+		double *dists, uint8_t *data, uint64_t data_capacity, uint64_t *data_len);
+GB200_API int gb200_decode_tiles_packed(gb200_plan *plan, const gb200_cblk_dec *blocks, const uint8_t *data, uint64_t data_len,
+		void *const *planes_out);
+GB200_API int gb200_encode_upload_packed(gb200_plan *plan, const void *const *planes);
+GB200_API int gb200_decode_download_packed(gb200_plan *plan, void *const *planes_out);
 
 /* ---- the same path split in upload / run / download, so a caller can time the device part ---- */
 GB200_API int gb200_encode_upload(gb200_plan *plan, const int32_t *const *planes);

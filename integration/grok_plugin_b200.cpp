@@ -205,19 +205,22 @@ void build_tree(Tree &T, gb200_plan *plan, uint32_t nc, const gb200_comp_params 
 			grk_plugin_band *bands = T.bands.back().get();
 			for (uint32_t b = 0; b < nbands; ++b) {
 				const uint32_t orient = r ? b + 1 : 0, bi = r ? 3 * r - 2 + b : 0;
-				/* precincts and blocks of this band: highest indices present in the table */
-				size_t nprec = 0;
+				/* every precinct of the resolution's grid exists in the host's tree, also those (and those bands) without a
+				 * block: the host indexes precincts[precno] for precno < pw * ph (plugin_bridge.cpp:38-43) */
+				uint32_t gpw = 0, gph = 0;
+				gb200_precinct_grid(&cps[c], r, &gpw, &gph);
+				size_t nprec = (size_t) gpw * gph;
 				for (size_t i = 0; i < nb; ++i)
 					if (info[i].compno == c && info[i].resno == r && info[i].bandno == orient) nprec = std::max<size_t>(nprec, info[i].precno + 1);
 				T.precs.emplace_back(new grk_plugin_precinct[nprec ? nprec : 1]);
-				T.prec_ptrs.emplace_back(nprec);
+				T.prec_ptrs.emplace_back(nprec ? nprec : 1, nullptr);
 				grk_plugin_precinct *precs = T.precs.back().get();
 				std::vector<size_t> nblk(nprec, 0);
 				for (size_t i = 0; i < nb; ++i)
 					if (info[i].compno == c && info[i].resno == r && info[i].bandno == orient)
 						nblk[info[i].precno] = std::max<size_t>(nblk[info[i].precno], info[i].cblkno + 1);
 				for (size_t pr = 0; pr < nprec; ++pr) {
-					T.blk_ptrs.emplace_back(nblk[pr]);
+					T.blk_ptrs.emplace_back(nblk[pr] ? nblk[pr] : 1, nullptr); /* never a NULL array */
 					precs[pr].numBlocks = nblk[pr];
 					precs[pr].blocks = T.blk_ptrs.back().data();
 					T.prec_ptrs.back()[pr] = precs + pr;
@@ -531,6 +534,8 @@ struct DecodeJob {
 	gb200_tile_params tp;
 	Tree T;
 	std::vector<uint64_t> offset; /* of each block in T.data */
+	std::vector<uint64_t> capacity; /* bytes reserved for each block */
+	uint64_t file_bytes = 0;       /* size of the codestream file: no block carries more */
 	bool ready = false;
 	int status = 0;
 };
@@ -569,13 +574,21 @@ int decode_init(grk_header_info *h, grk_image *img) {
 	gb200_plan *geo = nullptr; /* only for its block table */
 	if (gb200_plan_create(g_ctx, 1, &J.tp, 0, &geo) != GB200_OK) { say("gb200_plan_create"); return 1; }
 	build_tree(J.T, geo, nc, J.cps.data());
-	/* the host writes each block's bytes without a capacity field (plugin_bridge.cpp:71-78): give every block the
-	 * reference encoder's own worst case (TileProcessor.cpp:2003-2018) plus slack */
+	/* the host writes each block's bytes without a capacity field (plugin_bridge.cpp:71-78): every block gets the
+	 * reference encoder's own worst case (TileProcessor.cpp:2003-2018) plus slack as its slot, and the arena ends with
+	 * as many spare bytes as the whole codestream file holds.  No block can carry more bytes than the file, so even a
+	 * crafted stream that overfills a slot stays inside the arena; decode_one checks every length against its slot after
+	 * the Tier-2 callback and leaves such a stream to the host. */
 	const size_t nb = J.T.blocks.size();
 	J.offset.resize(nb);
+	J.capacity.resize(nb);
 	uint64_t total = 0;
-	for (size_t i = 0; i < nb; ++i) { J.offset[i] = total; total += (J.T.blocks[i].numPix * 4 + 64 + 15) / 16 * 16; }
-	J.T.data.assign(total + 64, 0);
+	for (size_t i = 0; i < nb; ++i) {
+		J.offset[i] = total;
+		J.capacity[i] = (J.T.blocks[i].numPix * 4 + 64 + 15) / 16 * 16;
+		total += J.capacity[i];
+	}
+	J.T.data.assign(total + J.file_bytes + 64, 0);
 	for (size_t i = 0; i < nb; ++i) J.T.blocks[i].compressedData = J.T.data.data() + J.offset[i];
 	gb200_plan_destroy(geo);
 	J.ready = true;
@@ -592,6 +605,13 @@ int32_t decode_one(grk_decompress_parameters *dp, const std::string &infile, con
 		grk::PLUGIN_DECODE_USER_CALLBACK callback) {
 	DecodeJob J;
 	J.reduce = dp->core.cp_reduce;
+	{
+		FILE *f = fopen(infile.c_str(), "rb");
+		if (!f) return 2;
+		if (fseek(f, 0, SEEK_END) == 0) { const long n = ftell(f); if (n > 0) J.file_bytes = (uint64_t) n; }
+		fclose(f);
+		if (!J.file_bytes) return 2;
+	}
 	g_job = &J;
 	grk::PluginDecodeCallbackInfo info(infile, outfile, dp, fmt, GRK_DECODE_HEADER);
 	info.init_decoders_func = decode_init;
@@ -612,6 +632,8 @@ int32_t decode_one(grk_decompress_parameters *dp, const std::string &infile, con
 	if (rc || !info.image) return clean(rc ? rc : 1);
 	/* ---- device decode ---- */
 	const size_t nb = J.T.blocks.size();
+	for (size_t k = 0; k < nb; ++k) /* a block that outgrew its slot has overwritten its neighbours: not decodable from this arena */
+		if (J.T.blocks[k].compressedDataLength > J.capacity[k]) return clean(8);
 	for (uint32_t c = 0; c < J.nc; ++c) {
 		const grk_plugin_tile_component *tc = J.T.tile.tileComponents[c];
 		for (uint32_t r = 0; r < tc->numResolutions; ++r)
@@ -657,7 +679,7 @@ int32_t decode_one(grk_decompress_parameters *dp, const std::string &infile, con
 		if (!ic->data && !grk_image_single_component_data_alloc(ic)) return clean(5);
 		planes[c] = ic->data;
 	}
-	if (gb200_decode_tiles(plan, in.data(), J.T.data.data(), J.T.data.size() - 64, planes.data()) != GB200_OK) { say("gb200_decode_tiles"); return clean(4); }
+	if (gb200_decode_tiles(plan, in.data(), J.T.data.data(), J.T.data.size() - 64 - J.file_bytes, planes.data()) != GB200_OK) { say("gb200_decode_tiles"); return clean(4); }
 	g_decodes++;
 	info.decode_flags = GRK_DECODE_POST_T1;
 	try { rc = callback(&info); } catch (...) { rc = 7; }

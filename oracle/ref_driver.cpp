@@ -285,6 +285,17 @@ static int32_t g_roi_compno = -1;
 static uint32_t g_roi_shift = 0;
 void ref_set_roi(int32_t compno, uint32_t shift) { g_roi_compno = compno; g_roi_shift = shift; }
 
+/* precinct sizes (grk_compress -c [w,h],[w,h],...: first entry = highest resolution, the last one is halved for every further
+ * resolution, j2k.cpp:2001-2048) for the following ref_encode_image calls; n = 0: the default (maximal precincts) */
+static uint32_t g_prc_n = 0, g_prc_w[GRK_J2K_MAXRLVLS], g_prc_h[GRK_J2K_MAXRLVLS];
+void ref_set_precincts(uint32_t n, const uint32_t *w, const uint32_t *h) {
+	g_prc_n = n > GRK_J2K_MAXRLVLS ? GRK_J2K_MAXRLVLS : n;
+	for (uint32_t i = 0; i < g_prc_n; ++i) { g_prc_w[i] = w[i]; g_prc_h[i] = h[i]; }
+}
+/* progression order (grk_compress -p: 0 LRCP, 1 RLCP, 2 RPCL, 3 PCRL, 4 CPRL) for the following ref_encode_image calls; < 0: default */
+static int g_prog = -1;
+void ref_set_progression(int prog) { g_prog = prog; }
+
 /* grk_compress-equivalent: planar int32 image -> raw J2K codestream.
  *   tile_w/tile_h 0 = single tile;  rates[numlayers] = compression ratios (-r); numlayers 0 = lossless
  *   cinema2k_fps 24/48 = -w profile.  Returns the codestream length, or -1. */
@@ -305,6 +316,12 @@ int64_t ref_encode_image(uint32_t numcomps, uint32_t w, uint32_t h, uint32_t pre
 	param.cblk_sty = (uint8_t) g_cblk_sty;
 	param.roi_compno = g_roi_compno;
 	param.roi_shift = g_roi_compno >= 0 ? g_roi_shift : 0;
+	if (g_prc_n) {
+		param.csty |= 0x01;
+		param.res_spec = g_prc_n;
+		for (uint32_t i = 0; i < g_prc_n; ++i) { param.prcw_init[i] = g_prc_w[i]; param.prch_init[i] = g_prc_h[i]; }
+	}
+	if (g_prog >= 0) param.prog_order = (GRK_PROG_ORDER) g_prog;
 	if (tile_w && tile_h) {
 		param.tile_size_on = true;
 		param.cp_tdx = tile_w;
@@ -543,12 +560,19 @@ int ref_plugin_decode(const char *plugin_dir, const uint8_t *buf, uint64_t len, 
 	param.core.cp_layer = layers;
 	param.decod_format = GRK_J2K_FMT;
 	param.cod_format = GRK_PXM_FMT;
-	strcpy(param.infile, "memory.j2k");
+	/* the plugin sizes its byte arena from the codestream FILE (as under grk_decompress -i); the decode itself reads the memory stream */
+	snprintf(param.infile, sizeof(param.infile), "/tmp/grkref_plugin_%d.j2k", (int) getpid());
+	{
+		FILE *f = fopen(param.infile, "wb");
+		if (!f || fwrite(buf, 1, len, f) != len) { if (f) fclose(f); grk_plugin_cleanup(); return -4; }
+		fclose(f);
+	}
 	strcpy(param.outfile, "memory.ppm");
 	g_dec_from_files = false;
 	g_dec_in = buf; g_dec_in_len = len; g_dec_out = planes_out; g_dec_cap = plane_capacity; g_dec_dims = dims; g_dec_stored = 0;
 	int32_t rc = grk_plugin_decode(&param, plugin_dec_cb);
 	grk_plugin_cleanup();
+	remove(param.infile);
 	if (rc) return -2;
 	return g_dec_stored ? 0 : -3;
 }

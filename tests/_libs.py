@@ -11,6 +11,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
+PLUGIN_DIR = os.path.join(ROOT, "integration", "_build")  # where grk_plugin_load finds libgrok_plugin.so (`-g <dir>`)
 
 i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
 f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
@@ -75,6 +76,29 @@ def oracle():
     return L
 
 
+_tap = None
+
+
+def tap():
+    """oracle/_ref/libgrkref_tap.so (oracle/ref_tap.cpp): must be loaded BEFORE ref() so that the reference's stage calls
+    resolve to the tap's forwarding definitions"""
+    global _tap
+    if _tap is None:
+        assert _ref is None, "load the tap before the reference driver"
+        L = C.CDLL(os.path.join(ORACLE_DIR, "_ref", "libgrkref_tap.so"), mode=C.RTLD_GLOBAL)
+        L.ref_tap_seconds.argtypes = [C.c_int]
+        L.ref_tap_seconds.restype = C.c_double
+        L.ref_tap_calls.argtypes = [C.c_int]
+        L.ref_tap_calls.restype = C.c_uint64
+        L.ref_tap_geometry.argtypes = [C.c_int]
+        L.ref_tap_geometry.restype = C.c_uint64
+        _tap = L
+    return _tap
+
+
+TAP_STAGES = ("dc_enc", "mct_enc", "dwt_enc", "t1_enc", "t1_dec", "dwt_dec", "mct_dec", "dc_dec", "encode_tile", "decode_tile")
+
+
 def have_ref():
     return os.path.exists(os.path.join(ORACLE_DIR, "_ref", "libgrkref_driver.so"))
 
@@ -102,6 +126,8 @@ def ref():
     L.ref_t1_decode_cblk.argtypes = [u8p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                      C.c_uint32, C.c_uint32, i32p]
     L.ref_set_cblk_sty.argtypes = [C.c_uint32]
+    L.ref_set_precincts.argtypes = [C.c_uint32, u32p, u32p]
+    L.ref_set_progression.argtypes = [C.c_int]
     L.ref_set_roi.argtypes = [C.c_int32, C.c_uint32]
     L.ref_set_decode_area.argtypes = [C.c_uint32] * 4
     L.ref_t1_want_terms.argtypes = [u8p]
@@ -142,24 +168,28 @@ def write_pnm(path, planes, prec):
 
 
 def ref_plugin_encode_file(infile, area, tile=(0, 0), numres=6, cblk=(64, 64), irreversible=False, rates=(), rc_algorithm=1):
-    """`grk_compress -g oracle/_ref -i infile`: grk_plugin_load / init / encode with libgrok_plugin.so (integration/
+    """`grk_compress -g integration/_build -i infile`: grk_plugin_load / init / encode with libgrok_plugin.so (integration/
     grok_plugin_b200.cpp).  Returns the codestream bytes, or the negative status of ref_plugin_encode_file."""
     L = ref()
     cap = area * 4 * 3 + (1 << 20)
     out = np.zeros(cap, np.uint8)
     r = np.ascontiguousarray(rates, np.float64)
-    n = L.ref_plugin_encode_file(os.path.join(ORACLE_DIR, "_ref").encode(), infile.encode(), tile[0] or 0, tile[1] or 0, numres,
+    n = L.ref_plugin_encode_file(PLUGIN_DIR.encode(), infile.encode(), tile[0] or 0, tile[1] or 0, numres,
                                  cblk[0], cblk[1], int(irreversible), len(r), r.ctypes.data if len(r) else None, rc_algorithm, out, cap)
     return bytes(out[:n]) if n > 0 else int(n)
 
 
 def ref_encode_image(planes, prec, sgnd=0, tile=(0, 0), numres=6, cblk=(64, 64), irreversible=False, rates=(),
-                     cinema2k_fps=0, rc_algorithm=0, cblk_sty=0, roi=(-1, 0)):
+                     cinema2k_fps=0, rc_algorithm=0, cblk_sty=0, roi=(-1, 0), precincts=(), progression=-1):
     """planes: list of int32 [h,w] -> J2K codestream bytes produced by the unmodified reference (cblk_sty = grk_compress -M,
-    roi = (component, shift) = -ROI c=..,U=..)"""
+    roi = (component, shift) = -ROI c=..,U=.., precincts = [(w, h), ...] = -c, highest resolution first, progression = -p)"""
     L = ref()
     L.ref_set_cblk_sty(cblk_sty)
     L.ref_set_roi(roi[0], roi[1])
+    pw = np.ascontiguousarray([p[0] for p in precincts] or [0], np.uint32)
+    ph = np.ascontiguousarray([p[1] for p in precincts] or [0], np.uint32)
+    L.ref_set_precincts(len(precincts), pw, ph)
+    L.ref_set_progression(progression)
     h, w = planes[0].shape
     keep = [aligned(np.ascontiguousarray(p, np.int32)) for p in planes]
     pa = (C.c_void_p * len(keep))(*[k.ctypes.data for k in keep])
@@ -192,14 +222,14 @@ def ref_decode_image(cs, numcomps, width, height, reduce=0, layers=0, window=Non
 
 
 def ref_plugin_batch_encode(in_dir, max_frames, frame_area, numres=6, cblk=(64, 64), irreversible=False, rates=(), rc_algorithm=1):
-    """`grk_compress -g oracle/_ref -y in_dir`: the plugin owns the frame loop.  Returns the list of codestreams in file-name
+    """`grk_compress -g integration/_build -y in_dir`: the plugin owns the frame loop.  Returns the list of codestreams in file-name
     order, or the negative status of ref_plugin_batch_encode."""
     L = ref()
     cap = max_frames * (frame_area * 4 * 3 + (1 << 20))
     out = np.zeros(cap, np.uint8)
     lens = np.zeros(max_frames, np.uint64)
     r = np.ascontiguousarray(rates, np.float64)
-    n = L.ref_plugin_batch_encode(os.path.join(ORACLE_DIR, "_ref").encode(), in_dir.encode(), numres, cblk[0], cblk[1], int(irreversible),
+    n = L.ref_plugin_batch_encode(PLUGIN_DIR.encode(), in_dir.encode(), numres, cblk[0], cblk[1], int(irreversible),
                                   len(r), r.ctypes.data if len(r) else None, rc_algorithm, out, cap, lens, max_frames)
     if n < 0:
         return int(n)
@@ -211,12 +241,12 @@ def ref_plugin_batch_encode(in_dir, max_frames, frame_area, numres=6, cblk=(64, 
 
 
 def ref_plugin_batch_decode(in_dir, max_frames, plane_area, reduce=0):
-    """`grk_decompress -g oracle/_ref -y in_dir`: the plugin walks the codestreams of the directory.  Returns a list of
+    """`grk_decompress -g integration/_build -y in_dir`: the plugin walks the codestreams of the directory.  Returns a list of
     (comps, h, w) int32 arrays in file-name order, or the negative status of ref_plugin_batch_decode."""
     L = ref()
     out = np.zeros(max_frames * 3 * plane_area, np.int32)
     dims = np.zeros(max_frames * 3, np.uint32)
-    n = L.ref_plugin_batch_decode(os.path.join(ORACLE_DIR, "_ref").encode(), in_dir.encode(), reduce, out, plane_area, dims, max_frames)
+    n = L.ref_plugin_batch_decode(PLUGIN_DIR.encode(), in_dir.encode(), reduce, out, plane_area, dims, max_frames)
     if n < 0:
         return int(n)
     res = []
@@ -227,14 +257,14 @@ def ref_plugin_batch_decode(in_dir, max_frames, plane_area, reduce=0):
 
 
 def ref_plugin_decode(cs, numcomps, width, height, reduce=0, layers=0):
-    """`grk_decompress -g oracle/_ref`: grk_plugin_load / init / decode.  Returns the planes, or the negative status."""
+    """`grk_decompress -g integration/_build`: grk_plugin_load / init / decode.  Returns the planes, or the negative status."""
     L = ref()
     buf = np.frombuffer(cs, np.uint8).copy()
     cd = lambda v: (v + (1 << reduce) - 1) >> reduce
     planes = [np.zeros((cd(height), cd(width)), np.int32) for _ in range(numcomps)]
     pa = (C.c_void_p * numcomps)(*[p.ctypes.data for p in planes])
     dims = np.zeros(4, np.uint32)
-    rc = L.ref_plugin_decode(os.path.join(ORACLE_DIR, "_ref").encode(), buf, len(buf), reduce, layers, pa, planes[0].size, dims)
+    rc = L.ref_plugin_decode(PLUGIN_DIR.encode(), buf, len(buf), reduce, layers, pa, planes[0].size, dims)
     if rc:
         return int(rc)
     assert (dims[0], dims[1], dims[2]) == (planes[0].shape[1], planes[0].shape[0], numcomps), dims

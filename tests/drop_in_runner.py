@@ -47,6 +47,28 @@ CASES = {
     "roi53": (200, 150, 3, 8, True, (64, 64), 4, (32, 32), (), 1),
     "roi97": (256, 192, 1, 8, False, (0, 0), 5, (64, 64), (20, 5), 0),
 }
+# non-default precincts / profiles (TileComponent.cpp:303-328, 437-489; the cinema profile forces 32x32 blocks,
+# 256x256 precincts (128x128 at the lowest resolution), CPRL and a byte budget: j2kprofile.cpp:941-1080)
+CASES.update({
+    "cinema2k": (2048, 1080, 3, 12, False, (0, 0), 6, (32, 32), (), 0),
+    "prc53_64": (300, 217, 3, 8, True, (128, 96), 5, (32, 32), (), 1),
+    "prc97_mixed": (512, 384, 3, 8, False, (256, 256), 6, (64, 64), (20, 5), 0),
+    "prc53_clip": (211, 157, 1, 8, True, (0, 0), 4, (64, 64), (), 1),        # precincts smaller than the nominal code block
+    "prc97_rpcl": (400, 300, 3, 8, False, (0, 0), 5, (32, 32), (30, 8), 2),
+    # BASELINE.json configs at their full size, compared by digest (the arrays would be gigabytes)
+    "c2_full": (4096, 2160, 3, 8, False, (1024, 1024), 6, (64, 64), (40, 20, 10, 5), 0),
+    "c3_full": (8192, 8192, 3, 16, True, (1024, 1024), 6, (64, 64), (), 0),
+    "c5_53": (16384, 16384, 1, 8, True, (1024, 1024), 6, (64, 64), (), "sweep3"),
+    "c5_97": (16384, 16384, 1, 8, False, (1024, 1024), 6, (64, 64), (10,), "sweep3"),
+})
+EXTRA = {
+    "cinema2k": dict(cinema2k_fps=24),
+    "prc53_64": dict(precincts=[(64, 64)]),
+    "prc97_mixed": dict(precincts=[(256, 256), (128, 128)]),
+    "prc53_clip": dict(precincts=[(32, 32), (16, 16)]),
+    "prc97_rpcl": dict(precincts=[(128, 64), (64, 64), (32, 64)], progression=2),
+}
+DIGEST_ONLY = ("c2_full", "c3_full", "c5_53", "c5_97")
 ROI = {"roi53": (1, 5), "roi97": (0, 3)}
 # region (window) decodes, grk_decompress -d x0,y0,x1,y1 (full-resolution image coordinates), optionally reduced
 WINDOWS = {"rgb53_tiled": [((40, 30, 150, 120), 0), ((70, 10, 131, 75), 1)], "rgb97_layers": [((10, 20, 200, 180), 0), ((64, 64, 192, 160), 2)],
@@ -59,7 +81,7 @@ def main():
     names = sys.argv[3:] or ["gray53", "rgb53_tiled", "rgb97_layers", "rgb16_53"]
     shim = None
     if mode == "shim":
-        shim = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libgrok_b200_tcd.so"), mode=C.RTLD_GLOBAL)
+        shim = C.CDLL(os.path.join(ROOT, "integration", "_build", "libgrok_b200_tcd.so"), mode=C.RTLD_GLOBAL)
     import _libs
     from grokimagecompression_b200.synth import synthetic_planes
     res = {}
@@ -67,9 +89,29 @@ def main():
         case = CASES[name]
         w, h, nc, prec, rev, tile, numres, cblk, rates, reduce = case[:10]
         kind = case[10] if len(case) > 10 else "smooth"
-        img = synthetic_planes(w, h, nc, prec, seed=len(name) + w, kind=kind)
+        if name.startswith("c5_"):  # 16K x 16K: a 4096 x 4096 synthetic image repeated, every 1024 x 1024 tile shifted differently
+            base = synthetic_planes(4096, 4096, nc, prec, seed=16)
+            ty, tx = np.arange(h, dtype=np.int32)[:, None] // 1024, np.arange(w, dtype=np.int32)[None, :] // 1024
+            img = [((np.tile(b, (h // 4096, w // 4096)) + 5 * ty + 3 * tx) % (1 << prec)).astype(np.int32) for b in base]
+            del base, ty, tx
+        else:
+            img = synthetic_planes(w, h, nc, prec, seed=len(name) + w, kind=kind)
         # rate-control algorithm 1 so that a single lossless layer is formed from the synced pass data
-        cs = _libs.ref_encode_image(img, prec, tile=tile, numres=numres, cblk=cblk, irreversible=not rev, rates=rates, rc_algorithm=1, cblk_sty=STYLES.get(name, 0), roi=ROI.get(name, (-1, 0)))
+        cs = _libs.ref_encode_image(img, prec, tile=tile, numres=numres, cblk=cblk, irreversible=not rev, rates=rates, rc_algorithm=1, cblk_sty=STYLES.get(name, 0), roi=ROI.get(name, (-1, 0)),
+                                    **EXTRA.get(name, {}))
+        if name in DIGEST_ONLY:
+            import hashlib
+            digest = lambda a: np.frombuffer(hashlib.sha1(np.ascontiguousarray(a).tobytes()).digest(), np.uint8)
+            res[name + "_cs"] = digest(np.frombuffer(cs, np.uint8))
+            res[name + "_cslen"] = np.array([len(cs)])
+            dec = _libs.ref_decode_image(cs, nc, w, h)
+            res[name + "_dec"] = digest(np.stack(dec))
+            res[name + "_lossless"] = np.array([all((d == i).all() for d, i in zip(dec, img))])
+            del dec
+            if reduce == "sweep3":
+                for r in (1, 2, 3):
+                    res[name + f"_dec_r{r}"] = digest(np.stack(_libs.ref_decode_image(cs, nc, w, h, reduce=r)))
+            continue
         res[name + "_cs"] = np.frombuffer(cs, np.uint8)
         res[name + "_dec"] = np.stack(_libs.ref_decode_image(cs, nc, w, h))
         if reduce == "sweep":

@@ -57,20 +57,29 @@ CASES = [
     (130, 70, 3, 12, False, (None, None), 6, (5, 5)),
     (190, 133, 3, 16, True, (96, 64), 3, (6, 4)),
     (65, 33, 1, 8, True, (None, None), 1, (6, 6)),
+    # explicit precincts (exponent per resolution, lowest first; TileComponent.cpp:303-328, 437-489): 64x64 everywhere,
+    # the cinema profile's 128 / 256, precincts smaller than the nominal code block, non-square ones
+    (300, 217, 3, 8, True, (128, 128), 4, (5, 5), 6),
+    (640, 360, 3, 12, False, (None, None), 6, (5, 5), [7] + [8] * 32),
+    (211, 157, 1, 8, True, (None, None), 4, (6, 6), [4, 4, 4, 5] + [5] * 29),
+    (256, 200, 3, 8, False, (128, 112), 5, (5, 5), [(5, 6), (6, 5), (7, 6), (6, 6), (7, 5)] + [(7, 7)] * 28),
 ]
 
 
 @pytest.mark.parametrize("case", CASES)
 def test_encode_decode_vs_oracle(ctx, case):
-    width, height, nc, prec, rev, tile, numres, cblk = case
+    width, height, nc, prec, rev, tile, numres, cblk = case[:8]
+    prc = case[8] if len(case) > 8 else 15
     img = synthetic_planes(width, height, nc, prec, seed=width + height, kind="smooth")
     rc = not rev
-    tiles = P.image_tiles(width, height, nc, prec, rev, tile, numres, rate_control=rc, cblk_expn=cblk)
+    tiles = P.image_tiles(width, height, nc, prec, rev, tile, numres, rate_control=rc, cblk_expn=cblk, prc_expn=prc)
     planes = P.split_planes(img, width, height, tile)
     plan, res, rates, dists, data, ob = _check_encode(ctx, tiles, planes)
+    if prc != 15:
+        assert int(plan.blocks["precno"].max()) > 0  # the case really has several precincts
     # decode what was encoded (all passes), full resolution and reduced
     for nd in (0, max(1, numres - 2)):
-        tiles_d = P.image_tiles(width, height, nc, prec, rev, tile, numres, cblk_expn=cblk, encoder=False, numres_decode=nd)
+        tiles_d = P.image_tiles(width, height, nc, prec, rev, tile, numres, cblk_expn=cblk, encoder=False, numres_decode=nd, prc_expn=prc)
         dplan = gb.Plan(ctx, tiles_d, encoder=False)
         keep = np.array([(nd == 0) or (plan.blocks[i]["resno"] < nd) for i in range(plan.num_blocks)], bool)
         assert dplan.num_blocks == int(keep.sum())
@@ -86,7 +95,7 @@ def test_encode_decode_vs_oracle(ctx, case):
                 assert (a == b).all()
 
 
-@pytest.mark.parametrize("case", [c for c in CASES if not c[4]] + [(512, 384, 3, 8, False, (256, 256), 6, (6, 6))])
+@pytest.mark.parametrize("case", [c for c in CASES if not c[4] and len(c) == 8] + [(512, 384, 3, 8, False, (256, 256), 6, (6, 6))])
 def test_rd_slopes_vs_oracle(ctx, case):
     """PCRD preparation on the device (gb200_encode_slopes = RateControl::convexHull, t2/RateControl.cpp:31-168): feasible
     truncation points and 8.8 log slopes of every block equal the oracle's on the encoder's own pass tables"""

@@ -1,5 +1,5 @@
 """GPU: drop-in parity through Grok's official plugin ABI (SURVEY.md 8(b) "B1").  The unmodified reference is asked
-to encode a PNM file the way `grk_compress -g <dir>` does: grk_plugin_load finds oracle/_ref/libgrok_plugin.so
+to encode a PNM file the way `grk_compress -g <dir>` does: grk_plugin_load finds integration/_build/libgrok_plugin.so
 (integration/grok_plugin_b200.cpp), plugin_encode runs DC shift + MCT + DWT + quantisation + Tier-1 on the B200 and hands
 the host a grk_plugin_tile; the host's own PCRD, Tier-2 and codestream writer finish the job.  The codestream must be
 byte-identical to a pure CPU run of the reference on the same pixels."""
@@ -12,10 +12,10 @@ import pytest
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-REF = os.path.join(ROOT, "oracle", "_ref")
+REF = os.path.join(ROOT, "integration", "_build")
 
 pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not os.path.exists(os.path.join(REF, "libgrok_plugin.so")), reason="oracle/_ref not built")]
+              pytest.mark.skipif(not os.path.exists(os.path.join(REF, "libgrok_plugin.so")), reason="integration/_build not built")]
 
 CASES = {
     # name: (width, height, comps, prec, reversible, numres, cblk, rates)

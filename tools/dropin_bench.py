@@ -23,7 +23,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 def child(mode, name, reps):
     shim = None
     if mode == "shim":
-        shim = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libgrok_b200_tcd.so"), mode=C.RTLD_GLOBAL)
+        shim = C.CDLL(os.path.join(ROOT, "integration", "_build", "libgrok_b200_tcd.so"), mode=C.RTLD_GLOBAL)
     import _libs
     import bench
     from grokimagecompression_b200.synth import synthetic_planes

@@ -39,19 +39,16 @@ def main():
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     if not variants:
-        variants = ["legacy", "rows=0,unroll=2", "rows=0,unroll=1", "rows=0,unroll=4", "rows=32,unroll=2", "rows=64,unroll=2", "rows=128,unroll=2",
+        variants = ["rows=0,unroll=2", "rows=0,unroll=1", "rows=0,unroll=4", "rows=32,unroll=2", "rows=64,unroll=2", "rows=128,unroll=2",
                     "rows=256,unroll=2", "rows=0,unroll=2,fill=8", "rows=0,unroll=2,fill=32"]
     print(f"workload {name}: {nbytes / 1e6:.1f} MB algorithmic per direction, {launches} level launches, peak {peak} GB/s")
     out = []
     for v in variants:
-        for k in ("GB200_DWT_LEGACY", "GB200_DWT_ROWS", "GB200_DWT_UNROLL", "GB200_DWT_FILL", "GB200_DWT_HL", "GB200_DWT_ONLY", "GB200_DWT_RING"):
+        for k in ("GB200_DWT_ROWS", "GB200_DWT_UNROLL", "GB200_DWT_FILL", "GB200_DWT_HL", "GB200_DWT_ONLY", "GB200_DWT_RING"):
             os.environ.pop(k, None)
-        if v == "legacy":
-            os.environ["GB200_DWT_LEGACY"] = "1"
-        else:
-            for kv in v.split(","):
-                k, x = kv.split("=")
-                os.environ["GB200_DWT_" + k.upper()] = x
+        for kv in v.split(","):
+            k, x = kv.split("=")
+            os.environ["GB200_DWT_" + k.upper()] = x
         res = {"variant": v}
         for enc, tiles in ((True, tiles_e), (False, tiles_d)):
             plan = gb.Plan(ctx, tiles, encoder=enc)
