@@ -57,7 +57,7 @@ T1_BLOCK_DTYPE = np.dtype([("x", np.uint32), ("y", np.uint32), ("w", np.uint32),
 
 # every symbol include/grok_b200.h declares
 SYMBOLS = [
-    "gb200_abi_version", "gb200_last_error", "gb200_create", "gb200_destroy", "gb200_launch_count", "gb200_stream",
+    "gb200_abi_version", "gb200_last_error", "gb200_device_count", "gb200_create", "gb200_destroy", "gb200_launch_count", "gb200_stream",
     "gb200_plan_create", "gb200_plan_destroy", "gb200_plan_num_blocks", "gb200_plan_num_pass_slots",
     "gb200_plan_num_samples", "gb200_plan_blocks", "gb200_plan_data_capacity", "gb200_precinct_grid", "gb200_enumerate_blocks",
     "gb200_plan_set_sample_bytes", "gb200_encode_tiles_packed", "gb200_decode_tiles_packed", "gb200_encode_upload_packed",
@@ -87,6 +87,7 @@ def lib():
     vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int32
     L.gb200_abi_version.restype = C.c_int
     L.gb200_last_error.restype = C.c_char_p
+    L.gb200_device_count.restype = C.c_int
     L.gb200_create.argtypes = [C.c_int, C.POINTER(vp)]
     L.gb200_destroy.argtypes = [vp]
     L.gb200_destroy.restype = None

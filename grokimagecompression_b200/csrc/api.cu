@@ -110,6 +110,11 @@ extern "C" {
 int gb200_abi_version(void) { return GB200_ABI_VERSION; }
 const char *gb200_last_error(void) { return g_err.c_str(); }
 
+int gb200_device_count(void) {
+	int n = 0;
+	return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}
+
 int gb200_create(int device, gb200_ctx **out) {
 	if (!out) FAIL(GB200_ERR_PARAM, "gb200_create: out is NULL");
 	int n = 0;

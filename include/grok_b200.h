@@ -121,6 +121,10 @@ typedef struct gb200_cblk_seg {
 /* ---- context ---------------------------------------------------------------------------------- */
 GB200_API int gb200_abi_version(void);
 GB200_API const char *gb200_last_error(void); /* thread-local, never NULL */
+/* number of usable CUDA devices (0 when there is none or the driver is missing).  A context belongs to ONE device; a host
+ * that wants several GPUs creates one context per device and drives each from its own thread, dealing independent units
+ * (tiles, frames) to them -- there is no cross-device state in this library ("Several GPUs"). */
+GB200_API int gb200_device_count(void);
 GB200_API int gb200_create(int device, gb200_ctx **out);
 GB200_API void gb200_destroy(gb200_ctx *ctx);
 /* number of kernels this context has launched so far (for bench.py's gpu_launches) */

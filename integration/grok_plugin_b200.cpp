@@ -52,9 +52,12 @@
 
 namespace {
 
+/* one context per device in use: plugin_init(deviceId = -1) takes every GPU of the box (grk_compress -G -1, "A value of -1 will
+ * specify all devices", grk_compress.cpp:423-426); g_ctx = the first one, used by the single-image entry points */
+std::vector<gb200_ctx*> g_ctxs;
 gb200_ctx *g_ctx = nullptr;
 bool g_verbose = false;
-uint64_t g_encodes = 0, g_blocks = 0, g_decodes = 0;
+std::atomic<uint64_t> g_encodes{0}, g_blocks{0}, g_decodes{0};
 
 void say(const char *what) {
 	if (g_verbose) fprintf(stderr, "grok_plugin_b200: %s: %s\n", what, gb200_last_error());
@@ -169,6 +172,46 @@ bool fill_comp(const grk_cparameters *p, const grk_image *img, uint32_t c, bool 
 	return true;
 }
 
+/* plans cached per context by the bytes of their parameters: the frames of a batch share one geometry, and a plan owns
+ * gigabytes of device buffers whose allocation costs more than coding a frame */
+struct PlanCache {
+	struct Entry { std::vector<uint8_t> key; gb200_plan *plan; uint64_t stamp; };
+	std::mutex mu;
+	std::vector<Entry> entries;
+	uint64_t stamp = 0;
+	gb200_plan *get(gb200_ctx *ctx, const gb200_tile_params &tp, bool encoder) {
+		std::vector<uint8_t> key(sizeof(gb200_tile_params) + tp.numcomps * sizeof(gb200_comp_params) + 1);
+		gb200_tile_params head = tp;
+		head.comps = nullptr;
+		memcpy(key.data(), &head, sizeof(head));
+		memcpy(key.data() + sizeof(head), tp.comps, tp.numcomps * sizeof(gb200_comp_params));
+		key.back() = encoder ? 1 : 0;
+		std::lock_guard<std::mutex> lk(mu);
+		for (auto &e : entries)
+			if (e.key == key) { e.stamp = ++stamp; return e.plan; }
+		if (entries.size() >= 4) {
+			size_t lru = 0;
+			for (size_t i = 1; i < entries.size(); ++i) if (entries[i].stamp < entries[lru].stamp) lru = i;
+			gb200_plan_destroy(entries[lru].plan);
+			entries.erase(entries.begin() + (long) lru);
+		}
+		gb200_plan *plan = nullptr;
+		if (gb200_plan_create(ctx, 1, &tp, encoder ? 1 : 0, &plan) != GB200_OK) return nullptr;
+		entries.push_back({std::move(key), plan, ++stamp});
+		return plan;
+	}
+	void clear() {
+		std::lock_guard<std::mutex> lk(mu);
+		for (auto &e : entries) gb200_plan_destroy(e.plan);
+		entries.clear();
+	}
+};
+std::vector<std::unique_ptr<PlanCache>> g_caches; /* parallel to g_ctxs */
+PlanCache *cache_of(gb200_ctx *ctx) {
+	for (size_t i = 0; i < g_ctxs.size(); ++i) if (g_ctxs[i] == ctx) return g_caches[i].get();
+	return nullptr;
+}
+
 /* the grk_plugin_tile tree over the encoder results; owns every node and the compressed bytes */
 struct Tree {
 	grk_plugin_tile tile;
@@ -186,9 +229,7 @@ struct Tree {
 };
 
 /* the tree, sized from the block table of a plan (host order: comp, resno, band, precinct, block) */
-void build_tree(Tree &T, gb200_plan *plan, uint32_t nc, const gb200_comp_params *cps) {
-	const size_t nb = gb200_plan_num_blocks(plan);
-	const gb200_cblk_info *info = gb200_plan_blocks(plan);
+void build_tree(Tree &T, const gb200_cblk_info *info, size_t nb, uint32_t nc, const gb200_comp_params *cps) {
 	T.blocks.resize(nb);
 	for (auto &b : T.blocks) memset(&b, 0, sizeof(b));
 	T.comps.resize(nc);
@@ -258,7 +299,11 @@ void build_tree(Tree &T, gb200_plan *plan, uint32_t nc, const gb200_comp_params 
 
 /* ---- minpf registration (minpf_plugin.h:24-57, loader minpf_plugin_manager.cpp:146-162) --------------------- */
 extern "C" PLUGIN_API int32_t grok_b200_plugin_exit() {
-	if (g_ctx) { gb200_destroy(g_ctx); g_ctx = nullptr; }
+	for (auto &c : g_caches) c->clear();
+	g_caches.clear();
+	for (gb200_ctx *c : g_ctxs) gb200_destroy(c);
+	g_ctxs.clear();
+	g_ctx = nullptr;
 	return 0;
 }
 static void *plugin_create(grk::minpf_object_params *) { return nullptr; }
@@ -283,18 +328,32 @@ extern "C" PLUGIN_API grk::minpf_exit_func minpf_post_load_plugin(const char *, 
 extern "C" PLUGIN_API bool plugin_init(grk_plugin_init_info info) {
 	g_verbose = info.verbose;
 	if (g_ctx) return true;
-	const char *d = getenv("GROK_B200_DEVICE");
-	const int dev = d ? atoi(d) : (info.deviceId > 0 ? info.deviceId : 0);
-	if (gb200_create(dev, &g_ctx) != GB200_OK) { /* false => the host silently keeps its CPU path */
-		say("plugin_init");
-		g_ctx = nullptr;
-		return false;
+	const char *d = getenv("GROK_B200_DEVICE"); /* overrides -G (test harnesses hard-wire deviceId) */
+	const int want = d ? atoi(d) : info.deviceId;
+	std::vector<int> devices;
+	if (want < 0) { /* all devices: the batch entry points deal frames to them round robin */
+		const int n = gb200_device_count();
+		for (int i = 0; i < n; ++i) devices.push_back(i);
+	} else devices.push_back(want);
+	for (int dev : devices) {
+		gb200_ctx *c = nullptr;
+		if (gb200_create(dev, &c) != GB200_OK) { say("plugin_init"); continue; }
+		g_ctxs.push_back(c);
+		g_caches.emplace_back(new PlanCache());
 	}
+	if (g_ctxs.empty()) return false; /* false => the host silently keeps its CPU path */
+	g_ctx = g_ctxs[0];
 	return true;
 }
 
 /* counters for the parity tests: 0 = images encoded on the device, 1 = code blocks handed to the host */
-extern "C" PLUGIN_API uint64_t grok_b200_plugin_stat(int i) { return i == 0 ? g_encodes : i == 1 ? g_blocks : g_decodes; }
+/* 3 = contexts (devices) in use, 4 + k = frames coded on device k */
+std::atomic<uint64_t> g_per_device[16];
+extern "C" PLUGIN_API uint64_t grok_b200_plugin_stat(int i) {
+	if (i == 3) return g_ctxs.size();
+	if (i >= 4 && i < 20) return g_per_device[i - 4];
+	return i == 0 ? g_encodes : i == 1 ? g_blocks : g_decodes;
+}
 
 /* ---- encode -------------------------------------------------------------------------------------------------- */
 namespace {
@@ -309,7 +368,7 @@ struct EncodedFrame {
 
 /* read p->infile, run DC shift .. Tier-1 on the device, describe the result as a grk_plugin_tile.  0 = ok; 1 = a request
  * this ABI / build cannot express (the host keeps its CPU path); >1 = failure */
-int encode_frame(const grk_cparameters *p, EncodedFrame &F) {
+int encode_frame(gb200_ctx *ctx, const grk_cparameters *p, EncodedFrame &F) {
 	/* what the single grk_plugin_tile of this ABI, or this build of the kernels, cannot express -> host CPU path */
 	/* (terminating styles would need pass->term, which encode_synch_with_plugin never sets: plugin_bridge.cpp:148-260) */
 	if (p->isHT || p->cblk_sty != 0 || p->decod_format != GRK_PXM_FMT) return 1;
@@ -332,9 +391,8 @@ int encode_frame(const grk_cparameters *p, EncodedFrame &F) {
 	tp.mct = mct ? 1 : 0;
 	tp.rate_control = 1; /* the host decides later whether it uses the distortions (needs_rate_control) */
 	tp.comps = cps.data();
-	gb200_plan *plan = nullptr;
-	if (gb200_plan_create(g_ctx, 1, &tp, 1, &plan) != GB200_OK) { say("gb200_plan_create"); return 3; }
-	struct PlanGuard { gb200_plan *p; ~PlanGuard() { gb200_plan_destroy(p); } } pguard{plan};
+	gb200_plan *plan = cache_of(ctx)->get(ctx, tp, true); /* owned by the context's cache */
+	if (!plan) { say("gb200_plan_create"); return 3; }
 	const size_t nb = gb200_plan_num_blocks(plan);
 	std::vector<gb200_cblk_enc> enc(nb);
 	std::vector<uint32_t> rates(gb200_plan_num_pass_slots(plan) + 1);
@@ -348,8 +406,8 @@ int encode_frame(const grk_cparameters *p, EncodedFrame &F) {
 		say("gb200_encode_tiles");
 		return 4;
 	}
-	build_tree(T, plan, nc, cps.data());
 	const gb200_cblk_info *info = gb200_plan_blocks(plan);
+	build_tree(T, info, nb, nc, cps.data());
 	for (size_t i = 0; i < nb; ++i) {
 		grk_plugin_code_block &B = T.blocks[i];
 		const gb200_cblk_enc &e = enc[i];
@@ -368,6 +426,7 @@ int encode_frame(const grk_cparameters *p, EncodedFrame &F) {
 	}
 	g_encodes++;
 	g_blocks += nb;
+	for (size_t k = 0; k < g_ctxs.size() && k < 16; ++k) if (g_ctxs[k] == ctx) g_per_device[k]++;
 	return 0;
 }
 
@@ -395,27 +454,29 @@ int hand_over(EncodedFrame &F, grk_cparameters *p, grk::PLUGIN_ENCODE_USER_CALLB
 extern "C" PLUGIN_API int32_t plugin_encode(grk_cparameters *p, grk::PLUGIN_ENCODE_USER_CALLBACK callback) {
 	if (!g_ctx || !p || !callback) return -1;
 	EncodedFrame F;
-	const int rc = encode_frame(p, F);
+	const int rc = encode_frame(g_ctx, p, F);
 	if (rc) return rc;
 	return hand_over(F, p, callback, false);
 }
 
 /* ---- batch encode: the plugin owns the frame loop (plugin_interface.h:80-86, grk_compress.cpp:2222-2240) -----------------
- * plugin_batch_encode returns at once; a producer thread runs every PNM file of input_dir through the device path, a
+ * plugin_batch_encode returns at once; one producer thread per device in use (plugin_init with deviceId -1: every GPU of the
+ * box) runs the PNM files of input_dir through the device path, frame i on device i mod N, no data crosses between devices; a
  * consumer thread hands the finished frames to the host's callback in file-name order (the callback is the host's
- * single-threaded PCRD / Tier-2 / file writer), so the device works on frame i+1 while the host finishes frame i.
+ * single-threaded PCRD / Tier-2 / file writer), so the devices work on the next frames while the host finishes frame i.
  * Frames the ABI cannot express are handed over with tile = NULL: the host's callback then encodes them itself. */
 namespace {
 
 struct Batch {
-	std::thread producer, consumer;
+	std::vector<std::thread> producers; /* one per context (device): frame i is coded on device i mod N */
+	std::thread consumer;
 	std::mutex mu;
 	std::condition_variable cv;
-	std::deque<std::unique_ptr<EncodedFrame>> ready;
+	std::vector<std::unique_ptr<EncodedFrame>> ready; /* slot i = frame i once coded */
+	size_t next = 0;                                  /* next frame the host gets */
 	std::vector<std::string> files;
 	grk_cparameters params;
 	grk::PLUGIN_ENCODE_USER_CALLBACK callback = nullptr;
-	bool produced_all = false;
 	std::atomic<bool> stop{false}, complete{true};
 };
 Batch *g_batch = nullptr;
@@ -429,7 +490,7 @@ bool has_pnm_extension(const std::string &n) {
 }
 
 void batch_join(Batch *b) {
-	if (b->producer.joinable()) b->producer.join();
+	for (auto &t : b->producers) if (t.joinable()) t.join();
 	if (b->consumer.joinable()) b->consumer.join();
 }
 
@@ -456,34 +517,39 @@ extern "C" PLUGIN_API int32_t plugin_batch_encode(const char *input_dir, const c
 	b->callback = callback;
 	b->complete = false;
 	g_batch = b;
-	b->producer = std::thread([b]() {
-		for (const std::string &f : b->files) {
-			if (b->stop) break;
-			std::unique_ptr<EncodedFrame> F(new EncodedFrame());
-			grk_cparameters fp = b->params;
-			snprintf(fp.infile, sizeof(fp.infile), "%s", f.c_str());
-			const int rc = encode_frame(&fp, *F);
-			F->infile = f;
-			F->outfile = f; /* relative: the host keeps the base name */
-			if (rc) { F->T.tile.tileComponents = nullptr; F->T.tile.numComponents = 0; if (F->img) { grk_image_destroy(F->img); F->img = nullptr; } }
-			std::unique_lock<std::mutex> lk(b->mu);
-			b->cv.wait(lk, [b]() { return b->ready.size() < 2 || b->stop; }); /* at most two frames ahead of the host */
-			b->ready.push_back(std::move(F));
-			b->cv.notify_all();
-		}
-		std::lock_guard<std::mutex> lk(b->mu);
-		b->produced_all = true;
-		b->cv.notify_all();
-	});
+	b->ready.resize(b->files.size());
+	const size_t ndev = g_ctxs.size();
+	for (size_t k = 0; k < ndev; ++k)
+		b->producers.emplace_back([b, k, ndev]() {
+			gb200_ctx *ctx = g_ctxs[k];
+			for (size_t i = k; i < b->files.size(); i += ndev) {
+				{ /* at most two frames per device ahead of the host */
+					std::unique_lock<std::mutex> lk(b->mu);
+					b->cv.wait(lk, [&]() { return i < b->next + 2 * ndev || b->stop; });
+				}
+				if (b->stop) break;
+				const std::string &f = b->files[i];
+				std::unique_ptr<EncodedFrame> F(new EncodedFrame());
+				grk_cparameters fp = b->params;
+				snprintf(fp.infile, sizeof(fp.infile), "%s", f.c_str());
+				const int rc = encode_frame(ctx, &fp, *F);
+				F->infile = f;
+				F->outfile = f; /* relative: the host keeps the base name */
+				if (rc) { F->T.tile.tileComponents = nullptr; F->T.tile.numComponents = 0; if (F->img) { grk_image_destroy(F->img); F->img = nullptr; } }
+				std::lock_guard<std::mutex> lk(b->mu);
+				b->ready[i] = std::move(F);
+				b->cv.notify_all();
+			}
+		});
 	b->consumer = std::thread([b]() {
-		for (;;) {
+		for (; b->next < b->files.size();) { /* file-name order, whatever device finished first */
 			std::unique_ptr<EncodedFrame> F;
 			{
 				std::unique_lock<std::mutex> lk(b->mu);
-				b->cv.wait(lk, [b]() { return !b->ready.empty() || b->produced_all; });
-				if (b->ready.empty()) break;
-				F = std::move(b->ready.front());
-				b->ready.pop_front();
+				b->cv.wait(lk, [b]() { return b->ready[b->next] != nullptr || b->stop; });
+				if (!b->ready[b->next]) break;
+				F = std::move(b->ready[b->next]);
+				b->next++;
 				b->cv.notify_all();
 			}
 			grk_cparameters fp = b->params; /* the callback may settle tcp_mct etc. in its copy */
@@ -533,13 +599,26 @@ struct DecodeJob {
 	std::vector<gb200_comp_params> cps;
 	gb200_tile_params tp;
 	Tree T;
+	std::vector<gb200_cblk_info> table; /* every block of the image, host order */
 	std::vector<uint64_t> offset; /* of each block in T.data */
 	std::vector<uint64_t> capacity; /* bytes reserved for each block */
 	uint64_t file_bytes = 0;       /* size of the codestream file: no block carries more */
 	bool ready = false;
 	int status = 0;
 };
-DecodeJob *g_job = nullptr;
+thread_local DecodeJob *g_job = nullptr; /* the host calls decode_init back synchronously, on the thread that called its callback */
+
+/* block table of a whole single-tile image (every resolution), component by component: pure geometry, no device */
+void enumerate_image(const std::vector<gb200_comp_params> &cps, std::vector<gb200_cblk_info> &out) {
+	out.clear();
+	for (uint32_t c = 0; c < cps.size(); ++c) {
+		const uint64_t n = gb200_enumerate_blocks(&cps[c], 0, nullptr, 0);
+		const size_t at = out.size();
+		out.resize(at + n);
+		gb200_enumerate_blocks(&cps[c], 0, out.data() + at, n);
+		for (size_t i = at; i < out.size(); ++i) out[i].compno = c;
+	}
+}
 
 int decode_init(grk_header_info *h, grk_image *img) {
 	using namespace grk;
@@ -571,9 +650,8 @@ int decode_init(grk_header_info *h, grk_image *img) {
 	J.tp.mct = h->mct;
 	J.tp.numres_decode = 0; /* the tree spans every resolution; the decode plan is cut to numresolutions - reduce later */
 	J.tp.comps = J.cps.data();
-	gb200_plan *geo = nullptr; /* only for its block table */
-	if (gb200_plan_create(g_ctx, 1, &J.tp, 0, &geo) != GB200_OK) { say("gb200_plan_create"); return 1; }
-	build_tree(J.T, geo, nc, J.cps.data());
+	enumerate_image(J.cps, J.table);
+	build_tree(J.T, J.table.data(), J.table.size(), nc, J.cps.data());
 	/* the host writes each block's bytes without a capacity field (plugin_bridge.cpp:71-78): every block gets the
 	 * reference encoder's own worst case (TileProcessor.cpp:2003-2018) plus slack as its slot, and the arena ends with
 	 * as many spare bytes as the whole codestream file holds.  No block can carry more bytes than the file, so even a
@@ -590,7 +668,6 @@ int decode_init(grk_header_info *h, grk_image *img) {
 	}
 	J.T.data.assign(total + J.file_bytes + 64, 0);
 	for (size_t i = 0; i < nb; ++i) J.T.blocks[i].compressedData = J.T.data.data() + J.offset[i];
-	gb200_plan_destroy(geo);
 	J.ready = true;
 	J.status = 0;
 	return 0;
@@ -601,8 +678,20 @@ int decode_init(grk_header_info *h, grk_image *img) {
 namespace {
 
 /* one codestream through the staged protocol; infile / outfile as the callback shall see them */
-int32_t decode_one(grk_decompress_parameters *dp, const std::string &infile, const std::string &outfile, GRK_SUPPORTED_FILE_FMT fmt,
-		grk::PLUGIN_DECODE_USER_CALLBACK callback) {
+/* the host's callback is its own single-threaded code (stream, codec, image store): with several devices working on
+ * different codestreams the calls into it are serialised, and the POST_T1 calls (the host stores the image) keep file order */
+std::mutex g_host_mu;
+struct PostOrder {
+	std::mutex mu;
+	std::condition_variable cv;
+	size_t next = 0;
+	void wait_turn(size_t i) { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&]() { return next == i; }); }
+	void done(size_t i) { std::lock_guard<std::mutex> lk(mu); if (next == i) next = i + 1; cv.notify_all(); }
+};
+
+int32_t decode_one(gb200_ctx *ctx, grk_decompress_parameters *dp, const std::string &infile, const std::string &outfile, GRK_SUPPORTED_FILE_FMT fmt,
+		grk::PLUGIN_DECODE_USER_CALLBACK user_callback, PostOrder *order = nullptr, size_t index = 0) {
+	auto callback = [&](grk::PluginDecodeCallbackInfo *i) { std::lock_guard<std::mutex> lk(g_host_mu); return user_callback(i); };
 	DecodeJob J;
 	J.reduce = dp->core.cp_reduce;
 	{
@@ -641,20 +730,14 @@ int32_t decode_one(grk_decompress_parameters *dp, const std::string &infile, con
 				J.cps[c].stepsize[r ? 3 * r - 2 + b : 0] = tc->resolutions[r]->bands[b]->stepsize; /* carries the decoder's x0.5 */
 	}
 	J.tp.numres_decode = J.cps[0].numres - J.reduce;
-	gb200_plan *plan = nullptr;
-	if (gb200_plan_create(g_ctx, 1, &J.tp, 0, &plan) != GB200_OK) { say("gb200_plan_create"); return clean(3); }
-	struct PlanGuard { gb200_plan *p; ~PlanGuard() { gb200_plan_destroy(p); } } pguard{plan};
+	gb200_plan *plan = cache_of(ctx)->get(ctx, J.tp, false); /* owned by the context's cache */
+	if (!plan) { say("gb200_plan_create"); return clean(3); }
 	const size_t nbd = gb200_plan_num_blocks(plan); /* blocks of the resolutions that are reconstructed */
 	const gb200_cblk_info *dinfo = gb200_plan_blocks(plan);
 	std::vector<gb200_cblk_dec> in(nbd);
 	{ /* the reduced table is the full one minus the blocks of the dropped resolutions, same order */
 		size_t i = 0;
-		const gb200_cblk_info *unused = nullptr; (void) unused;
-		gb200_plan *full = nullptr;
-		gb200_tile_params tpf = J.tp;
-		tpf.numres_decode = 0;
-		if (gb200_plan_create(g_ctx, 1, &tpf, 0, &full) != GB200_OK) return clean(3);
-		const gb200_cblk_info *finfo = gb200_plan_blocks(full);
+		const gb200_cblk_info *finfo = J.table.data();
 		for (size_t k = 0; k < nb && i < nbd; ++k) {
 			if (finfo[k].compno != dinfo[i].compno || finfo[k].resno != dinfo[i].resno || finfo[k].bandno != dinfo[i].bandno
 					|| finfo[k].precno != dinfo[i].precno || finfo[k].cblkno != dinfo[i].cblkno) continue;
@@ -666,7 +749,6 @@ int32_t decode_one(grk_decompress_parameters *dp, const std::string &infile, con
 			in[i].data_offset = J.offset[k];
 			++i;
 		}
-		gb200_plan_destroy(full);
 		if (i != nbd) return clean(5);
 	}
 	std::vector<int32_t*> planes(J.nc);
@@ -681,6 +763,8 @@ int32_t decode_one(grk_decompress_parameters *dp, const std::string &infile, con
 	}
 	if (gb200_decode_tiles(plan, in.data(), J.T.data.data(), J.T.data.size() - 64 - J.file_bytes, planes.data()) != GB200_OK) { say("gb200_decode_tiles"); return clean(4); }
 	g_decodes++;
+	for (size_t k = 0; k < g_ctxs.size() && k < 16; ++k) if (g_ctxs[k] == ctx) g_per_device[k]++;
+	if (order) order->wait_turn(index); /* the host stores the images in file order */
 	info.decode_flags = GRK_DECODE_POST_T1;
 	try { rc = callback(&info); } catch (...) { rc = 7; }
 	return clean(rc);
@@ -690,7 +774,7 @@ int32_t decode_one(grk_decompress_parameters *dp, const std::string &infile, con
 
 extern "C" PLUGIN_API int32_t plugin_decode(grk_decompress_parameters *dp, grk::PLUGIN_DECODE_USER_CALLBACK callback) {
 	if (!g_ctx || !dp || !callback) return -1;
-	return decode_one(dp, dp->infile, dp->outfile, dp->decod_format, callback);
+	return decode_one(g_ctx, dp, dp->infile, dp->outfile, dp->decod_format, callback);
 }
 
 /* ---- batch decode: plugin_init_batch_decode / plugin_batch_decode / plugin_stop_batch_decode (plugin_interface.h:124-130).
@@ -702,7 +786,9 @@ extern "C" PLUGIN_API int32_t plugin_decode(grk_decompress_parameters *dp, grk::
 namespace {
 
 struct DecBatch {
-	std::thread worker;
+	std::vector<std::thread> workers; /* one per context (device): codestream i is decoded on device i mod N */
+	PostOrder order;
+	std::atomic<size_t> finished{0};
 	std::vector<std::string> files;
 	std::string out_dir;
 	grk_decompress_parameters params;
@@ -732,7 +818,7 @@ extern "C" PLUGIN_API int32_t plugin_init_batch_decode(const char *input_dir, co
 	if (!g_ctx || !input_dir || !output_dir || !dp || !callback) return -1;
 	if (g_dec_batch) {
 		if (!g_dec_batch->complete) return -1;
-		if (g_dec_batch->worker.joinable()) g_dec_batch->worker.join();
+		for (auto &t : g_dec_batch->workers) if (t.joinable()) t.join();
 		delete g_dec_batch;
 		g_dec_batch = nullptr;
 	}
@@ -755,25 +841,35 @@ extern "C" PLUGIN_API int32_t plugin_init_batch_decode(const char *input_dir, co
 	b->complete = false;
 	g_dec_batch = b;
 	const std::string in_dir = input_dir;
-	b->worker = std::thread([b, in_dir]() {
-		for (const std::string &n : b->files) {
-			if (b->stop) break;
-			const size_t dot = n.rfind('.');
-			std::string ext = n.substr(dot + 1);
-			for (auto &c : ext) c = (char) tolower(c);
-			const GRK_SUPPORTED_FILE_FMT fmt = ext == "jp2" ? GRK_JP2_FMT : GRK_J2K_FMT;
-			const std::string in = in_dir + "/" + n, out = b->out_dir + "/" + n.substr(0, dot) + "." + out_extension(b->params.cod_format);
-			grk_decompress_parameters fp = b->params;
-			fp.infile[0] = 0; fp.outfile[0] = 0; /* the callback takes the names from the info struct */
-			fp.decod_format = fmt;
-			const int32_t rc = decode_one(&fp, in, out, fmt, b->callback);
-			if (rc) { /* not ours: let the host decode this one on its own in a single callback */
-				grk::PluginDecodeCallbackInfo info(in, out, &fp, fmt, GRK_DECODE_ALL);
-				try { b->callback(&info); } catch (...) {}
+	const size_t ndev = g_ctxs.size();
+	if (b->files.empty()) b->complete = true;
+	for (size_t k = 0; k < ndev; ++k)
+		b->workers.emplace_back([b, in_dir, k, ndev]() {
+			for (size_t i = k; i < b->files.size(); i += ndev) {
+				const std::string &n = b->files[i];
+				if (!b->stop) {
+					const size_t dot = n.rfind('.');
+					std::string ext = n.substr(dot + 1);
+					for (auto &c : ext) c = (char) tolower(c);
+					const GRK_SUPPORTED_FILE_FMT fmt = ext == "jp2" ? GRK_JP2_FMT : GRK_J2K_FMT;
+					const std::string in = in_dir + "/" + n, out = b->out_dir + "/" + n.substr(0, dot) + "." + out_extension(b->params.cod_format);
+					grk_decompress_parameters fp = b->params;
+					fp.infile[0] = 0; fp.outfile[0] = 0; /* the callback takes the names from the info struct */
+					fp.decod_format = fmt;
+					/* decode_one waits for this codestream's turn in the file order before the host stores the image; a stream
+					 * the ABI cannot express is decoded by the host on its own, in one callback, when its turn has come */
+					const int32_t rc = decode_one(g_ctxs[k], &fp, in, out, fmt, b->callback, &b->order, i);
+					b->order.wait_turn(i);
+					if (rc) {
+						grk::PluginDecodeCallbackInfo info(in, out, &fp, fmt, GRK_DECODE_ALL);
+						std::lock_guard<std::mutex> lk(g_host_mu);
+						try { b->callback(&info); } catch (...) {}
+					}
+					b->order.done(i);
+				} else { b->order.wait_turn(i); b->order.done(i); }
+				if (++b->finished == b->files.size()) b->complete = true;
 			}
-		}
-		b->complete = true;
-	});
+		});
 	return 0;
 }
 
@@ -783,7 +879,7 @@ extern "C" PLUGIN_API int32_t plugin_batch_decode(void) { return g_dec_batch ? 0
 extern "C" PLUGIN_API void plugin_stop_batch_decode(void) {
 	if (!g_dec_batch) return;
 	g_dec_batch->stop = true;
-	if (g_dec_batch->worker.joinable()) g_dec_batch->worker.join();
+	for (auto &t : g_dec_batch->workers) if (t.joinable()) t.join();
 	delete g_dec_batch;
 	g_dec_batch = nullptr;
 }

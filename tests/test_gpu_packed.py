@@ -47,7 +47,7 @@ def test_packed_planes_equal_int32_planes(ctx, case):
     assert (b2[0] == b[0]).all() and bytes(b2[3]) == bytes(b[3])
     # the int32 entry point refuses a packed plan instead of misreading the buffers
     with pytest.raises(gb.GrokB200Error):
-        gb.lib().gb200_encode_upload(narrow._h, narrow._ptr_array(planes))
+        gb.binding.check(gb.lib().gb200_encode_upload(narrow._h, narrow._ptr_array(planes)))
     inp = np.zeros(len(a[0]), gb.CBLK_DEC_DTYPE)
     for k in ("numbps", "numpasses", "data_len", "data_offset"):
         inp[k] = a[0][k]

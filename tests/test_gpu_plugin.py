@@ -145,3 +145,32 @@ def test_plugin_batch_decode_walks_the_directory(tmp_path):
     geometry, precision and wavelet) is decoded on the device and handed to the host's callback; pixels equal the pure reference's"""
     out = subprocess.check_output([sys.executable, "-X", "faulthandler", "-c", BATCH_DEC_RUNNER, HERE, str(tmp_path)], timeout=600, text=True)
     assert "batch decode ok 5" in out
+
+
+ALL_DEVICES_TAIL = r"""
+import ctypes, torch
+P = ctypes.CDLL(os.path.join(os.path.dirname(sys.argv[1]), "integration", "_build", "libgrok_plugin.so"))
+P.grok_b200_plugin_stat.restype = ctypes.c_uint64
+P.grok_b200_plugin_stat.argtypes = [ctypes.c_int]
+per_device = [int(P.grok_b200_plugin_stat(4 + k)) for k in range(16)]
+ndev = torch.cuda.device_count()
+print("per device", per_device[:ndev], "devices", ndev)
+assert sum(per_device) >= WANT_FRAMES, per_device
+assert sum(1 for v in per_device if v) == min(ndev, WANT_FRAMES), per_device   # every GPU of the box got frames
+assert max(per_device) - min(per_device[:ndev]) <= 1 * REPEATS                    # dealt round robin
+"""
+
+
+def test_plugin_batch_on_all_devices(tmp_path):
+    """grk_compress / grk_decompress -G -1 ("all devices", grk_compress.cpp:423-426): plugin_init takes every GPU of the box, the
+    batch entry points deal frame i to device i mod N, the host still sees the frames in file-name order and every codestream /
+    image equals the pure reference's.  On a one-GPU box this runs the same code with N = 1."""
+    env = dict(os.environ, GROK_B200_DEVICE="-1")
+    (tmp_path / "enc").mkdir()
+    (tmp_path / "dec").mkdir()
+    code = BATCH_RUNNER + ALL_DEVICES_TAIL.replace("WANT_FRAMES", "7").replace("REPEATS", "1")
+    out = subprocess.check_output([sys.executable, "-c", code, HERE, str(tmp_path / "enc")], timeout=600, text=True, env=env)
+    assert "batch ok 7" in out
+    code = BATCH_DEC_RUNNER + ALL_DEVICES_TAIL.replace("WANT_FRAMES", "10").replace("REPEATS", "2")
+    out = subprocess.check_output([sys.executable, "-X", "faulthandler", "-c", code, HERE, str(tmp_path / "dec")], timeout=600, text=True, env=env)
+    assert "batch decode ok 5" in out

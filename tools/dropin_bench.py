@@ -32,6 +32,8 @@ def child(mode, name, reps):
     cb = (1 << w["cblk"][0], 1 << w["cblk"][1])
     kw = dict(tile=(w["tile"][0] or 0, w["tile"][1] or 0), numres=w["numres"], cblk=cb, irreversible=not w["reversible"],
               rates=w["rates"], rc_algorithm=1)
+    if w.get("cinema"):
+        kw["cinema2k_fps"] = w["cinema"]
     te, td = [], []
     cs = None
     for i in range(reps + 1):
@@ -59,14 +61,25 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] in ("pure", "shim"):
         child(sys.argv[1], sys.argv[2], int(sys.argv[3]))
         sys.exit(0)
-    name = sys.argv[1] if len(sys.argv) > 1 else "c2"
-    reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+    as_json = "--json" in sys.argv
+    argv = [a for a in sys.argv if a != "--json"]
+    name = argv[1] if len(argv) > 1 else "c2"
+    reps = int(argv[2]) if len(argv) > 2 else 3
     res = {}
     for mode in ("pure", "shim"):
         out = subprocess.check_output([sys.executable, os.path.abspath(__file__), mode, name, str(reps)], text=True)
         res[mode] = json.loads([l for l in out.splitlines() if l.startswith("{")][-1])
     p, s = res["pure"], res["shim"]
     mp = p["pixels"] / 1e6
+    if as_json:  # one line for bench.py's `drop_in` object
+        t = s.get("secs") or [0.0] * 8
+        print(json.dumps({"what": "unmodified reference codec, public grk API, memory streams: pure CPU vs TCD stage seam bound to libgrok_b200 (wall clock)",
+                          "workload": name, "host_cores": p["cores"], "codestreams_identical": p["sha"] == s["sha"],
+                          "encode_x": round(p["enc_s"] / s["enc_s"], 2), "decode_x": round(p["dec_s"] / s["dec_s"], 2),
+                          "pure_encode_ms": round(p["enc_s"] * 1e3, 1), "seam_encode_ms": round(s["enc_s"] * 1e3, 1),
+                          "pure_decode_ms": round(p["dec_s"] * 1e3, 1), "seam_decode_ms": round(s["dec_s"] * 1e3, 1),
+                          "inside_seam_encode_ms": round(1e3 * (t[0] + t[3]), 1), "inside_seam_decode_ms": round(1e3 * (t[4] + t[6]), 1)}))
+        sys.exit(0)
     print(f"{name}: codestreams identical: {p['sha'] == s['sha']} ({p['bytes']} bytes), host cores {p['cores']}")
     print(f"  encode  pure {mp / p['enc_s']:8.1f} Mpixel/s ({p['enc_s'] * 1e3:7.1f} ms)   with the seam on the B200 {mp / s['enc_s']:8.1f} Mpixel/s ({s['enc_s'] * 1e3:7.1f} ms)   x{p['enc_s'] / s['enc_s']:.1f}")
     if s.get("secs"):
