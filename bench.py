@@ -48,12 +48,17 @@ WORKLOADS = {
     "c4x30": dict(width=2048, height=1080, comps=3, prec=12, reversible=False, tile=(None, None), numres=6, cblk=(5, 5), rates=(10,), frames=30,
                   prc=[7] + [8] * 32, cinema=24),
 }
+# the same images through the HTJ2K block coder (grk_compress -M 64): no rate control in the reference's HT path
+WORKLOADS["c2ht"] = dict(WORKLOADS["c2"], rates=(), ht=True)
+WORKLOADS["c3ht"] = dict(WORKLOADS["c3"], ht=True)
 WORKLOAD_TEXT = {
     "c1": "configs[0]: 2048x2048 8-bit gray, lossless 5/3, 1 tile, 64x64 blocks, 5 levels",
     "c2": "configs[1]: 4096x2160 RGB 8-bit, irreversible 9/7 + ICT, quantised, 4 quality layers, 1024x1024 tiles",
     "c3": "configs[2]: 8192x8192 3x16-bit, lossless 5/3 + RCT, 1024x1024 tiles",
     "c4": "configs[3]: one DCI 2K frame 2048x1080 3x12-bit, 9/7 + ICT, 32x32 blocks, 128/256 precincts",
     "c4x30": "configs[3]: batch of 30 DCI 2K frames 2048x1080 3x12-bit (240 frames over 8 GPUs), 9/7 + ICT, 32x32 blocks, 128/256 precincts",
+    "c2ht": "configs[1] image with the HTJ2K block coder (-M 64): 4096x2160 RGB 8-bit, 9/7 + ICT, 1024x1024 tiles",
+    "c3ht": "configs[2] image with the HTJ2K block coder (-M 64): 8192x8192 3x16-bit, 5/3 + RCT, 1024x1024 tiles",
 }
 T1_SOURCES = ("t1_enc.cu", "t1_dec.cu", "t1_tables.cuh", "common.cuh")
 DWT_SOURCES = ("dwt_stream.cuh", "dwt.cu", "dwt_plane.h")
@@ -126,9 +131,9 @@ def make_workload(name, seed):
         fimg = synthetic_planes(w["width"], w["height"], w["comps"], w["prec"], seed=seed + f)
         img = fimg if img is None else img  # the correctness gate looks at the first frame
         tiles_e += P.image_tiles(w["width"], w["height"], w["comps"], w["prec"], w["reversible"], w["tile"], w["numres"],
-                                 rate_control=rc, cblk_expn=w["cblk"], prc_expn=prc)
+                                 rate_control=rc, cblk_expn=w["cblk"], prc_expn=prc, ht=w.get("ht", False))
         tiles_d += P.image_tiles(w["width"], w["height"], w["comps"], w["prec"], w["reversible"], w["tile"], w["numres"],
-                                 cblk_expn=w["cblk"], encoder=False, prc_expn=prc)
+                                 cblk_expn=w["cblk"], encoder=False, prc_expn=prc, ht=w.get("ht", False))
         planes += P.split_planes(fimg, w["width"], w["height"], w["tile"])
     return w, img, tiles_e, tiles_d, planes
 
@@ -170,6 +175,8 @@ def cpu_reference_run(name, steps, warmup, budget_s=150.0, seed=1):
     kw = {}
     if w.get("cinema"):  # grk_compress -w: the profile sets 32x32 blocks, 128 / 256 precincts, CPRL and the byte budget itself
         kw["cinema2k_fps"] = w["cinema"]
+    if w.get("ht"):
+        kw["cblk_sty"] = 64
 
     def secs(idx):
         return sum(tap.ref_tap_seconds(i) for i in idx) if tap is not None else float("nan")

@@ -93,6 +93,7 @@ struct gb200_plan {
 	uint32_t max_bw = 1, max_bh = 1; // largest code block of the table
 	bool uniform = true; // every tile shares mct / qmfbid / shift / range parameters
 	bool styles = false; // some component uses code-block style switches
+	bool ht = false;     // every component uses the HTJ2K block coder (tcp->isHT is per tile in the reference, T1Factory.cpp:36)
 	std::vector<EncResult> h_results;
 	// where each tile-component's final decoded plane lives (0 A, 1 B, 2 C)
 	std::vector<int> final_role;
@@ -269,8 +270,17 @@ int gb200_plan_create(gb200_ctx *ctx, uint32_t ntiles, const gb200_tile_params *
 			cg.p = tp.comps[c];
 			const gb200_comp_params &p = cg.p;
 			if (p.numres < 1 || p.numres > GB200_MAX_RES || p.x1 < p.x0 || p.y1 < p.y0) return bail(GB200_ERR_PARAM, "bad component rectangle / numres");
-			if (p.cblk_sty & ~(uint32_t) STY_ALL) return bail(GB200_ERR_UNSUPPORTED, "HT code blocks (cblk_sty 0x40) are not implemented");
-			if (p.cblk_sty) pl->styles = true;
+			if (p.cblk_sty & ~(uint32_t) (STY_ALL | STY_HT)) return bail(GB200_ERR_PARAM, "unknown code-block style bits");
+			if (p.cblk_sty & STY_HT) {
+				// grk_compress.cpp:1131-1141: HT cannot be combined with another mode switch; it holds for the whole tile
+				if (p.cblk_sty != STY_HT) return bail(GB200_ERR_PARAM, "the HT block coder cannot be combined with other code-block styles");
+				if (p.roishift) return bail(GB200_ERR_UNSUPPORTED, "ROI up-shift with the HT block coder");
+				if ((t || c) && !pl->ht) return bail(GB200_ERR_UNSUPPORTED, "HT and Part-1 block coders mixed in one plan");
+				pl->ht = true;
+			} else {
+				if (pl->ht) return bail(GB200_ERR_UNSUPPORTED, "HT and Part-1 block coders mixed in one plan");
+				if (p.cblk_sty) pl->styles = true;
+			}
 			if (p.roishift > 30 - 1) return bail(GB200_ERR_UNSUPPORTED, "ROI shift of 30 or more bit planes (t1.cpp:1056)");
 			if (p.cblkw_expn > 6 || p.cblkh_expn > 6 || p.cblkw_expn < 2 || p.cblkh_expn < 2)
 				return bail(GB200_ERR_UNSUPPORTED, "code blocks larger than 64x64 are not implemented");
@@ -475,12 +485,14 @@ int gb200_plan_create(gb200_ctx *ctx, uint32_t ntiles, const gb200_tile_params *
 					eb.pass_offset = bi.pass_offset;
 					eb.max_passes = bi.max_passes;
 					// the reference's bound (TileProcessor.cpp:2003-2018); terminated passes add a few flush bytes each
-					eb.scratch_cap = (uint32_t) align_up((uint64_t) bw * bh * 4 + 2 + (p.cblk_sty ? 4 * bi.max_passes : 0), 16);
+					eb.scratch_cap = (uint32_t) align_up((uint64_t) bw * bh * 4 + 2 + (pl->ht ? t1_ht_scratch_extra() : p.cblk_sty ? 4 * bi.max_passes : 0), 16);
 					eb.scratch_off = scratch_off;
 					eb.sty = (uint8_t) p.cblk_sty;
+					eb.band_numbps = (uint8_t) p.band_numbps[g.band_index];
+					eb.stepsize = p.stepsize[g.band_index];
 					eb.rd_weight = p.rd_weight[g.band_index];
 					eb.sym_off = sym_off;
-					eb.sym_cap = t1_symbol_capacity(bw, bh, std::max<uint32_t>(p.band_numbps[g.band_index], 1));
+					eb.sym_cap = pl->ht ? 0 : t1_symbol_capacity(bw, bh, std::max<uint32_t>(p.band_numbps[g.band_index], 1)); // no symbol stream in the HT path
 					sym_off += eb.sym_cap;
 					scratch_off += eb.scratch_cap;
 					pl->encblocks.push_back(eb);
@@ -495,6 +507,7 @@ int gb200_plan_create(gb200_ctx *ctx, uint32_t ntiles, const gb200_tile_params *
 					db.sty = (uint8_t) p.cblk_sty;
 					db.roishift = (uint8_t) p.roishift;
 					db.stepsize = p.stepsize[g.band_index];
+					db.band_numbps = p.band_numbps[g.band_index];
 					pl->decblocks.push_back(db);
 				}
 			}
@@ -719,11 +732,15 @@ static int run_t1_enc(gb200_plan *pl) {
 	if (!nb) return GB200_OK;
 	int rc = 0;
 	for (auto &tg : pl->tiles) rc |= (int) tg.rate_control;
-	launch_t1_encode((const EncBlock*) pl->d_blocks.p, nb, rc, pl->styles ? 1 : 0, (uint8_t*) pl->d_symbols.p, (uint8_t*) pl->d_scratch.p,
-			(EncResult*) pl->d_results.p, (uint32_t*) pl->d_rates.p, (double*) pl->d_dists.p, ctx->stream);
+	if (pl->ht)
+		launch_t1_ht_encode((const EncBlock*) pl->d_blocks.p, nb, (uint8_t*) pl->d_scratch.p, (EncResult*) pl->d_results.p,
+				(uint32_t*) pl->d_rates.p, (double*) pl->d_dists.p, ctx->stream);
+	else
+		launch_t1_encode((const EncBlock*) pl->d_blocks.p, nb, rc, pl->styles ? 1 : 0, (uint8_t*) pl->d_symbols.p, (uint8_t*) pl->d_scratch.p,
+				(EncResult*) pl->d_results.p, (uint32_t*) pl->d_rates.p, (double*) pl->d_dists.p, ctx->stream);
 	launch_t1_gather((const EncBlock*) pl->d_blocks.p, (EncResult*) pl->d_results.p, nb, (const uint8_t*) pl->d_scratch.p,
 			(uint8_t*) pl->d_data.p, (uint64_t*) pl->d_total.p, ctx->stream);
-	return launch_check(ctx, 4);
+	return launch_check(ctx, pl->ht ? 3 : 4);
 }
 
 int gb200_encode_run_stage(gb200_plan *pl, int stage) {
@@ -843,6 +860,10 @@ int gb200_decode_upload(gb200_plan *pl, const gb200_cblk_dec *blocks, const uint
 		// the reference fails the decode of such a block (t1.cpp:1055-1058); never leave it silently zero
 		if (blocks[i].data_len && blocks[i].numbps + pl->decblocks[i].roishift > 30)
 			FAIL(GB200_ERR_UNSUPPORTED, "a code block has more than 30 bit planes (t1.cpp:1056)");
+		if (pl->ht && blocks[i].data_len) {
+			if (blocks[i].numpasses > 1) FAIL(GB200_ERR_UNSUPPORTED, "HT blocks with refinement passes (SigProp / MagRef) are not implemented: cleanup pass only");
+			if (blocks[i].numbps > pl->decblocks[i].band_numbps) FAIL(GB200_ERR_PARAM, "HT block with more bit planes than its band");
+		}
 	}
 	if (pl->d_data.bytes < data_len + T1_DEC_DATA_SLACK) {
 		if (pl->d_data.alloc(align_up(data_len + T1_DEC_DATA_SLACK, 256))) FAIL(GB200_ERR_NOMEM, "cudaMalloc failed for the compressed data");
@@ -874,6 +895,11 @@ int gb200_decode_set_segments(gb200_plan *pl, const uint32_t *seg_start, const g
 static int run_t1_dec(gb200_plan *pl) {
 	const uint32_t nb = (uint32_t) pl->blocks.size();
 	if (!nb) return GB200_OK;
+	if (pl->ht) {
+		if (pl->have_segs) FAIL(GB200_ERR_UNSUPPORTED, "HT blocks arrive as one segment (cleanup pass only)");
+		launch_t1_ht_decode((const DecBlock*) pl->d_blocks.p, (const DecInput*) pl->d_inputs.p, nb, (const uint8_t*) pl->d_data.p, pl->ctx->stream);
+		return launch_check(pl->ctx, 1);
+	}
 	if (launch_t1_decode((const DecBlock*) pl->d_blocks.p, (const DecInput*) pl->d_inputs.p, nb, (const uint8_t*) pl->d_data.p,
 			pl->max_bw, pl->max_bh, pl->styles ? 1 : 0, pl->have_segs ? (const uint32_t*) pl->d_seg_start.p : nullptr,
 			pl->have_segs ? (const DecSeg*) pl->d_segs.p : nullptr, pl->ctx->stream))
@@ -1170,7 +1196,7 @@ int gb200_t1_encode_blocks(gb200_ctx *ctx, const int32_t *plane, uint32_t width,
 		e.src = (const int32_t*) d_plane.p + (size_t) b.y * width + b.x;
 		e.stride = width; e.w = (uint16_t) b.w; e.h = (uint16_t) b.h; e.orient = (uint8_t) b.orient;
 		e.reversible = b.qmfbid == 1; e.inv_step = (int32_t) b.inv_step;
-		if (b.cblk_sty & ~(uint32_t) STY_ALL) { freeall(); FAIL(GB200_ERR_UNSUPPORTED, "HT code blocks are not implemented"); }
+		if (b.cblk_sty & ~(uint32_t) STY_ALL) { freeall(); FAIL(GB200_ERR_UNSUPPORTED, "the block-list entry points take Part-1 blocks; HT blocks go through a plan"); }
 		e.sty = (uint8_t) b.cblk_sty;
 		styles |= b.cblk_sty != 0;
 		e.pass_offset = i * max_passes; e.max_passes = max_passes;
@@ -1245,7 +1271,7 @@ int gb200_t1_decode_blocks_segs(gb200_ctx *ctx, int32_t *plane, uint32_t width, 
 		d.dst = (int32_t*) d_plane.p + (size_t) b.y * width + b.x;
 		d.stride = width; d.w = (uint16_t) b.w; d.h = (uint16_t) b.h; d.orient = (uint8_t) b.orient;
 		d.reversible = b.qmfbid == 1; d.stepsize = b.stepsize;
-		if (b.cblk_sty & ~(uint32_t) STY_ALL) { freeall(); FAIL(GB200_ERR_UNSUPPORTED, "HT code blocks are not implemented"); }
+		if (b.cblk_sty & ~(uint32_t) STY_ALL) { freeall(); FAIL(GB200_ERR_UNSUPPORTED, "the block-list entry points take Part-1 blocks; HT blocks go through a plan"); }
 		d.sty = (uint8_t) b.cblk_sty;
 		styles |= b.cblk_sty != 0;
 		if (b.roishift > 29) { freeall(); FAIL(GB200_ERR_UNSUPPORTED, "ROI shift of 30 or more bit planes"); }

@@ -11,7 +11,7 @@ struct EncBlock {
 	const int32_t *src;  // top-left coefficient of the block inside its sub-band (DWT output)
 	uint32_t stride;
 	uint16_t w, h;
-	uint8_t orient, reversible, sty /* code-block style switches, STY_* */, pad1;
+	uint8_t orient, reversible, sty /* code-block style switches, STY_* */, band_numbps /* band->numbps: the HT coder's missing MSBs */;
 	int32_t inv_step;
 	uint32_t pass_offset; // first slot in rates/dists
 	uint32_t max_passes;
@@ -20,11 +20,11 @@ struct EncBlock {
 	double rd_weight;
 	uint64_t sym_off;     // byte offset of the block's (context, decision) stream, 16-byte aligned
 	uint32_t sym_cap;     // bytes reserved for it (t1_symbol_capacity)
-	uint32_t pad2;
+	float stepsize;       // band->stepsize: the HT path quantises with 1 / stepsize in float (T1HT.cpp:88-92)
 };
 
 // code-block style switches (tccp->cblk_sty, grok.h GRK_CBLKSTY_*)
-enum { STY_LAZY = 1, STY_RESET = 2, STY_TERMALL = 4, STY_VSC = 8, STY_PTERM = 16, STY_SEGSYM = 32, STY_ALL = 63 };
+enum { STY_LAZY = 1, STY_RESET = 2, STY_TERMALL = 4, STY_VSC = 8, STY_PTERM = 16, STY_SEGSYM = 32, STY_ALL = 63, STY_HT = 64 /* HTJ2K block coder: not combinable with the others */ };
 
 struct EncResult { // == gb200_cblk_enc
 	uint32_t numbps, numpasses, data_len, decisions;
@@ -38,7 +38,7 @@ struct DecBlock {
 	uint16_t w, h;
 	uint8_t orient, reversible, sty, roishift /* ROI up-shift of the component (decoding starts roishift planes higher) */;
 	float stepsize;
-	uint32_t pad2;
+	uint32_t band_numbps; // band->numbps: the HT decoder's missing MSBs are band_numbps - numbps of the block
 };
 
 struct DecSeg { // == gb200_cblk_seg: one codeword segment of a block (TERMALL / LAZY streams)
@@ -90,6 +90,12 @@ void launch_t1_encode(const EncBlock *blocks, uint32_t nblocks, int rate_control
 // total (may be NULL): receives the byte count of the compacted data
 void launch_t1_gather(const EncBlock *blocks, EncResult *results, uint32_t nblocks, const uint8_t *scratch,
 		uint8_t *data, uint64_t *total, cudaStream_t s);
+// ht.cu : the HTJ2K block coder (cleanup pass), one thread per block; the encoder leaves its bytes in the block's scratch area
+// like the MQ coder does (launch_t1_gather compacts them); the decoder writes de-quantised samples (no clear / finish pass)
+uint32_t t1_ht_scratch_extra(); // bytes an HT block needs beyond 4 w h: the MEL and VLC staging areas
+void launch_t1_ht_encode(const EncBlock *blocks, uint32_t nblocks, uint8_t *scratch, EncResult *results, uint32_t *rates, double *dists,
+		cudaStream_t s);
+void launch_t1_ht_decode(const DecBlock *blocks, const DecInput *inputs, uint32_t nblocks, const uint8_t *data, cudaStream_t s);
 // rd.cu : feasible truncation points and 8.8 log slopes of every block (RateControl.cpp:31-168); cache: one double per pass slot
 void launch_rd_slopes(const EncBlock *blocks, const EncResult *results, uint32_t nblocks, const uint32_t *rates, const double *dists,
 		uint16_t *slopes, double *cache, cudaStream_t s);

@@ -32,6 +32,7 @@
 // The reference's artificial FF FF end marker (mqc_dec.cpp:161-177) is emulated by reading 0xFF
 // past the end of the segment.
 #include "common.cuh"
+#include <algorithm>
 #include "t1_tables.cuh"
 
 namespace gb {
@@ -44,7 +45,11 @@ namespace gb {
 #ifndef DT_SPARSE_BLOCKS_PER_SM
 #define DT_SPARSE_BLOCKS_PER_SM 16
 #endif
-constexpr int DT_MAX_THREADS = 1024;
+// CTAs per SM the decode kernel is compiled for (register cap) and threads per CTA: 1 x 1024 (64 registers) or 2 x 768 (40)
+#ifndef DT_MINB
+#define DT_MINB 1
+#endif
+constexpr int DT_MAX_THREADS = DT_MINB == 1 ? 1024 : 768;
 constexpr int DT_CTX_WORDS = 20;  // 19 context rows per block, padded
 constexpr int DT_FIXED_WORDS = 96 + 512 + 64; // MQ table, zero-coding table (4 x 512 B), sign table (256 B)
 
@@ -313,7 +318,7 @@ __device__ __forceinline__ void run_pass(Blk &b, uint32_t *F, int w, int fw, int
 }
 
 template<int LANES, bool STY>
-__global__ void __launch_bounds__(DT_MAX_THREADS, 1) t1_decode_kernel(const DecBlock *__restrict__ blocks,
+__global__ void __launch_bounds__(DT_MAX_THREADS, DT_MINB) t1_decode_kernel(const DecBlock *__restrict__ blocks,
 		const DecInput *__restrict__ inputs, uint32_t nblocks, const uint8_t *__restrict__ data, int fw, int fwords, int nslots,
 		const uint32_t *__restrict__ seg_start, const DecSeg *__restrict__ segs) {
 	extern __shared__ __align__(16) uint32_t sm[];
@@ -447,17 +452,19 @@ int launch_t1_decode(const DecBlock *blocks, const DecInput *inputs, uint32_t nb
 		uint32_t max_w, uint32_t max_h, int styles, const uint32_t *seg_start, const DecSeg *segs, cudaStream_t s) {
 	if (!nblocks) return 0;
 	ensure_t1_tables();
-	int dev = 0, sms = 148, smem_max = 0;
+	int dev = 0, sms = 148, smem_max = 0, smem_sm = 0;
 	cudaGetDevice(&dev);
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 	cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+	cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+	if (DT_MINB > 1) smem_max = std::min(smem_max, smem_sm / DT_MINB - 1024); // every resident CTA also reserves 1 KB
 	if (max_w < 1) max_w = 1;
 	if (max_h < 1) max_h = 1;
 	const int fw = (int) max_w + 2;
 	int fwords = (int) ((max_h + 3) / 4) * fw;
 	fwords += fwords & 1;
-	int want = (int) ((nblocks + (uint32_t) sms - 1) / (uint32_t) sms); // spread a small job over every SM
-	const int lanes = want <= DT_SPARSE_BLOCKS_PER_SM ? 1 : DT_LANES;
+	int want = (int) ((nblocks + (uint32_t) (sms * DT_MINB) - 1) / (uint32_t) (sms * DT_MINB)); // spread a small job over every SM
+	const int lanes = want * DT_MINB <= DT_SPARSE_BLOCKS_PER_SM ? 1 : DT_LANES;
 	// slots of one warp start 32 / lanes banks apart
 	int bank0 = 32 / lanes % 32;
 	if (bank0 & 1) bank0 = 2;

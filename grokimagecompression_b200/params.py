@@ -80,8 +80,12 @@ MCT_NORMS_REV = (1.732, 0.8292, 0.8292)   # norms of the RCT / ICT synthesis bas
 MCT_NORMS_IRREV = (1.732, 1.805, 1.573)
 
 
-def band_quant(numres, prec, reversible, guard_bits=2, mct_norm=1.0, encoder=True, compno=0):
-    """Per band (host order): stepsize, inv_step, numbps, rd_weight for the stand-alone defaults."""
+def band_quant(numres, prec, reversible, guard_bits=2, mct_norm=1.0, encoder=True, compno=0, ht=False):
+    """Per band (host order): stepsize, inv_step, numbps, rd_weight for the stand-alone defaults.
+    ht: the HTJ2K block coder -- one guard bit (j2k.cpp:1834), and on the decoder side the irreversible step size is scaled
+    down to the MSB-aligned magnitudes the HT decoder returns (Quantizer.cpp:98-104)"""
+    if ht:
+        guard_bits = 1
     nb = 3 * numres - 2
     step = np.ones(nb, np.float32)
     inv = np.zeros(nb, np.uint32)
@@ -112,13 +116,16 @@ def band_quant(numres, prec, reversible, guard_bits=2, mct_norm=1.0, encoder=Tru
         step[b] = s
         inv[b] = np.uint32(int(8192.0 / float(np.float32((1.0 + mant / 2048.0) * math.pow(2.0, numbps_nominal - expn))) + 0.5))
         nbps[b] = max(expn + guard_bits - 1, 1)
+        if ht and not encoder and not reversible:
+            step[b] = np.float32(step[b] / np.float32(1 << (30 - int(nbps[b]))))
         rdw[b] = (mct_norm * dwt_norm(level, orient, reversible)) * float(step[b])
     return step, inv, nbps, rdw
 
 
 def comp_params(x0, y0, x1, y1, numres, reversible, prec, sgnd=0, cblk_expn=(6, 6), prc_expn=15, quant=None,
-                mct_norm=1.0, encoder=True, guard_bits=2):
+                mct_norm=1.0, encoder=True, guard_bits=2, ht=False):
     p = CompParams()
+    p.cblk_sty = 0x40 if ht else 0
     p.x0, p.y0, p.x1, p.y1 = x0, y0, x1, y1
     p.numres = numres
     p.cblkw_expn, p.cblkh_expn = cblk_expn
@@ -132,7 +139,7 @@ def comp_params(x0, y0, x1, y1, numres, reversible, prec, sgnd=0, cblk_expn=(6, 
     p.prec = prec
     p.sgnd = sgnd
     p.dc_shift = 0 if sgnd else 1 << (prec - 1)
-    step, inv, nbps, rdw = quant if quant is not None else band_quant(numres, prec, reversible, guard_bits, mct_norm, encoder)
+    step, inv, nbps, rdw = quant if quant is not None else band_quant(numres, prec, reversible, guard_bits, mct_norm, encoder, ht=ht)
     for b in range(3 * numres - 2):
         p.stepsize[b] = float(step[b])
         p.inv_step[b] = int(inv[b])
@@ -142,7 +149,7 @@ def comp_params(x0, y0, x1, y1, numres, reversible, prec, sgnd=0, cblk_expn=(6, 
 
 
 def image_tiles(width, height, numcomps, prec, reversible, tile=(None, None), numres=6, mct=None, rate_control=False,
-                cblk_expn=(6, 6), sgnd=0, encoder=True, numres_decode=0, prc_expn=15):
+                cblk_expn=(6, 6), sgnd=0, encoder=True, numres_decode=0, prc_expn=15, ht=False):
     """Tile grid of an image (origin 0,0, no sub-sampling) -> list of tile dicts for binding.Plan, in raster order."""
     tw = tile[0] or width
     th = tile[1] or height
@@ -156,7 +163,7 @@ def image_tiles(width, height, numcomps, prec, reversible, tile=(None, None), nu
             for c in range(numcomps):
                 mn = norms[c] if (mct and c < 3) else 1.0
                 comps.append(comp_params(tx, ty, min(tx + tw, width), min(ty + th, height), numres, reversible, prec, sgnd,
-                                         cblk_expn, prc_expn, mct_norm=mn, encoder=encoder))
+                                         cblk_expn, prc_expn, mct_norm=mn, encoder=encoder, ht=ht))
             tiles.append({"comps": comps, "mct": mct, "rate_control": int(rate_control), "numres_decode": numres_decode})
     return tiles
 

@@ -66,7 +66,10 @@ typedef struct gb200_comp_params {
 	uint32_t sgnd;                      /* image component signedness */
 	int32_t dc_shift;                   /* tccp->m_dc_level_shift */
 	uint32_t cblk_sty;                  /* tccp->cblk_sty: LAZY 0x01, RESET 0x02, TERMALL 0x04, VSC 0x08, PTERM 0x10, SEGSYM 0x20
-	                                     * (t1.cpp:1131-1151, 1223-1298); HT 0x40 is not implemented */
+	                                     * (t1.cpp:1131-1151, 1223-1298); HT 0x40 alone = the HTJ2K block coder (t1/t1_ht, every
+	                                     * component of a plan or none): the encoder emits the cleanup pass as one pass with numbps 1
+	                                     * like T1HT::encode, the decoder takes single-pass blocks; band_numbps and stepsize must
+	                                     * then be the host's values on BOTH sides (k_msbs = band_numbps - numbps, Tier1.cpp:86,166) */
 	uint32_t roishift;                  /* tccp->roishift (max-shift ROI): the encoder only sees it through band_numbps, the decoder
 	                                     * starts roishift planes higher and shifts the ROI samples back (T1Part1.cpp:230-252) */
 	float stepsize[GB200_MAX_BANDS];    /* band->stepsize (decoder side already carries the x0.5) */

@@ -22,7 +22,8 @@
  * walks a tile component by component (TileProcessor.cpp:1141-1177); the shim defers the per-component calls and runs
  * Tier-1, de-quantisation, inverse DWT, inverse MCT and level shift of ALL components of the tile in one batch when the
  * host reaches mct_decode, so that the serial Tier-1 chains of every component overlap.  Plans (geometry, block tables,
- * device buffers) are cached by tile geometry, so equal tiles cost no allocation.  Region (window) decodes
+ * device buffers) are cached by tile geometry, so equal tiles cost no allocation.  Tiles coded with the HTJ2K block coder
+ * (cblk_sty 0x40, grk_compress -M 64) take the same path: the library's HT cleanup-pass kernels stand in for T1HT.  Region (window) decodes
  * (grk_set_decode_area) reconstruct the whole tile on the device and cut the window out.  GROK_B200_DEVICE selects the GPU.
  */
 #include "grok_includes.h"
@@ -114,6 +115,7 @@ struct PendingComp {
 	/* the band step sizes, taken while tilec->resolutions is alive: TileComponent::release_mem() frees it right after
 	 * Wavelet::decode (TileProcessor.cpp:1166) */
 	float stepsize[GB200_MAX_BANDS];
+	uint32_t band_numbps[GB200_MAX_BANDS]; /* band->numbps: the HT decoder's missing MSBs are counted from it (Tier1.cpp:166) */
 };
 std::map<grk::TileComponent*, PendingComp> g_pending;
 std::map<grk::grk_tcd_tile*, bool> g_tile_done; /* tiles whose level shift already happened on the device */
@@ -310,10 +312,6 @@ bool Tier1::decodeCodeblocks(grk_tcp *, uint16_t, uint16_t, std::vector<decodeBl
 	Timer timer(4);
 	if (!blocks || blocks->empty()) return true;
 	auto tilec = (*blocks)[0]->tilec;
-	if ((*blocks)[0]->cblk_sty & GRK_CBLKSTY_HT) {
-		fprintf(stderr, "grok_tcd_shim: HT blocks are outside this build's scope\n");
-		abort();
-	}
 	/* only collect; the tile runs as one batch in TileProcessor::mct_decode */
 	std::lock_guard<std::mutex> lk(g_mu2);
 	PendingComp &P = g_pending[tilec];
@@ -355,7 +353,10 @@ bool Wavelet::decode(TileProcessor *, TileComponent *tilec, uint32_t numres, uin
 		P.dwt_seen = true;
 		for (uint32_t r = 0; r < tilec->numresolutions; ++r) {
 			auto res = tilec->resolutions + r;
-			for (uint32_t b = 0; b < res->numbands; ++b) P.stepsize[r == 0 ? 0 : 3 * r - 2 + b] = res->bands[b].stepsize; /* carries the x0.5 */
+			for (uint32_t b = 0; b < res->numbands; ++b) {
+				P.stepsize[r == 0 ? 0 : 3 * r - 2 + b] = res->bands[b].stepsize; /* carries the x0.5 (and the HT scaling, Quantizer.cpp:98-104) */
+				P.band_numbps[r == 0 ? 0 : 3 * r - 2 + b] = res->bands[b].numbps;
+			}
 		}
 		return true;
 	}
@@ -396,7 +397,7 @@ bool TileProcessor::mct_decode() {
 		for (uint32_t bi = 0; bi < 3 * p.numres - 2; ++bi) {
 			p.stepsize[bi] = pend[c]->stepsize[bi];
 			p.inv_step[bi] = 8192;
-			p.band_numbps[bi] = 16;
+			p.band_numbps[bi] = pend[c]->band_numbps[bi];
 			p.rd_weight[bi] = 1.0;
 		}
 		const uint32_t nd = pend[c]->numres_decode;

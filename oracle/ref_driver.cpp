@@ -18,6 +18,9 @@
  * Only the reference's headers are included (a build-time include dependency); no reference
  * source is copied here.
  */
+#include "ojph_block_encoder.h" /* before grok_includes.h, which poisons malloc / free (as T1HT.cpp does) */
+#include "ojph_block_decoder.h"
+#include "ojph_mem.h"
 #include "grok_includes.h"
 #include "t1_common.h"
 #include "Tier1.h"
@@ -269,6 +272,25 @@ void ref_band_stepsize(uint32_t expn, uint32_t mant, uint32_t resno, uint32_t ba
 
 static void quiet_cb(const char *, void *) {}
 
+/* ---- HTJ2K block coder (t1/t1_ht/coding): the cleanup-pass encoder and decoder on one block of sign-magnitude samples, the form
+ * T1HT::preEncode hands them over in (T1HT.cpp:56-133, 135-175) */
+int ref_ht_encode_block(const int32_t *sm, int w, int h, int stride, int missing_msbs, uint8_t *out, int cap) {
+	ojph::mem_elastic_allocator elastic(1048576);
+	ojph::coded_lists *coded = nullptr;
+	int lengths[2] = {0, 0};
+	ojph::local::ojph_encode_codeblock((ojph::si32*) sm, missing_msbs, 1, w, h, stride, lengths, &elastic, coded);
+	if (!coded || lengths[0] > cap) return -1;
+	memcpy(out, coded->buf, (size_t) lengths[0]);
+	return lengths[0];
+}
+int ref_ht_decode_block(const uint8_t *data, int len, int missing_msbs, int w, int h, int stride, int32_t *out) {
+	/* the decoder moves 32 bits at a time and may touch a few bytes either side of the segment */
+	std::vector<uint8_t> padded((size_t) len + 64, 0);
+	memcpy(padded.data() + 32, data, (size_t) len);
+	ojph::local::ojph_decode_codeblock(padded.data() + 32, (ojph::si32*) out, missing_msbs, 1, len, 0, w, h, stride);
+	return 0;
+}
+
 /* code-block style byte (grk_compress -M) applied by the following ref_encode_image / ref_plugin_encode_file calls */
 static uint32_t g_cblk_sty = 0;
 /* RateControl::convexHull (t2/RateControl.cpp:31) on one block's pass table: len / cumulative distortion in, log slopes out */
@@ -314,6 +336,7 @@ int64_t ref_encode_image(uint32_t numcomps, uint32_t w, uint32_t h, uint32_t pre
 	param.irreversible = irreversible != 0;
 	param.rateControlAlgorithm = rc_algorithm;
 	param.cblk_sty = (uint8_t) g_cblk_sty;
+	param.isHT = (g_cblk_sty & GRK_CBLKSTY_HT) != 0; /* grk_compress -M 64 (grk_compress.cpp:1131-1141) */
 	param.roi_compno = g_roi_compno;
 	param.roi_shift = g_roi_compno >= 0 ? g_roi_shift : 0;
 	if (g_prc_n) {

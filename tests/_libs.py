@@ -47,7 +47,7 @@ def oracle():
         return _oracle
     so = os.path.join(ORACLE_DIR, "libgb_oracle.so")
     src = os.path.join(ORACLE_DIR, "gb_oracle.c")
-    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(os.path.join(ORACLE_DIR, "gb_oracle_ht.c"))):
         subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "libgb_oracle.so"])
     L = C.CDLL(so)
     L.gbo_dc_shift_fwd.argtypes = [i32p, C.c_uint64, C.c_int32, C.c_int]
@@ -72,6 +72,11 @@ def oracle():
     L.gbo_nmsedec_tables.argtypes = [i16p] * 4
     L.gbo_context_tables.argtypes = [u8p, u8p, u8p]
     L.gbo_enumerate_blocks.argtypes = [C.c_uint32] * 7 + [u32p, C.c_void_p]
+    L.gbo_ht_encode_block.argtypes = [i32p, C.c_int, C.c_int, C.c_int, C.c_int, u8p, C.c_int]
+    L.gbo_ht_decode_block.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i32p]
+    L.gbo_ht_quantise_block.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_float, C.c_uint32, i32p]
+    L.gbo_ht_quantise_block.restype = C.c_uint32
+    L.gbo_ht_dequantise_block.argtypes = [i32p, C.c_uint32, C.c_uint32, C.c_int, C.c_float, C.c_uint32, C.c_void_p, C.c_uint32]
     _oracle = L
     return L
 
@@ -125,6 +130,8 @@ def ref():
     L.ref_rd_convex_hull.restype = None
     L.ref_t1_decode_cblk.argtypes = [u8p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                      C.c_uint32, C.c_uint32, i32p]
+    L.ref_ht_encode_block.argtypes = [i32p, C.c_int, C.c_int, C.c_int, C.c_int, u8p, C.c_int]
+    L.ref_ht_decode_block.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i32p]
     L.ref_set_cblk_sty.argtypes = [C.c_uint32]
     L.ref_set_precincts.argtypes = [C.c_uint32, u32p, u32p]
     L.ref_set_progression.argtypes = [C.c_int]

@@ -68,12 +68,19 @@ EXTRA = {
     "prc53_clip": dict(precincts=[(32, 32), (16, 16)]),
     "prc97_rpcl": dict(precincts=[(128, 64), (64, 64), (32, 64)], progression=2),
 }
+# the HTJ2K block coder (grk_compress -M 64): the reference's T1HT replaced by the device's HT cleanup-pass kernels
+CASES.update({
+    "ht53": (300, 217, 3, 8, True, (128, 128), 5, (64, 64), (), 1),
+    "ht53_gray16": (130, 90, 1, 16, True, (0, 0), 3, (32, 32), (), 0),
+    "ht97": (256, 200, 3, 8, False, (128, 112), 6, (64, 64), (), 2),
+    "ht97_12": (173, 131, 1, 12, False, (0, 0), 6, (32, 16), (), 0),
+})
 DIGEST_ONLY = ("c2_full", "c3_full", "c5_53", "c5_97")
 ROI = {"roi53": (1, 5), "roi97": (0, 3)}
 # region (window) decodes, grk_decompress -d x0,y0,x1,y1 (full-resolution image coordinates), optionally reduced
 WINDOWS = {"rgb53_tiled": [((40, 30, 150, 120), 0), ((70, 10, 131, 75), 1)], "rgb97_layers": [((10, 20, 200, 180), 0), ((64, 64, 192, 160), 2)],
            "sweep53": [((300, 200, 1100, 900), 0)], "lazy53": [((100, 50, 260, 190), 1)]}
-STYLES = {"lazy53": 1, "termall97": 4, "resetvsc53": 2 | 8, "allmodes53": 63, "lazyterm97": 1 | 4 | 16, "segsympterm16": 16 | 32}
+STYLES = {"ht53": 64, "ht53_gray16": 64, "ht97": 64, "ht97_12": 64, "lazy53": 1, "termall97": 4, "resetvsc53": 2 | 8, "allmodes53": 63, "lazyterm97": 1 | 4 | 16, "segsympterm16": 16 | 32}
 
 
 def main():

@@ -50,6 +50,19 @@ def encode_tiles(tiles, planes, count_only=False):
                 bi = band_index(b)
                 q = np.zeros((h, w), np.int32)
                 base = work[c].ctypes.data + 4 * (b.off_y * stride + b.off_x)
+                if cp.cblk_sty & 0x40:  # HTJ2K block coder: one cleanup pass, numbps 1 (T1HT.cpp:104-133)
+                    if w == 0 or h == 0:
+                        results.append(dict(tileno=t, compno=c, resno=b.resno, orient=b.orient, x0=b.x0, y0=b.y0, x1=b.x1, y1=b.y1,
+                                            data=b"", numbps=0, rates=np.zeros(0, np.uint32), dists=np.zeros(0), nsym=0))
+                        continue
+                    k_msbs = int(cp.band_numbps[bi])
+                    O.gbo_ht_quantise_block(base, stride, w, h, int(cp.qmfbid == 1), float(cp.stepsize[bi]), k_msbs, q.ravel())
+                    buf = np.zeros(w * h * 8 + 8192, np.uint8)
+                    n = O.gbo_ht_encode_block(q.ravel(), w, h, w, k_msbs, buf, len(buf))
+                    assert n > 0
+                    results.append(dict(tileno=t, compno=c, resno=b.resno, orient=b.orient, x0=b.x0, y0=b.y0, x1=b.x1, y1=b.y1,
+                                        data=bytes(buf[:n]), numbps=1, rates=np.array([n], np.uint32), dists=np.zeros(1), nsym=0))
+                    continue
                 O.gbo_quantise_block(base, stride, w, h, int(cp.qmfbid == 1), int(cp.inv_step[bi]), q.ravel())
                 data, numbps, rates, dists, nsym = oracle_t1_encode(q, b.orient, bool(tile.get("rate_control")), cp.rd_weight[bi])
                 results.append(dict(tileno=t, compno=c, resno=b.resno, orient=b.orient, x0=b.x0, y0=b.y0, x1=b.x1, y1=b.y1,
@@ -78,8 +91,15 @@ def decode_tiles(tiles, block_inputs):
                 k += 1
                 if not inp["numpasses"] or not len(inp["data"]):
                     continue
-                dec = oracle_t1_decode(inp["data"], inp["numpasses"], inp["numbps"], b.orient, bw, bh)
                 base = plane.ctypes.data + 4 * (b.off_y * w + b.off_x)
+                if cp.cblk_sty & 0x40:
+                    k_msbs = int(cp.band_numbps[band_index(b)]) - int(inp["numbps"])
+                    dec = np.zeros((bh, bw), np.int32)
+                    d = np.frombuffer(inp["data"], np.uint8).copy()
+                    if O.gbo_ht_decode_block(d, len(d), k_msbs, bw, bh, bw, dec.ravel()) == 0:
+                        O.gbo_ht_dequantise_block(dec.ravel(), bw, bh, int(cp.qmfbid == 1), float(cp.stepsize[band_index(b)]), k_msbs, base, w)
+                    continue
+                dec = oracle_t1_decode(inp["data"], inp["numpasses"], inp["numbps"], b.orient, bw, bh)
                 O.gbo_dequantise_block(dec.ravel(), bw, bh, int(cp.qmfbid == 1), float(cp.stepsize[band_index(b)]), base, w)
             if plane.size:
                 O.gbo_dwt_inv(plane.ravel(), cp.x0, cp.y0, cp.x1, cp.y1, cp.numres, nd, int(cp.qmfbid == 1))

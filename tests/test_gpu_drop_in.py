@@ -29,6 +29,8 @@ def _run(mode, out, cases):
                                    ["roi53", "roi97"],
                                    # non-default precincts, the DCI 2K cinema profile (configs[3] as BASELINE states it)
                                    ["cinema2k", "prc53_64", "prc97_mixed", "prc53_clip", "prc97_rpcl"],
+                                   # the HTJ2K block coder (-M 64)
+                                   ["ht53", "ht53_gray16", "ht97", "ht97_12"],
                                    # BASELINE configs[1], [2] and [4] at their full size (compared by digest)
                                    ["c2_full"], ["c3_full"], ["c5_53"], ["c5_97"]])
 def test_codestreams_and_pixels_identical(tmp_path, cases):
@@ -38,11 +40,11 @@ def test_codestreams_and_pixels_identical(tmp_path, cases):
     assert calls[0] > 0 and calls[3] > 0 and calls[4] > 0 and calls[5] > 0, calls  # the seam really was taken
     # ... including the rate allocator's per-block RateControl::convexHull, answered with the slopes computed on the device
     # (a single lossless layer needs no slopes: the host does not ask, TileProcessor.cpp:407)
-    if any("97" in n or n in ("c2_crop", "c4_frame", "c2_full", "cinema2k") for n in cases):
+    if any(("97" in n and not n.startswith("ht")) or n in ("c2_crop", "c4_frame", "c2_full", "cinema2k") for n in cases):
         assert int(shim["hulls"][0]) > 0
     for name in cases:
         lossless = name in ("gray53", "rgb53_tiled", "rgb16_53", "c1_full", "random53", "constant53", "ragged53", "tiny", "onepixel", "sweep53",
-                            "lazy53", "resetvsc53", "allmodes53", "segsympterm16", "prc53_64", "prc53_clip", "c3_full", "c5_53")  # (with -ROI the reference itself is not lossless: its encoder
+                            "lazy53", "resetvsc53", "allmodes53", "segsympterm16", "prc53_64", "prc53_clip", "c3_full", "c5_53", "ht53", "ht53_gray16")  # (with -ROI the reference itself is not lossless: its encoder
         # declares the shift without applying it; the seam must reproduce exactly that)
         assert pure[name + "_cs"].tobytes() == shim[name + "_cs"].tobytes(), f"{name}: codestream differs"
         assert (pure[name + "_dec"] == shim[name + "_dec"]).all(), f"{name}: decoded pixels differ"

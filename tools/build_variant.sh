@@ -7,7 +7,7 @@ name=$1; file=$2; defs=$3
 ARCH="-gencode arch=compute_100a,code=sm_100a"
 nvcc $ARCH -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-fvisibility=hidden --fmad=false $defs -c $file -o /tmp/var_${name}.o
 objs=""
-for f in api mct dwt t1_enc t1_dec rd; do
+for f in api mct dwt t1_enc t1_dec rd ht; do
   if [ "$f.cu" == "$file" ]; then objs="$objs /tmp/var_${name}.o"; else objs="$objs $f.o"; fi
 done
 nvcc $ARCH -shared -cudart static -o ../libgrok_b200_${name}.so $objs
