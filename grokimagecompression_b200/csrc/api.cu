@@ -896,7 +896,7 @@ static int run_t1_dec(gb200_plan *pl) {
 	const uint32_t nb = (uint32_t) pl->blocks.size();
 	if (!nb) return GB200_OK;
 	if (pl->ht) {
-		if (pl->have_segs) FAIL(GB200_ERR_UNSUPPORTED, "HT blocks arrive as one segment (cleanup pass only)");
+		// (a segment table, if the caller set one, holds one segment per block here: gb200_decode_upload refuses HT blocks with more passes)
 		launch_t1_ht_decode((const DecBlock*) pl->d_blocks.p, (const DecInput*) pl->d_inputs.p, nb, (const uint8_t*) pl->d_data.p, pl->ctx->stream);
 		return launch_check(pl->ctx, 1);
 	}
