@@ -31,7 +31,10 @@
 
 namespace gb {
 
-constexpr int ENC_WARPS = 4;
+#ifndef ENC_WARPS_PER_CTA
+#define ENC_WARPS_PER_CTA 4
+#endif
+constexpr int ENC_WARPS = ENC_WARPS_PER_CTA;
 #ifndef ENC_MIN_CTAS
 #define ENC_MIN_CTAS 6
 #endif
@@ -353,7 +356,10 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, ENC_MIN_CTAS) t1_model_kernel(
 // (mqc_enc.cpp:168-243), with the SWITCH column folded into a 94-entry (state, mps) table and A kept in the
 // high half-word so that one CLZ gives the renormalisation shift.
 
-constexpr int MQ_WARPS = 4;
+#ifndef MQ_WARPS_PER_CTA
+#define MQ_WARPS_PER_CTA 4
+#endif
+constexpr int MQ_WARPS = MQ_WARPS_PER_CTA;
 #ifndef MQ_LANES
 #define MQ_LANES 2   // active lanes (code blocks) per warp
 #endif
