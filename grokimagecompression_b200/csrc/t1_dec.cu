@@ -33,12 +33,13 @@
 // past the end of the segment.
 #include "common.cuh"
 #include <algorithm>
+#include <cstdlib>
 #include "t1_tables.cuh"
 
 namespace gb {
 
 #ifndef DT_LANES
-#define DT_LANES 2          // code blocks (active lanes) per warp when the launch fills the machine
+#define DT_LANES 2          // code blocks (active lanes) per warp of a single-wave launch; 1, 2, 4 or 8
 #endif
 // a launch with few blocks per SM (one small image) is bound by the latency of one block's chain: then every block gets
 // a warp of its own, so that no two chains share an instruction stream
@@ -461,16 +462,38 @@ int launch_t1_decode(const DecBlock *blocks, const DecInput *inputs, uint32_t nb
 	if (max_w < 1) max_w = 1;
 	if (max_h < 1) max_h = 1;
 	const int fw = (int) max_w + 2;
-	int fwords = (int) ((max_h + 3) / 4) * fw;
-	fwords += fwords & 1;
-	int want = (int) ((nblocks + (uint32_t) (sms * DT_MINB) - 1) / (uint32_t) (sms * DT_MINB)); // spread a small job over every SM
-	const int lanes = want * DT_MINB <= DT_SPARSE_BLOCKS_PER_SM ? 1 : DT_LANES;
-	// slots of one warp start 32 / lanes banks apart
-	int bank0 = 32 / lanes % 32;
-	if (bank0 & 1) bank0 = 2;
-	while (fwords % 32 != bank0) fwords += 2;
+	const int want = (int) ((nblocks + (uint32_t) (sms * DT_MINB) - 1) / (uint32_t) (sms * DT_MINB)); // spread a small job over every SM
+	// flag words per block and block slots that fit the shared memory of a CTA, for `lanes` blocks per warp (the slots of one
+	// warp start 32 / lanes banks apart)
+	auto shape = [&](int lanes, int &fwords, int &cap) {
+		fwords = (int) ((max_h + 3) / 4) * fw;
+		fwords += fwords & 1;
+		int bank0 = 32 / lanes % 32;
+		if (bank0 & 1) bank0 = 2;
+		while (fwords % 32 != bank0) fwords += 2;
+		cap = (smem_max - DT_FIXED_WORDS * 4) / ((fwords + DT_CTX_WORDS) * 4);
+	};
+	// Blocks per warp.  A launch with few blocks per SM is bound by the latency of one block's chain: every block gets a warp of
+	// its own.  A single wave (configs[1]: 46 blocks per SM) runs best with two blocks per warp.  A launch of many waves is bound by
+	// warp instructions issued, and an instruction costs the same with one live lane or eight: as many blocks per warp as leave
+	// about twenty warps resident per SM (measured, profiles/README.md: 30 cinema frames, 32x32 blocks, 189 slots per SM:
+	// 68 ms at 2 per warp, 48 at 4, 41 at 8, 46 at 16; configs[2] planes, 64x64 blocks, 48 slots per SM: 133 ms at 2, 147 at 6).
+	int lanes, fwords, cap;
+	if (want * DT_MINB <= DT_SPARSE_BLOCKS_PER_SM) lanes = 1;
+	else {
+		lanes = DT_LANES;
+		shape(lanes, fwords, cap);
+		if (want > cap && !getenv("GB200_T1_DEC_LANES")) {
+			for (int l : {8, 4}) {
+				int f, c;
+				shape(l, f, c);
+				if (c >= 20 * l) { lanes = l; break; }
+			}
+		}
+	}
+	if (const char *e = getenv("GB200_T1_DEC_LANES")) { const int l = atoi(e); if (l == 1 || l == 2 || l == 4 || l == 8) lanes = l; } // measurement knob
+	shape(lanes, fwords, cap);
 	const int per_slot = (fwords + DT_CTX_WORDS) * 4;
-	int cap = (smem_max - DT_FIXED_WORDS * 4) / per_slot;
 	int nslots = cap < want ? cap : want;
 	const int max_slots = DT_MAX_THREADS / 32 * lanes;
 	if (nslots > max_slots) nslots = max_slots;
@@ -479,8 +502,11 @@ int launch_t1_decode(const DecBlock *blocks, const DecInput *inputs, uint32_t nb
 	if (nslots < lanes) nslots = cap; // a partial warp: blocks too large for `lanes` of them
 	if (nslots < 1) return 1;
 	const size_t smem = (size_t) DT_FIXED_WORDS * 4 + (size_t) nslots * per_slot;
-	auto kernel = (styles || seg_start) ? (lanes == 1 ? t1_decode_kernel<1, true> : t1_decode_kernel<DT_LANES, true>)
-			: (lanes == 1 ? t1_decode_kernel<1, false> : t1_decode_kernel<DT_LANES, false>);
+	const bool sty = styles || seg_start;
+	auto kernel = lanes == 1 ? (sty ? t1_decode_kernel<1, true> : t1_decode_kernel<1, false>)
+			: lanes == 2 ? (sty ? t1_decode_kernel<2, true> : t1_decode_kernel<2, false>)
+			: lanes == 4 ? (sty ? t1_decode_kernel<4, true> : t1_decode_kernel<4, false>)
+			: (sty ? t1_decode_kernel<8, true> : t1_decode_kernel<8, false>);
 	if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) != cudaSuccess) return 1;
 	const int threads = (nslots + lanes - 1) / lanes * 32;
 	t1_dec_clear_kernel<<<(nblocks + 7) / 8, 256, 0, s>>>(blocks, nblocks);

@@ -27,6 +27,7 @@
 //  load already in flight, bytes leave with a one-byte carry delay.  Pass rates (t1.cpp:1255-1324)
 //  are produced here.
 #include "common.cuh"
+#include <cstdlib>
 #include "t1_tables.cuh"
 
 namespace gb {
@@ -360,9 +361,6 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, ENC_MIN_CTAS) t1_model_kernel(
 #define MQ_WARPS_PER_CTA 4
 #endif
 constexpr int MQ_WARPS = MQ_WARPS_PER_CTA;
-#ifndef MQ_LANES
-#define MQ_LANES 2   // active lanes (code blocks) per warp
-#endif
 #ifndef MQ_SPARSE_BLOCKS_PER_SM
 #define MQ_SPARSE_BLOCKS_PER_SM 16
 #endif
@@ -628,16 +626,25 @@ void launch_t1_encode(const EncBlock *blocks, uint32_t nblocks, int rate_control
 	if (!nblocks) return;
 	ensure_t1_tables();
 	t1_model_kernel<<<(nblocks + ENC_WARPS - 1) / ENC_WARPS, ENC_WARPS * 32, 0, s>>>(blocks, nblocks, rate_control, symbols, results, dists);
-	// few blocks per SM: the launch is bound by the latency of one coder's chain, give every coder its own warp
+	// Coders per warp.  Few blocks per SM: the launch is bound by the latency of one coder's chain, every coder gets its own warp.
+	// Otherwise the kernel is bound by warp instructions issued, and the coders of a warp share most of theirs (one uniform
+	// loop, 1.6 of 2 lanes live on average): the more blocks a launch has per SM, the more coders a warp can carry without
+	// starving the SM of warps.  Measured (profiles/README.md), model + MQ time: configs[1], 46 blocks per SM: 6.22 ms at 2 coders
+	// per warp, 5.63 at 4, 5.86 at 6, 6.71 at 16; configs[2] planes, 336 per SM: 89 / 53 / 45 / 42 ms at 2 / 8 / 16 / 32; 30 cinema
+	// frames, 1360 per SM: 58 / 38 / 34 / 31 ms.
 	int dev = 0, sms = 148;
 	cudaGetDevice(&dev);
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-	if (styles)
-		t1_mq_kernel<1, true><<<(nblocks + MQ_WARPS - 1) / MQ_WARPS, MQ_WARPS * 32, 0, s>>>(blocks, nblocks, symbols, scratch, results, rates);
-	else if (nblocks <= (uint32_t) sms * MQ_SPARSE_BLOCKS_PER_SM)
-		t1_mq_kernel<1, false><<<(nblocks + MQ_WARPS - 1) / MQ_WARPS, MQ_WARPS * 32, 0, s>>>(blocks, nblocks, symbols, scratch, results, rates);
-	else
-		t1_mq_kernel<MQ_LANES, false><<<(nblocks + MQ_WARPS * MQ_LANES - 1) / (MQ_WARPS * MQ_LANES), MQ_WARPS * 32, 0, s>>>(blocks, nblocks, symbols, scratch, results, rates);
+	const uint32_t per_sm = (nblocks + (uint32_t) sms - 1) / (uint32_t) sms;
+	int lanes = styles ? 1 : per_sm <= MQ_SPARSE_BLOCKS_PER_SM ? 1 : per_sm <= 64 ? 4 : per_sm <= 160 ? 8 : per_sm <= 320 ? 16 : 32;
+	if (const char *e = getenv("GB200_T1_MQ_LANES")) { const int l = atoi(e); if (!styles && (l == 1 || l == 4 || l == 8 || l == 16 || l == 32)) lanes = l; } // measurement knob
+	const uint32_t per_cta = (uint32_t) (MQ_WARPS * lanes), grid = (nblocks + per_cta - 1) / per_cta;
+	if (styles) t1_mq_kernel<1, true><<<grid, MQ_WARPS * 32, 0, s>>>(blocks, nblocks, symbols, scratch, results, rates);
+	else if (lanes == 1) t1_mq_kernel<1, false><<<grid, MQ_WARPS * 32, 0, s>>>(blocks, nblocks, symbols, scratch, results, rates);
+	else if (lanes == 4) t1_mq_kernel<4, false><<<grid, MQ_WARPS * 32, 0, s>>>(blocks, nblocks, symbols, scratch, results, rates);
+	else if (lanes == 8) t1_mq_kernel<8, false><<<grid, MQ_WARPS * 32, 0, s>>>(blocks, nblocks, symbols, scratch, results, rates);
+	else if (lanes == 16) t1_mq_kernel<16, false><<<grid, MQ_WARPS * 32, 0, s>>>(blocks, nblocks, symbols, scratch, results, rates);
+	else t1_mq_kernel<32, false><<<grid, MQ_WARPS * 32, 0, s>>>(blocks, nblocks, symbols, scratch, results, rates);
 }
 
 // bytes of symbol stream to reserve for a w x h block with at most `planes` coded bit-planes: every sample

@@ -1,0 +1,41 @@
+"""GPU: the Tier-1 kernels pick how many code blocks share a warp from the size of the launch (t1_enc.cu / t1_dec.cu launch code).
+Every instantiation must give the same bytes and the same samples: the measurement knobs GB200_T1_MQ_LANES / GB200_T1_DEC_LANES
+force each one on the same image (the default choice is checked against the oracle elsewhere)."""
+import os
+
+import numpy as np
+import pytest
+
+import grokimagecompression_b200 as gb
+from grokimagecompression_b200 import params as P
+from grokimagecompression_b200.synth import synthetic_planes
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("rev", [True, False])
+def test_every_lane_count_gives_the_same_result(ctx, rev):
+    w, h, nc = 640, 512, 3
+    img = synthetic_planes(w, h, nc, 8, seed=11)
+    tiles = P.image_tiles(w, h, nc, 8, rev, (256, 256), 5, rate_control=not rev, cblk_expn=(5, 5))
+    planes = P.split_planes(img, w, h, (256, 256))
+    tiles_d = P.image_tiles(w, h, nc, 8, rev, (256, 256), 5, cblk_expn=(5, 5), encoder=False)
+    try:
+        ref = gb.Plan(ctx, tiles, encoder=True).encode(planes)
+        assert len(ref[0]) > 1000
+        inp = np.zeros(len(ref[0]), gb.CBLK_DEC_DTYPE)
+        for k in ("numbps", "numpasses", "data_len", "data_offset"):
+            inp[k] = ref[0][k]
+        ref_dec = gb.Plan(ctx, tiles_d, encoder=False).decode(inp, ref[3])
+        for lanes in (1, 4, 8, 16, 32):
+            os.environ["GB200_T1_MQ_LANES"] = str(lanes)
+            got = gb.Plan(ctx, tiles, encoder=True).encode(planes)
+            assert (got[0] == ref[0]).all() and (got[1] == ref[1]).all() and (got[2] == ref[2]).all() and bytes(got[3]) == bytes(ref[3]), lanes
+        for lanes in (1, 2, 4, 8):
+            os.environ["GB200_T1_DEC_LANES"] = str(lanes)
+            got = gb.Plan(ctx, tiles_d, encoder=False).decode(inp, ref[3])
+            for a, b in zip(got, ref_dec):
+                assert (a == b).all(), lanes
+    finally:
+        os.environ.pop("GB200_T1_MQ_LANES", None)
+        os.environ.pop("GB200_T1_DEC_LANES", None)
