@@ -887,7 +887,23 @@ def main():
                 if it >= args.warmup:
                     acc_h += (e[0].elapsed_time(e[2]), e[3].elapsed_time(e[5]), e[1].elapsed_time(e[2]), e[3].elapsed_time(e[4]))
             acc_h /= args.steps
+            # end to end through the C ABI from one host thread, packed host samples (as `e2e.single_thread`)
+            h_ph = [pinned_like(p) for p in ph]
+            o_h = (pinned(pe.num_blocks * gb.CBLK_ENC_DTYPE.itemsize, np.uint8).view(gb.CBLK_ENC_DTYPE), pinned(max(pe.num_pass_slots, 1), np.int32).view(np.uint32),
+                   pinned(max(pe.num_pass_slots, 1), np.float64), pinned(data_cap, np.uint8))
+            hi_h = pinned(ih.nbytes, np.uint8).view(gb.CBLK_DEC_DTYPE)
+            hi_h[...] = ih
+            ho_h = [pinned(sh, pe.sample_dtype(0)) for sh in pd.comp_shapes]
+            nbytes_h = len(rh[3])
+            for it in range(args.warmup + args.steps):
+                if it == args.warmup:
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                pe.encode(h_ph, o_h)
+                pd.decode(hi_h, o_h[3][:nbytes_h], ho_h)
+            t_ht_e2e = (time.perf_counter() - t0) / args.steps
             line["ht"] = {"workload": WORKLOAD_TEXT["c2ht"], "kernels": "t1_ht_encode_kernel / t1_ht_decode_kernel (csrc/ht.cu): one warp per code block",
+                          "e2e_single_thread": {"value": round(2 * pixels / t_ht_e2e / 1e6, 1), "ms_per_step": round(t_ht_e2e * 1e3, 3)},
                           "value": round(2 * pixels / ((acc_h[0] + acc_h[1]) * 1e-3) / 1e6, 1), "unit": "Mpixel/s (device-resident, like `value`)",
                           "encode_ms": round(float(acc_h[0]), 4), "decode_ms": round(float(acc_h[1]), 4),
                           "t1_encode_ms": round(float(acc_h[2]), 4), "t1_decode_ms": round(float(acc_h[3]), 4), "encoded_bytes": int(len(rh[3]))}
@@ -904,6 +920,13 @@ def main():
             line["drop_in"] = json.loads([ln for ln in outp.splitlines() if ln.startswith("{")][-1])
         except Exception as exc:
             line["drop_in"] = {"error": repr(exc)[:200]}
+        if args.workload == "c2":  # the same image with -M 64: the reference's T1HT against the device's HT kernels
+            try:
+                outp = subprocess.check_output([sys.executable, os.path.join(ROOT, "tools", "dropin_bench.py"), "c2ht", "2", "--json"],
+                                               text=True, timeout=300, stderr=subprocess.DEVNULL)
+                line["drop_in_ht"] = json.loads([ln for ln in outp.splitlines() if ln.startswith("{")][-1])
+            except Exception as exc:
+                line["drop_in_ht"] = {"error": repr(exc)[:200]}
     if not args.no_cpu_baseline and world == 1:
         r = cpu_reference_run(args.workload, steps=2, warmup=1, budget_s=25.0, seed=1000)
         line["cpu_baseline"] = cpu_baseline_object(r) if r is not None else {"value": None, "unit": "Mpixel/s", "cores": 0, "kind": "reference",

@@ -602,7 +602,7 @@ __global__ void __launch_bounds__(HTW_WARPS * 32) t1_ht_decode_kernel(const DecB
 		const int Uq = u + kappa;
 		int m[4], tb = 0;
 		#pragma unroll
-		for (int i = 0; i < 4; ++i) { m[i] = (rho >> i & 1) ? Uq - (ek >> i & 1) : 0; tb += m[i]; }
+		for (int i = 0; i < 4; ++i) { m[i] = (rho >> i & 1) ? min(Uq - (ek >> i & 1), 31) : 0; tb += m[i]; } // (31: a corrupt stream cannot widen a field past the bit buffer)
 		int incl = tb;
 		#pragma unroll
 		for (int d = 1; d < 32; d <<= 1) {
@@ -930,7 +930,7 @@ __global__ void __launch_bounds__(HT_THREADS) t1_ht_decode_thread_kernel(const D
 					uint32_t val = 0;
 					int e = 0;
 					if (rho >> i & 1) {
-						const int m = Uq - (ek >> i & 1);
+						const int m = min(Uq - (ek >> i & 1), 31);
 						const uint32_t b = ht_fwd_peek(ms);
 						ms.acc >>= m; ms.bits -= m;
 						uint32_t vn = b & ((1u << m) - 1u);

@@ -494,7 +494,8 @@ GBO_API int gbo_ht_decode_block(const uint8_t *data, int lcup, int missing_msbs,
 					int32_t val = 0;
 					int e = 0;
 					if (rho >> i & 1) {
-						const int m = Uq - (ek >> i & 1);
+						int m = Uq - (ek >> i & 1);
+						if (m > 31) m = 31; /* only a corrupt stream gets here; keeps the shifts defined */
 						const uint32_t b = fwd_peek(&ms);
 						fwd_skip(&ms, m);
 						uint32_t vn = b & ((1u << m) - 1u);

@@ -34,6 +34,8 @@ def child(mode, name, reps):
               rates=w["rates"], rc_algorithm=1)
     if w.get("cinema"):
         kw["cinema2k_fps"] = w["cinema"]
+    if w.get("ht"):
+        kw["cblk_sty"] = 64
     te, td = [], []
     cs = None
     for i in range(reps + 1):
