@@ -46,6 +46,17 @@ namespace gb {
 #ifndef DT_SPARSE_BLOCKS_PER_SM
 #define DT_SPARSE_BLOCKS_PER_SM 16
 #endif
+// launches of up to this many blocks per SM go to the warp-uniform kernel (0 = never)
+#ifndef DT_UNIFORM_BLOCKS_PER_SM
+#define DT_UNIFORM_BLOCKS_PER_SM 0
+#endif
+// the warp-uniform kernel: CTAs per SM it is compiled for and threads per CTA (2 x 768: 40 registers, 48 blocks per SM)
+#ifndef DU_MINB
+#define DU_MINB 2
+#endif
+#ifndef DU_MAX_THREADS
+#define DU_MAX_THREADS 768
+#endif
 // CTAs per SM the decode kernel is compiled for (register cap) and threads per CTA: 1 x 1024 (64 registers) or 2 x 768 (40)
 #ifndef DT_MINB
 #define DT_MINB 1
@@ -140,12 +151,12 @@ __device__ __forceinline__ void mq_init(MqT &q, const uint8_t *buf, uint32_t len
 	q.a = 0x80000000u;
 }
 
-// context rows: qe << 16 | mps << 15 | next(LPS) << 8 | next(MPS); the successors index the 94-entry table
-// of (state, mps) pairs, so the SWITCH column of Table C.2 is folded into them.
+// context rows: qe << 16 | next(LPS) << 9 | next(MPS) << 2 | mps; the successors are byte offsets into the 94-entry
+// table of (state, mps) pairs (so the SWITCH column of Table C.2 is folded into them), every field is one AND away.
 // DECODE + RENORMD, mqc_dec_inl.h:60-86, 136-169
 __device__ __forceinline__ uint32_t mq_decode(MqT &q, uint32_t *crow, const uint32_t *tab) {
 	const uint32_t row = *crow;
-	const uint32_t qs = row & 0xFFFF0000u, mps = (row >> 15) & 1u;
+	const uint32_t qs = row & 0xFFFF0000u, mps = row & 1u;
 	const uint32_t a = q.a - qs, cs = q.c - qs;
 	const bool lpsint = q.c < qs; // (C >> 16) < Qe : the LPS sub-interval
 	if (!lpsint && (a & 0x80000000u)) { // MPS, no renormalisation: the one early exit
@@ -158,7 +169,7 @@ __device__ __forceinline__ uint32_t mq_decode(MqT &q, uint32_t *crow, const uint
 	const bool lps = (a < qs) != lpsint;
 	q.c = lpsint ? q.c : cs;
 	q.a = lpsint ? qs : a;
-	*crow = tab[lps ? (row >> 8) & 0x7Fu : row & 0x7Fu];
+	*crow = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(tab) + (lps ? (row >> 7) & 0x1FCu : row & 0x1FCu));
 	int sh = __clz(q.a);
 	q.a <<= sh;
 	if (sh > q.ct) {
@@ -188,6 +199,7 @@ struct Blk {
 	const uint8_t *rbuf;  // raw (bypass) segment reader, mqc_dec_inl.h:90-112
 	uint32_t rpos, rlen, rc;
 	int rct;
+	uint32_t lane;        // warp-uniform decoder only: lane 0 adds to the coefficient plane
 };
 
 // one raw bit; bytes past the segment read as 0xFF, the byte after 0xFF carries 7 bits
@@ -205,8 +217,17 @@ __device__ __forceinline__ uint32_t raw_bit(Blk &b) {
 
 constexpr uint32_t F_OWNSIG = 0x2490u; // significance of the own column, rows 0..3
 
+// UNI: the warp-uniform decoder (t1_decode_uniform_kernel): all 32 lanes of a warp walk the SAME block with the same
+// values, so a neighbour update is a plain read-modify-write (every lane writes the same word) and only lane 0 adds to
+// the coefficient plane.  Otherwise (one thread per block): result-less shared atomics, one instruction each.
+template<bool UNI>
+__device__ __forceinline__ void flag_or(uint32_t *p, uint32_t v) {
+	if (UNI) *p |= v;
+	else atomicOr(p, v);
+}
+
 // sign of a sample that just turned significant (t1.cpp:115-140), mid-point store, neighbour updates (t1.cpp:168-195)
-template<int K, bool STY = false, bool RAW = false>
+template<int K, bool STY = false, bool RAW = false, bool UNI = false>
 __device__ __forceinline__ void sign_and_mark(Blk &b, uint32_t &f, uint32_t *cw, int s, uint32_t off, int32_t oph) {
 	uint32_t neg;
 	if (RAW) neg = raw_bit(b); // raw passes carry the sign itself (t1.cpp:233-260)
@@ -220,56 +241,62 @@ __device__ __forceinline__ void sign_and_mark(Blk &b, uint32_t &f, uint32_t *cw,
 	f |= fsig(K + 1, 1) | (neg << (19 + K));
 	b.dst[off + K * b.stride] = neg ? -oph : oph;
 	// the sample is the east neighbour of column x-1 and the west neighbour of column x+1
-	atomicOr(cw - 1, fsig(K + 1, 2));
-	atomicOr(cw + 1, fsig(K + 1, 0));
+	flag_or<UNI>(cw - 1, fsig(K + 1, 2));
+	flag_or<UNI>(cw + 1, fsig(K + 1, 0));
 	if (K == 0 && s > 0 && !(STY && b.vsc)) { // row 4 of the stripe above
 		uint32_t *up = cw - b.fw;
-		atomicOr(up - 1, fsig(5, 2));
-		atomicOr(up, fsig(5, 1) | (neg << 23));
-		atomicOr(up + 1, fsig(5, 0));
+		flag_or<UNI>(up - 1, fsig(5, 2));
+		flag_or<UNI>(up, fsig(5, 1) | (neg << 23));
+		flag_or<UNI>(up + 1, fsig(5, 0));
 	}
 	if (K == 3 && s + 1 < b.nstripes) { // row -1 of the stripe below
 		uint32_t *dn = cw + b.fw;
-		atomicOr(dn - 1, fsig(0, 2));
-		atomicOr(dn, fsig(0, 1) | (neg << 18));
-		atomicOr(dn + 1, fsig(0, 0));
+		flag_or<UNI>(dn - 1, fsig(0, 2));
+		flag_or<UNI>(dn, fsig(0, 1) | (neg << 18));
+		flag_or<UNI>(dn + 1, fsig(0, 0));
 	}
 }
 
 // significance propagation, t1.cpp:381-441
-template<int K, bool STY = false, bool RAW = false>
+template<int K, bool STY = false, bool RAW = false, bool UNI = false>
 __device__ __forceinline__ void sig_row(Blk &b, uint32_t &f, uint32_t *cw, int s, uint32_t off, int32_t oph) {
 	if ((f & (fsig(K + 1, 1) | (1u << (24 + K)))) == 0 && (f & (0x1EFu << (3 * K))) != 0) {
 		const uint32_t d = RAW ? raw_bit(b) : mq_decode(b.q, b.C + b.zc[(f >> (3 * K)) & 0x1FFu], b.tab);
 		f |= 1u << (24 + K);
-		if (d) sign_and_mark<K, STY, RAW>(b, f, cw, s, off, oph);
+		if (d) sign_and_mark<K, STY, RAW, UNI>(b, f, cw, s, off, oph);
 	}
 }
 
 // magnitude refinement: +-half a step towards the decoded bit, t1.cpp:476-496, 588-637
-template<int K, bool RAW = false>
+template<int K, bool RAW = false, bool UNI = false>
 __device__ __forceinline__ void ref_row(Blk &b, uint32_t &f, uint32_t off, int32_t half) {
 	if ((f & (fsig(K + 1, 1) | (1u << (24 + K)))) == fsig(K + 1, 1)) {
 		const uint32_t cx = (f & (1u << (28 + K))) ? CTX_MR0 + 2 : (f & (0x1EFu << (3 * K))) ? CTX_MR0 + 1 : CTX_MR0;
 		const uint32_t d = RAW ? raw_bit(b) : mq_decode(b.q, b.C + cx, b.tab);
 		const uint32_t neg = (f >> (19 + K)) & 1u;
-		atomicAdd(b.dst + off + K * b.stride, (d ^ neg) ? half : -half);
+		if (UNI) { // one predicated RED, not a branch around it: the instruction stream of the warp stays uniform
+			int32_t v = (d ^ neg) ? half : -half;
+			int32_t *p = b.dst + off + K * b.stride;
+			asm volatile("" : "+r"(v), "+l"(p)); // value and address are formed outside the predicate
+			asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %2, 0;\n\t@p red.global.add.s32 [%0], %1;\n\t}" :: "l"(p), "r"(v), "r"(b.lane) : "memory");
+		}
+		else atomicAdd(b.dst + off + K * b.stride, (d ^ neg) ? half : -half);
 		f |= 1u << (28 + K);
 	}
 }
 
 // cleanup, t1.cpp:784-870; start / implied: the row whose 1 the run-length code already delivered
-template<int K, bool STY = false>
+template<int K, bool STY = false, bool UNI = false>
 __device__ __forceinline__ void cln_row(Blk &b, uint32_t &f, uint32_t *cw, int s, uint32_t off, int32_t oph, int start, bool implied) {
 	if (K >= start && (f & (fsig(K + 1, 1) | (1u << (24 + K)))) == 0) {
 		uint32_t d = 1;
 		if (!(implied && K == start)) d = mq_decode(b.q, b.C + b.zc[(f >> (3 * K)) & 0x1FFu], b.tab);
-		if (d) sign_and_mark<K, STY, false>(b, f, cw, s, off, oph);
+		if (d) sign_and_mark<K, STY, false, UNI>(b, f, cw, s, off, oph);
 	}
 }
 
 // one coding pass over the whole block
-template<bool STY, bool RAW>
+template<bool STY, bool RAW, bool UNI = false>
 __device__ __forceinline__ void run_pass(Blk &b, uint32_t *F, int w, int fw, int type, int bp1, uint32_t last_pi) {
 	// values carry one extra low bit: the plane weight is 1 << bp1, the mid-point sits half a step above
 	const int32_t half = (1 << bp1) >> 1, oph = (1 << bp1) | half;
@@ -280,20 +307,20 @@ __device__ __forceinline__ void run_pass(Blk &b, uint32_t *F, int w, int fw, int
 			for (int x = 0; x < w; ++x, ++cw, ++off) {
 				uint32_t f = *cw;
 				if (!(f & F_SIGMA_ALL) || (f & F_OWNSIG) == F_OWNSIG) continue; // nothing significant around / nothing left to find
-				sig_row<0, STY, RAW>(b, f, cw, s, off, oph);
-				sig_row<1, STY, RAW>(b, f, cw, s, off, oph);
-				sig_row<2, STY, RAW>(b, f, cw, s, off, oph);
-				sig_row<3, STY, RAW>(b, f, cw, s, off, oph);
+				sig_row<0, STY, RAW, UNI>(b, f, cw, s, off, oph);
+				sig_row<1, STY, RAW, UNI>(b, f, cw, s, off, oph);
+				sig_row<2, STY, RAW, UNI>(b, f, cw, s, off, oph);
+				sig_row<3, STY, RAW, UNI>(b, f, cw, s, off, oph);
 				*cw = f;
 			}
 		} else if (type == 1) {
 			for (int x = 0; x < w; ++x, ++cw, ++off) {
 				uint32_t f = *cw;
 				if (!(f & F_OWNSIG)) continue;
-				ref_row<0, RAW>(b, f, off, half);
-				ref_row<1, RAW>(b, f, off, half);
-				ref_row<2, RAW>(b, f, off, half);
-				ref_row<3, RAW>(b, f, off, half);
+				ref_row<0, RAW, UNI>(b, f, off, half);
+				ref_row<1, RAW, UNI>(b, f, off, half);
+				ref_row<2, RAW, UNI>(b, f, off, half);
+				ref_row<3, RAW, UNI>(b, f, off, half);
 				*cw = f;
 			}
 		} else if (!RAW) {
@@ -308,11 +335,59 @@ __device__ __forceinline__ void run_pass(Blk &b, uint32_t *F, int w, int fw, int
 					start |= (int) mq_decode(b.q, b.C + CTX_UNI, b.tab);
 					implied = true;
 				}
-				cln_row<0, STY>(b, f, cw, s, off, oph, start, implied);
-				cln_row<1, STY>(b, f, cw, s, off, oph, start, implied);
-				cln_row<2, STY>(b, f, cw, s, off, oph, start, implied);
-				cln_row<3, STY>(b, f, cw, s, off, oph, start, implied);
+				cln_row<0, STY, UNI>(b, f, cw, s, off, oph, start, implied);
+				cln_row<1, STY, UNI>(b, f, cw, s, off, oph, start, implied);
+				cln_row<2, STY, UNI>(b, f, cw, s, off, oph, start, implied);
+				cln_row<3, STY, UNI>(b, f, cw, s, off, oph, start, implied);
 				*cw = (f & ~F_PI_ALL) | keep_pi;
+			}
+		}
+	}
+}
+
+// the coding passes of one block in order: cln(numbps), then sig / ref / cln per lower plane (t1.cpp:1067-1114)
+template<bool STY, bool UNI>
+__device__ __forceinline__ void run_block(Blk &b, uint32_t *F, const uint32_t *tab, const DecBlock &B, const DecInput &I, uint32_t bid,
+		const uint8_t *__restrict__ data, int w, int fw, int top, int numbps, uint32_t last_pi,
+		const uint32_t *__restrict__ seg_start, const DecSeg *__restrict__ segs) {
+	int bp1 = top, type = 2;
+	if (!STY) {
+		mq_init(b.q, data + I.data_offset, I.data_len);
+		const int npass = min((int) I.numpasses, 3 * top - 2);
+		for (int pass = 0; pass < npass; ++pass) {
+			run_pass<false, false, UNI>(b, F, w, fw, type, bp1, last_pi);
+			if (++type == 3) { type = 0; bp1--; }
+		}
+	} else {
+		// codeword segments as Tier-2 delivers them (t1.cpp:1067-1114): every segment restarts the MQ decoder, or the raw
+		// reader for the bypassed passes of LAZY; RESET clears the contexts after every MQ pass; SEGSYM appends four
+		// UNIFORM decisions to every cleanup pass
+		const uint32_t sty = B.sty;
+		b.vsc = (sty & STY_VSC) != 0;
+		const uint32_t s0 = seg_start ? seg_start[bid] : 0u, nsegs = seg_start ? seg_start[bid + 1] - s0 : 1u;
+		uint32_t off = 0;
+		for (uint32_t sg = 0; sg < nsegs && bp1 >= 1; ++sg) {
+			// a segment never reaches past the block's bytes (corrupt packet headers: sum of the lengths > data_len); what is
+			// missing reads as the 0xFF fill of an exhausted segment
+			const uint32_t left = off < I.data_len ? I.data_len - off : 0u;
+			const uint32_t len = min(seg_start ? segs[s0 + sg].len : I.data_len, left), np = seg_start ? segs[s0 + sg].numpasses : I.numpasses;
+			const bool raw = (sty & STY_LAZY) && bp1 <= numbps - 4 && type < 2;
+			const uint8_t *seg = data + I.data_offset + off;
+			if (raw) { b.rbuf = seg; b.rpos = 0; b.rlen = len; b.rc = 0; b.rct = 0; } // mqc_raw_init_dec
+			else mq_init(b.q, seg, len);
+			off += len;
+			for (uint32_t p = 0; p < np && bp1 >= 1; ++p) {
+				if (raw) run_pass<true, true, UNI>(b, F, w, fw, type, bp1, last_pi);
+				else {
+					run_pass<true, false, UNI>(b, F, w, fw, type, bp1, last_pi);
+					if (type == 2 && (sty & STY_SEGSYM)) // t1_dec_clnpass_check_segsym: read, a mismatch only warns
+						for (int i = 0; i < 4; ++i) mq_decode(b.q, b.C + CTX_UNI, b.tab);
+					if (sty & STY_RESET) {
+						#pragma unroll
+						for (int i = 0; i < NCTX; ++i) b.C[i] = tab[2 * (i == CTX_ZC0 ? 4 : i == CTX_AGG ? 3 : i == CTX_UNI ? 46 : 0)];
+					}
+				}
+				if (++type == 3) { type = 0; bp1--; }
 			}
 		}
 	}
@@ -331,7 +406,7 @@ __global__ void __launch_bounds__(DT_MAX_THREADS, DT_MINB) t1_decode_kernel(cons
 	for (int i = threadIdx.x; i < 94; i += blockDim.x) {
 		const uint32_t r = c_mq[i >> 1], mps = i & 1u, sw = (r >> 28) & 1u;
 		const uint32_t nm = ((r >> 16) & 63u) * 2u + mps, nl = ((r >> 22) & 63u) * 2u + (mps ^ sw);
-		tab[i] = (r << 16) | (mps << 15) | (nl << 8) | nm;
+		tab[i] = (r << 16) | (nl << 9) | (nm << 2) | mps;
 	}
 	for (int i = threadIdx.x; i < 2048; i += blockDim.x) {
 		const int o = i >> 9, n9 = i & 511;
@@ -376,48 +451,73 @@ __global__ void __launch_bounds__(DT_MAX_THREADS, DT_MINB) t1_decode_kernel(cons
 	b.sc = Lsc;
 	b.dst = B.dst;
 	b.stride = B.stride;
-	// passes go cln(numbps), then sig / ref / cln per lower plane
-	int bp1 = top, type = 2;
-	if (!STY) {
-		mq_init(b.q, data + I.data_offset, I.data_len);
-		const int npass = min((int) I.numpasses, 3 * top - 2);
-		for (int pass = 0; pass < npass; ++pass) {
-			run_pass<false, false>(b, F, w, fw, type, bp1, last_pi);
-			if (++type == 3) { type = 0; bp1--; }
-		}
-	} else {
-		// codeword segments as Tier-2 delivers them (t1.cpp:1067-1114): every segment restarts the MQ decoder, or the raw
-		// reader for the bypassed passes of LAZY; RESET clears the contexts after every MQ pass; SEGSYM appends four
-		// UNIFORM decisions to every cleanup pass
-		const uint32_t sty = B.sty;
-		b.vsc = (sty & STY_VSC) != 0;
-		const uint32_t s0 = seg_start ? seg_start[bid] : 0u, nsegs = seg_start ? seg_start[bid + 1] - s0 : 1u;
-		uint32_t off = 0;
-		for (uint32_t sg = 0; sg < nsegs && bp1 >= 1; ++sg) {
-			// a segment never reaches past the block's bytes (corrupt packet headers: sum of the lengths > data_len); what is
-			// missing reads as the 0xFF fill of an exhausted segment
-			const uint32_t left = off < I.data_len ? I.data_len - off : 0u;
-			const uint32_t len = min(seg_start ? segs[s0 + sg].len : I.data_len, left), np = seg_start ? segs[s0 + sg].numpasses : I.numpasses;
-			const bool raw = (sty & STY_LAZY) && bp1 <= numbps - 4 && type < 2;
-			const uint8_t *seg = data + I.data_offset + off;
-			if (raw) { b.rbuf = seg; b.rpos = 0; b.rlen = len; b.rc = 0; b.rct = 0; } // mqc_raw_init_dec
-			else mq_init(b.q, seg, len);
-			off += len;
-			for (uint32_t p = 0; p < np && bp1 >= 1; ++p) {
-				if (raw) run_pass<true, true>(b, F, w, fw, type, bp1, last_pi);
-				else {
-					run_pass<true, false>(b, F, w, fw, type, bp1, last_pi);
-					if (type == 2 && (sty & STY_SEGSYM)) // t1_dec_clnpass_check_segsym: read, a mismatch only warns
-						for (int i = 0; i < 4; ++i) mq_decode(b.q, b.C + CTX_UNI, b.tab);
-					if (sty & STY_RESET) {
-						#pragma unroll
-						for (int i = 0; i < NCTX; ++i) b.C[i] = tab[2 * (i == CTX_ZC0 ? 4 : i == CTX_AGG ? 3 : i == CTX_UNI ? 46 : 0)];
-					}
-				}
-				if (++type == 3) { type = 0; bp1--; }
-			}
-		}
+	run_block<STY, false>(b, F, tab, B, I, bid, data, w, fw, top, numbps, last_pi, seg_start, segs);
+}
+
+// ---- warp-uniform decoder: one WARP per code block, every lane running the same chain --------------------
+// For launches that cannot fill the machine with thread-per-block chains (one image: 6 804 blocks, 11.5 per scheduler).
+// All 32 lanes of a warp decode the SAME block redundantly: every address and every branch condition derives from
+// blockIdx and from loads at warp-uniform addresses, so the compiler emits no reconvergence bookkeeping (BSSY / BSYNC /
+// BREAK: 10 of the 65 instructions per decision of the kernel above), branches are uniform, and twice as many warps per
+// scheduler hide the latency of a chain.  An instruction costs an issue slot and a pass through the pipe whether one lane
+// or 32 are live, so the redundant lanes are free.
+template<bool STY>
+__global__ void __launch_bounds__(DU_MAX_THREADS, DU_MINB) t1_decode_uniform_kernel(const DecBlock *__restrict__ blocks,
+		const DecInput *__restrict__ inputs, uint32_t nblocks, const uint8_t *__restrict__ data, int fw, int fwords,
+		const uint32_t *__restrict__ seg_start, const DecSeg *__restrict__ segs) {
+	extern __shared__ __align__(16) uint32_t sm[];
+	uint32_t *tab = sm;                                        // 94 (state, mps) rows
+	uint8_t *Lzc = reinterpret_cast<uint8_t*>(sm + 96);        // zero-coding context by the 9 neighbourhood bits of a word
+	uint8_t *Lsc = Lzc + 2048;
+	for (int i = threadIdx.x; i < 94; i += blockDim.x) {
+		const uint32_t r = c_mq[i >> 1], mps = i & 1u, sw = (r >> 28) & 1u;
+		const uint32_t nm = ((r >> 16) & 63u) * 2u + mps, nl = ((r >> 22) & 63u) * 2u + (mps ^ sw);
+		tab[i] = (r << 16) | (nl << 9) | (nm << 2) | mps;
 	}
+	for (int i = threadIdx.x; i < 2048; i += blockDim.x) {
+		const int o = i >> 9, n9 = i & 511;
+		const int idx8 = (n9 & 7) | ((n9 >> 3) & 1) << 3 | ((n9 >> 5) & 1) << 4 | ((n9 >> 6) & 7) << 5;
+		Lzc[i] = c_zc[o][idx8];
+	}
+	for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+		const int orig = (i >> 1 & 1) | (i >> 3 & 1) << 1 | (i >> 5 & 1) << 2 | (i >> 7 & 1) << 3
+				| (i & 1) << 4 | (i >> 2 & 1) << 5 | (i >> 4 & 1) << 6 | (i >> 6 & 1) << 7;
+		Lsc[i] = c_sc[orig];
+	}
+	__syncthreads();
+	const int lane = threadIdx.x & 31;
+	// the warp index as the compiler can see it is the same in every lane (a shuffle from lane 0): what follows is uniform
+	const uint32_t wid = (uint32_t) __shfl_sync(0xffffffffu, (int) (threadIdx.x >> 5), 0);
+	// warp k of CTA c takes block c + k * gridDim.x: the blocks of one SM come from all over the image (the table is ordered
+	// by tile, component, resolution), so every SM gets the same mix of heavy and light blocks
+	const uint32_t bid = blockIdx.x + wid * gridDim.x;
+	if (bid >= nblocks) return;
+	uint32_t *F = sm + DT_FIXED_WORDS + wid * (uint32_t) (fwords + DT_CTX_WORDS); // word of stripe s, column x: F[s * fw + x + 1]
+	const DecBlock B = blocks[bid];
+	const DecInput I = inputs[bid];
+	const int w = B.w, h = B.h;
+	const int numbps = (int) I.numbps;
+	const int top = numbps + (int) B.roishift;
+	if (I.numpasses == 0 || I.data_len == 0 || top == 0 || top > 30 || w == 0 || h == 0) return;
+	Blk b;
+	b.nstripes = (h + 3) >> 2;
+	b.fw = fw;
+	b.lane = (uint32_t) lane;
+	for (int i = lane; i < b.nstripes * fw; i += 32) F[i] = 0;
+	__syncwarp();
+	const uint32_t last_pi = (0xFu << (h - 4 * (b.nstripes - 1)) & 0xFu) << 24;
+	if (last_pi)
+		for (int x = lane; x < w; x += 32) F[(b.nstripes - 1) * fw + 1 + x] = last_pi;
+	b.C = F + fwords;
+	b.tab = tab;
+	#pragma unroll
+	for (int i = 0; i < NCTX; ++i) b.C[i] = tab[2 * (i == CTX_ZC0 ? 4 : i == CTX_AGG ? 3 : i == CTX_UNI ? 46 : 0)]; // mqc_dec.cpp:207-214
+	__syncwarp();
+	b.zc = Lzc + 512 * B.orient;
+	b.sc = Lsc;
+	b.dst = B.dst;
+	b.stride = B.stride;
+	run_block<STY, true>(b, F, tab, B, I, bid, data, w, fw, top, numbps, last_pi, seg_start, segs);
 }
 
 // ---- before / after: one warp per block, coalesced ---------------------------------------------------
@@ -478,6 +578,29 @@ int launch_t1_decode(const DecBlock *blocks, const DecInput *inputs, uint32_t nb
 	// warp instructions issued, and an instruction costs the same with one live lane or eight: as many blocks per warp as leave
 	// about twenty warps resident per SM (measured, profiles/README.md: 30 cinema frames, 32x32 blocks, 189 slots per SM:
 	// 68 ms at 2 per warp, 48 at 4, 41 at 8, 46 at 16; configs[2] planes, 64x64 blocks, 48 slots per SM: 133 ms at 2, 147 at 6).
+	// one image's worth of blocks (more than a sparse launch, not enough to fill the machine with thread-per-block chains):
+	// the warp-uniform kernel, one block per 32-thread CTA
+	int uniform = want > DT_SPARSE_BLOCKS_PER_SM && want <= DT_UNIFORM_BLOCKS_PER_SM;
+	if (const char *e = getenv("GB200_T1_DEC_UNIFORM")) uniform = atoi(e) != 0; // measurement knob
+	if (uniform) {
+		int fwords = (int) ((max_h + 3) / 4) * fw;
+		const int per_warp = (fwords + DT_CTX_WORDS) * 4;
+		// warps (= blocks) per CTA: DU_MINB CTAs per SM hold the SM's share of the blocks when shared memory and the thread
+		// limit allow it (one wave), else as many as fit
+		int warps = (want + DU_MINB - 1) / DU_MINB;
+		const int cap = (smem_sm / DU_MINB - 1024 - DT_FIXED_WORDS * 4) / per_warp;
+		if (warps > cap) warps = cap;
+		if (warps > DU_MAX_THREADS / 32) warps = DU_MAX_THREADS / 32;
+		if (warps < 1) return 1;
+		const size_t smem = (size_t) DT_FIXED_WORDS * 4 + (size_t) warps * per_warp;
+		const bool sty = styles || seg_start;
+		auto kernel = sty ? t1_decode_uniform_kernel<true> : t1_decode_uniform_kernel<false>;
+		if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) != cudaSuccess) return 1;
+		t1_dec_clear_kernel<<<(nblocks + 7) / 8, 256, 0, s>>>(blocks, nblocks);
+		kernel<<<(nblocks + warps - 1) / warps, warps * 32, smem, s>>>(blocks, inputs, nblocks, data, fw, fwords, seg_start, segs);
+		t1_dec_finish_kernel<<<(nblocks + 7) / 8, 256, 0, s>>>(blocks, nblocks);
+		return 0;
+	}
 	int lanes, fwords, cap;
 	if (want * DT_MINB <= DT_SPARSE_BLOCKS_PER_SM) lanes = 1;
 	else {

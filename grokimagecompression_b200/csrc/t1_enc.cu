@@ -365,6 +365,9 @@ constexpr int MQ_WARPS = MQ_WARPS_PER_CTA;
 #define MQ_SPARSE_BLOCKS_PER_SM 16
 #endif
 constexpr int MQ_CTX_WORDS = 20;
+#ifndef MQ_PREFETCH
+#define MQ_PREFETCH 1
+#endif
 
 struct MqT {
 	uint32_t a, c;     // A kept in the high half-word (a << 16) so that the renormalisation shift is clz(a)
@@ -390,13 +393,13 @@ template<int LANES, bool STY>
 __global__ void __launch_bounds__(MQ_WARPS * 32) t1_mq_kernel(const EncBlock *__restrict__ blocks, uint32_t nblocks,
 		const uint8_t *__restrict__ symbols, uint8_t *__restrict__ scratch, EncResult *__restrict__ results,
 		uint32_t *__restrict__ rates) {
-	// context rows: qe << 16 | mps << 15 | next(LPS) << 8 | next(MPS); successors index the (state, mps) table
+	// context rows: qe << 16 | next(LPS) << 9 | next(MPS) << 2 | mps; successors are byte offsets into the (state, mps) table
 	__shared__ uint32_t tab[96];
 	__shared__ uint32_t ctx[MQ_WARPS * LANES][MQ_CTX_WORDS];
 	for (int i = threadIdx.x; i < 94; i += blockDim.x) {
 		const uint32_t r = c_mq[i >> 1], mps = i & 1u, sw = (r >> 28) & 1u;
 		const uint32_t nm = ((r >> 16) & 63u) * 2u + mps, nl = ((r >> 22) & 63u) * 2u + (mps ^ sw);
-		tab[i] = (r << 16) | (mps << 15) | (nl << 8) | nm;
+		tab[i] = (r << 16) | (nl << 9) | (nm << 2) | mps;
 	}
 	__syncthreads();
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -422,13 +425,13 @@ __global__ void __launch_bounds__(MQ_WARPS * 32) t1_mq_kernel(const EncBlock *__
 	// CODEMPS / CODELPS + RENORME for one (context, decision) byte
 	uint32_t tab_s = (uint32_t) __cvta_generic_to_shared(tab);
 	asm volatile("" : "+r"(tab_s)); // the shared-window address of the table stays in a register
-	auto tabrow = [&](uint32_t i) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(tab_s + 4u * i)); return v; };
-	auto code = [&](uint32_t sym) {
-		uint32_t *cr = C + (sym >> 1);
-		const uint32_t row = *cr;
+	auto tabrow = [&](uint32_t off) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(tab_s + off)); return v; };
+	// `row` is the context's row as loaded by the caller, `pre` / `pcr` a row loaded ahead for the NEXT symbol and where it came
+	// from: when this symbol rewrites that very context, the row in flight is replaced by the new one
+	auto code_row = [&](uint32_t sym, uint32_t *cr, uint32_t row, uint32_t &pre, const uint32_t *pcr) {
 		const uint32_t qs = row & 0xFFFF0000u;
 		const uint32_t a = q.a - qs;
-		const bool ismps = !(((row >> 15) ^ sym) & 1u);
+		const bool ismps = !((row ^ sym) & 1u);
 		if (ismps && (a & 0x80000000u)) { // CODEMPS without renormalisation: the one early exit
 			q.a = a;
 			q.c += qs >> 16;
@@ -438,7 +441,9 @@ __global__ void __launch_bounds__(MQ_WARPS * 32) t1_mq_kernel(const EncBlock *__
 		const bool takeq = ismps == (a < qs);
 		q.a = takeq ? qs : a;
 		q.c += takeq ? 0u : qs >> 16;
-		*cr = tabrow(ismps ? row & 0x7Fu : (row >> 8) & 0x7Fu);
+		const uint32_t nrow = tabrow(ismps ? row & 0x1FCu : (row >> 7) & 0x1FCu);
+		*cr = nrow;
+		if (pcr == cr) pre = nrow;
 		int sh = __clz(q.a); // RENORME
 		q.a <<= sh;
 		while (sh >= q.ct) { // a byte is completed inside this shift
@@ -448,6 +453,11 @@ __global__ void __launch_bounds__(MQ_WARPS * 32) t1_mq_kernel(const EncBlock *__
 		}
 		q.c <<= sh;
 		q.ct -= sh;
+	};
+	auto code = [&](uint32_t sym) {
+		uint32_t *cr = C + (sym >> 1);
+		uint32_t none = 0;
+		code_row(sym, cr, *cr, none, nullptr);
 	};
 
 	const uint2 *sp = reinterpret_cast<const uint2*>(symbols + B.sym_off); // sym_off is 16-byte aligned
@@ -461,8 +471,23 @@ __global__ void __launch_bounds__(MQ_WARPS * 32) t1_mq_kernel(const EncBlock *__
 			const uint2 cur = nxt;
 			nxt = sp[word++];
 			if (((cur.x | cur.y) & 0x80808080u) == 0) {
+#if MQ_PREFETCH
+				// the context row of symbol j + 1 is loaded before symbol j is coded: the shared-memory latency leaves the chain
+				uint32_t sym = cur.x & 0xFFu;
+				uint32_t *cr = C + (sym >> 1);
+				uint32_t row = *cr;
+				#pragma unroll
+				for (int j = 0; j < 8; ++j) {
+					const uint32_t nsym = j < 7 ? ((j + 1 < 4 ? cur.x : cur.y) >> (8 * ((j + 1) & 3))) & 0xFFu : 0u;
+					uint32_t *ncr = C + (nsym >> 1);
+					uint32_t nrow = j < 7 ? *ncr : 0u;
+					code_row(sym, cr, row, nrow, j < 7 ? ncr : nullptr);
+					sym = nsym; cr = ncr; row = nrow;
+				}
+#else
 				#pragma unroll
 				for (int j = 0; j < 8; ++j) code(((j < 4 ? cur.x : cur.y) >> (8 * (j & 3))) & 0xFFu);
+#endif
 			} else {
 				uint64_t grp = (uint64_t) cur.x | ((uint64_t) cur.y << 32);
 				#pragma unroll 1

@@ -33,9 +33,15 @@ def test_every_lane_count_gives_the_same_result(ctx, rev):
             assert (got[0] == ref[0]).all() and (got[1] == ref[1]).all() and (got[2] == ref[2]).all() and bytes(got[3]) == bytes(ref[3]), lanes
         for lanes in (1, 2, 4, 8):
             os.environ["GB200_T1_DEC_LANES"] = str(lanes)
+            os.environ["GB200_T1_DEC_UNIFORM"] = "0"
             got = gb.Plan(ctx, tiles_d, encoder=False).decode(inp, ref[3])
             for a, b in zip(got, ref_dec):
                 assert (a == b).all(), lanes
+        os.environ["GB200_T1_DEC_UNIFORM"] = "1"  # the warp-uniform decoder (one warp per block)
+        got = gb.Plan(ctx, tiles_d, encoder=False).decode(inp, ref[3])
+        for a, b in zip(got, ref_dec):
+            assert (a == b).all(), "uniform"
     finally:
         os.environ.pop("GB200_T1_MQ_LANES", None)
         os.environ.pop("GB200_T1_DEC_LANES", None)
+        os.environ.pop("GB200_T1_DEC_UNIFORM", None)
