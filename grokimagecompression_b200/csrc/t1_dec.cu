@@ -1,15 +1,21 @@
-// K5: EBCOT Tier-1 decoder, one THREAD per code block, de-quantisation in a following pass.
+// K5: EBCOT Tier-1 decoder: two kernels over the same pass code, de-quantisation in a following pass.
 //
 //   T1Part1::decode / post_decode   T1Part1.cpp:135-329   segment concat, /2 or x stepsize, scatter
 //   t1_decode_cblk                  t1.cpp:1038-1130      plane loop, pass order
 //   sig / ref / cln pass            t1.cpp:381-441, 588-637, 784-870
 //   MQ decoder                      mqc_dec.cpp:161-214, mqc_dec_inl.h:60-189
 //
-// Decoding a block is one serial chain: every decision selects the next context.  A warp that
-// works on ONE block spends 32 issue slots per step of that chain, and the machine runs out of
-// issue bandwidth long before it runs out of blocks (round-1 kernel: 125 warp instructions per
-// decision, 19 ms for configs[1]).  Here a block belongs to one thread, so a warp instruction
-// advances up to DT_LANES chains, and what bounds the kernel is the latency of one chain:
+// Decoding a block is one serial chain: every decision selects the next context.  A warp whose 32 lanes
+// co-operate on ONE block spends its issue slots on communication (round-1 kernel: 125 warp instructions per
+// decision, 19 ms for configs[1]), so a chain is always run by one instruction stream, CPU style (the three
+// passes with the four rows of a stripe column unrolled on constant bit positions, one flag word per column
+// in a register), and the two kernels differ in how chains are laid onto warps:
+//  * t1_decode_kernel<LANES>: a block belongs to one THREAD, LANES (1..8) blocks per warp.  A warp
+//    instruction then advances up to LANES chains, as far as their scan positions agree: for batches (tens of
+//    thousands of blocks) the machine is bound by warp instructions issued and eight chains per warp win.
+//  * t1_decode_uniform_kernel: a block belongs to one WARP whose 32 lanes all execute the same chain on the
+//    same values (see there).  For launches that fit the machine with a warp per block (one image).
+// Common to both:
 //  * The whole state of a block lives on chip.  One 32-bit word per stripe column holds the
 //    significance of its 3x6 neighbourhood, the signs of its own column, the visited and refined
 //    bits (the reference's flag word, t1.h:97-168, re-laid row major); a 64x64 block takes 4.2 KB
@@ -17,12 +23,8 @@
 //    wave over 148 SMs.  The MQ probability state of the 19 contexts is kept as packed Table C.2
 //    rows (Qe, both transitions, MPS) so a decision costs one shared load before the interval
 //    arithmetic starts.
-//  * Threads of a warp sit in different blocks and in different coding passes.  To keep them on
-//    one instruction stream the column scan is a small state machine (zero coding / refinement,
-//    sign, run-length AGG, two UNI bits) around a SINGLE inlined MQ decode, so the expensive part
-//    of every step is shared by all lanes whatever pass each one is in.
-//  * A sample that turns significant updates its neighbours' words with shared-memory atomics
-//    that return nothing; magnitudes go straight to the coefficient plane: a store of the
+//  * A sample that turns significant updates its neighbours' words in shared memory (result-less atomics /
+//    plain read-modify-writes); magnitudes go straight to the coefficient plane: a store of the
 //    mid-point value when the sample turns significant, a fire-and-forget RED.ADD of +-half a
 //    step per refinement (t1.cpp:392-394, 485).  Nothing on the critical chain waits for memory
 //    further away than shared.
@@ -46,9 +48,9 @@ namespace gb {
 #ifndef DT_SPARSE_BLOCKS_PER_SM
 #define DT_SPARSE_BLOCKS_PER_SM 16
 #endif
-// launches of up to this many blocks per SM go to the warp-uniform kernel (0 = never)
-#ifndef DT_UNIFORM_BLOCKS_PER_SM
-#define DT_UNIFORM_BLOCKS_PER_SM 0
+// 1: launches that fit the machine with one warp per block go to the warp-uniform kernel
+#ifndef DT_UNIFORM
+#define DT_UNIFORM 1
 #endif
 // the warp-uniform kernel: CTAs per SM it is compiled for and threads per CTA (2 x 768: 40 registers, 48 blocks per SM)
 #ifndef DU_MINB
@@ -64,6 +66,7 @@ namespace gb {
 constexpr int DT_MAX_THREADS = DT_MINB == 1 ? 1024 : 768;
 constexpr int DT_CTX_WORDS = 20;  // 19 context rows per block, padded
 constexpr int DT_FIXED_WORDS = 96 + 512 + 64; // MQ table, zero-coding table (4 x 512 B), sign table (256 B)
+constexpr int DU_RACC_WORDS = 16; // warp-uniform decoder: one byte per column of a stripe (refinement results)
 
 // stripe-column word: bit 3r+j = significance of row r-1 (r = 0..5), column j-1 (j = 0 west, 1 own, 2 east);
 // bit 18+r = sign of own column row r-1; bit 24+k = visited (k = 0..3); bit 28+k = refined before
@@ -199,7 +202,8 @@ struct Blk {
 	const uint8_t *rbuf;  // raw (bypass) segment reader, mqc_dec_inl.h:90-112
 	uint32_t rpos, rlen, rc;
 	int rct;
-	uint32_t lane;        // warp-uniform decoder only: lane 0 adds to the coefficient plane
+	uint32_t lane;        // warp-uniform decoder only
+	uint8_t *racc;        // warp-uniform decoder only: per column of the stripe, the refinements decoded (ref_row)
 };
 
 // one raw bit; bytes past the segment read as 0xFF, the byte after 0xFF carries 7 bits
@@ -226,18 +230,32 @@ __device__ __forceinline__ void flag_or(uint32_t *p, uint32_t v) {
 	else atomicOr(p, v);
 }
 
-// sign of a sample that just turned significant (t1.cpp:115-140), mid-point store, neighbour updates (t1.cpp:168-195)
+// sign context of row K (t1.cpp:115-140): context | xor bit << 5
+template<int K>
+__device__ __forceinline__ uint32_t sign_ctx(const Blk &b, uint32_t f, const uint32_t *cw) {
+	const uint32_t fW = cw[-1], fE = cw[1];
+	const uint32_t idx = ((f >> (3 * K)) & 0xAAu) | ((f >> (18 + K)) & 1u) | ((fW >> (17 + K)) & 4u) | ((fE >> (15 + K)) & 0x10u)
+			| ((f >> (14 + K)) & 0x40u);
+	return b.sc[idx];
+}
+
+template<int K, bool STY, bool UNI> __device__ __forceinline__ void mark(Blk &b, uint32_t &f, uint32_t *cw, int s, uint32_t off, int32_t oph, uint32_t neg);
+
+// sign of a sample that just turned significant, mid-point store, neighbour updates (t1.cpp:168-195)
 template<int K, bool STY = false, bool RAW = false, bool UNI = false>
 __device__ __forceinline__ void sign_and_mark(Blk &b, uint32_t &f, uint32_t *cw, int s, uint32_t off, int32_t oph) {
 	uint32_t neg;
 	if (RAW) neg = raw_bit(b); // raw passes carry the sign itself (t1.cpp:233-260)
 	else {
-		const uint32_t fW = cw[-1], fE = cw[1];
-		const uint32_t idx = ((f >> (3 * K)) & 0xAAu) | ((f >> (18 + K)) & 1u) | ((fW >> (17 + K)) & 4u) | ((fE >> (15 + K)) & 0x10u)
-				| ((f >> (14 + K)) & 0x40u);
-		const uint32_t v = b.sc[idx];
+		const uint32_t v = sign_ctx<K>(b, f, cw);
 		neg = mq_decode(b.q, b.C + (v & 31u), b.tab) ^ (v >> 5);
 	}
+	mark<K, STY, UNI>(b, f, cw, s, off, oph, neg);
+}
+
+
+template<int K, bool STY, bool UNI>
+__device__ __forceinline__ void mark(Blk &b, uint32_t &f, uint32_t *cw, int s, uint32_t off, int32_t oph, uint32_t neg) {
 	f |= fsig(K + 1, 1) | (neg << (19 + K));
 	b.dst[off + K * b.stride] = neg ? -oph : oph;
 	// the sample is the east neighbour of column x-1 and the west neighbour of column x+1
@@ -268,20 +286,34 @@ __device__ __forceinline__ void sig_row(Blk &b, uint32_t &f, uint32_t *cw, int s
 }
 
 // magnitude refinement: +-half a step towards the decoded bit, t1.cpp:476-496, 588-637
+// UNI: the four rows of a column only collect (member, decoded bit ^ sign) in `acc`; ref_flush then lets lane k add to row k
 template<int K, bool RAW = false, bool UNI = false>
-__device__ __forceinline__ void ref_row(Blk &b, uint32_t &f, uint32_t off, int32_t half) {
+__device__ __forceinline__ void ref_row(Blk &b, uint32_t &f, uint32_t off, int32_t half, uint32_t &acc) {
 	if ((f & (fsig(K + 1, 1) | (1u << (24 + K)))) == fsig(K + 1, 1)) {
 		const uint32_t cx = (f & (1u << (28 + K))) ? CTX_MR0 + 2 : (f & (0x1EFu << (3 * K))) ? CTX_MR0 + 1 : CTX_MR0;
 		const uint32_t d = RAW ? raw_bit(b) : mq_decode(b.q, b.C + cx, b.tab);
-		const uint32_t neg = (f >> (19 + K)) & 1u;
-		if (UNI) { // one predicated RED, not a branch around it: the instruction stream of the warp stays uniform
-			int32_t v = (d ^ neg) ? half : -half;
-			int32_t *p = b.dst + off + K * b.stride;
-			asm volatile("" : "+r"(v), "+l"(p)); // value and address are formed outside the predicate
-			asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %2, 0;\n\t@p red.global.add.s32 [%0], %1;\n\t}" :: "l"(p), "r"(v), "r"(b.lane) : "memory");
+		if (UNI) acc |= (0x10u | (d ^ (f >> (19 + K)) & 1u)) << K; // bit 4 + K: member, bit K: up (1) or down (0)
+		else {
+			const uint32_t neg = (f >> (19 + K)) & 1u;
+			atomicAdd(b.dst + off + K * b.stride, (d ^ neg) ? half : -half);
 		}
-		else atomicAdd(b.dst + off + K * b.stride, (d ^ neg) ? half : -half);
 		f |= 1u << (28 + K);
+	}
+}
+// end of a stripe of a refinement pass: lane l looks at columns l and l + 32 and adds to the rows that were refined
+// (fire-and-forget REDs, the one divergent region of the pass)
+// Out of line on purpose: inlined (and unrolled) into the pass code it cost 16 % of the kernel's time (configs[1]: 9.5 ms
+// against 8.2).
+__device__ __noinline__ void ref_flush(uint8_t *racc, int32_t *dst, uint32_t stride, uint32_t lane, int w, uint32_t off0, int32_t half) {
+	#pragma unroll 1
+	for (int x = (int) lane; x < w; x += 32) {
+		const uint32_t acc = racc[x];
+		if (!acc) continue;
+		racc[x] = 0;
+		int32_t *p = dst + off0 + x;
+		#pragma unroll
+		for (int k = 0; k < 4; ++k)
+			if (acc & (0x10u << k)) atomicAdd(p + k * stride, (acc >> k & 1u) ? half : -half);
 	}
 }
 
@@ -317,12 +349,15 @@ __device__ __forceinline__ void run_pass(Blk &b, uint32_t *F, int w, int fw, int
 			for (int x = 0; x < w; ++x, ++cw, ++off) {
 				uint32_t f = *cw;
 				if (!(f & F_OWNSIG)) continue;
-				ref_row<0, RAW, UNI>(b, f, off, half);
-				ref_row<1, RAW, UNI>(b, f, off, half);
-				ref_row<2, RAW, UNI>(b, f, off, half);
-				ref_row<3, RAW, UNI>(b, f, off, half);
+				uint32_t acc = 0;
+				ref_row<0, RAW, UNI>(b, f, off, half, acc);
+				ref_row<1, RAW, UNI>(b, f, off, half, acc);
+				ref_row<2, RAW, UNI>(b, f, off, half, acc);
+				ref_row<3, RAW, UNI>(b, f, off, half, acc);
+				if (UNI && acc) b.racc[x] = (uint8_t) acc;
 				*cw = f;
 			}
+			if (UNI) ref_flush(b.racc, b.dst, b.stride, b.lane, w, (uint32_t) (4 * s) * b.stride, half);
 		} else if (!RAW) {
 			const uint32_t keep_pi = s == b.nstripes - 1 ? last_pi : 0u;
 			for (int x = 0; x < w; ++x, ++cw, ++off) {
@@ -457,10 +492,14 @@ __global__ void __launch_bounds__(DT_MAX_THREADS, DT_MINB) t1_decode_kernel(cons
 // ---- warp-uniform decoder: one WARP per code block, every lane running the same chain --------------------
 // For launches that cannot fill the machine with thread-per-block chains (one image: 6 804 blocks, 11.5 per scheduler).
 // All 32 lanes of a warp decode the SAME block redundantly: every address and every branch condition derives from
-// blockIdx and from loads at warp-uniform addresses, so the compiler emits no reconvergence bookkeeping (BSSY / BSYNC /
-// BREAK: 10 of the 65 instructions per decision of the kernel above), branches are uniform, and twice as many warps per
-// scheduler hide the latency of a chain.  An instruction costs an issue slot and a pass through the pipe whether one lane
-// or 32 are live, so the redundant lanes are free.
+// blockIdx, a warp index taken through a shuffle, and loads at warp-uniform addresses, so the compiler sees uniform control
+// flow and emits no reconvergence bookkeeping (BSSY / BSYNC / BREAK: 10 of the 65 instructions per decision of the kernel
+// above), and twice as many warps per scheduler hide the latency of a chain (issue slots busy 79 % against 66 %).  An
+// instruction costs an issue slot and a pass through the pipe whether one lane or 32 are live, so the redundant lanes are
+// free.  The one place lanes differ is the end of a stripe of a refinement pass: the pass only notes, per column, which rows
+// it refined and in which direction (one shared-memory byte, ref_row), and ref_flush lets the lanes add the half steps to
+// the coefficient plane for 32 columns at a time -- per refinement that replaces address arithmetic, a predicated RED and
+// its reconvergence region on the serial chain by three instructions.  Two CTAs of up to 24 warps per SM (40 registers).
 template<bool STY>
 __global__ void __launch_bounds__(DU_MAX_THREADS, DU_MINB) t1_decode_uniform_kernel(const DecBlock *__restrict__ blocks,
 		const DecInput *__restrict__ inputs, uint32_t nblocks, const uint8_t *__restrict__ data, int fw, int fwords,
@@ -492,7 +531,7 @@ __global__ void __launch_bounds__(DU_MAX_THREADS, DU_MINB) t1_decode_uniform_ker
 	// by tile, component, resolution), so every SM gets the same mix of heavy and light blocks
 	const uint32_t bid = blockIdx.x + wid * gridDim.x;
 	if (bid >= nblocks) return;
-	uint32_t *F = sm + DT_FIXED_WORDS + wid * (uint32_t) (fwords + DT_CTX_WORDS); // word of stripe s, column x: F[s * fw + x + 1]
+	uint32_t *F = sm + DT_FIXED_WORDS + wid * (uint32_t) (fwords + DT_CTX_WORDS + DU_RACC_WORDS); // word of stripe s, column x: F[s * fw + x + 1]
 	const DecBlock B = blocks[bid];
 	const DecInput I = inputs[bid];
 	const int w = B.w, h = B.h;
@@ -510,6 +549,8 @@ __global__ void __launch_bounds__(DU_MAX_THREADS, DU_MINB) t1_decode_uniform_ker
 		for (int x = lane; x < w; x += 32) F[(b.nstripes - 1) * fw + 1 + x] = last_pi;
 	b.C = F + fwords;
 	b.tab = tab;
+	b.racc = reinterpret_cast<uint8_t*>(F + fwords + DT_CTX_WORDS);
+	if (lane < DU_RACC_WORDS) F[fwords + DT_CTX_WORDS + lane] = 0;
 	#pragma unroll
 	for (int i = 0; i < NCTX; ++i) b.C[i] = tab[2 * (i == CTX_ZC0 ? 4 : i == CTX_AGG ? 3 : i == CTX_UNI ? 46 : 0)]; // mqc_dec.cpp:207-214
 	__syncwarp();
@@ -578,28 +619,30 @@ int launch_t1_decode(const DecBlock *blocks, const DecInput *inputs, uint32_t nb
 	// warp instructions issued, and an instruction costs the same with one live lane or eight: as many blocks per warp as leave
 	// about twenty warps resident per SM (measured, profiles/README.md: 30 cinema frames, 32x32 blocks, 189 slots per SM:
 	// 68 ms at 2 per warp, 48 at 4, 41 at 8, 46 at 16; configs[2] planes, 64x64 blocks, 48 slots per SM: 133 ms at 2, 147 at 6).
-	// one image's worth of blocks (more than a sparse launch, not enough to fill the machine with thread-per-block chains):
-	// the warp-uniform kernel, one block per 32-thread CTA
-	int uniform = want > DT_SPARSE_BLOCKS_PER_SM && want <= DT_UNIFORM_BLOCKS_PER_SM;
-	if (const char *e = getenv("GB200_T1_DEC_UNIFORM")) uniform = atoi(e) != 0; // measurement knob
-	if (uniform) {
-		int fwords = (int) ((max_h + 3) / 4) * fw;
-		const int per_warp = (fwords + DT_CTX_WORDS) * 4;
-		// warps (= blocks) per CTA: DU_MINB CTAs per SM hold the SM's share of the blocks when shared memory and the thread
-		// limit allow it (one wave), else as many as fit
+	// Launches whose blocks all fit on the machine at once with a warp each (one image: configs[0] 7 blocks per SM, configs[1]
+	// 46, one cinema frame 45) go to the warp-uniform kernel: DU_MINB CTAs per SM, each holding its half of the SM's share.
+	// Measured (profiles/README.md): configs[1] 8.19 ms against 9.10 with two blocks per warp, configs[0] 4.92 against 6.07, one
+	// cinema frame 4.00 against 4.57; batches (30 cinema frames: 84 ms against 41, configs[2]: 157 against 131) stay with the
+	// thread-per-block kernel below, where eight chains share a warp's instruction stream.
+	{
+		const int ufwords = (int) ((max_h + 3) / 4) * fw;
+		const int per_warp = (ufwords + DT_CTX_WORDS + DU_RACC_WORDS) * 4;
+		const int ucap = std::min((smem_sm / DU_MINB - 1024 - DT_FIXED_WORDS * 4) / per_warp, DU_MAX_THREADS / 32); // warps (= blocks) per CTA
 		int warps = (want + DU_MINB - 1) / DU_MINB;
-		const int cap = (smem_sm / DU_MINB - 1024 - DT_FIXED_WORDS * 4) / per_warp;
-		if (warps > cap) warps = cap;
-		if (warps > DU_MAX_THREADS / 32) warps = DU_MAX_THREADS / 32;
-		if (warps < 1) return 1;
-		const size_t smem = (size_t) DT_FIXED_WORDS * 4 + (size_t) warps * per_warp;
-		const bool sty = styles || seg_start;
-		auto kernel = sty ? t1_decode_uniform_kernel<true> : t1_decode_uniform_kernel<false>;
-		if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) != cudaSuccess) return 1;
-		t1_dec_clear_kernel<<<(nblocks + 7) / 8, 256, 0, s>>>(blocks, nblocks);
-		kernel<<<(nblocks + warps - 1) / warps, warps * 32, smem, s>>>(blocks, inputs, nblocks, data, fw, fwords, seg_start, segs);
-		t1_dec_finish_kernel<<<(nblocks + 7) / 8, 256, 0, s>>>(blocks, nblocks);
-		return 0;
+		int uniform = DT_UNIFORM && warps <= ucap;
+		if (const char *e = getenv("GB200_T1_DEC_UNIFORM")) uniform = atoi(e) != 0; // measurement knob
+		if (uniform) {
+			if (warps > ucap) warps = ucap; // forced by the knob: several waves
+			if (warps < 1) return 1;
+			const size_t smem = (size_t) DT_FIXED_WORDS * 4 + (size_t) warps * per_warp;
+			const bool sty = styles || seg_start;
+			auto kernel = sty ? t1_decode_uniform_kernel<true> : t1_decode_uniform_kernel<false>;
+			if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) != cudaSuccess) return 1;
+			t1_dec_clear_kernel<<<(nblocks + 7) / 8, 256, 0, s>>>(blocks, nblocks);
+			kernel<<<(nblocks + warps - 1) / warps, warps * 32, smem, s>>>(blocks, inputs, nblocks, data, fw, ufwords, seg_start, segs);
+			t1_dec_finish_kernel<<<(nblocks + 7) / 8, 256, 0, s>>>(blocks, nblocks);
+			return 0;
+		}
 	}
 	int lanes, fwords, cap;
 	if (want * DT_MINB <= DT_SPARSE_BLOCKS_PER_SM) lanes = 1;
