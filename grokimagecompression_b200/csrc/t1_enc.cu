@@ -662,10 +662,11 @@ void launch_t1_encode(const EncBlock *blocks, uint32_t nblocks, int rate_control
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 	const uint32_t per_sm = (nblocks + (uint32_t) sms - 1) / (uint32_t) sms;
 	int lanes = styles ? 1 : per_sm <= MQ_SPARSE_BLOCKS_PER_SM ? 1 : per_sm <= 64 ? 4 : per_sm <= 160 ? 8 : per_sm <= 320 ? 16 : 32;
-	if (const char *e = getenv("GB200_T1_MQ_LANES")) { const int l = atoi(e); if (!styles && (l == 1 || l == 4 || l == 8 || l == 16 || l == 32)) lanes = l; } // measurement knob
+	if (const char *e = getenv("GB200_T1_MQ_LANES")) { const int l = atoi(e); if (!styles && (l == 1 || l == 2 || l == 4 || l == 8 || l == 16 || l == 32)) lanes = l; } // measurement knob
 	const uint32_t per_cta = (uint32_t) (MQ_WARPS * lanes), grid = (nblocks + per_cta - 1) / per_cta;
 	if (styles) t1_mq_kernel<1, true><<<grid, MQ_WARPS * 32, 0, s>>>(blocks, nblocks, symbols, scratch, results, rates);
 	else if (lanes == 1) t1_mq_kernel<1, false><<<grid, MQ_WARPS * 32, 0, s>>>(blocks, nblocks, symbols, scratch, results, rates);
+	else if (lanes == 2) t1_mq_kernel<2, false><<<grid, MQ_WARPS * 32, 0, s>>>(blocks, nblocks, symbols, scratch, results, rates);
 	else if (lanes == 4) t1_mq_kernel<4, false><<<grid, MQ_WARPS * 32, 0, s>>>(blocks, nblocks, symbols, scratch, results, rates);
 	else if (lanes == 8) t1_mq_kernel<8, false><<<grid, MQ_WARPS * 32, 0, s>>>(blocks, nblocks, symbols, scratch, results, rates);
 	else if (lanes == 16) t1_mq_kernel<16, false><<<grid, MQ_WARPS * 32, 0, s>>>(blocks, nblocks, symbols, scratch, results, rates);

@@ -54,7 +54,7 @@ if os.path.exists(p):
     inst = {}
     for r in rows:
         name = r[ki]
-        key = "decode" if "t1_decode_kernel" in name else "mq" if "t1_mq_kernel" in name else "model" if "t1_model_kernel" in name else None
+        key = "decode" if ("t1_decode_kernel" in name or "t1_decode_uniform_kernel" in name) else "mq" if "t1_mq_kernel" in name else "model" if "t1_model_kernel" in name else None
         if key and key not in inst:
             inst[key] = float(r[ii].replace(",", "")) / decisions
             text += f"---- {key}: {inst[key]:.2f} warp instructions per MQ decision ({decisions} decisions), {float(r[ti]):.2f} active threads per instruction\n"
