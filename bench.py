@@ -181,6 +181,8 @@ def cpu_reference_run(name, steps, warmup, budget_s=150.0, seed=1):
     def secs(idx):
         return sum(tap.ref_tap_seconds(i) for i in idx) if tap is not None else float("nan")
 
+    sim = [0.0, 0]  # T2::encode_packets_simulate of the last encode: seconds, calls
+
     def one(crop_rows):
         hh = min(w["height"], crop_rows * th)
         sub = [np.ascontiguousarray(p[:hh]) for p in img]
@@ -193,6 +195,7 @@ def cpu_reference_run(name, steps, warmup, budget_s=150.0, seed=1):
         _libs.ref_decode_image(cs, w["comps"], w["width"], hh)
         t2 = time.perf_counter()
         # stage indices of _libs.TAP_STAGES: dc, mct, dwt, t1 (encode) / t1, dwt, mct, dc (decode)
+        sim[0], sim[1] = secs((10,)), (tap.ref_tap_calls(10) if tap is not None else 0)
         return hh * w["width"], t1 - t0, t2 - t1, secs((0, 1, 2, 3)), secs((4, 5, 6, 7))
 
     crop = rows
@@ -207,7 +210,7 @@ def cpu_reference_run(name, steps, warmup, budget_s=150.0, seed=1):
         px, te, td, he, hd = one(crop)
         acc += (te, td, he, hd)
     t_enc, t_dec, h_enc, h_dec = acc / steps
-    return dict(pixels=px, t_enc=t_enc, t_dec=t_dec, hot_enc=h_enc, hot_dec=h_dec, cores=cores, tapped=tap is not None,
+    return dict(pixels=px, t_enc=t_enc, t_dec=t_dec, hot_enc=h_enc, hot_dec=h_dec, cores=cores, tapped=tap is not None, simulate_s=sim[0], simulate_calls=int(sim[1]),
                 sample=f"{w['width']}x{px // w['width']} crop ({crop}/{rows} tile rows) of {WORKLOAD_TEXT[name]}; "
                        f"unmodified reference through its public grk API, memory streams, {cores} threads")
 
@@ -219,6 +222,8 @@ def cpu_baseline_object(r):
            "whole_codec_encode_mpix_s": round(r["pixels"] / r["t_enc"] / 1e6, 3), "whole_codec_decode_mpix_s": round(r["pixels"] / r["t_dec"] / 1e6, 3)}
     if r["tapped"] and r["hot_enc"] > 0 and r["hot_dec"] > 0:
         hot = 2 * r["pixels"] / (r["hot_enc"] + r["hot_dec"]) / 1e6
+        out.update({"pcrd_simulate": {"ms_per_encode": round(r.get("simulate_s", 0.0) * 1e3, 2), "calls": r.get("simulate_calls", 0),
+                                      "what": "the reference's T2::encode_packets_simulate (packet-length simulation of every probe of its rate allocation): serial host code that stays the codec's, DESIGN.md section 9"}})
         out.update({"value": round(hot, 3), "hot_path_mpix_s": round(hot, 3),
                     "hot_path_encode_mpix_s": round(r["pixels"] / r["hot_enc"] / 1e6, 3), "hot_path_decode_mpix_s": round(r["pixels"] / r["hot_dec"] / 1e6, 3),
                     "what": "value = hot path only: wall clock inside the reference's dc_level_shift / mct / dwt / t1 stage calls and their inverses "

@@ -22,7 +22,8 @@
 
 namespace {
 
-enum { S_DC_ENC, S_MCT_ENC, S_DWT_ENC, S_T1_ENC, S_T1_DEC, S_DWT_DEC, S_MCT_DEC, S_DC_DEC, S_ENCODE_TILE, S_DECODE_TILE, S_COUNT };
+enum { S_DC_ENC, S_MCT_ENC, S_DWT_ENC, S_T1_ENC, S_T1_DEC, S_DWT_DEC, S_MCT_DEC, S_DC_DEC, S_ENCODE_TILE, S_DECODE_TILE,
+	S_SIMULATE /* T2::encode_packets_simulate: the serial part of the rate allocation, inside S_ENCODE_TILE */, S_COUNT };
 double g_secs[S_COUNT] = {0};
 uint64_t g_calls[S_COUNT] = {0};
 uint64_t g_geo_blocks = 0, g_geo_mismatch = 0, g_geo_tilecomps = 0;
@@ -126,6 +127,16 @@ bool TileProcessor::encode_tile(uint16_t tile_no, BufferedStream *p_stream, uint
 	static Fn real = next<Fn>("_ZN3grk13TileProcessor11encode_tileEtPNS_14BufferedStreamEPmmP20_grk_codestream_info");
 	Timer t(S_ENCODE_TILE);
 	return real(this, tile_no, p_stream, p_data_written, max_length, p_cstr_info);
+}
+
+/* the host-side rate allocation the GPU path leaves to the codec: the packet-length simulation every probe of the threshold
+ * bisection runs (TileProcessor.cpp:371-506, t2/T2.cpp:131-193) -- how much of encode_tile it is */
+bool T2::encode_packets_simulate(uint16_t tile_no, grk_tcd_tile *p_tile, uint32_t max_layers, uint64_t *p_data_written, uint64_t max_len,
+		uint32_t tp_pos) {
+	using Fn = bool (*)(T2*, uint16_t, grk_tcd_tile*, uint32_t, uint64_t*, uint64_t, uint32_t);
+	static Fn real = next<Fn>("_ZN3grk2T223encode_packets_simulateEtPNS_12grk_tcd_tileEjPmmj");
+	Timer t(S_SIMULATE);
+	return real(this, tile_no, p_tile, max_layers, p_data_written, max_len, tp_pos);
 }
 
 bool TileProcessor::decode_tile(ChunkBuffer *src_buf, uint16_t tile_no) {

@@ -101,7 +101,7 @@ def tap():
     return _tap
 
 
-TAP_STAGES = ("dc_enc", "mct_enc", "dwt_enc", "t1_enc", "t1_dec", "dwt_dec", "mct_dec", "dc_dec", "encode_tile", "decode_tile")
+TAP_STAGES = ("dc_enc", "mct_enc", "dwt_enc", "t1_enc", "t1_dec", "dwt_dec", "mct_dec", "dc_dec", "encode_tile", "decode_tile", "simulate")
 
 
 def have_ref():
