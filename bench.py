@@ -60,6 +60,7 @@ WORKLOAD_TEXT = {
     "c2ht": "configs[1] image with the HTJ2K block coder (-M 64): 4096x2160 RGB 8-bit, 9/7 + ICT, 1024x1024 tiles",
     "c3ht": "configs[2] image with the HTJ2K block coder (-M 64): 8192x8192 3x16-bit, 5/3 + RCT, 1024x1024 tiles",
 }
+STRONG_WORKERS = 2  # host workers per rank in the strong-scaling encode partitions (own context, plans, pinned buffers)
 T1_SOURCES = ("t1_enc.cu", "t1_dec.cu", "t1_tables.cuh", "common.cuh")
 DWT_SOURCES = ("dwt_stream.cuh", "dwt.cu", "dwt_plane.h")
 
@@ -266,7 +267,7 @@ def _tile_planes(base, index, prec, dtype):
 def strong_scaling(gb, torch, dist, ctx, rank, world, dev, steps):
     """configs[2] encode dealt by tile, configs[3] (240 frames) encode dealt by frame, configs[4] decode dealt by tile: unit u goes
     to rank u mod N, no data-path collective.  Every rank drives the C ABI with pinned HOST buffers (packed samples in, code-block
-    bytes out / bytes in, packed samples out); `ms` = wall clock of the slowest rank for one pass over all units, so the figures
+    bytes out / bytes in, packed samples out), the encode partitions from two host workers that take the chunks alternately; `ms` = wall clock of the slowest rank for one pass over all units, so the figures
     of the N = 1, 2, 4, 8 runs compare directly.  Afterwards rank 0 gathers the results of all ranks (gloo, host memory; in a
     one-process host such as the plugin adapter the results are already in its memory, `host_gather_ms` is what the
     process-per-GPU layout of this bench costs) and compares them byte for byte with its own one-GPU run of the same units;
@@ -331,43 +332,65 @@ def strong_scaling(gb, torch, dist, ctx, rank, world, dev, steps):
             if not units:
                 return 0.0, None, np.zeros(0, np.uint8)
             csz = min(chunk, len(units))
-            plan = gb.Plan(ctx, unit_tiles * csz, encoder=True, sample_bytes=sb)
+            chunks = [units[c0:c0 + csz] for c0 in range(0, len(units), csz)]
             tail = len(units) % csz
-            tplan = gb.Plan(ctx, unit_tiles * tail, encoder=True, sample_bytes=sb) if tail else None
-            h_in = [pinned((h, w), dt) for _ in range(csz * nc)]
-            outs = (pinned(plan.num_blocks * gb.CBLK_ENC_DTYPE.itemsize, np.uint8).view(gb.CBLK_ENC_DTYPE),
-                    pinned(max(plan.num_pass_slots, 1), np.int32).view(np.uint32), pinned(max(plan.num_pass_slots, 1), np.float64),
-                    pinned(csz * nc * w * h * 2 + (1 << 20), np.uint8))
+            # two host workers, each with its own context (stream), plans and pinned buffers, take the chunks alternately: one
+            # worker's staging copy and transfers run beside the other's kernels (the host owns the frame loop here)
+            nwork = min(STRONG_WORKERS, len(chunks))
+            ctxs = [ctx] + [gb.Context(dev.index or 0) for _ in range(nwork - 1)]
+            work = []
+            for wi in range(nwork):
+                plan = gb.Plan(ctxs[wi], unit_tiles * csz, encoder=True, sample_bytes=sb)
+                has_tail = tail and (len(chunks) - 1) % nwork == wi
+                tplan = gb.Plan(ctxs[wi], unit_tiles * tail, encoder=True, sample_bytes=sb) if has_tail else None
+                h_in = [pinned((h, w), dt) for _ in range(csz * nc)]
+                outs = (pinned(plan.num_blocks * gb.CBLK_ENC_DTYPE.itemsize, np.uint8).view(gb.CBLK_ENC_DTYPE),
+                        pinned(max(plan.num_pass_slots, 1), np.int32).view(np.uint32), pinned(max(plan.num_pass_slots, 1), np.float64),
+                        pinned(csz * nc * w * h * 2 + (1 << 20), np.uint8))
+                work.append((plan, tplan, h_in, outs))
             src = {u: source(u) for u in units}  # host images, prepared outside the timed region
             pieces, best = [], None
-            for it in range(1 + timed_steps):
-                pieces = []
-                sync()
-                t0 = time.perf_counter()
-                for c0 in range(0, len(units), csz):
-                    us = units[c0:c0 + csz]
+
+            def worker(wi, keep, pieces):
+                plan, tplan, h_in, outs = work[wi]
+                for ci in range(wi, len(chunks), nwork):
+                    us = chunks[ci]
                     pl = plan if len(us) == csz else tplan
                     k = 0
                     for u in us:  # the host hands over its frames: copy into the pinned staging buffers (part of the host's work)
-                        for p in src[u]:
-                            h_in[k][...] = p
+                        for p_ in src[u]:
+                            h_in[k][...] = p_
                             k += 1
                     o = outs if pl is plan else (outs[0][:pl.num_blocks], outs[1][:max(pl.num_pass_slots, 1)], outs[2][:max(pl.num_pass_slots, 1)], outs[3])
                     res, rates, dists, data = pl.encode(h_in[:len(us) * nc], o)
-                    if it == timed_steps:  # keep the last pass's results for the comparison: block records, the pass rates that exist, the bytes
+                    if keep:  # the last pass's results for the comparison: block records, the pass rates that exist, the bytes
                         np_ = res["numpasses"].astype(np.int64)
                         d = np.zeros(pl.num_pass_slots + 1, np.int64)
                         np.add.at(d, pl.blocks["pass_offset"].astype(np.int64), 1)
                         np.add.at(d, pl.blocks["pass_offset"].astype(np.int64) + np_, -1)
                         valid = np.cumsum(d)[:pl.num_pass_slots] > 0
-                        pieces.append((res.copy(), np.where(valid, rates[:pl.num_pass_slots], 0).astype(np.uint32), data.copy()))
+                        pieces[ci] = (res.copy(), np.where(valid, rates[:pl.num_pass_slots], 0).astype(np.uint32), data.copy())
+
+            for it in range(1 + timed_steps):
+                pieces = [None] * len(chunks)
+                sync()
+                t0 = time.perf_counter()
+                ths = [threading.Thread(target=worker, args=(wi, it == timed_steps, pieces)) for wi in range(1, nwork)]
+                for t in ths:
+                    t.start()
+                worker(0, it == timed_steps, pieces)
+                for t in ths:
+                    t.join()
                 torch.cuda.synchronize()
                 dt_ = time.perf_counter() - t0
                 if it > 0:
                     best = dt_ if best is None else min(best, dt_)
-            plan.close()
-            if tplan:
-                tplan.close()
+            for plan, tplan, _, _ in work:
+                plan.close()
+                if tplan:
+                    tplan.close()
+            for c_ in ctxs[1:]:
+                c_.close()
             best = best or 0.0
             blob = np.concatenate([np.concatenate([r.view(np.uint8).reshape(-1), ra.view(np.uint8).reshape(-1), d]) for r, ra, d in pieces])
             return best, None, blob
