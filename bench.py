@@ -60,7 +60,7 @@ WORKLOAD_TEXT = {
     "c2ht": "configs[1] image with the HTJ2K block coder (-M 64): 4096x2160 RGB 8-bit, 9/7 + ICT, 1024x1024 tiles",
     "c3ht": "configs[2] image with the HTJ2K block coder (-M 64): 8192x8192 3x16-bit, 5/3 + RCT, 1024x1024 tiles",
 }
-STRONG_WORKERS = 2  # host workers per rank in the strong-scaling encode partitions (own context, plans, pinned buffers)
+STRONG_WORKERS = 3  # host workers per rank in the strong-scaling encode partitions (own context, plans, pinned buffers)
 T1_SOURCES = ("t1_enc.cu", "t1_dec.cu", "t1_tables.cuh", "common.cuh")
 DWT_SOURCES = ("dwt_stream.cuh", "dwt.cu", "dwt_plane.h")
 
@@ -267,7 +267,7 @@ def _tile_planes(base, index, prec, dtype):
 def strong_scaling(gb, torch, dist, ctx, rank, world, dev, steps):
     """configs[2] encode dealt by tile, configs[3] (240 frames) encode dealt by frame, configs[4] decode dealt by tile: unit u goes
     to rank u mod N, no data-path collective.  Every rank drives the C ABI with pinned HOST buffers (packed samples in, code-block
-    bytes out / bytes in, packed samples out), the encode partitions from two host workers that take the chunks alternately; `ms` = wall clock of the slowest rank for one pass over all units, so the figures
+    bytes out / bytes in, packed samples out), the encode partitions from three host workers that take the chunks in turn; `ms` = wall clock of the slowest rank for one pass over all units, so the figures
     of the N = 1, 2, 4, 8 runs compare directly.  Afterwards rank 0 gathers the results of all ranks (gloo, host memory; in a
     one-process host such as the plugin adapter the results are already in its memory, `host_gather_ms` is what the
     process-per-GPU layout of this bench costs) and compares them byte for byte with its own one-GPU run of the same units;
@@ -421,7 +421,7 @@ def strong_scaling(gb, torch, dist, ctx, rank, world, dev, steps):
 
     # configs[2]: 8192x8192 3x16-bit lossless, 64 tiles of 1024x1024
     base3 = synthetic_planes(1024, 1024, 3, 16, seed=3)
-    encode_units("c3", 64, 16, (1024, 1024, 3), base3, 16, True, (6, 6), 15, False,
+    encode_units("c3", 64, 8, (1024, 1024, 3), base3, 16, True, (6, 6), 15, False,
                  "configs[2] encode: 64 tiles of 1024x1024x3 16-bit, 5/3 + RCT, tile t -> rank t mod N")
     # configs[3]: 240 DCI 2K frames, 30 per plan call
     base4 = synthetic_planes(2048, 1080, 3, 12, seed=1000)
@@ -439,33 +439,58 @@ def strong_scaling(gb, torch, dist, ctx, rank, world, dev, steps):
             sync = barrier if all_ranks else torch.cuda.synchronize
             if not units:
                 return 0.0, np.zeros(0, np.uint8)
-            n = len(units)
-            eplan = gb.Plan(ctx, enc_tiles * n, encoder=True, sample_bytes=1)
-            planes = []
-            for u in units:
-                planes += _tile_planes(base5, u, 8, np.uint8)
-            res, rates, dists, data = eplan.encode(planes)
-            keep = np.asarray(eplan.blocks["resno"]) < 6 - reduce
-            eplan.close()
-            inp = pinned(int(keep.sum()) * gb.CBLK_DEC_DTYPE.itemsize, np.uint8).view(gb.CBLK_DEC_DTYPE)
-            for k in ("numbps", "numpasses", "data_len", "data_offset"):
-                inp[k] = res[k][keep]
-            inp["reserved"] = 0
-            h_data = pinned(data.size, np.uint8)
-            h_data[...] = data
-            dplan = gb.Plan(ctx, dec_tiles * n, encoder=False, sample_bytes=1)
-            h_out = [pinned(s, np.uint8) for s in dplan.comp_shapes]
+            # chunks of up to 64 tiles, taken in turn by host workers with their own context, plan and pinned buffers: one
+            # worker's uploads and downloads run beside another's kernels
+            csz = min(64, len(units))
+            chunks = [units[c0:c0 + csz] for c0 in range(0, len(units), csz)]
+            nwork = min(STRONG_WORKERS, len(chunks))
+            ctxs = [ctx] + [gb.Context(dev.index or 0) for _ in range(nwork - 1)]
+            jobs = []  # per chunk: decoder inputs in pinned memory (the code blocks come from this repo's encoder, untimed)
+            for us in chunks:
+                n = len(us)
+                eplan = gb.Plan(ctx, enc_tiles * n, encoder=True, sample_bytes=1)
+                planes = []
+                for u in us:
+                    planes += _tile_planes(base5, u, 8, np.uint8)
+                res, rates, dists, data = eplan.encode(planes)
+                keep = np.asarray(eplan.blocks["resno"]) < 6 - reduce
+                eplan.close()
+                inp = pinned(int(keep.sum()) * gb.CBLK_DEC_DTYPE.itemsize, np.uint8).view(gb.CBLK_DEC_DTYPE)
+                for k in ("numbps", "numpasses", "data_len", "data_offset"):
+                    inp[k] = res[k][keep]
+                inp["reserved"] = 0
+                h_data = pinned(data.size, np.uint8)
+                h_data[...] = data
+                jobs.append((inp, h_data))
+            plans = {}
+            for wi in range(nwork):
+                for n in sorted({len(chunks[ci]) for ci in range(wi, len(chunks), nwork)}):
+                    plans[(wi, n)] = gb.Plan(ctxs[wi], dec_tiles * n, encoder=False, sample_bytes=1)
+            h_outs = [[pinned(s_, np.uint8) for s_ in plans[(ci % nwork, len(us))].comp_shapes] for ci, us in enumerate(chunks)]
+
+            def worker(wi):
+                for ci in range(wi, len(chunks), nwork):
+                    plans[(wi, len(chunks[ci]))].decode(jobs[ci][0], jobs[ci][1], h_outs[ci])
+
             best = None
             for it in range(1 + timed_steps):
                 sync()
                 t0 = time.perf_counter()
-                dplan.decode(inp, h_data, h_out)
+                ths = [threading.Thread(target=worker, args=(wi,)) for wi in range(1, nwork)]
+                for t in ths:
+                    t.start()
+                worker(0)
+                for t in ths:
+                    t.join()
                 torch.cuda.synchronize()
                 d = time.perf_counter() - t0
                 if it > 0:
                     best = d if best is None else min(best, d)
-            dplan.close()
-            return best or 0.0, np.concatenate([o.reshape(-1) for o in h_out])
+            for pl in plans.values():
+                pl.close()
+            for c_ in ctxs[1:]:
+                c_.close()
+            return best or 0.0, np.concatenate([o.reshape(-1) for ho in h_outs for o in ho])
 
         mine = list(range(rank, nunits, world))
         t_n, pix = run_dec(mine, steps, True)
