@@ -331,7 +331,9 @@ def strong_scaling(gb, torch, dist, ctx, rank, world, dev, steps):
             sync = barrier if all_ranks else torch.cuda.synchronize
             if not units:
                 return 0.0, None, np.zeros(0, np.uint8)
-            csz = min(chunk, len(units))
+            # units per plan call: `chunk` at most, and small enough that every worker gets two calls (a rank of an 8-GPU run
+            # holds an eighth of the units: one call would leave nothing to overlap its transfers with)
+            csz = max(1, min(chunk, len(units), -(-len(units) // (2 * STRONG_WORKERS))))
             chunks = [units[c0:c0 + csz] for c0 in range(0, len(units), csz)]
             tail = len(units) % csz
             # two host workers, each with its own context (stream), plans and pinned buffers, take the chunks alternately: one
@@ -441,7 +443,7 @@ def strong_scaling(gb, torch, dist, ctx, rank, world, dev, steps):
                 return 0.0, np.zeros(0, np.uint8)
             # chunks of up to 64 tiles, taken in turn by host workers with their own context, plan and pinned buffers: one
             # worker's uploads and downloads run beside another's kernels
-            csz = min(64, len(units))
+            csz = max(1, min(64, len(units), max(4, -(-len(units) // (2 * STRONG_WORKERS)))))
             chunks = [units[c0:c0 + csz] for c0 in range(0, len(units), csz)]
             nwork = min(STRONG_WORKERS, len(chunks))
             ctxs = [ctx] + [gb.Context(dev.index or 0) for _ in range(nwork - 1)]

@@ -598,6 +598,7 @@ int launch_t1_decode(const DecBlock *blocks, const DecInput *inputs, uint32_t nb
 	cudaGetDevice(&dev);
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 	cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+	const int smem_optin = smem_max;
 	cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
 	if (DT_MINB > 1) smem_max = std::min(smem_max, smem_sm / DT_MINB - 1024); // every resident CTA also reserves 1 KB
 	if (max_w < 1) max_w = 1;
@@ -637,7 +638,9 @@ int launch_t1_decode(const DecBlock *blocks, const DecInput *inputs, uint32_t nb
 			const size_t smem = (size_t) DT_FIXED_WORDS * 4 + (size_t) warps * per_warp;
 			const bool sty = styles || seg_start;
 			auto kernel = sty ? t1_decode_uniform_kernel<true> : t1_decode_uniform_kernel<false>;
-			if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) != cudaSuccess) return 1;
+			// always the device's limit, never this launch's size: contexts on several host threads launch the same kernel with
+			// different sizes, and a smaller value set by one thread would fail the other's launch
+			if (smem > (size_t) smem_optin || cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin) != cudaSuccess) return 1;
 			t1_dec_clear_kernel<<<(nblocks + 7) / 8, 256, 0, s>>>(blocks, nblocks);
 			kernel<<<(nblocks + warps - 1) / warps, warps * 32, smem, s>>>(blocks, inputs, nblocks, data, fw, ufwords, seg_start, segs);
 			t1_dec_finish_kernel<<<(nblocks + 7) / 8, 256, 0, s>>>(blocks, nblocks);
@@ -673,7 +676,7 @@ int launch_t1_decode(const DecBlock *blocks, const DecInput *inputs, uint32_t nb
 			: lanes == 2 ? (sty ? t1_decode_kernel<2, true> : t1_decode_kernel<2, false>)
 			: lanes == 4 ? (sty ? t1_decode_kernel<4, true> : t1_decode_kernel<4, false>)
 			: (sty ? t1_decode_kernel<8, true> : t1_decode_kernel<8, false>);
-	if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) != cudaSuccess) return 1;
+	if (smem > (size_t) smem_optin || cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin) != cudaSuccess) return 1; // see above
 	const int threads = (nslots + lanes - 1) / lanes * 32;
 	t1_dec_clear_kernel<<<(nblocks + 7) / 8, 256, 0, s>>>(blocks, nblocks);
 	kernel<<<(nblocks + nslots - 1) / nslots, threads, smem, s>>>(blocks, inputs, nblocks, data, fw, fwords, nslots, seg_start, segs);

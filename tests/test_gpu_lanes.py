@@ -45,3 +45,41 @@ def test_every_lane_count_gives_the_same_result(ctx, rev):
         os.environ.pop("GB200_T1_MQ_LANES", None)
         os.environ.pop("GB200_T1_DEC_LANES", None)
         os.environ.pop("GB200_T1_DEC_UNIFORM", None)
+
+
+def test_contexts_on_two_threads_with_different_launch_shapes():
+    """Two host threads, each with its own context, decode images of different sizes at the same time: the decoder kernel is
+    launched with different amounts of dynamic shared memory (85 KB and 24 KB), and neither launch may disturb the other (the
+    opt-in limit is a property of the kernel function, shared by every context of the process)."""
+    import threading
+    jobs = []
+    for side, seed in ((4096, 5), (2048, 6)):
+        img = synthetic_planes(side, side, 1, 8, seed=seed)
+        tiles = P.image_tiles(side, side, 1, 8, True, (None, None), 6)
+        tiles_d = P.image_tiles(side, side, 1, 8, True, (None, None), 6, encoder=False)
+        planes = P.split_planes(img, side, side, (None, None))
+        c = gb.Context(0)
+        res, rates, dists, data = gb.Plan(c, tiles, encoder=True).encode(planes)
+        inp = np.zeros(len(res), gb.CBLK_DEC_DTYPE)
+        for k in ("numbps", "numpasses", "data_len", "data_offset"):
+            inp[k] = res[k]
+        jobs.append((c, tiles_d, inp, data, planes))
+    errors = []
+
+    def run(job):
+        c, tiles_d, inp, data, planes = job
+        try:
+            plan = gb.Plan(c, tiles_d, encoder=False)
+            for _ in range(25):
+                got = plan.decode(inp, data)
+            for a, b in zip(got, planes):
+                assert (a == b).all()
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    ths = [threading.Thread(target=run, args=(j,)) for j in jobs]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    assert not errors, errors
