@@ -821,7 +821,7 @@ def main():
         try:
             ti = json.load(open(ip))
             if ti.get("source_sha1") != source_sha1(T1_SOURCES):
-                issue = {"stale": True, "note": "profiles/t1_issue.json was captured on other Tier-1 kernel sources: re-capture with tools/t1_issue_capture.sh"}
+                issue = {"stale": True, "note": "profiles/t1_issue.json was captured on other Tier-1 kernel sources: re-capture with tools/capture_profiles.sh + profiles/update_constants.py"}
             else:
                 sms = torch.cuda.get_device_properties(dev).multi_processor_count
                 issue_peak = sms * 4 * (clk.get("sm_mhz") or 1965.0) * 1e6  # warp instructions per second

@@ -1,6 +1,7 @@
 #!/bin/bash
-# variants of the decode kernel: parity (lane test + stage tests) and Tier-1 timing per variant
-cd /root/repo
+# usage (on the GPU box): VARIANTS="a b" WLS="c2 c1" bash tools/variant_run.sh -- parity (lane / stage / pipeline tests) and Tier-1 timing of
+# grokimagecompression_b200/libgrok_b200_<variant>.so (tools/build_variant.sh), then of the default library
+cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 {
 for v in $VARIANTS; do
@@ -10,5 +11,5 @@ for v in $VARIANTS; do
 done
 unset GB200_LIB
 for wl in $WLS; do echo "== $wl default"; timeout 300 python tools/t1_bench.py $wl 5; done
-} > gpurun_out/r2k_t1.log 2>&1
-grep -v "^$" gpurun_out/r2k_t1.log | tail -60
+} > gpurun_out/variant_run.log 2>&1
+grep -v "^$" gpurun_out/variant_run.log | tail -60
