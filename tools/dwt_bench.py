@@ -44,7 +44,7 @@ def main():
     print(f"workload {name}: {nbytes / 1e6:.1f} MB algorithmic per direction, {launches} level launches, peak {peak} GB/s")
     out = []
     for v in variants:
-        for k in ("GB200_DWT_ROWS", "GB200_DWT_UNROLL", "GB200_DWT_FILL", "GB200_DWT_HL", "GB200_DWT_ONLY", "GB200_DWT_RING"):
+        for k in ("GB200_DWT_ROWS", "GB200_DWT_UNROLL", "GB200_DWT_FILL", "GB200_DWT_HL", "GB200_DWT_ONLY", "GB200_DWT_RING", "GB200_DWT_MINROWS"):
             os.environ.pop(k, None)
         for kv in v.split(","):
             k, x = kv.split("=")
