@@ -27,9 +27,6 @@ struct gb200_ctx {
 	uint64_t launches;
 };
 
-#ifndef DWT_NARROW
-#define DWT_NARROW 0     // 1: the forward transform uses the kernels with two columns per lane
-#endif
 #ifndef DWT_MIN_ROWS
 #define DWT_MIN_ROWS 2   // smallest number of rows per work item the wave model may pick (even)
 #endif
@@ -72,7 +69,6 @@ struct LevelLaunch {
 	std::vector<std::pair<uint32_t, uint32_t>> strips; // (strips across, rows incl. the parity offset) of every plane
 	int rows = 16;        // rows per work item (one warp each)
 	int unroll = 2, halo_lanes = 1;
-	bool narrow = false;  // forward only: the kernels with two columns per lane (dwt_stream.cuh)
 };
 
 } // namespace
@@ -345,13 +341,8 @@ int gb200_plan_create(gb200_ctx *ctx, uint32_t ntiles, const gb200_tile_params *
 	auto env_int = [](const char *name, int dflt) { const char *e = getenv(name); return e && *e ? atoi(e) : dflt; };
 	const int force_rows = env_int("GB200_DWT_ROWS", 0), unroll = env_int("GB200_DWT_UNROLL", 1), fill = env_int("GB200_DWT_FILL", 4);
 	const int halo_lanes = env_int("GB200_DWT_HL", 1) == 2 ? 2 : 1;
-	// valid columns per work item, per wavelet ([1] = 5/3): the forward transform may use the narrow kernels
-	const bool narrow = pl->encoder && env_int("GB200_DWT_NARROW", DWT_NARROW) != 0;
-	uint32_t stw_r[2];
-	for (int r = 0; r < 2; ++r) {
-		if (narrow) dwt_narrow_shape(r, &stw_r[r]);
-		else dwt_stream_shape(halo_lanes, &stw_r[r]);
-	}
+	uint32_t stw;
+	dwt_stream_shape(halo_lanes, &stw);
 	for (auto &tg : pl->tiles)
 		for (uint32_t c = 0; c < tg.numcomps; ++c) {
 			const CompGeom &cg = tg.comps[c];
@@ -361,7 +352,6 @@ int gb200_plan_create(gb200_ctx *ctx, uint32_t ntiles, const gb200_tile_params *
 				if (!rw || !rh) continue;
 				LevelLaunch &L = pl->lvl[cg.p.qmfbid == 1][i];
 				const uint32_t cx = cdiv2n(cg.p.x0, lvl) & 1, cy = cdiv2n(cg.p.y0, lvl) & 1;
-				const uint32_t stw = stw_r[cg.p.qmfbid == 1];
 				L.strips.emplace_back((rw + cx + stw - 1) / stw, rh + cy);
 			}
 		}
@@ -372,14 +362,13 @@ int gb200_plan_create(gb200_ctx *ctx, uint32_t ntiles, const gb200_tile_params *
 			for (auto &L : pl->lvl[r]) {
 				L.unroll = unroll;
 				L.halo_lanes = halo_lanes;
-				L.narrow = narrow;
 				{
 					// Rows per work item.  A launch runs in waves of `slots` resident warps, and a partly filled last wave
 					// costs as much as a full one, so the row count is chosen by a small model: waves x trips per item
 					// (rows / 2 + the warm-up trips every item spends before its first result + a fixed start-up term).
 					// Few items: the shortest strips win (latency of one warp); one wave or a few: the count that just
 					// fits; many waves: long strips (least warm-up work).
-					const int slots = sms * (narrow ? dwt_narrow_warps_per_sm(r) : dwt_stream_warps_per_sm(r, pl->encoder ? 1 : 0, unroll));
+					const int slots = sms * dwt_stream_warps_per_sm(r, pl->encoder ? 1 : 0, unroll);
 					const int warm = (r ? 2 : 4) + fill; // trips: 2 * LAG + start-up (tables, first rows), `fill` is the knob
 					int rows = 16;
 					double best = 1e300;
@@ -437,7 +426,6 @@ int gb200_plan_create(gb200_ctx *ctx, uint32_t ntiles, const gb200_tile_params *
 					role_final = dst_role;
 				}
 				// a strip starts cas columns / rows before the region (a low-pass line comes first)
-				const uint32_t stw = stw_r[rev];
 				d.tiles_x = (d.rw + d.cas_x + stw - 1) / stw;
 				d.tiles_y = (d.rh + d.cas_y + trows - 1) / trows;
 				if (d.rw == 0 || d.rh == 0) { d.tiles_x = d.tiles_y = 0; }
@@ -734,8 +722,7 @@ static int run_dwt(gb200_plan *pl, bool fwd) {
 		for (int r = 0; r < 2; ++r) {
 			LevelLaunch &L = pl->lvl[r][i];
 			if (!L.ctas || (only >= 0 && (int) i != only)) continue;
-			if (fwd && L.narrow) launch_dwt_fwd_narrow((const DwtPlane*) L.dev.p, (const uint32_t*) L.map.p, L.ctas, r, L.rows, ctx->stream);
-			else if (fwd) launch_dwt_fwd((const DwtPlane*) L.dev.p, (const uint32_t*) L.map.p, L.ctas, r, L.rows, L.unroll, L.halo_lanes, ctx->stream);
+			if (fwd) launch_dwt_fwd((const DwtPlane*) L.dev.p, (const uint32_t*) L.map.p, L.ctas, r, L.rows, L.unroll, L.halo_lanes, ctx->stream);
 			else launch_dwt_inv((const DwtPlane*) L.dev.p, (const uint32_t*) L.map.p, L.ctas, r, L.rows, L.unroll, L.halo_lanes, ctx->stream);
 			n++;
 		}

@@ -80,11 +80,6 @@ void launch_dwt_fwd(const DwtPlane *planes_dev, const uint32_t *item_plane_dev, 
 void launch_dwt_inv(const DwtPlane *planes_dev, const uint32_t *item_plane_dev, uint32_t total_items, int reversible, int rows,
 		int unroll, int halo_lanes, cudaStream_t s);
 int dwt_stream_warps_per_sm(int reversible, int forward, int unroll); // work items resident per SM (occupancy of that kernel)
-// narrow forward kernels (two columns per lane, dwt_stream.cuh)
-void dwt_narrow_shape(int reversible, uint32_t *tw);
-int dwt_narrow_warps_per_sm(int reversible);
-void launch_dwt_fwd_narrow(const DwtPlane *planes_dev, const uint32_t *item_plane_dev, uint32_t total_items, int reversible, int rows,
-		cudaStream_t s);
 void dwt_stream_shape(int halo_lanes, uint32_t *tw); // valid columns per work item of the streaming kernels (halo_lanes 1 or 2)
 
 // t1_enc.cu / t1_dec.cu

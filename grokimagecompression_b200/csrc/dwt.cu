@@ -100,30 +100,6 @@ void launch_dwt_fwd(const DwtPlane *planes_dev, const uint32_t *item_plane_dev, 
 	launch_stream(true, reversible != 0, planes_dev, item_plane_dev, total_items, rows, unroll, halo_lanes, s);
 }
 
-// ---- narrow strips (two columns per lane), forward only ---------------------------------------------------------------
-void dwt_narrow_shape(int reversible, uint32_t *tw) { *tw = (uint32_t) dws_tw_narrow(reversible != 0); }
-
-int dwt_narrow_warps_per_sm(int reversible) {
-	int ctas = 0, warps = 8 * DWN_WARPS;
-	cudaError_t e = reversible ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, dwt_fwd_narrow_kernel<true, 2>, DWN_WARPS * 32, 0)
-			: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, dwt_fwd_narrow_kernel<false, 2>, DWN_WARPS * 32, 0);
-	if (e == cudaSuccess && ctas >= 1) warps = ctas * DWN_WARPS;
-	return warps;
-}
-
-void launch_dwt_fwd_narrow(const DwtPlane *planes_dev, const uint32_t *item_plane_dev, uint32_t total_items, int reversible, int rows,
-		cudaStream_t s) {
-	if (!total_items) return;
-	cudaLaunchConfig_t cfg = {};
-	cfg.gridDim = dim3((total_items + DWN_WARPS - 1) / DWN_WARPS); cfg.blockDim = dim3(DWN_WARPS * 32); cfg.dynamicSmemBytes = 0; cfg.stream = s;
-	cudaLaunchAttribute at[1];
-	at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-	at[0].val.programmaticStreamSerializationAllowed = 1;
-	cfg.attrs = at; cfg.numAttrs = 1;
-	if (reversible) cudaLaunchKernelEx(&cfg, dwt_fwd_narrow_kernel<true, 2>, planes_dev, item_plane_dev, total_items, rows);
-	else cudaLaunchKernelEx(&cfg, dwt_fwd_narrow_kernel<false, 2>, planes_dev, item_plane_dev, total_items, rows);
-}
-
 void launch_dwt_inv(const DwtPlane *planes_dev, const uint32_t *item_plane_dev, uint32_t total_items, int reversible, int rows,
 		int unroll, int halo_lanes, cudaStream_t s) {
 	if (!total_items) return;

@@ -442,160 +442,6 @@ __global__ void __launch_bounds__(DWS_WARPS * 32, DWS_MINB) dwt_fwd_stream_kerne
 	else dws_fwd_strip<REV, G, true, RING>(P, it, R, hl, my_ring);
 }
 
-// ---- forward, narrow strips: TWO columns per lane ---------------------------------------------------------
-// Same walk as dws_fwd_strip with half the state per lane (a lane holds one (low, high) pair of a row; a warp covers 64
-// columns): about 60 registers instead of 94, so an SM holds twice the warps.  The streaming kernels are bound by the
-// latency of a warp's dependent lifting chains (issue slots half used with 16-20 warps per SM), and the only way to more
-// warps is less state per warp.  The price: the horizontal halo is 2 lanes (9/7) / 1 lane (5/3) of 32 instead of 1 of 32,
-// and a shuffle serves two columns instead of four.
-struct Pair { int32_t e0, o0; };
-
-__host__ __device__ constexpr int dws_tw_narrow(bool rev) { return rev ? 60 : 56; } // valid columns per work item
-__host__ __device__ constexpr int dws_hl_narrow(bool rev) { return rev ? 1 : 2; }   // halo lanes each side
-
-// horizontal lifting of two rows in lock step; lanes hl .. 31 - hl come out exact
-template<bool REV>
-__device__ __forceinline__ void dws_hfwd2n(Pair &p, Pair &q) {
-	if (REV) {
-		int32_t pe1 = dws_down(p.e0), qe1 = dws_down(q.e0);
-		p.o0 -= (p.e0 + pe1) >> 1; q.o0 -= (q.e0 + qe1) >> 1;
-		int32_t pom = dws_up(p.o0), qom = dws_up(q.o0);
-		p.e0 += (pom + p.o0 + 2) >> 2; q.e0 += (qom + q.o0 + 2) >> 2;
-	} else {
-		int32_t pe1 = dws_down(p.e0), qe1 = dws_down(q.e0);
-		p.o0 -= dws_fix13(p.e0 + pe1, 12994); q.o0 -= dws_fix13(q.e0 + qe1, 12994);
-		int32_t pom = dws_up(p.o0), qom = dws_up(q.o0);
-		p.e0 -= dws_fix13(pom + p.o0, 434); q.e0 -= dws_fix13(qom + q.o0, 434);
-		pe1 = dws_down(p.e0); qe1 = dws_down(q.e0);
-		p.o0 += dws_fix13(p.e0 + pe1, 7233); q.o0 += dws_fix13(q.e0 + qe1, 7233);
-		pom = dws_up(p.o0); qom = dws_up(q.o0);
-		p.e0 += dws_fix13(pom + p.o0, 3633); q.e0 += dws_fix13(qom + q.o0, 3633);
-		p.e0 = dws_fix13(p.e0, 6659); q.e0 = dws_fix13(q.e0, 6659);
-		p.o0 = dws_fix13(p.o0, 5039); q.o0 = dws_fix13(q.o0, 5039);
-	}
-}
-template<bool REV>
-__device__ __forceinline__ void dws_hfwdn(Pair &p) {
-	Pair q = p;
-	dws_hfwd2n<REV>(p, q);
-}
-
-// EDGE as in dws_fwd_strip: false = every lane loads 8 aligned bytes of the region; true = 4-byte gathers through reflected
-// indices and predicated stores.  Register queue only.
-template<bool REV, int G, bool EDGE>
-__device__ __forceinline__ void dws_fwd_strip_narrow(const DwtPlane &P, const DwsItem &it, int R) {
-	constexpr int hl = dws_hl_narrow(REV);
-	const int rw = (int) P.rw, rh = (int) P.rh, casx = (int) P.cas_x, casy = (int) P.cas_y;
-	const int c = it.c;
-	const uint32_t sstr4 = P.src_stride * 4u, dstr4 = P.dst_stride * 4u;
-	const int32_t *s0 = P.src + (EDGE ? dws_reflect(c, rw) : c);
-	const int32_t *s1 = P.src + dws_reflect(c + 1, rw);
-	constexpr int K = G + 1; // row pairs in the queue; trip t lives in pair t % K
-	Pair regs[2 * K];
-	auto issue_row = [&](int y, int slot) {
-		const uint32_t gy = (uint32_t) dws_reflect(y, rh);
-		Pair &q = regs[slot];
-		if (!EDGE) {
-			const int2 v = dws_ld2(dws_at(s0, gy, sstr4));
-			q.e0 = v.x; q.o0 = v.y;
-		} else {
-			q.e0 = dws_ld1(dws_at(s0, gy, sstr4)); q.o0 = dws_ld1(dws_at(s1, gy, sstr4));
-		}
-	};
-	const bool lv = it.lane >= hl && it.lane <= 31 - hl;
-	const bool okE = lv && (unsigned) c < (unsigned) rw, okO = lv && (unsigned) (c + 1) < (unsigned) rw;
-	int32_t *const dL = P.dst + (c >> 1), *const dH = P.dst + ((int) P.sw + ((c + 1) >> 1));
-	auto store_row = [&](const Pair &q, uint32_t row) {
-		int32_t *oL = dws_at(dL, row, dstr4), *oH = dws_at(dH, row, dstr4);
-		if (!EDGE) {
-			if (lv) { dws_st1(oL, q.e0); dws_st1(oH, q.o0); }
-		} else {
-			if (okE) dws_st1(oL, q.e0);
-			if (okO) dws_st1(oH, q.o0);
-		}
-	};
-	const bool hlift = !EDGE || rw > 1;
-	auto emit1 = [&](Pair q, int y, bool high_row) {
-		if (hlift) dws_hfwdn<REV>(q);
-		else if (REV && casx) { q.e0 *= 2; q.o0 *= 2; } // dwt53.cpp:160
-		store_row(q, (uint32_t) ((y >> 1) + (high_row ? (int) P.sh : 0)));
-	};
-
-	if (rh == 1) { // a single row is not lifted vertically; with an odd origin it is a high-pass row (x2 for 5/3)
-		if (it.Y0 != 0) return;
-		issue_row(0, 0);
-		Pair q = regs[0];
-		if (REV && casy) { q.e0 *= 2; q.o0 *= 2; }
-		emit1(q, 0, casy != 0);
-		return;
-	}
-
-	constexpr int LAG = VFwd<REV>::LAG;
-	const int ys = it.Y0 - casy - 2 * LAG;
-	const int yv0 = max(it.Y0 - casy, 0), yv1 = min(it.Y0 - casy + R, rh);
-	if (yv1 <= yv0) return;
-	const int niter = LAG + ((yv1 - 1 - ys) >> 1) + 1;
-
-	VFwd<REV> v0, v1;
-	v0.init(); v1.init();
-	#pragma unroll
-	for (int g = 0; g < G; ++g)
-		if (g < niter) { issue_row(ys + 2 * g, 2 * g); issue_row(ys + 2 * g + 1, 2 * g + 1); }
-	regs[2 * (K - 1)] = Pair{0, 0}; regs[2 * (K - 1) + 1] = Pair{0, 0}; // "trip -1": part of the warm-up
-	for (int j0 = 0; j0 < niter; j0 += K) {
-		#pragma unroll
-		for (int u = 0; u < K; ++u) {
-			const int j = j0 + u;
-			if (j >= niter) break;
-			const int prev = (u + K - 1) % K; // pair of trip j - 1
-			const Pair a = regs[2 * u];
-			const Pair qa = regs[2 * prev], qb = regs[2 * prev + 1];
-			Pair lo, hi;
-			v0.feed(qa.e0, qb.e0, a.e0, lo.e0, hi.e0);
-			v1.feed(qa.o0, qb.o0, a.o0, lo.o0, hi.o0);
-			if (j + G < niter) { issue_row(ys + 2 * (j + G), 2 * prev); issue_row(ys + 2 * (j + G) + 1, 2 * prev + 1); }
-			const int yl = ys + 2 * (j - LAG);
-			const bool vl = yl >= yv0 && yl < yv1, vh = yl + 1 >= yv0 && yl + 1 < yv1;
-			if (vl && vh && hlift) {
-				dws_hfwd2n<REV>(lo, hi);
-				store_row(lo, (uint32_t) (yl >> 1));
-				store_row(hi, (uint32_t) (((yl + 1) >> 1) + (int) P.sh));
-			} else {
-				if (vl) emit1(lo, yl, false);
-				if (vh) emit1(hi, yl + 1, true);
-			}
-		}
-	}
-}
-
-#ifndef DWN_WARPS_PER_CTA
-#define DWN_WARPS_PER_CTA 4
-#endif
-#ifndef DWN_MINB
-#define DWN_MINB 1
-#endif
-constexpr int DWN_WARPS = DWN_WARPS_PER_CTA;
-
-template<bool REV, int G>
-__global__ void __launch_bounds__(DWN_WARPS * 32, DWN_MINB) dwt_fwd_narrow_kernel(const DwtPlane *__restrict__ planes,
-		const uint32_t *__restrict__ item_plane, uint32_t nitems, int R) {
-	dws_launch_dependents();
-	DwsItem it;
-	it.lane = threadIdx.x & 31;
-	uint32_t item = blockIdx.x * DWN_WARPS + (threadIdx.x >> 5);
-	if (item >= nitems) return;
-	DwtPlane P = planes[__ldg(item_plane + item)];
-	item -= P.first_cta;
-	it.X0 = (int) (item % P.tiles_x) * dws_tw_narrow(REV);
-	it.Y0 = (int) (item / P.tiles_x) * R;
-	it.c = it.X0 - 2 * dws_hl_narrow(REV) - (int) P.cas_x + 2 * it.lane;
-	dws_grid_wait(); // from here on the planes are read
-	const int c = it.c, rw = (int) P.rw;
-	const bool vld = c >= 0 && c + 1 < rw && (c & 1) == 0 && (P.src_stride & 1) == 0 && (((size_t) P.src) & 7) == 0;
-	if (__all_sync(0xffffffffu, vld)) dws_fwd_strip_narrow<REV, G, false>(P, it, R);
-	else dws_fwd_strip_narrow<REV, G, true>(P, it, R);
-}
-
 // =========================================================================================================
 // inverse
 // =========================================================================================================

@@ -92,41 +92,12 @@ static void launch(K kernel, const DwtPlane *planes, const uint32_t *map, uint32
 	for (auto &t : th) t.join();
 }
 
-template<typename K>
-static void launch_narrow(K kernel, const DwtPlane *planes, const uint32_t *map, uint32_t nitems, int R) {
-	const unsigned grid = (nitems + gb::DWN_WARPS - 1) / gb::DWN_WARPS;
-	std::vector<std::thread> th;
-	for (int lane = 0; lane < 32; ++lane)
-		th.emplace_back([=] {
-			emu_lane = lane;
-			for (unsigned b = 0; b < grid; ++b)
-				for (unsigned w = 0; w < (unsigned) gb::DWN_WARPS; ++w) {
-					blockIdx.x = b;
-					threadIdx.x = w * 32 + lane;
-					kernel(planes, map, nitems, R);
-				}
-		});
-	for (auto &t : th) t.join();
-}
-
 static uint32_t cdiv2n(uint32_t a, uint32_t n) { return (uint32_t) (((uint64_t) a + (1ull << n) - 1) >> n); }
 
 // the plan's table for one level of one plane (csrc/api.cu)
-static int g_hl = 1, g_ring = 1, g_narrow = 0; // g_narrow: the forward kernels with two columns per lane
+static int g_hl = 1, g_ring = 1;
 static void one_level(DwtPlane d, bool fwd, int rev, int R) {
 	const int hl = g_hl;
-	if (fwd && g_narrow) {
-		const uint32_t tw = (uint32_t) gb::dws_tw_narrow(rev != 0);
-		d.tiles_x = (d.rw + d.cas_x + tw - 1) / tw;
-		d.tiles_y = (d.rh + d.cas_y + R - 1) / R;
-		d.first_cta = 0;
-		if (!d.rw || !d.rh) return;
-		const uint32_t n = d.tiles_x * d.tiles_y;
-		std::vector<uint32_t> map(n, 0);
-		if (rev) launch_narrow(gb::dwt_fwd_narrow_kernel<true, 2>, &d, map.data(), n, R);
-		else launch_narrow(gb::dwt_fwd_narrow_kernel<false, 2>, &d, map.data(), n, R);
-		return;
-	}
 	d.tiles_x = (d.rw + d.cas_x + gb::dws_tw(hl) - 1) / gb::dws_tw(hl);
 	d.tiles_y = (d.rh + d.cas_y + R - 1) / R;
 	d.first_cta = 0;
@@ -229,9 +200,8 @@ int main(int argc, char **argv) {
 			if (U(0, 4) == 0) g.x1 = g.x0 + 4 * U(30, 130); // aligned widths reach the interior (vector) strips
 			g.nr = U(1, 6);
 			const int rev = (int) U(0, 1), R = (int) (2 * U(1, 40)); // the plan picks 2 rows per item for the smallest levels
-			g_hl = (int) U(1, 2); g_ring = (int) U(0, 1); g_narrow = (int) U(0, 1);
+			g_hl = (int) U(1, 2); g_ring = (int) U(0, 1);
 			fails += check_fwd(g, rev, R, rng);
-			g_narrow = 0;
 			fails += check_inv(g, U(1, g.nr), rev, R, rng);
 		}
 		printf("fuzz: %d cases, %d failed\n", 2 * n, fails);
@@ -253,7 +223,6 @@ int main(int argc, char **argv) {
 				g_hl = (R == 16 || R == 2) ? 1 : 2;
 				g_ring = R != 16 && R != 2;
 				fails += check_fwd(g, rev, R, rng); ++cases;
-				if (R != 4) { g_narrow = 1; fails += check_fwd(g, rev, R, rng); ++cases; g_narrow = 0; }
 				std::vector<uint32_t> nds = {g.nr, std::max(1u, g.nr - 1), g.nr > 3 ? g.nr - 3 : 1u, 1u};
 				std::sort(nds.begin(), nds.end());
 				nds.erase(std::unique(nds.begin(), nds.end()), nds.end());
