@@ -66,7 +66,10 @@ namespace gb {
 constexpr int DT_MAX_THREADS = DT_MINB == 1 ? 1024 : 768;
 constexpr int DT_CTX_WORDS = 20;  // 19 context rows per block, padded
 constexpr int DT_FIXED_WORDS = 96 + 512 + 64; // MQ table, zero-coding table (4 x 512 B), sign table (256 B)
-constexpr int DU_RACC_WORDS = 16; // warp-uniform decoder: one byte per column of a stripe (refinement results)
+#ifndef DU_MR_LIST
+#define DU_MR_LIST 1
+#endif
+constexpr int DU_RACC_WORDS = 16 + 32; // warp-uniform decoder, per column of a stripe: one byte of refinement results, one 16-bit refinement code
 
 // stripe-column word: bit 3r+j = significance of row r-1 (r = 0..5), column j-1 (j = 0 west, 1 own, 2 east);
 // bit 18+r = sign of own column row r-1; bit 24+k = visited (k = 0..3); bit 28+k = refined before
@@ -345,6 +348,45 @@ __device__ __forceinline__ void run_pass(Blk &b, uint32_t *F, int w, int fw, int
 				sig_row<3, STY, RAW, UNI>(b, f, cw, s, off, oph);
 				*cw = f;
 			}
+		} else if (type == 1 && UNI && DU_MR_LIST) {
+			// Warp-uniform decoder: which samples a refinement pass codes, and in which of the three contexts, is fixed when
+			// the pass starts (nothing turns significant in it).  The 32 lanes look at 32 columns of the stripe at once: members
+			// (significant, not visited), their contexts and signs go into one 16-bit code per column, the refined bits are set
+			// on the spot, and a ballot says which columns have members at all; the serial walk then touches only those
+			// columns and does nothing per sample but decode.
+			uint16_t *const codes = reinterpret_cast<uint16_t*>(b.racc + 64);
+			for (int x0 = 0; x0 < w; x0 += 32) {
+				const int xl = x0 + (int) b.lane;
+				uint32_t code = 0;
+				if (xl < w) {
+					const uint32_t f = cw[xl];
+					const uint32_t m4 = own_sig4(f) & ~(f >> 24) & 0xFu;
+					if (m4) {
+						const uint32_t refd = f >> 28, nb = nbr4(f);
+						uint32_t ctx = 0; // two bits per row: 2 = refined before, 1 = a significant neighbour, 0 = neither (t1.cpp:476-496)
+						#pragma unroll
+						for (int k = 0; k < 4; ++k) ctx |= ((refd >> k & 1u) ? 2u : (nb >> k & 1u)) << (2 * k);
+						code = m4 | ctx << 4 | ((f >> 19) & 0xFu) << 12;
+						cw[xl] = f | m4 << 28;
+					}
+					codes[xl] = (uint16_t) code;
+				}
+				uint32_t todo = __ballot_sync(0xffffffffu, code != 0);
+				while (todo) {
+					const int x = x0 + __ffs(todo) - 1;
+					todo &= todo - 1;
+					const uint32_t cd = codes[x];
+					uint32_t acc = (cd & 0xFu) << 4;
+					#pragma unroll
+					for (int k = 0; k < 4; ++k)
+						if (cd >> k & 1u) {
+							const uint32_t d = RAW ? raw_bit(b) : mq_decode(b.q, b.C + CTX_MR0 + ((cd >> (4 + 2 * k)) & 3u), b.tab);
+							acc |= ((d ^ (cd >> (12 + k))) & 1u) << k;
+						}
+					b.racc[x] = (uint8_t) acc;
+				}
+			}
+			ref_flush(b.racc, b.dst, b.stride, b.lane, w, (uint32_t) (4 * s) * b.stride, half);
 		} else if (type == 1) {
 			for (int x = 0; x < w; ++x, ++cw, ++off) {
 				uint32_t f = *cw;
@@ -496,10 +538,13 @@ __global__ void __launch_bounds__(DT_MAX_THREADS, DT_MINB) t1_decode_kernel(cons
 // flow and emits no reconvergence bookkeeping (BSSY / BSYNC / BREAK: 10 of the 65 instructions per decision of the kernel
 // above), and twice as many warps per scheduler hide the latency of a chain (issue slots busy 79 % against 66 %).  An
 // instruction costs an issue slot and a pass through the pipe whether one lane or 32 are live, so the redundant lanes are
-// free.  The one place lanes differ is the end of a stripe of a refinement pass: the pass only notes, per column, which rows
-// it refined and in which direction (one shared-memory byte, ref_row), and ref_flush lets the lanes add the half steps to
-// the coefficient plane for 32 columns at a time -- per refinement that replaces address arithmetic, a predicated RED and
-// its reconvergence region on the serial chain by three instructions.  Two CTAs of up to 24 warps per SM (40 registers).
+// free.  The lanes differ in the refinement pass only.  Before a stripe is walked they look at 32 columns at a time and write,
+// per column, which rows the pass codes, in which context and with which sign (membership is fixed when the pass starts), so
+// the serial walk visits only columns with members and does nothing per sample but decode; it notes per column which rows it
+// refined and in which direction (one shared-memory byte), and at the end of the stripe ref_flush lets the lanes add the half
+// steps to the coefficient plane for 32 columns at a time -- per refinement that replaces the row tests, the context
+// selection, address arithmetic, a predicated RED and its reconvergence region on the serial chain by a handful of
+// instructions.  Two CTAs of up to 24 warps per SM (40 registers).
 template<bool STY>
 __global__ void __launch_bounds__(DU_MAX_THREADS, DU_MINB) t1_decode_uniform_kernel(const DecBlock *__restrict__ blocks,
 		const DecInput *__restrict__ inputs, uint32_t nblocks, const uint8_t *__restrict__ data, int fw, int fwords,
@@ -550,7 +595,7 @@ __global__ void __launch_bounds__(DU_MAX_THREADS, DU_MINB) t1_decode_uniform_ker
 	b.C = F + fwords;
 	b.tab = tab;
 	b.racc = reinterpret_cast<uint8_t*>(F + fwords + DT_CTX_WORDS);
-	if (lane < DU_RACC_WORDS) F[fwords + DT_CTX_WORDS + lane] = 0;
+	if (lane < 16) F[fwords + DT_CTX_WORDS + lane] = 0; // the result bytes; the codes are written before they are read
 	#pragma unroll
 	for (int i = 0; i < NCTX; ++i) b.C[i] = tab[2 * (i == CTX_ZC0 ? 4 : i == CTX_AGG ? 3 : i == CTX_UNI ? 46 : 0)]; // mqc_dec.cpp:207-214
 	__syncwarp();
