@@ -312,7 +312,7 @@ def strong_scaling(gb, torch, dist, ctx, rank, world, dev, steps):
 
     out = {}
 
-    def encode_units(label, nunits, chunk, comp_geom, base, prec, reversible, cblk, prc, rate_control, text):
+    def encode_units(label, nunits, chunk, min_units, comp_geom, base, prec, reversible, cblk, prc, rate_control, text):
         """units = tiles or frames of identical geometry; each rank encodes its units in chunks of `chunk` units per plan call"""
         w, h, nc = comp_geom
         sb = sample_bytes_of(prec)
@@ -333,7 +333,8 @@ def strong_scaling(gb, torch, dist, ctx, rank, world, dev, steps):
                 return 0.0, None, np.zeros(0, np.uint8)
             # units per plan call: `chunk` at most, and small enough that every worker gets two calls (a rank of an 8-GPU run
             # holds an eighth of the units: one call would leave nothing to overlap its transfers with)
-            csz = max(1, min(chunk, len(units), -(-len(units) // (2 * STRONG_WORKERS))))
+            # (but not so small that a call is nothing but the latency of one launch chain: at least min_units)
+            csz = max(1, min(chunk, len(units), max(min_units, -(-len(units) // (2 * STRONG_WORKERS)))))
             chunks = [units[c0:c0 + csz] for c0 in range(0, len(units), csz)]
             tail = len(units) % csz
             # two host workers, each with its own context (stream), plans and pinned buffers, take the chunks alternately: one
@@ -423,11 +424,11 @@ def strong_scaling(gb, torch, dist, ctx, rank, world, dev, steps):
 
     # configs[2]: 8192x8192 3x16-bit lossless, 64 tiles of 1024x1024
     base3 = synthetic_planes(1024, 1024, 3, 16, seed=3)
-    encode_units("c3", 64, 8, (1024, 1024, 3), base3, 16, True, (6, 6), 15, False,
+    encode_units("c3", 64, 8, 4, (1024, 1024, 3), base3, 16, True, (6, 6), 15, False,
                  "configs[2] encode: 64 tiles of 1024x1024x3 16-bit, 5/3 + RCT, tile t -> rank t mod N")
     # configs[3]: 240 DCI 2K frames, 30 per plan call
     base4 = synthetic_planes(2048, 1080, 3, 12, seed=1000)
-    encode_units("c4x240", 240, 30, (2048, 1080, 3), base4, 12, False, (5, 5), [7] + [8] * 32, True,
+    encode_units("c4x240", 240, 30, 5, (2048, 1080, 3), base4, 12, False, (5, 5), [7] + [8] * 32, True,
                  "configs[3] encode: 240 frames of 2048x1080x3 12-bit, 9/7 + ICT, cinema precincts, frame f -> rank f mod N, 30 frames per plan call")
 
     # configs[4]: decode of a 16384x16384 3x8-bit image, 256 tiles of 1024x1024; the code blocks come from this repo's encoder (untimed)
@@ -443,7 +444,7 @@ def strong_scaling(gb, torch, dist, ctx, rank, world, dev, steps):
                 return 0.0, np.zeros(0, np.uint8)
             # chunks of up to 64 tiles, taken in turn by host workers with their own context, plan and pinned buffers: one
             # worker's uploads and downloads run beside another's kernels
-            csz = max(1, min(64, len(units), max(4, -(-len(units) // (2 * STRONG_WORKERS)))))
+            csz = max(1, min(64, len(units), max(16, -(-len(units) // (2 * STRONG_WORKERS)))))
             chunks = [units[c0:c0 + csz] for c0 in range(0, len(units), csz)]
             nwork = min(STRONG_WORKERS, len(chunks))
             ctxs = [ctx] + [gb.Context(dev.index or 0) for _ in range(nwork - 1)]
